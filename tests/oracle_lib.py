@@ -1,0 +1,107 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libzw_oracle.so) -- test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(ROOT, "oracle", "_build", "libzw_oracle.so")
+
+
+def build():
+    src = os.path.join(ROOT, "oracle", "zw_oracle.cpp")
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class MbRecord(C.Structure):
+    _fields_ = [("ymode", C.c_uint8), ("uvmode", C.c_uint8), ("segment", C.c_uint8), ("skip", C.c_uint8),
+                ("bmodes", C.c_uint8 * 16), ("top_nz", C.c_uint16), ("left_nz", C.c_uint16),
+                ("derr_left", C.c_int8 * 4), ("derr_top", C.c_int8 * 4), ("levels", (C.c_int16 * 16) * 25)]
+
+
+MB_DTYPE = np.dtype([("ymode", "u1"), ("uvmode", "u1"), ("segment", "u1"), ("skip", "u1"),
+                     ("bmodes", "u1", (16,)), ("top_nz", "<u2"), ("left_nz", "<u2"),
+                     ("derr_left", "i1", (4,)), ("derr_top", "i1", (4,)), ("levels", "<i2", (25, 16))])
+assert MB_DTYPE.itemsize == 832 == C.sizeof(MbRecord)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        u8p = C.POINTER(C.c_uint8)
+        L.zwo_encode_vp8.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(u8p), C.POINTER(C.c_size_t), C.c_void_p]
+        L.zwo_encode_webp.argtypes = L.zwo_encode_vp8.argtypes
+        L.zwo_free.argtypes = [C.c_void_p]
+        L.zwo_dump_new.restype = C.c_void_p
+        L.zwo_dump_free.argtypes = [C.c_void_p]
+        L.zwo_dump_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(u8p), C.POINTER(C.c_size_t)]
+        L.zwo_encode_batch_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        L.zwo_encode_batch_mt.restype = C.c_size_t
+        L.zwo_cbrt.restype = C.c_double
+        L.zwo_cbrt.argtypes = [C.c_double]
+        L.zwo_pow.restype = C.c_double
+        L.zwo_pow.argtypes = [C.c_double, C.c_double]
+        L.zwo_bool_encode.restype = C.c_size_t
+        L.zwo_bool_encode_tree.restype = C.c_size_t
+        L.zwo_rd_score.restype = C.c_uint32
+        L.zwo_residual_cost.restype = C.c_uint32
+        for f in ("zwo_fixed_cost_i16", "zwo_fixed_cost_uv", "zwo_fixed_cost_i4", "zwo_entropy_cost", "zwo_level_fixed_cost"):
+            getattr(L, f).restype = C.c_uint16
+    return _lib
+
+
+COLOR = {"L8": 0, "La8": 1, "Rgb8": 2, "Rgba8": 3}
+
+STAGES = ["YUV_Y", "YUV_U", "YUV_V", "BASE_QIDX", "SEG_ENABLED", "ALPHA", "ALPHA_HIST", "SEG_CENTERS", "SEG_MAP256",
+          "SEG_MID", "SEG_MAP", "SEG_QIDX", "SEG_TREE_PROBS", "SEG_UPDATE_MAP", "P1MB", "STATS", "PROBS",
+          "PROBS_UPDATED", "SKIP_PROB", "LCOST", "P2MB", "PART0", "PART1", "TOKEN_PROBS_FINAL", "VP8"]
+_STAGE_DTYPES = {"ALPHA_HIST": "<u4", "SEG_MID": "<i4", "STATS": "<u4", "LCOST": "<u2", "P1MB": MB_DTYPE, "P2MB": MB_DTYPE}
+
+
+def encode(img, quality, method, color="Rgb8", container=True, want_dump=False):
+    """img: uint8 array [h,w,c].  Returns (status, bytes, dump-dict-or-None)."""
+    L = lib()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[0], img.shape[1]
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    d = L.zwo_dump_new() if want_dump else None
+    fn = L.zwo_encode_webp if container else L.zwo_encode_vp8
+    rc = fn(img.ctypes.data, img.nbytes, w, h, COLOR[color], int(quality), int(method), C.byref(out), C.byref(n), d)
+    data = b""
+    if rc == 0:
+        data = C.string_at(out, n.value)
+        L.zwo_free(out)
+    dump = None
+    if want_dump:
+        dump = {}
+        for name in STAGES:
+            p = C.POINTER(C.c_uint8)()
+            ln = C.c_size_t(0)
+            if L.zwo_dump_get(d, name.encode(), C.byref(p), C.byref(ln)):
+                raw = C.string_at(p, ln.value)
+                dump[name] = np.frombuffer(raw, dtype=_STAGE_DTYPES.get(name, "u1")).copy()
+        L.zwo_dump_free(d)
+    return rc, data, dump
+
+
+def encode_raw(data: bytes, w, h, quality, method, color="Rgb8", container=True):
+    L = lib()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if data else b"\0")
+    fn = L.zwo_encode_webp if container else L.zwo_encode_vp8
+    rc = fn(buf, len(data), w, h, COLOR[color], int(quality), int(method), C.byref(out), C.byref(n), None)
+    res = b""
+    if rc == 0:
+        res = C.string_at(out, n.value)
+        L.zwo_free(out)
+    return rc, res
