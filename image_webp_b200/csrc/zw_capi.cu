@@ -1,0 +1,672 @@
+// zw_capi.cu -- host side of the C ABI (include/zenwebp_b200.h): validation, HBM layout of a
+// chunk, kernel sequencing, D2H and host chunk assembly.  Only RIFF/VP8 chunk assembly and the
+// tiny f64 quality->quantiser tables are computed on the host; there is no CPU encode fallback.
+//
+// Reference (file:line under /root/reference):
+//   quality_to_quant_index      src/encoder/vp8.rs:37-55       (+ fast_math.rs:15-43 cbrt)
+//   compute_segment_quant       src/encoder/analysis.rs:1145-1174 (+ fast_math.rs:48-122 pow)
+//   Segment::init_matrices      src/common/types.rs:806-853
+//   VP8Matrix::new              src/encoder/cost.rs:401-447
+//   compute_filter_level        src/encoder/cost.rs:271-294
+//   RIFF container              src/encoder/api.rs:1224-1241, :1320-1329
+// Compile the host part with -ffp-contract=off: Rust never fuses mul-add.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/zenwebp_b200.h"
+#include "zw_back.cuh"
+#include "zw_front.cuh"
+
+using namespace zw;
+
+namespace {
+
+thread_local int g_last_error = 0;
+
+// ---- f64 helpers (bit-exact restatement of the reference's no_std math) ----------------------
+static inline u64 f64_bits(double x) { u64 b; memcpy(&b, &x, 8); return b; }
+static inline double f64_from(u64 b) { double x; memcpy(&x, &b, 8); return x; }
+static double h_cbrt(double x) {
+  if (x == 0.0) return 0.0;
+  double y = f64_from((f64_bits(x) / 3) + (1023ull * 2 / 3) * (1ull << 52));
+  for (int i = 0; i < 4; i++) { double y2 = y * y; y = (2.0 * y + x / y2) / 3.0; }
+  return y;
+}
+static double h_log2(double x) {
+  const u64 bits = f64_bits(x);
+  const i64 e = (i64)((bits >> 52) & 0x7FF) - 1023;
+  const double m = f64_from((bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+  const double y = (m - 1.0) / (m + 1.0), y2 = y * y;
+  const double poly = 2.8853900817779268 + y2 * (0.9617966939259756 + y2 * (0.5770780163555854 + y2 * (0.4121985831111324 + y2 * 0.3205988987531030)));
+  return (double)e + y * poly;
+}
+static double h_exp2(double x) {
+  x = x < -1022.0 ? -1022.0 : (x > 1023.0 ? 1023.0 : x);
+  const i64 xi = x >= 0.0 ? (i64)x : (i64)x - 1;
+  const double xf = x - (double)xi;
+  const double LN2 = 0.693147180559945309417232121458176568;
+  const double C1 = LN2, C2 = LN2 * LN2 / 2.0, C3 = LN2 * LN2 * LN2 / 6.0, C4 = LN2 * LN2 * LN2 * LN2 / 24.0,
+               C5 = LN2 * LN2 * LN2 * LN2 * LN2 / 120.0;
+  const double poly = 1.0 + xf * (C1 + xf * (C2 + xf * (C3 + xf * (C4 + xf * C5))));
+  return poly * f64_from(((u64)(xi + 1023)) << 52);
+}
+static double h_pow(double x, double n) {
+  if (x <= 0.0) return 0.0;
+  if (x == 1.0 || n == 0.0) return 1.0;
+  if (n == 1.0) return x;
+  return h_exp2(n * h_log2(x));
+}
+static int quality_to_quant_index(int quality) {
+  const double c = (double)quality / 100.0;
+  const double lin = c < 0.75 ? c * (2.0 / 3.0) : 2.0 * c - 1.0;
+  const int q = (int)(i64)(127.0 * (1.0 - h_cbrt(lin)) + 0.5);
+  return std::min(std::max(q, 0), 127);
+}
+static int compute_segment_quant(int base_quant, int segment_alpha, int sns_strength) {
+  const double amp = 0.9 * (double)sns_strength / 100.0 / 128.0;
+  const double expn = 1.0 - amp * (double)segment_alpha;
+  if (expn <= 0.0) return base_quant;
+  const double c_base = 1.0 - ((double)base_quant / 127.0);
+  const double c = h_pow(c_base, expn);
+  const int q = (int)(127.0 * (1.0 - c));
+  return std::min(std::max(q, 0), 127);
+}
+static int compute_filter_level(int quant_index) {  // sharpness 0, filter_strength 50 (vp8.rs:2417-2420)
+  const u32 level0 = 5 * 50;
+  const u32 qstep = (u32)(host::kAcTable[quant_index] >> 2) & 255;
+  const u32 base = host::kLevelsFromDelta[0 * 64 + std::min<u32>(qstep, 63)];
+  const u32 f = base * level0 / 256;
+  return f < 2 ? 0 : (f > 63 ? 63 : (int)f);
+}
+static Matrix make_matrix(u32 q_dc, u32 q_ac, int type) {
+  static const u32 B[3][2] = {{96, 110}, {96, 108}, {110, 115}};
+  Matrix m;
+  m.q[0] = (u16)q_dc; m.q[1] = (u16)q_ac;
+  for (int i = 0; i < 2; i++) {
+    m.iq[i] = (u32)((1ull << 17) / (u64)m.q[i]);
+    m.bias[i] = ((B[type][i] << 17) + 128) >> 8;
+  }
+  return m;
+}
+static SegParams make_segparams(int idx) {
+  SegParams s;
+  memset(&s, 0, sizeof(s));
+  const u32 ydc = (u32)host::kDcQuant[idx], yac = (u32)host::kAcQuant[idx];
+  const u32 y2dc = ydc * 2, y2ac = std::max<u32>((u32)((int)yac * 155 / 100), 8);
+  const u32 uvdc = ydc, uvac = yac;  // note: not clamped to 132 (Q18)
+  s.y1 = make_matrix(ydc, yac, 0);
+  s.y2 = make_matrix(y2dc, y2ac, 1);
+  s.uv = make_matrix(uvdc, uvac, 2);
+  for (int i = 0; i < 16; i++) s.sharpen[i] = (u16)(((u32)host::kFreqSharpening[i] * (u32)s.y1.q[i > 0]) >> 11);
+  const u32 q_i4 = (ydc + 15 * yac + 8) >> 4, q_i16 = (y2dc + 15 * y2ac + 8) >> 4, q_uv = (uvdc + 15 * uvac + 8) >> 4;
+  s.lambda_trellis_i4 = std::max<u32>((7 * q_i4 * q_i4) >> 3, 1);
+  s.lambda_trellis_i16 = std::max<u32>((q_i16 * q_i16) >> 2, 1);
+  s.lambda_i4 = std::max<u32>((3 * q_i4 * q_i4) >> 7, 1);
+  s.lambda_i16 = std::max<u32>(3 * q_i16 * q_i16, 1);
+  s.lambda_uv = std::max<u32>((3 * q_uv * q_uv) >> 6, 1);
+  s.lambda_mode = std::max<u32>((q_i4 * q_i4) >> 7, 1);
+  s.tlambda = (50u * q_i4) >> 5;
+  s.uv_dc_zthresh = ((1u << 17) - 1 - s.uv.bias[0]) / s.uv.iq[0];
+  return s;
+}
+
+// ---- token trees (RFC 6386 / src/common/types.rs:191-205, :332, :700-703) --------------------
+static const i8 T_SEG[6] = {2, 4, 0, -1, -2, -3};
+static const i8 T_YMODE[8] = {-4, 2, 4, 6, 0, -1, -2, -3};
+static const i8 T_BMODE[18] = {0, 2, -1, 4, -2, 6, 8, 12, -3, 10, -5, -6, -4, 14, -7, 16, -8, -9};
+static const i8 T_UV[6] = {0, 2, -1, 4, -2, -3};
+static const i8 T_DCT[22] = {-11, 2, 0, 4, -1, 6, 8, 12, -2, 10, -3, -4, 14, 16, -5, -6, 18, 20, -7, -8, -9, -10};
+static void walk_tree(const i8* tree, int node, u32 code, int len, TreeCodes& out) {
+  for (int bit = 0; bit < 2; bit++) {
+    const int nx = tree[node + bit];
+    const u32 c = (code << 1) | (u32)bit;
+    // leaves are stored as -value; value 0 is stored as 0, which is never a valid child index
+    if (nx <= 0) { out.len[-nx] = (u8)(len + 1); out.code[-nx] = (u16)c; }
+    else walk_tree(tree, nx, c, len + 1, out);
+  }
+}
+static TokenTables make_token_tables() {
+  TokenTables t;
+  memset(&t, 0, sizeof(t));
+  memcpy(t.tree_dct, T_DCT, sizeof(T_DCT)); memcpy(t.tree_ymode, T_YMODE, sizeof(T_YMODE));
+  memcpy(t.tree_bmode, T_BMODE, sizeof(T_BMODE)); memcpy(t.tree_uv, T_UV, sizeof(T_UV)); memcpy(t.tree_seg, T_SEG, sizeof(T_SEG));
+  walk_tree(T_DCT, 0, 0, 0, t.dct); walk_tree(T_YMODE, 0, 0, 0, t.ymode); walk_tree(T_BMODE, 0, 0, 0, t.bmode);
+  walk_tree(T_UV, 0, 0, 0, t.uv); walk_tree(T_SEG, 0, 0, 0, t.seg);
+  return t;
+}
+
+// ---- device buffer that only grows -----------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+#define CK(expr)                                                         \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)_e; return g_last_error; } \
+  } while (0)
+
+}  // namespace
+
+struct zw_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t budget = 0;
+  int warps_per_sm_hint = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[16];
+  // constant tables
+  DevBuf d_segtab, d_lut;
+  // chunk buffers
+  DevBuf d_img, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
+      d_derr1, d_derr2, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
+      d_part, d_out, d_outoff;
+  // host mirrors of the staged chunk
+  std::vector<ImageDesc> img;
+  std::vector<ImageState> st;
+  std::vector<RowRef> rows;
+  std::vector<u64> out_off;
+  std::vector<int> img_status;  // host-side validation result per image of the chunk (0 = staged)
+  std::vector<int> slot_of;     // chunk image index -> position among staged (valid) images, or -1
+  std::vector<u8> h_out;
+  u8* h_pinned = nullptr;
+  size_t h_pinned_cap = 0;
+  u32 n_valid = 0, n_rows = 0, n_mb = 0, max_pw = 0, max_ph = 0, max_mb = 0;
+  u64 layout_key = 0;
+  bool staged = false, encoded = false;
+  int quality = -1, method = -1, base_qidx = 0;
+  int search_blocks1 = 0, search_blocks2 = 0, chroma_blocks = 0;
+  ChunkParams P;
+  zw_timing last;
+};
+
+static void fill_params(zw_ctx* c) {
+  ChunkParams& P = c->P;
+  memset(&P, 0, sizeof(P));
+  P.img = c->d_img.as<ImageDesc>(); P.st = c->d_st.as<ImageState>(); P.rows = c->d_rows.as<RowRef>();
+  P.segtab = c->d_segtab.as<SegParams>(); P.segquant_lut = c->d_lut.as<u8>();
+  P.n_img = c->n_valid; P.n_rows = c->n_rows; P.n_mb = c->n_mb;
+  P.rgb = c->d_rgb.as<u8>(); P.planes = c->d_planes.as<u8>();
+  P.alpha_hist = c->d_alpha_hist.as<u32>(); P.map256 = c->d_map256.as<u8>();
+  P.alpha = c->d_alpha.as<u8>(); P.segmap = c->d_segmap.as<u8>();
+  P.rec1 = c->d_rec1.as<MbRecord>(); P.rec2 = c->d_rec2.as<MbRecord>(); P.bottom = c->d_bottom.as<MbBottom>();
+  P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>();
+  P.progress = c->d_progress.as<int>(); P.ticket = c->d_ticket.as<u32>(); P.rowstats = c->d_rowstats.as<u32>();
+  P.stats = c->d_stats.as<u32>(); P.probs = c->d_probs.as<u8>(); P.lcost = c->d_lcost.as<u16>();
+  P.mb_hdr_cnt = c->d_hcnt.as<u32>(); P.mb_tok_cnt = c->d_tcnt.as<u32>();
+  P.hdr_tokens = c->d_htok.as<Token>(); P.tok_tokens = c->d_ttok.as<Token>();
+  P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
+}
+
+static int validate_image(const zw_image& im) {
+  if (im.data == nullptr) return ZW_ERR_INVALID_PARAM;
+  if (im.color != ZW_COLOR_RGB8 && im.color != ZW_COLOR_RGBA8) return ZW_ERR_INVALID_PARAM;
+  if (im.width == 0 || im.height == 0 || im.width > 16383 || im.height > 16383) return ZW_ERR_INVALID_DIMENSIONS;
+  const u64 bpp = im.color == ZW_COLOR_RGB8 ? 3 : 4;
+  if ((u64)im.width * im.height * bpp != (u64)im.len) return ZW_ERR_INVALID_BUFFER_SIZE;
+  return ZW_OK;
+}
+
+// Bytes of device memory one image needs (used to split a batch into chunks).
+static size_t image_footprint(u32 w, u32 h, u32 bpp) {
+  const size_t mbw = (w + 15) / 16, mbh = (h + 15) / 16, nmb = mbw * mbh;
+  size_t b = (size_t)w * h * bpp + 64;        // RGB
+  b += nmb * 384;                              // planes
+  b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8);
+  b += mbh * (2112 * 4 + 8 + 8);               // row statistics, progress, row table
+  b += 1056 * 7 + 6528 * 2 + 2048;             // per-image tables
+  b += nmb * 256 * 10 + nmb * 256;             // token streams (estimate: 5 symbols/px) + bitstream
+  return b;
+}
+
+extern "C" {
+
+const char* zw_version(void) { return "zenwebp_b200 0.1 (CUDA, sm_100a)"; }
+int zw_last_error(void) { return g_last_error; }
+void zw_free(void* p) { free(p); }
+size_t zw_max_output_size(uint32_t w, uint32_t h) {
+  const size_t mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+  return 64 + 16384 + mbw * mbh * (7700 * 7 / 8 + 200);
+}
+const char* zw_strerror(int code) {
+  switch (code) {
+    case ZW_OK: return "ok";
+    case ZW_ERR_INVALID_DIMENSIONS: return "invalid dimensions";
+    case ZW_ERR_INVALID_BUFFER_SIZE: return "invalid buffer size";
+    case ZW_ERR_INVALID_PARAM: return "invalid parameter";
+    case ZW_ERR_OUTPUT_TOO_SMALL: return "output buffer too small";
+    case ZW_ERR_PARTITION_TOO_LARGE: return "first partition exceeds the 19-bit size field";
+    case ZW_ERR_NOT_STAGED: return "no staged batch";
+    default: break;
+  }
+  if (code >= ZW_ERR_CUDA) return cudaGetErrorString((cudaError_t)(code - ZW_ERR_CUDA));
+  return "unknown error";
+}
+
+zw_ctx* zw_create(int device, const zw_limits* limits) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_last_error = ZW_ERR_CUDA + (int)(e != cudaSuccess ? e : cudaErrorNoDevice); return nullptr; }
+  if (device < 0 || device >= ndev) { g_last_error = ZW_ERR_INVALID_PARAM; return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; return nullptr; }
+  zw_ctx* c = new zw_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  c->sm_count = prop.multiProcessorCount;
+  c->budget = (limits && limits->max_device_bytes) ? limits->max_device_bytes : ((size_t)32 << 30);
+  c->warps_per_sm_hint = limits ? limits->persistent_warps_per_sm : 0;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; delete c; return nullptr; }
+  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  // constant tables
+  std::vector<SegParams> segtab(128);
+  for (int i = 0; i < 128; i++) segtab[i] = make_segparams(i);
+  std::vector<u8> lut(128 * 255);
+  for (int b = 0; b < 128; b++)
+    for (int a = -127; a <= 127; a++) lut[b * 255 + (a + 127)] = (u8)compute_segment_quant(b, a, 50);
+  const TokenTables tt = make_token_tables();
+  if (c->d_segtab.reserve(segtab.size() * sizeof(SegParams)) != cudaSuccess || c->d_lut.reserve(lut.size()) != cudaSuccess ||
+      c->d_ticket.reserve(64) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr; }
+  cudaMemcpy(c->d_segtab.p, segtab.data(), segtab.size() * sizeof(SegParams), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice);
+  cudaMemcpyToSymbol(c_tok, &tt, sizeof(tt));
+  int b1 = 0, b2 = 0, b3 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_chroma1, SEARCH_WARPS * 32, sizeof(SearchShared));
+  if (c->warps_per_sm_hint > 0) {
+    const int cap = std::max(1, c->warps_per_sm_hint / SEARCH_WARPS);
+    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b3 = std::min(b3, cap);
+  }
+  c->search_blocks1 = std::max(1, b1) * c->sm_count;
+  c->search_blocks2 = std::max(1, b2) * c->sm_count;
+  c->chroma_blocks = std::max(1, b3) * c->sm_count;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; zw_destroy(c); return nullptr; }
+  g_last_error = 0;
+  return c;
+}
+
+void zw_destroy(zw_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  DevBuf* all[] = {&c->d_segtab, &c->d_lut, &c->d_img, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist,
+                   &c->d_map256, &c->d_alpha, &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1,
+                   &c->d_derr2, &c->d_progress, &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost,
+                   &c->d_hcnt, &c->d_tcnt, &c->d_htok, &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
+  for (DevBuf* b : all) b->release();
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto& ev : c->ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
+  if (!c || (!imgs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (n > 65535) return g_last_error = ZW_ERR_INVALID_PARAM;  // grid.y / grid.z limit; the batch API chunks below this
+  CK(cudaSetDevice(c->device));
+  c->staged = false; c->encoded = false;
+  c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
+  u64 rgb_bytes = 0, plane_bytes = 0, key = 1469598103934665603ull;
+  u32 n_mb = 0, n_rows = 0, max_pw = 0, max_ph = 0, max_mb = 0, max_mbh = 0;
+  for (size_t i = 0; i < n; i++) {
+    const int v = validate_image(imgs[i]);
+    c->img_status[i] = v;
+    if (v != ZW_OK) continue;
+    ImageDesc d;
+    memset(&d, 0, sizeof(d));
+    d.width = imgs[i].width; d.height = imgs[i].height;
+    d.mbw = (d.width + 15) / 16; d.mbh = (d.height + 15) / 16;
+    d.bpp = imgs[i].color == ZW_COLOR_RGB8 ? 3 : 4;
+    d.mb_off = n_mb; d.row_off = n_rows;
+    d.use_segments = (d.mbw * d.mbh >= 256) ? 1 : 0;
+    d.rgb_off = rgb_bytes; d.y_off = plane_bytes;
+    rgb_bytes += ((u64)imgs[i].len + 15) & ~15ull;
+    plane_bytes += (u64)d.mbw * d.mbh * 384;
+    n_mb += d.mbw * d.mbh; n_rows += d.mbh;
+    max_pw = std::max(max_pw, d.mbw * 16); max_ph = std::max(max_ph, d.mbh * 16);
+    max_mb = std::max(max_mb, d.mbw * d.mbh); max_mbh = std::max(max_mbh, d.mbh);
+    c->slot_of[i] = (int)c->img.size();
+    c->img.push_back(d);
+    key = (key ^ (((u64)d.width << 32) | ((u64)d.height << 8) | d.bpp)) * 1099511628211ull;
+  }
+  c->n_valid = (u32)c->img.size(); c->n_mb = n_mb; c->n_rows = n_rows;
+  c->max_pw = max_pw; c->max_ph = max_ph; c->max_mb = max_mb;
+  if (c->n_valid == 0) { c->staged = true; return g_last_error = ZW_OK; }
+  const u32 ni = c->n_valid;
+  CK(c->d_img.reserve(ni * sizeof(ImageDesc))); CK(c->d_st.reserve(ni * sizeof(ImageState)));
+  CK(c->d_rows.reserve((size_t)n_rows * sizeof(RowRef))); CK(c->d_rgb.reserve(rgb_bytes + 64)); CK(c->d_planes.reserve(plane_bytes + 64));
+  CK(c->d_alpha_hist.reserve((size_t)ni * 1024)); CK(c->d_map256.reserve((size_t)ni * 256));
+  CK(c->d_alpha.reserve(n_mb)); CK(c->d_segmap.reserve(n_mb));
+  CK(c->d_rec1.reserve((size_t)n_mb * sizeof(MbRecord))); CK(c->d_rec2.reserve((size_t)n_mb * sizeof(MbRecord)));
+  CK(c->d_bottom.reserve((size_t)n_mb * sizeof(MbBottom))); CK(c->d_nz.reserve((size_t)n_mb * 2));
+  CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4));
+  CK(c->d_progress.reserve((size_t)n_rows * 2 * sizeof(int))); CK(c->d_rowstats.reserve((size_t)n_rows * 2112 * 4));
+  CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
+  CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
+  CK(c->d_outoff.reserve(((size_t)ni + 1) * 8));
+  // ticket order: macroblock row y of every image before row y+1 of any image ("many images
+  // interleaved"): each image has at most a couple of rows in flight, so rows rarely wait.
+  if (key != c->layout_key || c->rows.size() != n_rows) {
+    c->rows.resize(n_rows);
+    size_t k = 0;
+    for (u32 y = 0; y < max_mbh; y++)
+      for (u32 i = 0; i < ni; i++)
+        if (y < c->img[i].mbh) { c->rows[k].img = i; c->rows[k].mby = y; k++; }
+    CK(cudaMemcpyAsync(c->d_rows.p, c->rows.data(), (size_t)n_rows * sizeof(RowRef), cudaMemcpyHostToDevice, c->stream));
+    c->layout_key = key;
+  }
+  CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  for (size_t i = 0; i < n; i++) {
+    if (c->slot_of[i] < 0) continue;
+    const ImageDesc& d = c->img[c->slot_of[i]];
+    CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + d.rgb_off, imgs[i].data, imgs[i].len, cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  fill_params(c);
+  c->last = zw_timing();
+  c->last.h2d_bytes = rgb_bytes;
+  for (const ImageDesc& d : c->img) c->last.pixels += (u64)d.width * d.height;
+  c->staged = true;
+  return g_last_error = ZW_OK;
+}
+
+int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
+  if (!c) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (!c->staged) return g_last_error = ZW_ERR_NOT_STAGED;
+  if (quality < 0 || quality > 100 || method < 0) return g_last_error = ZW_ERR_INVALID_PARAM;
+  CK(cudaSetDevice(c->device));
+  c->encoded = false;
+  if (c->n_valid == 0) { c->encoded = true; return g_last_error = ZW_OK; }
+  method = std::min(method, 6);  // vp8.rs:1291
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  fill_params(c);
+  ChunkParams& P = c->P;
+  P.method = (u32)method;
+  P.base_qidx = (u32)quality_to_quant_index(quality);
+  P.do_trellis = method >= 4;
+  P.filter_level = (u8)compute_filter_level((int)P.base_qidx);
+  c->quality = quality; c->method = method; c->base_qidx = (int)P.base_qidx;
+  u64 launches = 0;
+  CK(cudaEventRecord(c->ev[2], s));
+  CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
+  CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
+  CK(cudaMemsetAsync(c->d_progress.p, 0, (size_t)c->n_rows * 2 * sizeof(int), s));
+  CK(cudaMemsetAsync(c->d_ticket.p, 0, 64, s));
+  {  // (1) RGB -> YUV420
+    dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + YUV_ROWPAIRS * 2 - 1) / (YUV_ROWPAIRS * 2), ni);
+    dim3 block(YUV_THREADS, YUV_ROWPAIRS);
+    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * ((YUV_TILE_W * 4 + 32) / 16) * 16;
+    k_yuv<<<grid, block, sm, s>>>(P);
+    launches++;
+  }
+  CK(cudaEventRecord(c->ev[3], s));
+  {  // (2) analysis + segments
+    bool any_seg = false;
+    for (const ImageDesc& d : c->img) any_seg |= d.use_segments != 0;
+    if (any_seg) {
+      dim3 grid((c->max_mb + AN_WARPS - 1) / AN_WARPS, ni);
+      k_analysis<<<grid, AN_WARPS * 32, 0, s>>>(P);
+      launches++;
+    }
+    k_segments<<<ni, 256, 0, s>>>(P);
+    launches++;
+  }
+  CK(cudaEventRecord(c->ev[4], s));
+  {  // (3) pass 1: luma wavefront, then the chroma chain
+    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    const int g3 = (int)std::min<u64>((u64)c->chroma_blocks, ((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[5], s));
+  {  // (4) token statistics -> probabilities, level costs, skip probability
+    k_rowstats<<<(c->n_rows + STAT_WARPS - 1) / STAT_WARPS, STAT_WARPS * 32, 0, s>>>(P);
+    k_probs<<<ni, 256, 0, s>>>(P);
+    launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[6], s));
+  {  // (3') pass 2
+    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_search<2><<<g2, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    launches++;
+  }
+  CK(cudaEventRecord(c->ev[7], s));
+  {  // (5a) count symbols, scan, size the streams
+    dim3 grid((c->max_mb + TOK_WARPS - 1) / TOK_WARPS, ni);
+    k_tokenize<0><<<grid, TOK_WARPS * 32, 0, s>>>(P);
+    k_tokscan<<<ni, 256, 0, s>>>(P);
+    launches += 2;
+    c->st.resize(ni);
+    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    u64 hoff = 0, toff = 0, poff = 0;
+    for (u32 i = 0; i < ni; i++) {
+      ImageDesc& d = c->img[i];
+      d.hdr_off = hoff; d.tok_off = toff; d.part_off = poff;
+      d.p0_cap = (u32)(((u64)c->st[i].hdr_tokens * 7) / 8 + 16);
+      d.p1_cap = (u32)(((u64)c->st[i].tok_tokens * 7) / 8 + 16);
+      hoff += ((u64)c->st[i].hdr_tokens + 7) & ~7ull;
+      toff += ((u64)c->st[i].tok_tokens + 7) & ~7ull;
+      poff += ((u64)d.p0_cap + d.p1_cap + 15) & ~15ull;
+    }
+    CK(c->d_htok.reserve(hoff * sizeof(Token) + 64)); CK(c->d_ttok.reserve(toff * sizeof(Token) + 64));
+    CK(c->d_part.reserve(poff + 64)); CK(c->d_out.reserve(poff + (u64)ni * 32 + 64));
+    fill_params(c);
+    P.method = (u32)method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = method >= 4;
+    P.filter_level = (u8)compute_filter_level(c->base_qidx);
+    CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, s));
+    k_tokenize<1><<<grid, TOK_WARPS * 32, 0, s>>>(P);
+    k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
+    launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[8], s));
+  k_boolcode<<<(2 * ni + 127) / 128, 128, 0, s>>>(P);
+  launches++;
+  CK(cudaEventRecord(c->ev[9], s));
+  k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
+  k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
+  launches += 2;
+  CK(cudaEventRecord(c->ev[10], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  zw_timing T = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
+  T.h2d_bytes = c->last.h2d_bytes; T.pixels = c->last.pixels;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); T.pass1_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); T.stats_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); T.pass2_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[10]); T.device_total_ms += ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms += ms;
+  T.kernel_launches += launches;
+  c->last = T;
+  if (timing) *timing = T;
+  c->encoded = true;
+  return g_last_error = ZW_OK;
+}
+
+int zw_download(zw_ctx* c, zw_output* outs, size_t n, int container, zw_timing* timing) {
+  if (!c || (!outs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (!c->staged || !c->encoded) return g_last_error = ZW_ERR_NOT_STAGED;
+  if (n != c->img_status.size()) return g_last_error = ZW_ERR_INVALID_PARAM;
+  CK(cudaSetDevice(c->device));
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  if (ni) {
+    c->st.resize(ni); c->out_off.resize(ni + 1);
+    CK(cudaEventRecord(c->ev[11], s));
+    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->out_off.data(), c->d_outoff.p, ((size_t)ni + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const size_t total = (size_t)c->out_off[ni];
+    if (total > c->h_pinned_cap) {
+      if (c->h_pinned) cudaFreeHost(c->h_pinned);
+      c->h_pinned = nullptr; c->h_pinned_cap = 0;
+      CK(cudaMallocHost((void**)&c->h_pinned, total + total / 4 + 4096));
+      c->h_pinned_cap = total + total / 4 + 4096;
+    }
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c->ev[12], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]);
+    c->last.d2h_ms += ms;
+    c->last.d2h_bytes += total + ni * sizeof(ImageState) + ((size_t)ni + 1) * 8;
+  }
+  for (size_t i = 0; i < n; i++) {
+    zw_output& o = outs[i];
+    o.len = 0;
+    if (c->slot_of[i] < 0) { o.status = c->img_status[i]; continue; }
+    const u32 k = (u32)c->slot_of[i];
+    const ImageState& st = c->st[k];
+    if (st.status != 0) { o.status = (int)st.status; continue; }
+    const size_t payload = st.vp8_bytes;
+    const size_t need = container ? 20 + payload + (payload & 1) : payload;
+    if (o.data == nullptr) {
+      o.data = (uint8_t*)malloc(need ? need : 1);
+      o.cap = need;
+      if (!o.data) { o.status = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; continue; }
+    } else if (o.cap < need) { o.status = ZW_ERR_OUTPUT_TOO_SMALL; o.len = need; continue; }
+    uint8_t* w = o.data;
+    if (container) {  // api.rs:1325-1329 + write_chunk :1232-1241
+      const u32 chunk = (u32)(payload + (payload & 1)) + 8;
+      const u32 riff = chunk + 4;
+      memcpy(w, "RIFF", 4); w[4] = (u8)riff; w[5] = (u8)(riff >> 8); w[6] = (u8)(riff >> 16); w[7] = (u8)(riff >> 24);
+      memcpy(w + 8, "WEBP", 4); memcpy(w + 12, "VP8 ", 4);
+      const u32 pl = (u32)payload;
+      w[16] = (u8)pl; w[17] = (u8)(pl >> 8); w[18] = (u8)(pl >> 16); w[19] = (u8)(pl >> 24);
+      w += 20;
+    }
+    memcpy(w, c->h_pinned + c->out_off[k], payload);
+    if (container && (payload & 1)) w[payload] = 0;
+    o.len = need;
+    o.status = ZW_OK;
+  }
+  if (timing) *timing = c->last;
+  return g_last_error = ZW_OK;
+}
+
+static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing,
+                        int container) {
+  if (!c || (!imgs && n) || (!outs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (quality < 0 || quality > 100 || method < 0) return g_last_error = ZW_ERR_INVALID_PARAM;
+  const auto t0 = std::chrono::steady_clock::now();
+  zw_timing acc = zw_timing();
+  size_t i0 = 0;
+  while (i0 < n) {
+    size_t i1 = i0, bytes = 0;
+    while (i1 < n && (i1 - i0) < 32768) {
+      const size_t f = validate_image(imgs[i1]) == ZW_OK ? image_footprint(imgs[i1].width, imgs[i1].height, imgs[i1].color == ZW_COLOR_RGB8 ? 3 : 4) : 0;
+      if (i1 > i0 && bytes + f > c->budget) break;
+      bytes += f; i1++;
+    }
+    int rc = zw_stage_batch(c, imgs + i0, i1 - i0);
+    if (rc != ZW_OK) return rc;
+    rc = zw_encode_resident(c, quality, method, nullptr);
+    if (rc != ZW_OK) return rc;
+    rc = zw_download(c, outs + i0, i1 - i0, container, nullptr);
+    if (rc != ZW_OK) return rc;
+    const zw_timing& L = c->last;
+    acc.h2d_ms += L.h2d_ms; acc.yuv_ms += L.yuv_ms; acc.analysis_ms += L.analysis_ms; acc.pass1_ms += L.pass1_ms;
+    acc.stats_ms += L.stats_ms; acc.pass2_ms += L.pass2_ms; acc.token_ms += L.token_ms; acc.boolcode_ms += L.boolcode_ms;
+    acc.assemble_ms += L.assemble_ms; acc.d2h_ms += L.d2h_ms; acc.device_total_ms += L.device_total_ms;
+    acc.kernel_launches += L.kernel_launches; acc.h2d_bytes += L.h2d_bytes; acc.d2h_bytes += L.d2h_bytes; acc.pixels += L.pixels;
+    i0 = i1;
+  }
+  acc.wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (timing) *timing = acc;
+  return g_last_error = ZW_OK;
+}
+
+int zw_encode_vp8_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing) {
+  return encode_batch(c, imgs, n, quality, method, outs, timing, 0);
+}
+int zw_encode_webp_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing) {
+  return encode_batch(c, imgs, n, quality, method, outs, timing, 1);
+}
+
+int zw_dump_stage(zw_ctx* c, size_t index, const char* stage, void* dst, size_t cap, size_t* len) {
+  if (!c || !stage || !len) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (!c->staged || !c->encoded || index >= c->slot_of.size() || c->slot_of[index] < 0) return g_last_error = ZW_ERR_NOT_STAGED;
+  CK(cudaSetDevice(c->device));
+  const u32 k = (u32)c->slot_of[index];
+  const ImageDesc& d = c->img[k];
+  const size_t nmb = (size_t)d.mbw * d.mbh, ysz = nmb * 256, csz = nmb * 64;
+  const std::string s(stage);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  std::vector<u8> tmp;
+  c->st.resize(c->n_valid);
+  CK(cudaMemcpy(c->st.data(), c->d_st.p, c->n_valid * sizeof(ImageState), cudaMemcpyDeviceToHost));
+  const ImageState& st = c->st[k];
+  if (s == "YUV_Y") { src = c->d_planes.as<u8>() + d.y_off; bytes = ysz; }
+  else if (s == "YUV_U") { src = c->d_planes.as<u8>() + d.y_off + ysz; bytes = csz; }
+  else if (s == "YUV_V") { src = c->d_planes.as<u8>() + d.y_off + ysz + csz; bytes = csz; }
+  else if (s == "ALPHA") { src = c->d_alpha.as<u8>() + d.mb_off; bytes = nmb; }
+  else if (s == "ALPHA_HIST") { src = c->d_alpha_hist.as<u8>() + (size_t)k * 1024; bytes = 1024; }
+  else if (s == "SEG_MAP256") { src = c->d_map256.as<u8>() + (size_t)k * 256; bytes = 256; }
+  else if (s == "SEG_MAP") { src = c->d_segmap.as<u8>() + d.mb_off; bytes = nmb; }
+  else if (s == "P1MB") { src = c->d_rec1.as<MbRecord>() + d.mb_off; bytes = nmb * sizeof(MbRecord); }
+  else if (s == "P2MB") { src = c->d_rec2.as<MbRecord>() + d.mb_off; bytes = nmb * sizeof(MbRecord); }
+  else if (s == "STATS") { src = c->d_stats.as<u8>() + (size_t)k * 1056 * 4; bytes = 1056 * 4; }
+  else if (s == "PROBS") { src = c->d_probs.as<u8>() + (size_t)k * 1056; bytes = 1056; }
+  else if (s == "LCOST") { src = c->d_lcost.as<u8>() + (size_t)k * 6528 * 2; bytes = 6528 * 2; }
+  else if (s == "PART0") { src = c->d_part.as<u8>() + d.part_off; bytes = st.part0_bytes; }
+  else if (s == "PART1") { src = c->d_part.as<u8>() + d.part_off + d.p0_cap; bytes = st.part1_bytes; }
+  else if (s == "HDR_TOKENS") { src = c->d_htok.as<Token>() + d.hdr_off; bytes = (size_t)st.hdr_tokens * 2; }
+  else if (s == "TOK_TOKENS") { src = c->d_ttok.as<Token>() + d.tok_off; bytes = (size_t)st.tok_tokens * 2; }
+  else if (s == "VP8") {
+    c->out_off.resize(c->n_valid + 1);
+    CK(cudaMemcpy(c->out_off.data(), c->d_outoff.p, ((size_t)c->n_valid + 1) * 8, cudaMemcpyDeviceToHost));
+    src = c->d_out.as<u8>() + c->out_off[k]; bytes = st.vp8_bytes;
+  } else {
+    // small scalar stages served from the host copy of ImageState
+    if (s == "SEG_QIDX") tmp.assign(st.seg_qidx, st.seg_qidx + 4);
+    else if (s == "SEG_TREE_PROBS") tmp.assign(st.tree_probs, st.tree_probs + 3);
+    else if (s == "SEG_UPDATE_MAP") tmp.assign(1, st.update_map);
+    else if (s == "SEG_ENABLED") tmp.assign(1, st.seg_enabled);
+    else if (s == "SEG_CENTERS") tmp.assign(st.centers, st.centers + 4);
+    else if (s == "SEG_MID") { tmp.resize(4); memcpy(tmp.data(), &st.mid_alpha, 4); }
+    else if (s == "SKIP_PROB") tmp.assign(1, st.skip_prob);
+    else if (s == "PROBS_UPDATED") tmp.assign(1, st.probs_updated);
+    else if (s == "BASE_QIDX") tmp.assign(1, (u8)c->base_qidx);
+    else return g_last_error = ZW_ERR_INVALID_PARAM;
+    *len = tmp.size();
+    if (cap < tmp.size()) return g_last_error = ZW_ERR_OUTPUT_TOO_SMALL;
+    memcpy(dst, tmp.data(), tmp.size());
+    return g_last_error = ZW_OK;
+  }
+  *len = bytes;
+  if (cap < bytes) return g_last_error = ZW_ERR_OUTPUT_TOO_SMALL;
+  if (bytes) CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return g_last_error = ZW_OK;
+}
+
+}  // extern "C"

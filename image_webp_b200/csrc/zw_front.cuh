@@ -1,0 +1,304 @@
+// zw_front.cuh -- front-end kernels: RGB->YUV420, macroblock analysis, segment assignment.
+#ifndef ZW_FRONT_CUH
+#define ZW_FRONT_CUH
+#include "zw_types.cuh"
+
+namespace zw {
+
+// ---------------------------------------------------------------------------------------------
+// (1) RGB(A) -> padded YUV 4:2:0 planes.   Reference: convert_image_yuv, src/decoder/yuv.rs:656-804
+//     (rgb_to_y :859, rgb_to_u/v_avg :866-886, raw :889-899), 16-bit fixed point, 2x2 box
+//     average with edge duplication, replicate padding to 16*mbw x 16*mbh.
+//
+// One CTA converts a strip of 2 source rows x YUV_TILE_W pixels.  The packed RGB bytes of both rows
+// are staged in shared memory with 128-bit loads (3 B/px is never 16-byte aligned per pixel, so
+// threads pick their pixels out of the staged span); each thread then produces an 8x2 luma patch
+// (two 64-bit stores) and 4 U + 4 V samples (two 32-bit stores).  HBM-bound: 3 B/px read,
+// 1.5 B/px written.
+// ---------------------------------------------------------------------------------------------
+constexpr int YUV_TILE_W = 512;                 // luma pixels per CTA strip
+constexpr int YUV_THREADS = YUV_TILE_W / 8;     // 64 threads, 8 px each
+constexpr int YUV_ROWPAIRS = 4;                 // row pairs per CTA (blockDim.y)
+
+__global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P) {
+  const ImageDesc d = P.img[blockIdx.z];
+  const int pw = d.mbw * 16, ph = d.mbh * 16;
+  const int x0 = blockIdx.x * YUV_TILE_W;
+  const int rp = blockIdx.y * YUV_ROWPAIRS + threadIdx.y;  // row pair index in the padded plane
+  if (x0 >= pw || blockIdx.y * YUV_ROWPAIRS * 2 >= ph) return;
+  const int w = d.width, h = d.height, bpp = d.bpp;
+  const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+  // span of source columns this strip needs (always non-empty: x0 < w because padding < 16)
+  const int xs = x0, xe = min(x0 + YUV_TILE_W, w);
+  const int span_bytes = (xe - xs) * bpp;
+  extern __shared__ uint4 smem4[];
+  const int row_slots = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row
+  u8* sm = reinterpret_cast<u8*>(smem4);
+  const bool active = rp * 2 < ph;
+  const int ccy = min(rp, chh - 1);
+  const int rowA = 2 * ccy, rowB = min(2 * ccy + 1, h - 1);
+  const u8* rgb = P.rgb + d.rgb_off;
+  int skew[2] = {0, 0};
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
+      const size_t al = (d.rgb_off + byte0) & ~(size_t)15;  // arena is 16-byte aligned
+      skew[r] = (int)((d.rgb_off + byte0) - al);
+      const int nvec = (skew[r] + span_bytes + 15) >> 4;
+      const uint4* src = reinterpret_cast<const uint4*>(P.rgb + al);
+      uint4* dst = smem4 + (threadIdx.y * 2 + r) * row_slots;
+      for (int i = threadIdx.x; i < nvec; i += YUV_THREADS) dst[i] = __ldg(src + i);
+    }
+  }
+  (void)rgb;
+  __syncthreads();
+  if (!active) return;
+  const u8* sA = sm + (size_t)(threadIdx.y * 2 + 0) * row_slots * 16 + skew[0];
+  const u8* sB = sm + (size_t)(threadIdx.y * 2 + 1) * row_slots * 16 + skew[1];
+  const int tx = x0 + threadIdx.x * 8;
+  if (tx >= pw) return;
+  // luma rows 2rp and 2rp+1: source rows min(2rp,h-1) and min(2rp+1,h-1)
+  const bool lumaA_is_A = (rp <= chh - 1);  // else row h-1 == rowB
+  u8* yp = P.planes + d.y_off;
+  u8* up = yp + (size_t)pw * ph;
+  u8* vp = up + (size_t)(pw >> 1) * (ph >> 1);
+  u32 y0w[2] = {0, 0}, y1w[2] = {0, 0}, uw = 0, vw = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int sx = min(tx + k, w - 1) - xs;
+    const u8* pa = (lumaA_is_A ? sA : sB) + sx * bpp;
+    const u8* pb = sB + sx * bpp;
+    const int ya = (16839 * pa[0] + 33059 * pa[1] + 6420 * pa[2] + 32768 + (16 << 16)) >> 16;
+    const int yb = (16839 * pb[0] + 33059 * pb[1] + 6420 * pb[2] + 32768 + (16 << 16)) >> 16;
+    y0w[k >> 2] |= (u32)ya << (8 * (k & 3));
+    y1w[k >> 2] |= (u32)yb << (8 * (k & 3));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int ccx = min((tx >> 1) + k, cw - 1);
+    const int c0 = 2 * ccx - xs, c1 = min(2 * ccx + 1, w - 1) - xs;
+    const u8 *p1 = sA + c0 * bpp, *p2 = sA + c1 * bpp, *p3 = sB + c0 * bpp, *p4 = sB + c1 * bpp;
+    const int r = p1[0] + p2[0] + p3[0] + p4[0];
+    const int g = p1[1] + p2[1] + p3[1] + p4[1];
+    const int b = p1[2] + p2[2] + p3[2] + p4[2];
+    const int u = (-9719 * r - 19081 * g + 28800 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+    const int v = (28800 * r - 24116 * g - 4684 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+    uw |= (u32)u << (8 * k);
+    vw |= (u32)v << (8 * k);
+  }
+  *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp) * pw + tx) = make_uint2(y0w[0], y0w[1]);
+  *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp + 1) * pw + tx) = make_uint2(y1w[0], y1w[1]);
+  *reinterpret_cast<u32*>(up + (size_t)rp * (pw >> 1) + (tx >> 1)) = uw;
+  *reinterpret_cast<u32*>(vp + (size_t)rp * (pw >> 1) + (tx >> 1)) = vw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) Analysis pass: per-macroblock "alpha" from DCT histograms of DC and TM predictions built
+//     from SOURCE neighbours (no reconstruction dependency -> every macroblock is independent).
+//     Reference: analyze_image src/encoder/analysis.rs:964, AnalysisIterator::import :622,
+//     make_luma16_preds :365, make_chroma8_preds :460, forward_dct_4x4 :172,
+//     collect_histogram_with_offset :922, DctHistogram :139-166, analyze_macroblock :951.
+//     One warp per macroblock: lanes 0..23 own one 4x4 block each (16 Y, 4 U, 4 V) and transform
+//     it against both predictions; 32-bin histograms live in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int AN_WARPS = 8;
+
+__device__ __forceinline__ void an_fdct_hist(const i32* res, u32* hist) {
+  i32 c[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) c[i] = res[i];
+  fdct4x4(c);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    // the reference narrows to i16 before |.| >> 3 (analysis.rs:204-207, :236); values fit i16
+    int v = imin(iabs(c[i]) >> 3, 31);
+    atomicAdd(&hist[v], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(AN_WARPS * 32) k_analysis(ChunkParams P) {
+  __shared__ u32 s_hist[AN_WARPS][4][32];  // [warp][y-dc, y-tm, uv-dc, uv-tm][bin]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 gmb = blockIdx.x * AN_WARPS + warp;
+  const int img = blockIdx.y;
+  const ImageDesc d = P.img[img];
+  const u32 nmb = d.mbw * d.mbh;
+  const bool valid = d.use_segments && gmb < nmb;
+  for (int i = lane; i < 128; i += 32) (&s_hist[warp][0][0])[i] = 0;
+  __syncwarp();
+  if (valid) {
+    const int mbx = gmb % d.mbw, mby = gmb / d.mbw;
+    const int pw = d.mbw * 16, cwid = d.mbw * 8;
+    const u8* yp = P.planes + d.y_off;
+    const u8* up = yp + (size_t)pw * d.mbh * 16;
+    const u8* vp = up + (size_t)cwid * d.mbh * 8;
+    const bool has_left = mbx > 0, has_top = mby > 0;
+    if (lane < 24) {
+      const u8* plane;
+      int stride, bx, by, size, px, py;
+      if (lane < 16) { plane = yp; stride = pw; bx = lane & 3; by = lane >> 2; size = 16; px = mbx * 16; py = mby * 16; }
+      else { plane = lane < 20 ? up : vp; stride = cwid; bx = lane & 1; by = (lane >> 1) & 1; size = 8; px = mbx * 8; py = mby * 8; }
+      const u8* o = plane + (size_t)py * stride + px;  // MB origin in this plane
+      // DC value over the whole MB border (analysis.rs:259-291 / :378-419)
+      int dcv;
+      {
+        int st = 0, sl = 0;
+        if (has_top) for (int i = 0; i < size; i++) st += o[i - stride];
+        if (has_left) for (int i = 0; i < size; i++) sl += o[(ptrdiff_t)i * stride - 1];
+        const int shift = size == 16 ? 5 : 4;
+        if (has_top && has_left) dcv = (st + sl + size) >> shift;
+        else if (has_top) dcv = (2 * st + size) >> shift;
+        else if (has_left) dcv = (2 * sl + size) >> shift;
+        else dcv = 0x80;
+      }
+      // corner (analysis.rs:594, :676-684): 127 on row 0 else the source pixel; x==0 never uses it
+      const int tl = has_top ? (has_left ? o[-stride - 1] : 129) : 127;
+      i32 rdc[16], rtm[16];
+#pragma unroll
+      for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const int xx = bx * 4 + x, yy = by * 4 + y;
+          const int s = o[(size_t)yy * stride + xx];
+          int tm;
+          if (has_left && has_top) tm = clip255((int)o[(ptrdiff_t)yy * stride - 1] + (int)o[xx - stride] - tl);
+          else if (has_left) tm = o[(ptrdiff_t)yy * stride - 1];   // horizontal_pred
+          else if (has_top) tm = o[xx - stride];                    // vertical_pred
+          else tm = 129;
+          rdc[y * 4 + x] = s - dcv;
+          rtm[y * 4 + x] = s - tm;
+        }
+      const int hsel = lane < 16 ? 0 : 2;
+      an_fdct_hist(rdc, s_hist[warp][hsel]);
+      an_fdct_hist(rtm, s_hist[warp][hsel + 1]);
+    }
+    __syncwarp();
+    // DctHistogram::from_distribution + get_alpha for the 4 histograms: lane = bin
+    int alpha[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 cnt = s_hist[warp][k][lane];
+      u32 mx = cnt;
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+      const u32 nzmask = __ballot_sync(0xffffffffu, cnt > 0);
+      const int last_nz = nzmask ? 31 - __clz(nzmask) : 1;
+      alpha[k] = mx > 1 ? (int)(510u * (u32)last_nz / mx) : 0;
+    }
+    if (lane == 0) {
+      const int best = max(max(alpha[0], alpha[1]), -1);
+      const int best_uv = max(max(alpha[2], alpha[3]), -1);
+      int a = (3 * best + best_uv + 2) >> 2;
+      a = clip255(255 - a);
+      P.alpha[d.mb_off + gmb] = (u8)a;
+      atomicAdd(&P.alpha_hist[(size_t)img * 256 + a], 1u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) Segments: 1-D k-means over the 256-bin alpha histogram, per-segment quantiser index,
+//     segment map, segment-tree probabilities.  One CTA per image; thread 0 runs the (tiny,
+//     strictly sequential) integer k-means, all threads map macroblocks.
+//     Reference: assign_segments_kmeans src/encoder/analysis.rs:1029-1130;
+//     analyze_and_assign_segments src/encoder/vp8.rs:2278-2388; compute_segment_quant
+//     analysis.rs:1145-1174 (f64 pow -> host-built LUT, bit-exact, see zw_capi.cu).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_segments(ChunkParams P) {
+  const int img = blockIdx.x;
+  const ImageDesc d = P.img[img];
+  ImageState& S = P.st[img];
+  __shared__ u8 s_map[256];
+  __shared__ u32 s_cnt[4];
+  if (!d.use_segments) {
+    if (threadIdx.x == 0) {
+      S.seg_enabled = 0; S.update_map = 0;
+      for (int i = 0; i < 4; i++) { S.seg_qidx[i] = (u8)P.base_qidx; S.seg_delta[i] = 0; }
+      S.tree_probs[0] = S.tree_probs[1] = S.tree_probs[2] = 255;
+    }
+    return;
+  }
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    const u32* alphas = P.alpha_hist + (size_t)img * 256;
+    int centers[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 256; i++) s_map[i] = 0;
+    int min_a = 0, max_a = 255;
+    for (int n = 0; n < 256; n++) if (alphas[n] > 0) { min_a = n; break; }
+    for (int n = 255; n >= min_a; n--) if (alphas[n] > 0) { max_a = n; break; }
+    const int range_a = max_a >= min_a ? max_a - min_a : 0;
+    for (int k = 0; k < 4; k++) centers[k] = (min_a + ((1 + 2 * k) * range_a) / 8) & 255;
+    u32 accum[4], dist_accum[4];
+    int weighted_average = 0;
+    u32 total_weight = 0;
+    for (int iter = 0; iter < 6; iter++) {
+      for (int i = 0; i < 4; i++) { accum[i] = 0; dist_accum[i] = 0; }
+      int cur = 0;
+      for (int a = min_a; a <= max_a; a++) {
+        if (alphas[a] > 0) {
+          while (cur + 1 < 4) {
+            const int dc = iabs(a - centers[cur]), dn = iabs(a - centers[cur + 1]);
+            if (dn < dc) cur++; else break;
+          }
+          s_map[a] = (u8)cur;
+          dist_accum[cur] += (u32)a * alphas[a];
+          accum[cur] += alphas[a];
+        }
+      }
+      int displaced = 0;
+      weighted_average = 0;
+      total_weight = 0;
+      for (int n = 0; n < 4; n++) {
+        if (accum[n] > 0) {
+          const int nc = (int)((dist_accum[n] + accum[n] / 2) / accum[n]) & 255;
+          displaced += iabs(centers[n] - nc);
+          centers[n] = nc;
+          weighted_average += nc * (int)accum[n];
+          total_weight += accum[n];
+        }
+      }
+      if (displaced < 5) break;
+    }
+    if (total_weight > 0) weighted_average = (weighted_average + (int)total_weight / 2) / (int)total_weight;
+    else weighted_average = 128;
+    int mn = 255, mx = 0;
+    for (int k = 0; k < 4; k++) { mn = min(mn, centers[k]); mx = max(mx, centers[k]); }
+    const int range = mx == mn ? 1 : mx - mn;
+    for (int k = 0; k < 4; k++) {
+      int ta = 255 * (centers[k] - weighted_average) / range;  // truncating division (vp8.rs:2326)
+      ta = imin(imax(ta, -127), 127);
+      const int q = P.segquant_lut[P.base_qidx * 255 + (ta + 127)];
+      S.seg_qidx[k] = (u8)q;
+      S.seg_delta[k] = (i8)(q - (int)P.base_qidx);
+      S.centers[k] = (u8)centers[k];
+    }
+    S.mid_alpha = weighted_average;
+    for (int i = 0; i < 256; i++) P.map256[(size_t)img * 256 + i] = s_map[i];
+  }
+  __syncthreads();
+  const u32 nmb = d.mbw * d.mbh;
+  u32 local[4] = {0, 0, 0, 0};
+  for (u32 i = threadIdx.x; i < nmb; i += blockDim.x) {
+    const u8 s = s_map[P.alpha[d.mb_off + i]];
+    P.segmap[d.mb_off + i] = s;
+    local[s]++;
+  }
+  for (int k = 0; k < 4; k++) if (local[k]) atomicAdd(&s_cnt[k], local[k]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    auto proba = [](u32 a, u32 b) -> u8 {
+      const u32 t = a + b;
+      return t == 0 ? 255 : (u8)((255 * a + t / 2) / t);
+    };
+    S.tree_probs[0] = proba(s_cnt[0] + s_cnt[1], s_cnt[2] + s_cnt[3]);
+    S.tree_probs[1] = proba(s_cnt[0], s_cnt[1]);
+    S.tree_probs[2] = proba(s_cnt[2], s_cnt[3]);
+    S.update_map = (S.tree_probs[0] != 255 || S.tree_probs[1] != 255 || S.tree_probs[2] != 255) ? 1 : 0;
+    S.seg_enabled = 1;
+    for (int k = 0; k < 4; k++) S.seg_count[k] = s_cnt[k];
+  }
+}
+
+}  // namespace zw
+#endif

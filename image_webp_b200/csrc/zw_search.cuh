@@ -1,0 +1,904 @@
+// zw_search.cuh -- the per-macroblock mode search + final transform, both passes (sm_100a).
+//
+// Scheduling: persistent kernels.  One warp owns one macroblock ROW of one image at a time and
+// walks it left to right; rows are handed out through a global ticket counter in an order in
+// which row y-1 of an image always precedes row y, many images interleaved.  Row y may process
+// macroblock x once row y-1 has finished x+1 (left / top / top-right dependency, SURVEY.md
+// Appendix C), which it learns from a per-row progress counter (st.release / ld.acquire).
+// Left-neighbour state (borders, complexities, chroma diffusion errors) never leaves the warp.
+//
+// Pass 1 is split in two kernels because of a reference quirk: in pass 1 the
+// chroma error-diffusion state `left_derr` is NOT reset at row starts, so chroma of row y depends
+// on the END of row y-1 -- a raster-order chain.  Luma does not depend on chroma, so
+//   k_search<1>  : luma only, wavefront-parallel (I16 / I4 search + final luma transform)
+//   k_chroma1    : chroma search + transform + skip/complexity bookkeeping, one warp per image
+//                  walking all macroblocks in raster order
+//   k_search<2>  : luma + chroma, wavefront-parallel (pass 2 resets left_derr per row)
+//
+// Reference (file:line under /root/reference, src/encoder/vp8.rs unless noted):
+//   choose_macroblock_info :2202   pick_best_intra16 :1504   pick_best_intra4 :1790
+//   pick_best_uv :2050             transform_luma_block :2647  transform_luma_blocks_4x4 :2785
+//   transform_chroma_blocks :3039  apply_chroma_error_diffusion :572  check_all_coeffs_zero :962
+//   create_border_luma/chroma src/common/prediction.rs:15/:85, predictors :164-554
+#ifndef ZW_SEARCH_CUH
+#define ZW_SEARCH_CUH
+#include "zw_types.cuh"
+
+namespace zw {
+
+constexpr int SEARCH_WARPS = 4;  // warps per CTA (each independent)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
+
+struct __align__(16) WarpScratch {
+  u8 src_y[256];
+  u8 src_u[64];
+  u8 src_v[64];
+  u8 yws[17 * 32];   // bordered luma work buffer (prediction.rs LUMA_STRIDE = 32)
+  u8 uvws[9 * 32];   // bordered chroma: U at columns 0..8, V at columns 16..24
+  u8 left_y[20];     // [0] corner, [1..16] left column
+  u8 left_u[12];
+  u8 left_v[12];
+  i32 dcbuf[32];
+  i16 nat[16][16];   // natural-order luma levels (I4 search winners / I16 simple quantisation)
+  u8 bmodes[16];
+  u8 nzflag[32];     // per-block non-zero flags (scratch)
+  MbRecord rec;      // staged record
+};
+
+struct SearchShared {
+  u16 pred_tab[8][16];
+  WarpScratch w[SEARCH_WARPS];
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ i64 shfl64(i64 v, int src) {
+  int lo = __shfl_sync(FULL, (int)(v & 0xffffffff), src);
+  int hi = __shfl_sync(FULL, (int)(v >> 32), src);
+  return (i64)(((u64)(u32)hi << 32) | (u64)(u32)lo);
+}
+__device__ __forceinline__ int red16_add(int v) {  // sum over each aligned group of 16 lanes
+  v += __shfl_xor_sync(FULL, v, 8);
+  v += __shfl_xor_sync(FULL, v, 4);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+__device__ __forceinline__ int red8_add(int v) {
+  v += __shfl_xor_sync(FULL, v, 4);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+
+// 16x16 / 8x8 whole-block predictors evaluated per pixel from the bordered work buffer
+// (predict_vpred/hpred/dcpred/tmpred, prediction.rs:164-324).  mode: 0 DC 1 V 2 H 3 TM.
+__device__ __forceinline__ int pred_big(const u8* ws, int cofs, int mode, int x, int y, int dcv) {
+  if (mode == 0) return dcv;
+  if (mode == 1) return ws[cofs + 1 + x];
+  if (mode == 2) return ws[(1 + y) * 32 + cofs];
+  return clip255((int)ws[(1 + y) * 32 + cofs] + (int)ws[cofs + 1 + x] - (int)ws[cofs]);
+}
+
+__device__ const u16 d_pred_tab[8][16] = ZW_PRED_TABLE_INIT;
+
+__device__ __forceinline__ void fetch_edges4(const u8* yws, int x0, int y0, u8* e) {
+  e[0] = yws[(y0 + 3) * 32 + x0 - 1];
+  e[1] = yws[(y0 + 2) * 32 + x0 - 1];
+  e[2] = yws[(y0 + 1) * 32 + x0 - 1];
+  e[3] = yws[(y0 + 0) * 32 + x0 - 1];
+#pragma unroll
+  for (int k = 0; k < 9; k++) e[4 + k] = yws[(y0 - 1) * 32 + x0 - 1 + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Source + border staging
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_luma_mb(WarpScratch& W, const ChunkParams& P, const u8* yp, int pw, int mbw,
+                                             int mbx, int mby, u32 up_mb0, int lane) {
+  if (lane < 16) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(yp + (size_t)(mby * 16 + lane) * pw + mbx * 16));
+    *reinterpret_cast<uint4*>(&W.src_y[lane * 16]) = v;
+  }
+  if (mby == 0) {
+    W.yws[lane] = 127;  // corner + 16 above + top-right: all 127 on the first row
+  } else {
+    const MbBottom* bt = &P.bottom[up_mb0 + mbx];
+    if (lane < 16) W.yws[1 + lane] = __ldcg(&bt->y[lane]);
+    else if (lane < 20)  // top-right 4 pixels: next MB's bottom row, or the replicated last pixel
+      W.yws[1 + lane] = (mbx == mbw - 1) ? __ldcg(&bt->y[15]) : __ldcg(&(bt + 1)->y[lane - 16]);
+  }
+  __syncwarp();
+  if (lane < 16) W.yws[(1 + lane) * 32] = (mbx == 0) ? 129 : W.left_y[1 + lane];
+  if (lane == 0) W.yws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_y[0]);
+  if (lane < 12) {  // top-right copies for sub-block rows 1..3 (prediction.rs:49-54)
+    const int r = 4 * (1 + lane / 4), c = 17 + (lane & 3);
+    W.yws[r * 32 + c] = W.yws[c];
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_chroma_mb(WarpScratch& W, const ChunkParams& P, const u8* up, const u8* vp,
+                                               int cwid, int mbx, int mby, u32 up_mb0, int lane) {
+  if (lane < 8) {
+    *reinterpret_cast<uint2*>(&W.src_u[lane * 8]) = __ldg(reinterpret_cast<const uint2*>(up + (size_t)(mby * 8 + lane) * cwid + mbx * 8));
+  } else if (lane < 16) {
+    const int r = lane - 8;
+    *reinterpret_cast<uint2*>(&W.src_v[r * 8]) = __ldg(reinterpret_cast<const uint2*>(vp + (size_t)(mby * 8 + r) * cwid + mbx * 8));
+  }
+  if (mby == 0) {
+    W.uvws[lane] = 127;
+  } else {
+    const MbBottom* bt = &P.bottom[up_mb0 + mbx];
+    if (lane < 8) W.uvws[1 + lane] = __ldcg(&bt->u[lane]);
+    else if (lane < 16) W.uvws[17 + (lane - 8)] = __ldcg(&bt->v[lane - 8]);
+  }
+  __syncwarp();
+  if (lane < 8) {
+    W.uvws[(1 + lane) * 32] = (mbx == 0) ? 129 : W.left_u[1 + lane];
+    W.uvws[(1 + lane) * 32 + 16] = (mbx == 0) ? 129 : W.left_v[1 + lane];
+  }
+  if (lane == 0) {
+    W.uvws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_u[0]);
+    W.uvws[16] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_v[0]);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Luma: I16 search, I4 search, final transform.  Leaves the reconstruction in W.yws, the coded
+// zig-zag levels in W.rec.levels[0..16] and the sub-block modes in W.bmodes.
+// ---------------------------------------------------------------------------------------------
+struct LumaOut {
+  bool use_i4;
+  int mode16;
+  u32 ynz;         // has_coeffs bit per coded luma block
+  int y2nz;        // Y2 has_coeffs (I16 only)
+  bool simple_nz;  // any SIMPLE-quantised luma level non-zero (skip test, Q13)
+};
+
+__device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParams& SP, const CostCtx& cc, int method,
+                           bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane) {
+  LumaOut R;
+  const int hb = lane >> 4, blk = lane & 15, bx = blk & 3, by = blk >> 2;
+  // ===== pick_best_intra16 (vp8.rs:1504-1681) =====
+  int dc16;
+  {
+    int s = 0;
+    if (lane < 16) s = (mby != 0 ? W.yws[1 + lane] : 0) + (mbx != 0 ? W.yws[(1 + lane) * 32] : 0);
+    s = red16_add(s);
+    s = __shfl_sync(FULL, s, 0);
+    const int shf = 3 + (mbx != 0) + (mby != 0);
+    dc16 = (mbx == 0 && mby == 0) ? 128 : (s + (1 << (shf - 1))) >> shf;  // predict_dcpred :183
+  }
+  bool is_flat;  // is_flat_source_16 (cost.rs:177)
+  int tsrc;      // TTransform of this lane's source block (cost.rs:73)
+  {
+    const int v0 = W.src_y[0];
+    bool same = true;
+    i32 px[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      px[k] = W.src_y[(by * 4 + (k >> 2)) * 16 + bx * 4 + (k & 3)];
+      same &= px[k] == v0;
+    }
+    is_flat = __all_sync(FULL, same);
+    tsrc = t_transform16(px, ZW_TAB(kWeightY));
+  }
+  int best16_mode = 0;
+  i64 best16_score = I64_MAX;
+  u32 best16_cc = 0, best16_mc = 0, best16_d = 0;
+  i32 best16_sd = 0;
+#pragma unroll 1
+  for (int round = 0; round < 2; round++) {
+    const int mode = round * 2 + hb;  // 0 DC, 1 V, 2 H, 3 TM (MODES order, vp8.rs:1509)
+    const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
+    i32 c[16], pr[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
+      pr[k] = pred_big(W.yws, 0, mode, x, y, dc16);
+      c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
+    }
+    fdct4x4(c);
+    W.dcbuf[lane] = c[0];
+    __syncwarp();
+    i32 y2[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) y2[k] = W.dcbuf[hb * 16 + k];
+    __syncwarp();
+    wht4x4(y2);
+#pragma unroll
+    for (int k = 0; k < 16; k++) y2[k] = quantize_coeff(y2[k], SP.y2, k);
+    const u32 cost_y2 = residual_cost(y2, 1, 0, 0, cc);
+#pragma unroll
+    for (int k = 0; k < 16; k++) y2[k] = dequantize(y2[k], SP.y2, k);
+    iwht4x4(y2);
+    i32 mydc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (k == blk) mydc = y2[k];
+    i32 lv[16];
+    lv[0] = 0;
+    int nzc = 0;
+#pragma unroll
+    for (int k = 1; k < 16; k++) { lv[k] = quantize_coeff(c[k], SP.y1, k); nzc += lv[k] != 0; }
+    int cost_ac = (int)residual_cost(lv, 0, 1, 0, cc);
+#pragma unroll
+    for (int k = 1; k < 16; k++) c[k] = dequantize(lv[k], SP.y1, k);
+    c[0] = mydc;
+    idct4x4(c);
+    int sse = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
+      c[k] = clip255(pr[k] + c[k]);
+      const int df = (i32)W.src_y[y * 16 + x] - c[k];
+      sse += df * df;
+    }
+    int td = iabs(t_transform16(c, ZW_TAB(kWeightY)) - tsrc) >> 5;  // tdisto_4x4 (cost.rs:122)
+    cost_ac = red16_add(cost_ac);
+    sse = red16_add(sse);
+    td = red16_add(td);
+    nzc = red16_add(nzc);
+    const u32 coeff_cost = cost_y2 + (u32)cost_ac;
+    i32 sd = SP.tlambda > 0 ? (i32)(((i32)SP.tlambda * td + 128) >> 8) : 0;
+    u32 dfin = (u32)sse;
+    if (is_flat && nzc == 0) { dfin = dfin * 2; sd = sd * 2; }  // is_flat_coeffs(.., 16, 0)
+    const u32 mode_cost = ZW_TAB(kFixedCostsI16)[mode];
+    i64 score = ((i64)mode_cost + (i64)coeff_cost) * (i64)SP.lambda_i16 + 256 * ((i64)dfin + (i64)sd);
+    if (!avail) score = I64_MAX;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {  // the two halves in MODES order; strict < keeps the first
+      const i64 s = shfl64(score, h * 16);
+      const u32 ccst = __shfl_sync(FULL, coeff_cost, h * 16);
+      const u32 dd = __shfl_sync(FULL, dfin, h * 16);
+      const i32 ss = __shfl_sync(FULL, sd, h * 16);
+      if (s < best16_score) {
+        best16_score = s; best16_mode = round * 2 + h; best16_cc = ccst;
+        best16_mc = ZW_TAB(kFixedCostsI16)[round * 2 + h]; best16_d = dd; best16_sd = ss;
+      }
+    }
+  }
+  u64 i16_score;
+  {
+    const i64 fs = ((i64)best16_mc + (i64)best16_cc) * (i64)SP.lambda_mode + 256 * ((i64)best16_d + (i64)best16_sd);
+    i16_score = (u64)(fs > 0 ? fs : 0);
+  }
+
+  // ===== pick_best_intra4 (vp8.rs:1790-2036), gated as in choose_macroblock_info (:2210-2231) =====
+  bool use_i4 = false;
+  if (method > 1 && (method >= 5 || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0)) {
+    use_i4 = true;
+    const int max_modes = method <= 3 ? 3 : (method == 4 ? 4 : 10);
+    u64 running = 211ull * (u64)SP.lambda_mode;
+    u32 total_mode_cost = 0;
+    u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
+      const int top_ctx = sby == 0 ? 0 : W.bmodes[i - 4];
+      const int left_ctx = sbx == 0 ? 0 : W.bmodes[i - 1];
+      const int ctx0 = (sby == 0 ? 0 : (int)((tnz4 >> sbx) & 1)) + (sbx == 0 ? 0 : (int)((lnz4 >> sby) & 1));
+      u8 e[13];
+      fetch_edges4(W.yws, x0, y0, e);
+      const int m = lane < 10 ? lane : 0;
+      i32 pr[16], c[16];
+      int psse = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        pr[k] = predict4_pixel(e, m, k, ptab);
+        c[k] = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - pr[k];
+        psse += c[k] * c[k];
+      }
+      // stable ascending rank by prediction SSE (sort_unstable_by_key is an insertion sort here, Q11)
+      int rank = 0;
+#pragma unroll
+      for (int o = 0; o < 10; o++) {
+        const int os = __shfl_sync(FULL, psse, o);
+        rank += (os < psse) || (os == psse && o < lane);
+      }
+      const bool cand = lane < 10 && rank < max_modes;
+      u64 key = ~0ull;
+      u32 my_sse = 0, my_rate = 0;
+      bool my_nz = false;
+      i32 q[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) q[k] = 0;
+      if (cand) {
+        fdct4x4(c);
+#pragma unroll
+        for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.y1, k); my_nz |= q[k] != 0; }
+        const u32 coeff_cost = residual_cost(q, 3, 0, ctx0, cc);
+#pragma unroll
+        for (int k = 0; k < 16; k++) c[k] = dequantize(q[k], SP.y1, k);
+        idct4x4(c);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          c[k] = clip255(pr[k] + c[k]);  // reconstructed pixel
+          const int df = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - c[k];
+          my_sse += (u32)(df * df);
+        }
+        const u32 mode_cost = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m];
+        my_rate = mode_cost + coeff_cost;
+        const u64 score = (u64)my_sse * 256ull + (u64)(my_rate & 0xffffu) * (u64)SP.lambda_i4;  // u16 truncation (Q8)
+        key = (score << 4) | (u64)rank;
+      }
+      u64 kmin = key;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const u64 other = (u64)shfl64((i64)kmin, lane ^ o);
+        kmin = other < kmin ? other : kmin;
+      }
+      const int win = __ffs(__ballot_sync(FULL, cand && key == kmin)) - 1;
+      if (lane == win) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          W.yws[(y0 + (k >> 2)) * 32 + x0 + (k & 3)] = (u8)c[k];
+          W.nat[i][k] = (i16)q[k];
+        }
+        W.bmodes[i] = (u8)m;
+      }
+      const u32 wsse = __shfl_sync(FULL, my_sse, win);
+      const u32 wrate = __shfl_sync(FULL, my_rate, win);
+      const int wnz = __shfl_sync(FULL, (int)my_nz, win);
+      __syncwarp();
+      tnz4 = (tnz4 & ~(1u << sbx)) | ((u32)wnz << sbx);
+      lnz4 = (lnz4 & ~(1u << sby)) | ((u32)wnz << sby);
+      total_mode_cost += ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + win];
+      running += (u64)wsse * 256ull + (u64)(wrate & 0xffffu) * (u64)SP.lambda_mode;
+      if (running >= i16_score || total_mode_cost > 16384u) { use_i4 = false; break; }
+    }
+  }
+
+  // ===== final luma transform -> coded levels + reconstruction =====
+  bool any_simple_nz = false;
+  u32 ynz = 0;
+  int y2nz = 0;
+  if (!use_i4) {
+    // ---- transform_luma_block (vp8.rs:2647-2780) ----
+    i32 c[16], pr[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
+      pr[k] = pred_big(W.yws, 0, best16_mode, x, y, dc16);
+      c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
+    }
+    fdct4x4(c);
+    if (lane < 16) W.dcbuf[lane] = c[0];
+    __syncwarp();
+    i32 mydc = 0;
+    {
+      i32 y2[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) y2[k] = W.dcbuf[k];
+      wht4x4(y2);
+#pragma unroll
+      for (int k = 0; k < 16; k++) { y2[k] = quantize_coeff(y2[k], SP.y2, k); y2nz |= y2[k] != 0; }
+#pragma unroll
+      for (int k = 0; k < 16; k++) if (k == lane) W.nat[0][ZW_TAB(kZigzag)[0] + 0 * k] = 0;  // (keeps nat[] defined)
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) W.rec.levels[0][k] = 0;
+      }
+      __syncwarp();
+      if (lane < 16) {
+        // zig-zag position p of natural index `lane`: scatter y2[lane] to levels[0][p]
+        int p = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (ZW_TAB(kZigzag)[k] == lane) p = k;
+        i32 v = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (k == lane) v = y2[k];
+        W.rec.levels[0][p] = (i16)v;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) y2[k] = dequantize(y2[k], SP.y2, k);
+      iwht4x4(y2);
+#pragma unroll
+      for (int k = 0; k < 16; k++) if (k == blk) mydc = y2[k];
+    }
+    any_simple_nz |= y2nz != 0;
+    bool my_simple = false;
+    i32 lv[16];
+    lv[0] = 0;
+#pragma unroll
+    for (int k = 1; k < 16; k++) { lv[k] = quantize_coeff(c[k], SP.y1, k); my_simple |= lv[k] != 0; }
+    if (lane >= 16) my_simple = false;
+    if (!trellis) {
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 1; k < 16; k++) c[k] = dequantize(lv[k], SP.y1, k);
+#pragma unroll
+        for (int k = 0; k < 16; k++) W.nat[lane][k] = (i16)lv[k];
+        W.nzflag[lane] = my_simple;
+      }
+      __syncwarp();
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) W.rec.levels[1 + lane][k] = W.nat[lane][ZW_TAB(kZigzag)[k]];
+      }
+    } else {
+      // trellis with the nz context chained in raster order (:2685-2728): sweep anti-diagonals
+      if (lane < 4) {
+        W.nzflag[16 + lane] = (in_top_nz >> (1 + lane)) & 1;
+        W.nzflag[20 + lane] = (in_left_nz >> (1 + lane)) & 1;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int dg = 0; dg < 7; dg++) {
+        if (lane < 16 && bx + by == dg) {
+          const int ctx0 = imin((int)W.nzflag[20 + by] + (int)W.nzflag[16 + bx], 2);
+          i32 zz[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) zz[k] = 0;
+          const bool nz = trellis_quantize(c, zz, SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0);
+#pragma unroll
+          for (int k = 0; k < 16; k++) W.rec.levels[1 + blk][k] = (i16)zz[k];
+          W.nzflag[lane] = nz;
+        }
+        __syncwarp();
+        if (lane < 16 && bx + by == dg) {
+          W.nzflag[16 + bx] = W.nzflag[lane];
+          W.nzflag[20 + by] = W.nzflag[lane];
+        }
+        __syncwarp();
+      }
+    }
+    if (lane < 16) {
+      c[0] = mydc;
+      idct4x4(c);
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
+        W.yws[(1 + y) * 32 + 1 + x] = (u8)clip255(pr[k] + c[k]);
+      }
+    }
+    any_simple_nz |= __any_sync(FULL, my_simple);
+    __syncwarp();
+    ynz = __ballot_sync(FULL, lane < 16 && W.nzflag[lane] != 0) & 0xffffu;
+  } else if (!trellis) {
+    // ---- transform_luma_blocks_4x4 without trellis == what the search already produced ----
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) W.rec.levels[0][k] = 0;
+    }
+    if (lane < 16) {
+      bool nz = false;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const i16 v = W.nat[lane][ZW_TAB(kZigzag)[k]];
+        W.rec.levels[1 + lane][k] = v;
+        nz |= v != 0;
+      }
+      W.nzflag[lane] = nz;
+    }
+    __syncwarp();
+    ynz = __ballot_sync(FULL, lane < 16 && W.nzflag[lane] != 0) & 0xffffu;
+    any_simple_nz |= ynz != 0;
+  } else {
+    // ---- transform_luma_blocks_4x4 with trellis (vp8.rs:2785-2916): strictly serial; every lane
+    //      runs the same block redundantly (no divergence), lanes 0..15 write one pixel each ----
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) W.rec.levels[0][k] = 0;
+    }
+    u32 tnz = (in_top_nz >> 1) & 15, lnz = (in_left_nz >> 1) & 15;
+    bool simple_any = false;
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
+      u8 e[13];
+      fetch_edges4(W.yws, x0, y0, e);
+      const int m = W.bmodes[i];
+      i32 pr[16], c[16], zz[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        pr[k] = predict4_pixel(e, m, k, ptab);
+        c[k] = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - pr[k];
+        zz[k] = 0;
+      }
+      fdct4x4(c);
+#pragma unroll
+      for (int k = 0; k < 16; k++) simple_any |= quantize_coeff(c[k], SP.y1, k) != 0;
+      const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
+      const bool nz = trellis_quantize(c, zz, SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0);
+      tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
+      lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
+      ynz |= (u32)nz << i;
+      idct4x4(c);
+      __syncwarp();
+      if (lane < 16) {
+        i32 v = 0, z = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (k == lane) { v = clip255(pr[k] + c[k]); z = zz[k]; }
+        W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)v;
+        W.rec.levels[1 + i][lane] = (i16)z;
+      }
+      __syncwarp();
+    }
+    any_simple_nz |= simple_any;
+  }
+  __syncwarp();
+  R.use_i4 = use_i4;
+  R.mode16 = best16_mode;
+  R.ynz = ynz;
+  R.y2nz = y2nz;
+  R.simple_nz = any_simple_nz;
+  return R;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chroma: pick_best_uv (vp8.rs:2050-2200) + transform_chroma_blocks with DC error diffusion
+// (:3039-3121, :572-647).  Leaves the reconstruction in W.uvws and the coded zig-zag levels in
+// W.rec.levels[17..24]; updates the packed diffusion state.
+// ---------------------------------------------------------------------------------------------
+struct ChromaOut {
+  int uv_mode;
+  u32 uvnz;  // has_coeffs bit per chroma block (== simple-quantised non-zero)
+};
+
+__device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCtx& cc, int mbx, int mby, u32& left_derr,
+                               u32& top_derr, int lane) {
+  ChromaOut R;
+  int dcU, dcV;
+  {
+    int su = 0, sv = 0;
+    if (lane < 8) {
+      su = (mby != 0 ? W.uvws[1 + lane] : 0) + (mbx != 0 ? W.uvws[(1 + lane) * 32] : 0);
+      sv = (mby != 0 ? W.uvws[17 + lane] : 0) + (mbx != 0 ? W.uvws[(1 + lane) * 32 + 16] : 0);
+    }
+    su = red8_add(su); sv = red8_add(sv);
+    su = __shfl_sync(FULL, su, 0); sv = __shfl_sync(FULL, sv, 0);
+    const int shf = 2 + (mbx != 0) + (mby != 0);
+    dcU = (mbx == 0 && mby == 0) ? 128 : (su + (1 << (shf - 1))) >> shf;
+    dcV = (mbx == 0 && mby == 0) ? 128 : (sv + (1 << (shf - 1))) >> shf;
+  }
+  const int b8 = lane & 7, ch = b8 >> 2, cbx = b8 & 1, cby = (b8 >> 1) & 1, cofs = ch * 16;
+  const u8* src = ch ? W.src_v : W.src_u;
+  int uv_mode;
+  {
+    const int mode = lane >> 3;  // lane = mode*8 + block (0..3 U, 4..7 V); MODES order DC,V,H,TM
+    const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
+    i32 c[16], pr[16], q[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
+      pr[k] = pred_big(W.uvws, cofs, mode, x, y, ch ? dcV : dcU);
+      c[k] = (i32)src[y * 8 + x] - pr[k];
+    }
+    fdct4x4(c);
+    int nzac = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.uv, k); if (k > 0) nzac += q[k] != 0; }
+    int cost = (int)residual_cost(q, 2, 0, 0, cc);
+#pragma unroll
+    for (int k = 0; k < 16; k++) c[k] = dequantize(q[k], SP.uv, k);
+    idct4x4(c);
+    int sse = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
+      const int df = (i32)src[y * 8 + x] - clip255(pr[k] + c[k]);
+      sse += df * df;
+    }
+    cost = red8_add(cost); sse = red8_add(sse); nzac = red8_add(nzac);
+    const u32 penalty = (mode > 0 && nzac <= 2) ? 140u * 8u : 0u;  // is_flat_coeffs(.., 8, 2) -> FLATNESS_PENALTY*8
+    i64 score = ((i64)ZW_TAB(kFixedCostsUV)[mode] + (i64)cost + (i64)penalty) * (i64)SP.lambda_uv + 256 * (i64)sse;
+    if (!avail) score = I64_MAX;
+    i64 best = I64_MAX;
+    uv_mode = 0;
+#pragma unroll
+    for (int mm = 0; mm < 4; mm++) {
+      const i64 s = shfl64(score, mm * 8);
+      if (s < best) { best = s; uv_mode = mm; }
+    }
+  }
+  // ---- transform_chroma_blocks ----
+  i32 c[16], pr[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
+    pr[k] = pred_big(W.uvws, cofs, uv_mode, x, y, ch ? dcV : dcU);
+    c[k] = (i32)src[y * 8 + x] - pr[k];
+  }
+  fdct4x4(c);
+  if (lane < 8) W.dcbuf[lane] = c[0];
+  __syncwarp();
+  // error diffusion of the 8 DCs, computed redundantly by every lane (tiny, strictly serial)
+  i32 ndc[8];
+  u32 new_left = 0, new_top = 0;
+#pragma unroll
+  for (int cch = 0; cch < 2; cch++) {
+    const i32 q = SP.uv.q[0];
+    const u32 iq = SP.uv.iq[0], bias = SP.uv.bias[0];
+    const i32 t0 = (i8)(top_derr >> (16 * cch)), t1 = (i8)(top_derr >> (16 * cch + 8));
+    const i32 l0 = (i8)(left_derr >> (16 * cch)), l1 = (i8)(left_derr >> (16 * cch + 8));
+    i32 errs[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const i32 te = b == 0 ? t0 : (b == 1 ? t1 : (b == 2 ? errs[0] : errs[1]));
+      const i32 le = b == 0 ? l0 : (b == 1 ? errs[0] : (b == 2 ? l1 : errs[2]));
+      i32 dc = W.dcbuf[cch * 4 + b];
+      dc += (7 * te + 8 * le) >> 3;
+      ndc[cch * 4 + b] = dc;
+      const bool sign = dc < 0;
+      const u32 a = (u32)iabs(dc);
+      const i32 level = a > SP.uv_dc_zthresh ? (i32)((a * iq + bias) >> 17) : 0;
+      const i32 err = (i32)a - level * q;
+      const i32 se = (sign ? -err : err) >> 1;
+      errs[b] = imin(imax(se, -127), 127);
+    }
+    const i32 nl0 = errs[1], nl1 = (3 * errs[3]) >> 2;
+    const i32 nt0 = errs[2], nt1 = errs[3] - nl1;
+    new_left |= ((u32)(u8)(i8)nl0 | ((u32)(u8)(i8)nl1 << 8)) << (16 * cch);
+    new_top |= ((u32)(u8)(i8)nt0 | ((u32)(u8)(i8)nt1 << 8)) << (16 * cch);
+  }
+  __syncwarp();
+  left_derr = new_left;
+  top_derr = new_top;
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k == lane) c[0] = ndc[k];
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const i32 q = quantize_coeff(c[k], SP.uv, k);
+      nz |= q != 0;
+      W.nat[lane][k] = (i16)q;
+      c[k] = dequantize(q, SP.uv, k);
+    }
+    idct4x4(c);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
+      W.uvws[(1 + y) * 32 + cofs + 1 + x] = (u8)clip255(pr[k] + c[k]);
+    }
+    W.nzflag[lane] = nz;
+  }
+  __syncwarp();
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) W.rec.levels[17 + lane][k] = W.nat[lane][ZW_TAB(kZigzag)[k]];
+  }
+  R.uvnz = __ballot_sync(FULL, lane < 8 && W.nzflag[lane] != 0) & 0xffu;
+  R.uv_mode = uv_mode;
+  __syncwarp();
+  return R;
+}
+
+// Complexity left behind by a macroblock for the row below (out_top) and the MB to the right
+// (out_left): encode_residual_data / record_residual_stats bookkeeping + the skip clear
+// (vp8.rs:1367-1374, :1468-1474, Complexity::clear :138).
+__device__ __forceinline__ void complexity_after(bool is_b, bool skip, int y2nz, u32 ynz, u32 uvnz, u32 in_top, u32 in_left,
+                                                 u32& out_top, u32& out_left) {
+  u32 yb = ynz, ub = uvnz & 15, vb = (uvnz >> 4) & 15;
+  int y2t = is_b ? (int)(in_top & 1) : (y2nz != 0);
+  int y2l = is_b ? (int)(in_left & 1) : (y2nz != 0);
+  if (skip) {
+    yb = 0; ub = 0; vb = 0;
+    if (!is_b) { y2t = 0; y2l = 0; }
+  }
+  out_top = (u32)y2t | (((yb >> 12) & 15) << 1) | (((ub >> 2) & 3) << 5) | (((vb >> 2) & 3) << 7);
+  const u32 yl = ((yb >> 3) & 1) | (((yb >> 7) & 1) << 1) | (((yb >> 11) & 1) << 2) | (((yb >> 15) & 1) << 3);
+  const u32 ul = ((ub >> 1) & 1) | (((ub >> 3) & 1) << 1);
+  const u32 vl = ((vb >> 1) & 1) | (((vb >> 3) & 1) << 1);
+  out_left = (u32)y2l | (yl << 1) | (ul << 5) | (vl << 7);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The wavefront kernel.  PASS 1: luma only (see file header).  PASS 2: luma + chroma.
+// ---------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(ChunkParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) (&SH.pred_tab[0][0])[i] = (&d_pred_tab[0][0])[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  WarpScratch& W = SH.w[threadIdx.x >> 5];
+  const u16(*ptab)[16] = SH.pred_tab;
+  int* progress = P.progress + (PASS - 1) * P.n_rows;
+  MbRecord* recs = PASS == 1 ? P.rec1 : P.rec2;
+  const bool trellis = (PASS == 2) && P.do_trellis;
+  const int method = P.method;
+
+  for (;;) {
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(&P.ticket[PASS - 1], 1u);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= P.n_rows) break;
+    const RowRef rr = P.rows[t];
+    const ImageDesc d = P.img[rr.img];
+    const ImageState& IS = P.st[rr.img];
+    const int mbw = d.mbw, mby = rr.mby;
+    const int pw = mbw * 16, cwid = mbw * 8;
+    const u8* yp = P.planes + d.y_off;
+    const u8* up = yp + (size_t)pw * d.mbh * 16;
+    const u8* vp = up + (size_t)cwid * d.mbh * 8;
+    const u32 row_mb0 = d.mb_off + mby * mbw;
+    const u32 up_mb0 = row_mb0 - mbw;  // only dereferenced when mby > 0
+    CostCtx cc;
+    cc.probs = PASS == 1 ? ZW_TAB(kCoeffProbs) : P.probs + (size_t)rr.img * 1056;
+    cc.level_cost = PASS == 1 ? nullptr : P.lcost + (size_t)rr.img * 6528;
+    const bool seg_on = IS.seg_enabled != 0;
+
+    // row-start state (vp8.rs:1339-1344 / :1423-1429)
+    u32 left_nz = 0;
+    u32 left_derr = 0;  // pass 2 resets it per row (:1425)
+    if (lane < 17) W.left_y[lane] = 129;
+    if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
+    __syncwarp();
+
+    for (int mbx = 0; mbx < mbw; mbx++) {
+      if (mby > 0) {  // wait for the top / top-right neighbours
+        const int need = min(mbx + 2, mbw);
+        if (lane == 0) {
+          while (ld_acquire(&progress[d.row_off + mby - 1]) < need) __nanosleep(100);
+        }
+        __syncwarp();
+      }
+      const u32 gmb = row_mb0 + mbx;
+      const int seg = seg_on ? P.segmap[gmb] : 0;
+      const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
+      u32 top_nz = 0, top_derr = 0;
+      if (PASS == 2) {
+        if (mby > 0) {
+          top_nz = __ldcg(&P.nz_after[up_mb0 + mbx]);
+          top_derr = __ldcg(&P.derr2[up_mb0 + mbx]);
+        } else {
+          // Q4: top_derr is not reset between passes -> row 0 of pass 2 starts from pass 1's last row
+          top_derr = __ldcg(&P.derr1[d.mb_off + (d.mbh - 1) * mbw + mbx]);
+        }
+      }
+      load_luma_mb(W, P, yp, pw, mbw, mbx, mby, up_mb0, lane);
+      if (PASS == 2) load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
+      for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;
+      __syncwarp();
+
+      const LumaOut L = luma_mb(W, ptab, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane);
+      ChromaOut C;
+      C.uv_mode = 0; C.uvnz = 0;
+      bool skip = false;
+      u32 out_top = 0, out_left = 0;
+      if (PASS == 2) {
+        C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
+        skip = !(L.simple_nz || C.uvnz != 0);
+        complexity_after(L.use_i4, skip, L.y2nz, L.ynz, C.uvnz, top_nz, left_nz, out_top, out_left);
+      }
+      if (lane == 0) {
+        W.rec.ymode = L.use_i4 ? 4 : (u8)L.mode16;
+        W.rec.uvmode = (u8)C.uv_mode;
+        W.rec.segment = (u8)seg;
+        W.rec.skip = skip;
+        if (PASS == 2) {
+          W.rec.top_nz = (u16)top_nz;
+          W.rec.left_nz = (u16)left_nz;
+        } else {
+          // pass 1: luma flags parked here until k_chroma1 completes the record
+          W.rec.top_nz = (u16)L.ynz;
+          W.rec.left_nz = (u16)((L.y2nz ? 1 : 0) | (L.simple_nz ? 2 : 0));
+        }
+        *reinterpret_cast<u32*>(W.rec.derr_left) = left_derr;
+        *reinterpret_cast<u32*>(W.rec.derr_top) = top_derr;
+      }
+      if (lane < 16) W.rec.bmodes[lane] = L.use_i4 ? W.bmodes[lane] : 0;
+      __syncwarp();
+      if (PASS == 2 && skip) {  // the reference codes nothing for a skipped MB; keep the dump canonical
+        for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;
+        __syncwarp();
+      }
+      {
+        const u32* s = reinterpret_cast<const u32*>(&W.rec);
+        u32* g = reinterpret_cast<u32*>(&recs[gmb]);
+        for (int k = lane; k < 208; k += 32) g[k] = s[k];
+      }
+      left_nz = out_left;
+      // borders for the neighbours
+      if (lane < 17) W.left_y[lane] = W.yws[lane * 32 + 16];
+      MbBottom* bo = &P.bottom[gmb];
+      if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
+      if (PASS == 2) {
+        if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+        if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
+        if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
+        if (lane == 0) {
+          P.nz_after[gmb] = (u16)out_top;
+          P.derr2[gmb] = top_derr;
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(&progress[d.row_off + mby], mbx + 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass-1 chroma chain: one warp per image, raster order (see file header).  Completes rec1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_chroma1(ChunkParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  WarpScratch& W = SH.w[threadIdx.x >> 5];
+  for (;;) {
+    u32 img = 0;
+    if (lane == 0) img = atomicAdd(&P.ticket[2], 1u);
+    img = __shfl_sync(FULL, img, 0);
+    if (img >= P.n_img) break;
+    const ImageDesc d = P.img[img];
+    ImageState& IS = P.st[img];
+    const int mbw = d.mbw, mbh = d.mbh, pw = mbw * 16, cwid = mbw * 8;
+    const u8* yp = P.planes + d.y_off;
+    const u8* up = yp + (size_t)pw * mbh * 16;
+    const u8* vp = up + (size_t)cwid * mbh * 8;
+    CostCtx cc;
+    cc.probs = ZW_TAB(kCoeffProbs);
+    cc.level_cost = nullptr;
+    const bool seg_on = IS.seg_enabled != 0;
+    u32 left_derr = 0;  // carried across rows in pass 1 (Q5)
+    u32 nskip = 0;
+    for (int mby = 0; mby < mbh; mby++) {
+      const u32 row_mb0 = d.mb_off + mby * mbw, up_mb0 = row_mb0 - mbw;
+      u32 left_nz = 0;
+      if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
+      __syncwarp();
+      for (int mbx = 0; mbx < mbw; mbx++) {
+        const u32 gmb = row_mb0 + mbx;
+        const int seg = seg_on ? P.segmap[gmb] : 0;
+        const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
+        u32 top_nz = 0, top_derr = 0;
+        if (mby > 0) {
+          top_nz = P.nz_after[up_mb0 + mbx];
+          top_derr = P.derr1[up_mb0 + mbx];
+        }
+        load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
+        const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
+        MbRecord* r = &P.rec1[gmb];
+        const u32 ynz = r->top_nz;
+        const u32 lf = r->left_nz;
+        const bool is_b = r->ymode == 4;
+        const bool skip = !((lf & 2) || C.uvnz != 0);
+        u32 out_top, out_left;
+        complexity_after(is_b, skip, (int)(lf & 1), ynz, C.uvnz, top_nz, left_nz, out_top, out_left);
+        __syncwarp();
+        if (skip) {
+          for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(r->levels)[k] = 0;
+        } else if (lane < 8) {
+          u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
+          const u32* s = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
+#pragma unroll
+          for (int k = 0; k < 8; k++) g[k] = s[k];
+        }
+        if (lane == 0) {
+          r->uvmode = (u8)C.uv_mode;
+          r->skip = skip;
+          r->top_nz = (u16)top_nz;
+          r->left_nz = (u16)left_nz;
+          *reinterpret_cast<u32*>(r->derr_left) = left_derr;
+          *reinterpret_cast<u32*>(r->derr_top) = top_derr;
+          P.nz_after[gmb] = (u16)out_top;
+          P.derr1[gmb] = top_derr;
+        }
+        nskip += skip;
+        left_nz = out_left;
+        if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+        MbBottom* bo = &P.bottom[gmb];
+        if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
+        if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
+        __syncwarp();
+      }
+    }
+    if (lane == 0) IS.n_skip1 = nskip;
+  }
+}
+
+}  // namespace zw
+#endif

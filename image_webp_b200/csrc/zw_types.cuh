@@ -1,0 +1,123 @@
+// zw_types.cuh -- device-side data layout of one staged chunk of images (see DESIGN.md "HBM layout").
+#ifndef ZW_TYPES_CUH
+#define ZW_TYPES_CUH
+#include "zw_cost.cuh"
+
+namespace zw {
+
+// Quantiser + lambda set of one quantiser index (Segment::init_matrices, src/common/types.rs:806-853;
+// VP8Matrix::new, src/encoder/cost.rs:401-447).  Built on the host for all 128 indices.
+struct SegParams {
+  Matrix y1, y2, uv;
+  u16 sharpen[16];  // y1 only
+  u32 lambda_i4, lambda_i16, lambda_uv, lambda_mode;
+  u32 lambda_trellis_i4, lambda_trellis_i16, tlambda;
+  u32 uv_dc_zthresh;  // ((1<<17)-1-bias)/iq of the chroma DC entry (error diffusion, vp8.rs:600)
+};
+
+// Per-macroblock record: the interface between the search passes, the statistics kernel and
+// the tokeniser, and the P1MB / P2MB parity dump (same POD layout as the oracle's zwo_mb_record).
+struct MbRecord {
+  u8 ymode;   // 0 DC 1 V 2 H 3 TM 4 B_PRED
+  u8 uvmode;  // 0 DC 1 V 2 H 3 TM
+  u8 segment;
+  u8 skip;
+  u8 bmodes[16];
+  u16 top_nz;   // incoming complexities: bit0 y2, 1..4 y[x], 5..6 u[x], 7..8 v[x]
+  u16 left_nz;  // bit0 y2, 1..4 y[y], 5..6 u[y], 7..8 v[y]
+  i8 derr_left[4];
+  i8 derr_top[4];
+  i16 levels[25][16];  // coded levels, zig-zag: [0] Y2, [1..16] Y, [17..20] U, [21..24] V
+};
+static_assert(sizeof(MbRecord) == 832, "MbRecord layout");
+
+// Bottom row of a reconstructed macroblock, read by the row below (top / top-right borders).
+struct MbBottom {
+  u8 y[16];
+  u8 u[8];
+  u8 v[8];
+};
+
+// Host-filled description of one image of the chunk.
+struct ImageDesc {
+  u32 width, height, mbw, mbh;
+  u32 bpp;       // 3 or 4
+  u32 mb_off;    // index of the image's first macroblock in the chunk-wide MB arrays
+  u32 row_off;   // index of its first macroblock row in the chunk-wide row arrays
+  u32 use_segments;  // mbw*mbh >= 256 (vp8.rs:2481)
+  u64 rgb_off;   // byte offset into the RGB arena (16-byte aligned)
+  u64 y_off;     // byte offset of the padded Y plane in the plane arena; U follows, then V
+  // filled in after the token count (second upload of the descriptor table):
+  u64 hdr_off;   // offset (in tokens) of the image's first-partition symbol stream
+  u64 tok_off;   // offset (in tokens) of the image's token-partition symbol stream
+  u64 part_off;  // byte offset of its coded partitions in the partition scratch: [p0 | p1]
+  u32 p0_cap, p1_cap;  // byte capacities of the two coded partitions
+};
+
+// Device-written per-image state.
+struct ImageState {
+  u32 seg_count[4];
+  u8 seg_qidx[4];
+  i8 seg_delta[4];
+  u8 tree_probs[3];
+  u8 update_map;
+  u8 seg_enabled;
+  u8 skip_prob;
+  u8 probs_updated;
+  u8 centers[4];
+  i32 mid_alpha;
+  u32 n_skip1;       // skipped macroblocks in pass 1
+  u32 hdr_tokens;    // tokens in the first-partition stream
+  u32 tok_tokens;    // tokens in the token-partition stream
+  u32 part0_bytes, part1_bytes;
+  u32 vp8_bytes;
+  u32 status;   // 0 or a ZW_ERR_* code raised on the device
+};
+static_assert(sizeof(ImageState) <= 80, "ImageState is copied back per image; keep it small");
+
+struct RowRef {
+  u32 img;
+  u32 mby;
+};
+
+// One boolean-coder input symbol: probability in the low byte, bit in bit 8.
+typedef u16 Token;
+
+// Everything the kernels need, passed by value.
+struct ChunkParams {
+  const ImageDesc* img;
+  ImageState* st;
+  const RowRef* rows;     // ticket -> (image, mb row), ordered so that row y-1 precedes row y
+  const SegParams* segtab;  // [128]
+  const u8* segquant_lut;   // [128][255]: compute_segment_quant(base, alpha-127..127)
+  u32 n_img, n_rows, n_mb;
+  u32 method, base_qidx, do_trellis;
+  u8 filter_level;
+  const u8* rgb;
+  u8* planes;
+  u32* alpha_hist;  // [n_img][256]
+  u8* map256;       // [n_img][256] alpha -> segment (parity dump only)
+  u8* alpha;     // [n_mb]
+  u8* segmap;    // [n_mb]
+  MbRecord* rec1;
+  MbRecord* rec2;
+  MbBottom* bottom;  // [n_mb]
+  u16* nz_after;     // [n_mb] top complexity left behind by each MB
+  u32* derr1;        // [n_mb] packed top_derr after pass 1
+  u32* derr2;        // [n_mb] same, pass 2
+  int* progress;     // [2][n_rows] macroblocks completed per row, per pass
+  u32* ticket;       // [4] work counters
+  u32* rowstats;     // [n_rows][1056][2] per-row (total, ones)
+  u32* stats;        // [n_img][1056] packed ProbaStats
+  u8* probs;         // [n_img][1056] final token probabilities
+  u16* lcost;        // [n_img][4*8*3*68]
+  u32* mb_hdr_cnt;   // [n_mb+1] tokens per MB header (then exclusive scan)
+  u32* mb_tok_cnt;   // [n_mb+1] tokens per MB residual
+  Token* hdr_tokens; // first-partition streams
+  Token* tok_tokens; // token-partition streams
+  u8* part_bytes;    // scratch for coded partitions
+  u8* out;           // output arena
+};
+
+}  // namespace zw
+#endif

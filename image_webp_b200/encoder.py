@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference's encoder API for the lossy path, on top of the C ABI.
+
+Mirrors (names, argument meaning, error behaviour) of imazen/image-webp `zenwebp` 0.2.0:
+  ColorType        src/encoder/api.rs:83-92
+  EncodingError    src/encoder/api.rs:35-48
+  EncoderParams    src/encoder/api.rs:419-459   (+ additive .method(m) builder)
+  WebPEncoder      src/encoder/api.rs:1244-1398 (new / set_params / encode)
+plus the batch entry point north_star asks for (`encode_batch`).
+
+The reference is Rust; no Rust toolchain exists in the build image, so this module (and the C++
+header include/zenwebp_b200.hpp) stand where the `zenwebp-b200` wrapper crate would: see
+INTEGRATION.md for the -sys crate a maintainer would add.  Only the lossy VP8 path is provided:
+lossless parameters raise NotImplementedError (out of scope).  No CPU fallback.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+
+
+class ColorType(enum.Enum):
+    L8 = 0
+    La8 = 1
+    Rgb8 = 2
+    Rgba8 = 3
+
+    def bytes_per_pixel(self):
+        return {ColorType.L8: 1, ColorType.La8: 2, ColorType.Rgb8: 3, ColorType.Rgba8: 4}[self]
+
+    def has_alpha(self):
+        return self in (ColorType.La8, ColorType.Rgba8)
+
+
+class EncodingError(Exception):
+    """EncodingError::{InvalidDimensions, InvalidBufferSize(String)} (+ device errors)."""
+
+    def __init__(self, kind, message=""):
+        super().__init__(("%s: %s" % (kind, message)) if message else kind)
+        self.kind = kind
+
+
+class InvalidDimensions(EncodingError):
+    def __init__(self):
+        super().__init__("Invalid dimensions")
+
+
+class InvalidBufferSize(EncodingError):
+    def __init__(self, msg=""):
+        super().__init__("Invalid buffer size", msg)
+
+
+class DeviceError(EncodingError):
+    def __init__(self, code, msg):
+        super().__init__("CUDA/encoder error %d" % code, msg)
+        self.code = code
+
+
+class EncoderParams:
+    """api.rs:419-459.  Public fields like the reference; Default = lossless, q95, method 4."""
+
+    def __init__(self, use_predictor_transform=True, use_lossy=False, lossy_quality=95, method=4):
+        self.use_predictor_transform = use_predictor_transform
+        self.use_lossy = use_lossy
+        self.lossy_quality = lossy_quality
+        self.method = method
+
+    @classmethod
+    def lossless(cls):
+        return cls()
+
+    @classmethod
+    def lossy(cls, quality):
+        return cls(use_lossy=True, lossy_quality=quality)
+
+    def with_method(self, m):  # the additive `EncoderParams::method(self, m) -> Self`
+        self.method = m
+        return self
+
+
+def _raise_for(status, lib):
+    if status == 0:
+        return
+    if status == 1:
+        raise InvalidDimensions()
+    if status == 2:
+        raise InvalidBufferSize("width/height doesn't match data length")
+    if status == 3:
+        raise ValueError("lossy quality must be between 0 and 100 / unsupported parameter")
+    raise DeviceError(status, lib.zw_strerror(status).decode())
+
+
+class Context:
+    """One encoder context per (host thread, GPU) -- wraps zw_create / zw_destroy."""
+
+    def __init__(self, device=0, max_device_bytes=0, persistent_warps_per_sm=0):
+        self.lib = _lib.load()
+        lim = _lib.ZwLimits(max_device_bytes, persistent_warps_per_sm, (C.c_int * 5)())
+        self.h = self.lib.zw_create(device, C.byref(lim))
+        if not self.h:
+            code = self.lib.zw_last_error()
+            raise DeviceError(code, self.lib.zw_strerror(code).decode() + " (no CPU fallback exists)")
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.lib.zw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------
+    @staticmethod
+    def _as_images(images, color):
+        arr = (_lib.ZwImage * len(images))()
+        keep = []
+        for i, im in enumerate(images):
+            if isinstance(im, tuple):  # (bytes-like, width, height)
+                data, w, h = im
+                buf = np.frombuffer(data, dtype=np.uint8)
+            else:
+                buf = np.ascontiguousarray(im, dtype=np.uint8)
+                h, w = buf.shape[0], buf.shape[1]
+            keep.append(buf)
+            arr[i] = _lib.ZwImage(buf.ctypes.data if buf.size else None, buf.size, w, h, color.value, 0)
+        return arr, keep
+
+    def _collect(self, outs, raise_errors):
+        res = []
+        for o in outs:
+            if o.status != 0:
+                if raise_errors:
+                    _raise_for(o.status, self.lib)
+                res.append(None)
+                continue
+            res.append(C.string_at(o.data, o.len))
+            self.lib.zw_free(o.data)
+        return res
+
+    # -- public ----------------------------------------------------------------------------
+    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+        """Batch entry point: list of uint8 arrays [h,w,c] (or (bytes,w,h) tuples) -> list of bytes.
+        Returns (outputs, timing dict)."""
+        if not params.use_lossy:
+            raise NotImplementedError("only the lossy VP8 path is implemented on the GPU (SURVEY.md §2)")
+        arr, keep = self._as_images(images, color)
+        outs = (_lib.ZwOutput * len(images))()
+        t = _lib.ZwTiming()
+        fn = self.lib.zw_encode_webp_batch if container else self.lib.zw_encode_vp8_batch
+        rc = fn(self.h, arr, len(images), int(params.lossy_quality), int(params.method), outs, C.byref(t))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return self._collect(outs, raise_errors), t.as_dict()
+
+    def stage(self, images, color=ColorType.Rgb8):
+        arr, keep = self._as_images(images, color)
+        self._keep = keep
+        rc = self.lib.zw_stage_batch(self.h, arr, len(images))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        self._n = len(images)
+
+    def encode_resident(self, params):
+        t = _lib.ZwTiming()
+        rc = self.lib.zw_encode_resident(self.h, int(params.lossy_quality), int(params.method), C.byref(t))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return t.as_dict()
+
+    def download(self, container=True, raise_errors=True):
+        outs = (_lib.ZwOutput * self._n)()
+        t = _lib.ZwTiming()
+        rc = self.lib.zw_download(self.h, outs, self._n, 1 if container else 0, C.byref(t))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return self._collect(outs, raise_errors), t.as_dict()
+
+    def dump_stage(self, index, name, dtype=np.uint8):
+        n = C.c_size_t(0)
+        rc = self.lib.zw_dump_stage(self.h, index, name.encode(), None, 0, C.byref(n))
+        if rc not in (0, 4):
+            _raise_for(rc, self.lib)
+        buf = np.zeros(max(1, n.value), np.uint8)
+        rc = self.lib.zw_dump_stage(self.h, index, name.encode(), buf.ctypes.data, buf.size, C.byref(n))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return buf[:n.value].view(dtype) if n.value else buf[:0].view(dtype)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class WebPEncoder:
+    """api.rs:1244-1398.  `writer` is a bytearray the encoder APPENDS to (like &mut Vec<u8>)."""
+
+    def __init__(self, writer, device=0):
+        self.writer = writer
+        self.params = EncoderParams()
+        self.device = device
+
+    def set_params(self, params):
+        self.params = params
+
+    def encode(self, data, width, height, color):
+        if not self.params.use_lossy:
+            raise NotImplementedError("lossless VP8L encoding is out of scope of the GPU path (SURVEY.md §2)")
+        if color not in (ColorType.Rgb8, ColorType.Rgba8):
+            raise NotImplementedError("L8/La8 input is a 'next' row (SURVEY.md §8f)")
+        if color.has_alpha():
+            raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f)")
+        if width > 65535 or height > 65535:
+            raise InvalidDimensions()
+        ctx = default_context(self.device)
+        outs, _ = ctx.encode_batch([(bytes(data), width, height)], self.params, color)
+        self.writer += outs[0]
+
+
+def encode_batch(images, params, color=ColorType.Rgb8, device=0):
+    """Convenience batch entry on the default context of `device`: list of images -> list of .webp bytes."""
+    return default_context(device).encode_batch(images, params, color)[0]

@@ -1,0 +1,122 @@
+/* zenwebp_b200.h -- C ABI of the B200-native lossy WebP (VP8 key-frame) encoder core.
+ *
+ * This is the drop-in boundary for ONE path of imazen/image-webp (crate `zenwebp` 0.2.0):
+ *     WebPEncoder::encode  ->  encode_frame_lossy(&mut Vec<u8>, &[u8], w, h, ColorType, quality, method)
+ *     reference: src/encoder/api.rs:1291-1329 (caller, RIFF wrap), src/encoder/vp8.rs:3132-3153 (seam)
+ * The reference has no FFI of its own (it is #![forbid(unsafe_code)] Rust); these entry points are
+ * what a `zenwebp-b200-sys` crate binds (see INTEGRATION.md for the Rust / ctypes stubs).
+ *
+ * Everything device-side is hand-written CUDA for sm_100a.  There is NO CPU fallback: every
+ * call fails with ZW_ERR_CUDA (>= 100) when no CUDA device / driver is usable.
+ * Plain C types only; no torch, no C++ in the signatures.
+ */
+#ifndef ZENWEBP_B200_H
+#define ZENWEBP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  0..3 mirror the reference's EncodingError / panics
+ * (src/encoder/api.rs:35-48, src/encoder/vp8.rs:1307-1313, :2401-2403, :3143-3148). */
+enum {
+  ZW_OK = 0,
+  ZW_ERR_INVALID_DIMENSIONS = 1, /* EncodingError::InvalidDimensions (w or h == 0 or > 16383)            */
+  ZW_ERR_INVALID_BUFFER_SIZE = 2,/* w*h*bpp != len  (reference: assert_eq! panic / InvalidBufferSize)     */
+  ZW_ERR_INVALID_PARAM = 3,      /* quality > 100 (reference panics); null pointers; unsupported colour   */
+  ZW_ERR_OUTPUT_TOO_SMALL = 4,   /* caller-provided output buffer smaller than the bitstream               */
+  ZW_ERR_PARTITION_TOO_LARGE = 5,/* first partition >= 2^19 bytes: the 19-bit size field would overflow
+                                    (the reference silently emits a corrupt tag here, vp8.rs:320)         */
+  ZW_ERR_NOT_STAGED = 6,         /* zw_encode_resident / zw_download without a staged batch                */
+  ZW_ERR_CUDA = 100              /* 100 + cudaError_t                                                      */
+};
+
+/* ColorType (src/encoder/api.rs:83-92).  This round the CUDA path accepts RGB8 and RGBA8
+ * (alpha ignored by the VP8 path exactly as vp8.rs:1296 does); L8/La8 return ZW_ERR_INVALID_PARAM. */
+enum { ZW_COLOR_L8 = 0, ZW_COLOR_LA8 = 1, ZW_COLOR_RGB8 = 2, ZW_COLOR_RGBA8 = 3 };
+
+typedef struct zw_ctx zw_ctx;
+
+typedef struct zw_limits {
+  size_t max_device_bytes; /* working-set budget per chunk of a batch; 0 = default (32 GiB)     */
+  int persistent_warps_per_sm; /* 0 = default; tuning knob of the wavefront kernels            */
+  int reserved[5];
+} zw_limits;
+
+/* One input image: caller-owned, tightly packed rows (stride = width * bpp), host memory
+ * (pinned memory makes the H2D copy asynchronous; pageable memory also works). */
+typedef struct zw_image {
+  const uint8_t* data;
+  size_t len;      /* bytes in data; must equal width*height*bpp                                  */
+  uint32_t width;  /* 1..16383                                                                     */
+  uint32_t height; /* 1..16383                                                                     */
+  uint32_t color;  /* ZW_COLOR_*                                                                   */
+  uint32_t reserved;
+} zw_image;
+
+/* One output slot.  If data == NULL the library allocates (malloc) and the caller releases with
+ * zw_free; otherwise `cap` bytes at `data` are caller-owned and `len` receives the size. */
+typedef struct zw_output {
+  uint8_t* data;
+  size_t cap;
+  size_t len;
+  int status; /* per-image ZW_* code */
+  int reserved;
+} zw_output;
+
+/* Per-stage device times (CUDA events on the library's stream), milliseconds, summed over chunks. */
+typedef struct zw_timing {
+  float h2d_ms, yuv_ms, analysis_ms, pass1_ms, stats_ms, pass2_ms, token_ms, boolcode_ms, assemble_ms, d2h_ms;
+  float device_total_ms; /* first kernel .. last kernel                                           */
+  float wall_ms;         /* host wall clock of the whole call                                     */
+  uint64_t kernel_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t pixels;
+} zw_timing;
+
+/* Create / destroy an encoder context bound to one CUDA device.  One context per (host thread,
+ * GPU); a context is not thread-safe, contexts are independent.  Returns NULL on failure
+ * (zw_last_error() tells why). */
+zw_ctx* zw_create(int device, const zw_limits* limits);
+void zw_destroy(zw_ctx* ctx);
+int zw_last_error(void);
+const char* zw_strerror(int code);
+void zw_free(void* p);
+/* Conservative bound for one output (payload + RIFF header). */
+size_t zw_max_output_size(uint32_t width, uint32_t height);
+
+/* Batch entry: n independent images -> n raw VP8 key-frame payloads, byte-identical to what the
+ * reference's encode_frame_lossy appends (vp8.rs:3132).  quality 0..100, method 0..6 (clamped
+ * like vp8.rs:1291).  Returns ZW_OK if the call ran; per-image results are in outs[i].status. */
+int zw_encode_vp8_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
+                        zw_output* outs, zw_timing* timing);
+
+/* Same, wrapped in the simple RIFF container exactly as WebPEncoder::encode does for opaque
+ * input without metadata (api.rs:1320-1329): these bytes ARE the .webp file. */
+int zw_encode_webp_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
+                         zw_output* outs, zw_timing* timing);
+
+/* Split form, for callers that keep inputs resident in HBM (and for kernel-only timing):
+ *   zw_stage_batch     validate + H2D copy of one chunk (must fit max_device_bytes)
+ *   zw_encode_resident run every kernel on the staged inputs; bitstreams stay on the device
+ *   zw_download        D2H + host chunk assembly into outs (container != 0 adds the RIFF wrap) */
+int zw_stage_batch(zw_ctx* ctx, const zw_image* imgs, size_t n);
+int zw_encode_resident(zw_ctx* ctx, int quality, int method, zw_timing* timing);
+int zw_download(zw_ctx* ctx, zw_output* outs, size_t n, int container, zw_timing* timing);
+
+/* Parity/debug: copy a named intermediate stage of image `index` of the last encoded chunk to
+ * host memory (names follow SURVEY.md Appendix F: "YUV_Y","YUV_U","YUV_V","ALPHA","ALPHA_HIST",
+ * "SEG_MAP","SEG_QIDX","SEG_TREE_PROBS","SEG_UPDATE_MAP","P1MB","STATS","PROBS","SKIP_PROB",
+ * "LCOST","P2MB","PART0","PART1","VP8").  *len receives the stage size; if cap is too small
+ * nothing is copied and ZW_ERR_OUTPUT_TOO_SMALL is returned. */
+int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
+
+/* Library build info, e.g. "zenwebp_b200 0.1 sm_100a". */
+const char* zw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZENWEBP_B200_H */

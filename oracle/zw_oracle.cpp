@@ -1985,7 +1985,7 @@ struct Vp8Encoder {
             proba_stats.should_update(t, b, c, p, old_prob, update_prob, should_update, new_p, savings);
             if (should_update && savings > 0) {
               updated[t][b][c][p] = new_p;
-              total_savings += savings;
+              total_savings = (i32)((u32)total_savings + (u32)savings);  // release-mode Rust wraps
               num_updates += 1;
             }
           }
