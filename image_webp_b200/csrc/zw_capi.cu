@@ -218,9 +218,9 @@ static void fill_params(zw_ctx* c) {
 }
 
 static int validate_image(const zw_image& im) {
-  if (im.data == nullptr) return ZW_ERR_INVALID_PARAM;
   if (im.color != ZW_COLOR_RGB8 && im.color != ZW_COLOR_RGBA8) return ZW_ERR_INVALID_PARAM;
   if (im.width == 0 || im.height == 0 || im.width > 16383 || im.height > 16383) return ZW_ERR_INVALID_DIMENSIONS;
+  if (im.data == nullptr) return im.len == 0 ? ZW_ERR_INVALID_BUFFER_SIZE : ZW_ERR_INVALID_PARAM;
   const u64 bpp = im.color == ZW_COLOR_RGB8 ? 3 : 4;
   if ((u64)im.width * im.height * bpp != (u64)im.len) return ZW_ERR_INVALID_BUFFER_SIZE;
   return ZW_OK;
