@@ -41,6 +41,7 @@ struct __align__(16) WarpScratch {
   u8 left_v[12];
   i32 dcbuf[32];
   i16 nat[16][16];   // natural-order luma levels (I4 search winners / I16 simple quantisation)
+  i32 coef[16][16];  // natural-order DCT coefficients handed to / returned by the cooperative trellis
   u8 bmodes[16];
   u8 nzflag[32];     // per-block non-zero flags (scratch)
   MbRecord rec;      // staged record
@@ -96,6 +97,155 @@ __device__ __forceinline__ void fetch_edges4(const u8* yws, int x0, int y0, u8* 
   e[3] = yws[(y0 + 0) * 32 + x0 - 1];
 #pragma unroll
   for (int k = 0; k < 9; k++) e[4 + k] = yws[(y0 - 1) * 32 + x0 - 1 + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative trellis: the 16 lanes of a half-warp own the 16 zig-zag positions of one block.
+// Same result as the serial trellis_quantize (zw_cost.cuh; reference cost.rs:788-1006), computed
+// as a prefix scan: the 2-node Viterbi step of position n is a 2x2 matrix M_n in the (min,+)
+// semiring, M_n[p][d] = rate(prev node p -> node d)*lambda + distortion(d); the node scores of all
+// positions are the prefix products M_first (x) ... (x) M_n applied to the initial score.  Integer
+// (min,+) products are exact and associative, so every score equals the sequential one; back
+// pointers, the terminal choice (first minimum in (n, delta) order, strictly below the skip score)
+// and the unwinding then follow the reference's tie rules.  Both half-warps always execute the
+// function (shuffles / ballots are warp-wide); `active` gates the stores.
+// ---------------------------------------------------------------------------------------------
+constexpr i64 T_INF = (i64)1 << 62;
+__device__ __forceinline__ i64 tadd(i64 a, i64 b) { return (a >= T_INF || b >= T_INF) ? T_INF : a + b; }
+__device__ __forceinline__ i64 tmin(i64 a, i64 b) { return a < b ? a : b; }
+__device__ __forceinline__ i64 shfl_up64_16(i64 v, int d) {
+  int lo = __shfl_up_sync(FULL, (int)(v & 0xffffffff), d, 16);
+  int hi = __shfl_up_sync(FULL, (int)(v >> 32), d, 16);
+  return (i64)(((u64)(u32)hi << 32) | (u64)(u32)lo);
+}
+__device__ __forceinline__ i64 shfl_xor64(i64 v, int m) {
+  int lo = __shfl_xor_sync(FULL, (int)(v & 0xffffffff), m);
+  int hi = __shfl_xor_sync(FULL, (int)(v >> 32), m);
+  return (i64)(((u64)(u32)hi << 32) | (u64)(u32)lo);
+}
+
+// coef: the block's 16 natural-order coefficients in shared memory (overwritten with the
+// dequantised levels); zz_out: 16 zig-zag levels.  Returns has_nz (uniform inside the half-warp).
+__device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
+                             const CostCtx& cc, int ctype, int ctx0, int lane) {
+  const int n = lane & 15, h = lane >> 4;
+  const int j = ZW_TAB(kZigzag)[n];
+  const int kq = j > 0;
+  const i32 q = m.q[kq];
+  const u32 iq = m.iq[kq];
+  const i64 lam = (i64)lambda;
+  const i32 c = coef[j];
+  const i32 thresh = ((i32)m.q[1] * (i32)m.q[1]) / 4;
+  const u32 big = (__ballot_sync(FULL, n >= first && c * c > thresh) >> (16 * h)) & 0xffffu;
+  int last = big ? 31 - __clz(big) : first - 1;
+  if (last < 15) last += 1;
+  const bool inrange = n >= first && n <= last;
+  const bool sign = c < 0;
+  const i32 cs = iabs(c) + (i32)sharpen[j];
+  const i32 level0 = imin(quantdiv((u32)cs, iq, 0), 2047);
+  const i32 thresh_level = imin(quantdiv((u32)cs, iq, 1u << 16), 2047);
+  const u8* PR = cc.probs + ctype * (8 * 3 * 11);
+  const u16* LC = cc.level_cost + ctype * (8 * 3 * 68);
+  const int band = ZW_TAB(kEncBands)[n];
+  i64 base[2];
+  u32 fx[2];
+  int lc[2], cx[2];
+  bool valid[2];
+  const i64 wgt = ZW_TAB(kWeightTrellis)[j];
+  const i64 orig_sq = (i64)(cs * cs);
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    const i32 level = level0 + d;
+    valid[d] = level <= thresh_level;
+    const i32 ne = cs - level * q;
+    base[d] = 256 * (wgt * ((i64)(ne * ne) - orig_sq));
+    fx[d] = (u32)ZW_TAB(kLevelFixedCosts)[imin(level, 2047)] + (level > 0 ? 256u : 0u);
+    lc[d] = imin(level, 67);
+    cx[d] = imin(level, 2);
+  }
+  // contexts of the previous position's two nodes (the initial context at `first`)
+  int pcx0 = __shfl_up_sync(FULL, cx[0], 1, 16), pcx1 = __shfl_up_sync(FULL, cx[1], 1, 16);
+  if (n == first) { pcx0 = ctx0; pcx1 = ctx0; }
+  if (n < first) { pcx0 = 0; pcx1 = 0; }
+  i64 rate[2][2];  // [prev node][this node], already multiplied by lambda
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    rate[0][d] = (i64)(fx[d] + (u32)LC[(band * 3 + pcx0) * 68 + lc[d]]) * lam;
+    rate[1][d] = (i64)(fx[d] + (u32)LC[(band * 3 + pcx1) * 68 + lc[d]]) * lam;
+  }
+  i64 P00, P01, P10, P11;  // prefix product, [from node of first-1 chain][to node]
+  if (inrange) {
+    P00 = valid[0] ? rate[0][0] + base[0] : T_INF;
+    P01 = valid[1] ? rate[0][1] + base[1] : T_INF;
+    P10 = valid[0] ? rate[1][0] + base[0] : T_INF;
+    P11 = valid[1] ? rate[1][1] + base[1] : T_INF;
+  } else {
+    P00 = 0; P11 = 0; P01 = T_INF; P10 = T_INF;  // identity
+  }
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const i64 L00 = shfl_up64_16(P00, d), L01 = shfl_up64_16(P01, d), L10 = shfl_up64_16(P10, d), L11 = shfl_up64_16(P11, d);
+    if (n >= d) {
+      const i64 n00 = tmin(tadd(L00, P00), tadd(L01, P10));
+      const i64 n01 = tmin(tadd(L00, P01), tadd(L01, P11));
+      const i64 n10 = tmin(tadd(L10, P00), tadd(L11, P10));
+      const i64 n11 = tmin(tadd(L10, P01), tadd(L11, P11));
+      P00 = n00; P01 = n01; P10 = n10; P11 = n11;
+    }
+  }
+  const int band0 = ZW_TAB(kEncBands)[first];
+  const u32 p0first = PR[(band0 * 3 + ctx0) * 11];
+  const i64 init = (ctx0 == 0 ? (i64)bit_cost(1, p0first) : 0) * lam;
+  const i64 skip_score = (i64)bit_cost(0, p0first) * lam;
+  i64 s[2];
+  s[0] = tadd(init, tmin(P00, P10));
+  s[1] = tadd(init, tmin(P01, P11));
+  // back pointers (ties keep predecessor 0, cost.rs:927)
+  i64 sp0 = shfl_up64_16(s[0], 1), sp1 = shfl_up64_16(s[1], 1);
+  if (n == first) { sp0 = init; sp1 = init; }
+  const bool bp0 = tadd(sp1, rate[1][0]) < tadd(sp0, rate[0][0]);
+  const bool bp1 = tadd(sp1, rate[1][1]) < tadd(sp0, rate[0][1]);
+  const u32 bpm0 = (__ballot_sync(FULL, inrange && bp0) >> (16 * h)) & 0xffffu;
+  const u32 bpm1 = (__ballot_sync(FULL, inrange && bp1) >> (16 * h)) & 0xffffu;
+  // terminal candidates in (n, delta) order
+  i64 best = T_INF;
+  int bidx = 64;
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    if (inrange && valid[d] && (level0 + d) != 0) {
+      const i64 eob = n < 15 ? (i64)bit_cost(0, PR[(ZW_TAB(kEncBands)[n + 1] * 3 + cx[d]) * 11]) : 0;
+      const i64 term = tadd(s[d], eob * lam);
+      if (term < best) { best = term; bidx = n * 2 + d; }
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    const i64 ob = shfl_xor64(best, o);
+    const int oi = __shfl_xor_sync(FULL, bidx, o);
+    if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  const bool have = best < skip_score;
+  const int best_n = have ? (bidx >> 1) : -1;
+  // unwind: node chosen at my position
+  int delta = bidx & 1, mine = 0;
+#pragma unroll
+  for (int k = 15; k >= 0; k--) {
+    if (k <= best_n) {
+      if (k == n) mine = delta;
+      delta = (int)(((delta ? bpm1 : bpm0) >> k) & 1);
+    }
+  }
+  i32 level = 0;
+  if (have && inrange && n <= best_n) {
+    level = level0 + mine;
+    if (sign) level = -level;
+  }
+  if (active && n >= first) {
+    zz_out[n] = (i16)level;
+    coef[j] = level * q;
+  }
+  const u32 nzm = (__ballot_sync(FULL, level != 0) >> (16 * h)) & 0xffffu;
+  return nzm != 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -381,13 +531,6 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       wht4x4(y2);
 #pragma unroll
       for (int k = 0; k < 16; k++) { y2[k] = quantize_coeff(y2[k], SP.y2, k); y2nz |= y2[k] != 0; }
-#pragma unroll
-      for (int k = 0; k < 16; k++) if (k == lane) W.nat[0][ZW_TAB(kZigzag)[0] + 0 * k] = 0;  // (keeps nat[] defined)
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) W.rec.levels[0][k] = 0;
-      }
-      __syncwarp();
       if (lane < 16) {
         // zig-zag position p of natural index `lane`: scatter y2[lane] to levels[0][p]
         int p = 0;
@@ -425,30 +568,41 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
         for (int k = 0; k < 16; k++) W.rec.levels[1 + lane][k] = W.nat[lane][ZW_TAB(kZigzag)[k]];
       }
     } else {
-      // trellis with the nz context chained in raster order (:2685-2728): sweep anti-diagonals
+      // trellis with the nz context chained in raster order (:2685-2728): blocks on one anti-diagonal
+      // are independent, so sweep the diagonals two blocks (one per half-warp) at a time
       if (lane < 4) {
         W.nzflag[16 + lane] = (in_top_nz >> (1 + lane)) & 1;
         W.nzflag[20 + lane] = (in_left_nz >> (1 + lane)) & 1;
       }
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) W.coef[lane][k] = c[k];
+      }
       __syncwarp();
+      {
+        // rounds: pairs of blocks from the same diagonal (-1 = idle half)
+        const int r0[10] = {0, 1, 2, 8, 3, 9, 7, 13, 11, 15};
+        const int r1[10] = {-1, 4, 5, -1, 6, 12, 10, -1, 14, -1};
 #pragma unroll 1
-      for (int dg = 0; dg < 7; dg++) {
-        if (lane < 16 && bx + by == dg) {
-          const int ctx0 = imin((int)W.nzflag[20 + by] + (int)W.nzflag[16 + bx], 2);
-          i32 zz[16];
-#pragma unroll
-          for (int k = 0; k < 16; k++) zz[k] = 0;
-          const bool nz = trellis_quantize(c, zz, SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0);
-#pragma unroll
-          for (int k = 0; k < 16; k++) W.rec.levels[1 + blk][k] = (i16)zz[k];
-          W.nzflag[lane] = nz;
+        for (int r = 0; r < 10; r++) {
+          const int b = hb ? r1[r] : r0[r];
+          const bool act = b >= 0;
+          const int bb = act ? b : 0;
+          const int tbx = bb & 3, tby = bb >> 2;
+          const int ctx0 = imin((int)W.nzflag[20 + tby] + (int)W.nzflag[16 + tbx], 2);
+          const bool nz = trellis_half(act, W.coef[bb], W.rec.levels[1 + bb], SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0, lane);
+          __syncwarp();
+          if (act && (lane & 15) == 0) {
+            W.nzflag[bb] = nz;
+            W.nzflag[16 + tbx] = nz;
+            W.nzflag[20 + tby] = nz;
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        if (lane < 16 && bx + by == dg) {
-          W.nzflag[16 + bx] = W.nzflag[lane];
-          W.nzflag[20 + by] = W.nzflag[lane];
-        }
-        __syncwarp();
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 1; k < 16; k++) c[k] = W.coef[lane][k];
       }
     }
     if (lane < 16) {
@@ -497,32 +651,40 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       u8 e[13];
       fetch_edges4(W.yws, x0, y0, e);
       const int m = W.bmodes[i];
-      i32 pr[16], c[16], zz[16];
+      i32 pr[16], c[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) {
         pr[k] = predict4_pixel(e, m, k, ptab);
         c[k] = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - pr[k];
-        zz[k] = 0;
       }
       fdct4x4(c);
+      if (lane < 16) {
+        i32 v = 0;
 #pragma unroll
-      for (int k = 0; k < 16; k++) simple_any |= quantize_coeff(c[k], SP.y1, k) != 0;
+        for (int k = 0; k < 16; k++) if (k == lane) v = c[k];
+        W.coef[0][lane] = v;
+        simple_any |= quantize_coeff(v, SP.y1, lane) != 0;
+      }
+      __syncwarp();
       const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
-      const bool nz = trellis_quantize(c, zz, SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0);
+      const bool nzh = trellis_half(lane < 16, W.coef[0], W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane);
+      const bool nz = __shfl_sync(FULL, (int)nzh, 0) != 0;
+      __syncwarp();
       tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
       lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
       ynz |= (u32)nz << i;
-      idct4x4(c);
-      __syncwarp();
-      if (lane < 16) {
-        i32 v = 0, z = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) if (k == lane) { v = clip255(pr[k] + c[k]); z = zz[k]; }
+      for (int k = 0; k < 16; k++) c[k] = W.coef[0][k];
+      idct4x4(c);
+      if (lane < 16) {
+        i32 v = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (k == lane) v = clip255(pr[k] + c[k]);
         W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)v;
-        W.rec.levels[1 + i][lane] = (i16)z;
       }
       __syncwarp();
     }
+    simple_any = __any_sync(FULL, simple_any);
     any_simple_nz |= simple_any;
   }
   __syncwarp();
