@@ -537,6 +537,16 @@ __global__ void k_frame_header(ChunkParams P) {
 //      Streams 0..n_img-1 are the token partitions, n_img..2n_img-1 the first partitions, so the
 //      lanes of a warp carry streams of similar length.
 // ---------------------------------------------------------------------------------------------
+// add_one_to_output (arithmetic.rs:47-60): ripple a carry through trailing 0xFF bytes.
+__device__ __forceinline__ void bool_carry(u8* out, u32 pos, u32 cap) {
+  u32 j = pos < cap ? pos : cap;
+  while (j > 0) {
+    j--;
+    if (out[j] < 255) { out[j]++; break; }
+    out[j] = 0;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_boolcode(ChunkParams P) {
   const u32 sid = blockIdx.x * blockDim.x + threadIdx.x;
   if (sid >= 2 * P.n_img) return;
@@ -546,48 +556,54 @@ __global__ void __launch_bounds__(128) k_boolcode(ChunkParams P) {
   ImageState& IS = P.st[img];
   const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
   const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
-  // partition scratch: [first partition | token partition] inside the image's output slot pair
+  // partition scratch: [first partition | token partition]
   u8* out = P.part_bytes + d.part_off + (is_hdr ? 0 : d.p0_cap);
   const u32 cap = is_hdr ? d.p0_cap : d.p1_cap;
   u32 bottom = 0, range = 255, pos = 0;
   int bit_num = 24;
   bool overflow = false;
-  for (u32 i = 0; i < n; i++) {
-    const u32 t = tk[i];
-    const u32 prob = t & 255;
-    const u32 split = 1 + (((range - 1) * prob) >> 8);
-    if (t >> 8) { bottom += split; range -= split; } else { range = split; }
-    while (range < 128) {
-      range <<= 1;
-      if (bottom & 0x80000000u) {  // add_one_to_output: ripple the carry through 0xFF bytes
-        u32 j = pos;
-        while (j > 0) {
-          j--;
-          if (out[j] < 255) { out[j]++; break; }
-          out[j] = 0;
+  // write_bool (arithmetic.rs:67-95) with the bit-at-a-time renormalisation loop collapsed: the
+  // `s` shifts a symbol needs are applied in at most two steps around the byte boundary.  Bits
+  // reaching bit 31 are carries into the bytes already written (at most one per symbol).
+  const uint4* tk4 = reinterpret_cast<const uint4*>(tk);  // streams start 16-byte aligned
+  uint4 cur = n ? __ldg(tk4) : make_uint4(0, 0, 0, 0);
+  for (u32 i0 = 0; i0 < n; i0 += 8) {
+    const uint4 nxt = (i0 + 8 < n) ? __ldg(tk4 + (i0 >> 3) + 1) : make_uint4(0, 0, 0, 0);  // prefetch
+    const u32 w4[4] = {cur.x, cur.y, cur.z, cur.w};
+    const u32 cnt = n - i0 < 8 ? n - i0 : 8;
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) {
+      if (k < cnt) {
+        const u32 t = (w4[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        const u32 split = 1 + (((range - 1) * (t & 255)) >> 8);
+        if (t >> 8) { bottom += split; range -= split; } else { range = split; }
+        int s2 = __clz(range) - 24;  // shifts needed to bring range back to >= 128
+        if (s2 > 0) {
+          range <<= s2;
+          if (s2 >= bit_num) {  // a byte completes inside this renormalisation
+            if (bottom >> (32 - bit_num)) bool_carry(out, pos, cap);
+            bottom <<= bit_num;
+            if (pos < cap) out[pos] = (u8)(bottom >> 24); else overflow = true;
+            pos++;
+            bottom &= 0xffffffu;
+            s2 -= bit_num;
+            bit_num = 8;
+          }
+          if (s2 > 0) {
+            if (bottom >> (32 - s2)) bool_carry(out, pos, cap);
+            bottom <<= s2;
+            bit_num -= s2;
+          }
         }
       }
-      bottom <<= 1;
-      if (--bit_num == 0) {
-        if (pos < cap) out[pos] = (u8)(bottom >> 24); else overflow = true;
-        pos++;
-        bottom &= 0xffffffu;
-        bit_num = 8;
-      }
     }
+    cur = nxt;
   }
   // flush_and_get_buffer (arithmetic.rs:176-195)
   {
     int c = bit_num;
     u32 v = bottom;
-    if (bottom & (1u << (32 - bit_num))) {
-      u32 j = pos;
-      while (j > 0) {
-        j--;
-        if (out[j] < 255) { out[j]++; break; }
-        out[j] = 0;
-      }
-    }
+    if (bottom & (1u << (32 - bit_num))) bool_carry(out, pos, cap);
     v <<= (c & 7);
     c = (c >> 3) - 1;
     while (c >= 0) { v <<= 8; c--; }

@@ -42,6 +42,10 @@ struct __align__(16) WarpScratch {
   i32 dcbuf[32];
   i16 nat[16][16];   // natural-order luma levels (I4 search winners / I16 simple quantisation)
   i32 coef[16][16];  // natural-order DCT coefficients handed to / returned by the cooperative trellis
+  u8 cand_px[10][16];   // I4 search: reconstructed pixels of each evaluated candidate (by rank)
+  i16 cand_lv[10][16];  // I4 search: natural-order levels of each evaluated candidate (by rank)
+  u32 psse[10];         // I4 search: prediction SSE per mode
+  u8 cand_mode[12];     // I4 search: mode with rank r
   u8 bmodes[16];
   u8 nzflag[32];     // per-block non-zero flags (scratch)
   MbRecord rec;      // staged record
@@ -97,6 +101,95 @@ __device__ __forceinline__ void fetch_edges4(const u8* yws, int x0, int y0, u8* 
   e[3] = yws[(y0 + 0) * 32 + x0 - 1];
 #pragma unroll
   for (int k = 0; k < 9; k++) e[4 + k] = yws[(y0 - 1) * 32 + x0 - 1 + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative 4x4 primitives: the 16 lanes of a half-warp hold one pixel / coefficient each
+// (natural order, n = lane & 15 = 4*row + col) and exchange operands with xor-shuffles, so one
+// warp works on two blocks per step.  Same arithmetic as fdct4x4 / idct4x4 / residual_cost in
+// zw_prims.cuh / zw_cost.cuh (reference transform.rs:35-79,176-207; cost.rs:1670-1729).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ i32 coop_fdct(i32 v, int lane) {
+  const int x = lane & 3, y = (lane >> 2) & 3;
+  // rows: lanes x=0..3 end up holding outputs 0,2,1,3 of their row
+  i32 p = __shfl_xor_sync(FULL, v, 3);
+  i32 t = (x < 2 ? v + p : p - v) * 8;
+  i32 p2 = __shfl_xor_sync(FULL, t, 1);
+  i32 r;
+  if (x == 0) r = t + p2;
+  else if (x == 1) r = p2 - t;
+  else if (x == 2) r = (t * 2217 + p2 * 5352 + 14500) >> 12;
+  else r = (t * 2217 - p2 * 5352 + 7500) >> 12;
+  // columns: lanes y=0..3 end up holding outputs 0,2,1,3 of their column
+  p = __shfl_xor_sync(FULL, r, 12);
+  t = y < 2 ? r + p : p - r;
+  p2 = __shfl_xor_sync(FULL, t, 4);
+  i32 o;
+  if (y == 0) o = (t + p2 + 7) >> 4;
+  else if (y == 1) o = (p2 - t + 7) >> 4;
+  else if (y == 2) o = ((t * 2217 + p2 * 5352 + 12000) >> 16) + (p2 != 0 ? 1 : 0);
+  else o = (t * 2217 - p2 * 5352 + 51000) >> 16;
+  // lane (x,y) holds coefficient (R[x], R[y]), R = {0,2,1,3} (an involution): un-permute
+  const int rx = ((x & 1) << 1) | (x >> 1), ry = ((y & 1) << 1) | (y >> 1);
+  return __shfl_sync(FULL, o, (lane & 16) | (ry * 4 + rx));
+}
+
+__device__ __forceinline__ i32 coop_idct(i32 v, int lane) {
+  const int x = lane & 3, y = (lane >> 2) & 3;
+  // vertical pass: rows 0/2 form a1,b1; rows 1/3 form c1,d1
+  i32 p = __shfl_xor_sync(FULL, v, 8);
+  i32 t;
+  if (y == 0) t = v + p;                                                    // a1
+  else if (y == 2) t = p - v;                                               // b1
+  else if (y == 1) t = ((v * 35468) >> 16) - (p + ((p * 20091) >> 16));     // c1
+  else t = (p + ((p * 20091) >> 16)) + ((v * 35468) >> 16);                 // d1
+  p = __shfl_xor_sync(FULL, t, 12);
+  i32 r;
+  if (y == 0) r = t + p;       // a1 + d1
+  else if (y == 3) r = p - t;  // a1 - d1
+  else if (y == 1) r = p + t;  // b1 + c1
+  else r = t - p;              // b1 - c1
+  // horizontal pass with the final rounding
+  p = __shfl_xor_sync(FULL, r, 2);
+  if (x == 0) t = r + p;
+  else if (x == 2) t = p - r;
+  else if (x == 1) t = ((r * 35468) >> 16) - (p + ((p * 20091) >> 16));
+  else t = (p + ((p * 20091) >> 16)) + ((r * 35468) >> 16);
+  p = __shfl_xor_sync(FULL, t, 3);
+  i32 o;
+  if (x == 0) o = t + p;
+  else if (x == 3) o = p - t;
+  else if (x == 1) o = p + t;
+  else o = t - p;
+  return (o + 4) >> 3;
+}
+
+__device__ __forceinline__ int half_sum(int v) {  // sum over the 16 lanes of each half-warp
+  v += __shfl_xor_sync(FULL, v, 8);
+  v += __shfl_xor_sync(FULL, v, 4);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+
+// residual_cost with one level per lane (natural order n = lane & 15).  Uniform per half-warp.
+__device__ __forceinline__ u32 coop_residual_cost(i32 lv, int ctype, int first, int ctx0, const CostCtx& cc, int lane, bool& has_nz) {
+  const int n = lane & 15, h = lane >> 4;
+  const int v = iabs(lv);
+  const u32 nzm = (__ballot_sync(FULL, lv != 0) >> (16 * h)) & 0xffffu;
+  const int last = nzm ? 31 - __clz(nzm) : -1;
+  has_nz = nzm != 0;
+  const u32 p0 = cc.probs[((ctype * 8 + ZW_TAB(kEncBands)[first]) * 3 + ctx0) * 11];
+  const int pv = __shfl_up_sync(FULL, v, 1, 16);
+  const int ctx = n == first ? ctx0 : imin(pv, 2);
+  u32 c = 0;
+  if (n >= first && n <= last) {
+    c = level_cost_at(cc, ctype, n, ctx, v);
+    if (n == last && n < 15) c += bit_cost(0, cc.probs[((ctype * 8 + ZW_TAB(kEncBands)[n + 1]) * 3 + (v == 1 ? 1 : 2)) * 11]);
+    if (n == first && ctx0 == 0) c += bit_cost(1, p0);
+  }
+  const u32 sum = (u32)half_sum((int)c);
+  return last < 0 ? bit_cost(0, p0) : sum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,10 +516,12 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
   }
 
   // ===== pick_best_intra4 (vp8.rs:1790-2036), gated as in choose_macroblock_info (:2210-2231) =====
+  // Cooperative: each half-warp evaluates one prediction mode at a time, one pixel per lane.
   bool use_i4 = false;
   if (method > 1 && (method >= 5 || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0)) {
     use_i4 = true;
     const int max_modes = method <= 3 ? 3 : (method == 4 ? 4 : 10);
+    const int n16 = lane & 15;
     u64 running = 211ull * (u64)SP.lambda_mode;
     u32 total_mode_cost = 0;
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
@@ -438,71 +533,74 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       const int ctx0 = (sby == 0 ? 0 : (int)((tnz4 >> sbx) & 1)) + (sbx == 0 ? 0 : (int)((lnz4 >> sby) & 1));
       u8 e[13];
       fetch_edges4(W.yws, x0, y0, e);
-      const int m = lane < 10 ? lane : 0;
-      i32 pr[16], c[16];
-      int psse = 0;
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        pr[k] = predict4_pixel(e, m, k, ptab);
-        c[k] = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - pr[k];
-        psse += c[k] * c[k];
+      const i32 srcpx = W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)];
+      // prediction SSE of the ten modes, two modes per step
+#pragma unroll 1
+      for (int r = 0; r < 5; r++) {
+        const int m = 2 * r + hb;
+        const i32 df = srcpx - predict4_pixel(e, m, n16, ptab);
+        const int sse = half_sum(df * df);
+        if (n16 == 0) W.psse[m] = (u32)sse;
       }
-      // stable ascending rank by prediction SSE (sort_unstable_by_key is an insertion sort here, Q11)
-      int rank = 0;
-#pragma unroll
-      for (int o = 0; o < 10; o++) {
-        const int os = __shfl_sync(FULL, psse, o);
-        rank += (os < psse) || (os == psse && o < lane);
-      }
-      const bool cand = lane < 10 && rank < max_modes;
-      u64 key = ~0ull;
-      u32 my_sse = 0, my_rate = 0;
-      bool my_nz = false;
-      i32 q[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) q[k] = 0;
-      if (cand) {
-        fdct4x4(c);
-#pragma unroll
-        for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.y1, k); my_nz |= q[k] != 0; }
-        const u32 coeff_cost = residual_cost(q, 3, 0, ctx0, cc);
-#pragma unroll
-        for (int k = 0; k < 16; k++) c[k] = dequantize(q[k], SP.y1, k);
-        idct4x4(c);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          c[k] = clip255(pr[k] + c[k]);  // reconstructed pixel
-          const int df = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - c[k];
-          my_sse += (u32)(df * df);
-        }
-        const u32 mode_cost = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m];
-        my_rate = mode_cost + coeff_cost;
-        const u64 score = (u64)my_sse * 256ull + (u64)(my_rate & 0xffffu) * (u64)SP.lambda_i4;  // u16 truncation (Q8)
-        key = (score << 4) | (u64)rank;
-      }
-      u64 kmin = key;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const u64 other = (u64)shfl64((i64)kmin, lane ^ o);
-        kmin = other < kmin ? other : kmin;
-      }
-      const int win = __ffs(__ballot_sync(FULL, cand && key == kmin)) - 1;
-      if (lane == win) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          W.yws[(y0 + (k >> 2)) * 32 + x0 + (k & 3)] = (u8)c[k];
-          W.nat[i][k] = (i16)q[k];
-        }
-        W.bmodes[i] = (u8)m;
-      }
-      const u32 wsse = __shfl_sync(FULL, my_sse, win);
-      const u32 wrate = __shfl_sync(FULL, my_rate, win);
-      const int wnz = __shfl_sync(FULL, (int)my_nz, win);
       __syncwarp();
-      tnz4 = (tnz4 & ~(1u << sbx)) | ((u32)wnz << sbx);
-      lnz4 = (lnz4 & ~(1u << sby)) | ((u32)wnz << sby);
-      total_mode_cost += ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + win];
-      running += (u64)wsse * 256ull + (u64)(wrate & 0xffffu) * (u64)SP.lambda_mode;
+      // stable ascending rank by prediction SSE (sort_unstable_by_key is an insertion sort here, Q11)
+      if (lane < 10) {
+        const u32 mine = W.psse[lane];
+        int rank = 0;
+#pragma unroll
+        for (int o = 0; o < 10; o++) {
+          const u32 os = W.psse[o];
+          rank += (os < mine) || (os == mine && o < lane);
+        }
+        W.cand_mode[rank] = (u8)lane;
+      }
+      __syncwarp();
+      // evaluate the best `max_modes` candidates in rank order, two per step
+      u64 best_key = ~0ull;
+      u32 best_sse = 0, best_rate = 0;
+      int best_nz = 0;
+#pragma unroll 1
+      for (int r = 0; r < max_modes; r += 2) {
+        const int rank = r + hb;
+        const bool act = rank < max_modes;
+        const int m = W.cand_mode[act ? rank : 0];
+        const i32 pr = predict4_pixel(e, m, n16, ptab);
+        const i32 cf = coop_fdct(srcpx - pr, lane);
+        const i32 q = quantize_coeff(cf, SP.y1, n16);
+        bool nz;
+        const u32 coeff_cost = coop_residual_cost(q, 3, 0, ctx0, cc, lane, nz);
+        const i32 rec = clip255(pr + coop_idct(dequantize(q, SP.y1, n16), lane));
+        const i32 df = srcpx - rec;
+        const u32 sse = (u32)half_sum(df * df);
+        if (act) {
+          W.cand_px[rank][n16] = (u8)rec;
+          W.cand_lv[rank][n16] = (i16)q;
+        }
+        const u32 rate = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m] + coeff_cost;
+        const u64 score = (u64)sse * 256ull + (u64)(rate & 0xffffu) * (u64)SP.lambda_i4;  // u16 truncation (Q8)
+        const u64 key = act ? ((score << 4) | (u64)rank) : ~0ull;
+        // both halves in rank order; strict < keeps the earlier candidate on ties
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const u64 k2 = (u64)shfl64((i64)key, hh * 16);
+          const u32 s2 = __shfl_sync(FULL, sse, hh * 16), r2 = __shfl_sync(FULL, rate, hh * 16);
+          const int z2 = __shfl_sync(FULL, (int)nz, hh * 16);
+          if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
+        }
+      }
+      __syncwarp();
+      const int wrank = (int)(best_key & 15);
+      const int wmode = W.cand_mode[wrank];
+      if (lane < 16) {
+        W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = W.cand_px[wrank][lane];
+        W.nat[i][lane] = W.cand_lv[wrank][lane];
+      }
+      if (lane == 0) W.bmodes[i] = (u8)wmode;
+      __syncwarp();
+      tnz4 = (tnz4 & ~(1u << sbx)) | ((u32)best_nz << sbx);
+      lnz4 = (lnz4 & ~(1u << sby)) | ((u32)best_nz << sby);
+      total_mode_cost += ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + wmode];
+      running += (u64)best_sse * 256ull + (u64)(best_rate & 0xffffu) * (u64)SP.lambda_mode;
       if (running >= i16_score || total_mode_cost > 16384u) { use_i4 = false; break; }
     }
   }
@@ -637,34 +735,21 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     ynz = __ballot_sync(FULL, lane < 16 && W.nzflag[lane] != 0) & 0xffffu;
     any_simple_nz |= ynz != 0;
   } else {
-    // ---- transform_luma_blocks_4x4 with trellis (vp8.rs:2785-2916): strictly serial; every lane
-    //      runs the same block redundantly (no divergence), lanes 0..15 write one pixel each ----
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 16; k++) W.rec.levels[0][k] = 0;
-    }
+    // ---- transform_luma_blocks_4x4 with trellis (vp8.rs:2785-2916): strictly serial over the 16
+    //      sub-blocks; half-warp 0 works one pixel / coefficient per lane, half-warp 1 shadows it ----
     u32 tnz = (in_top_nz >> 1) & 15, lnz = (in_left_nz >> 1) & 15;
     bool simple_any = false;
+    const int n16 = lane & 15;
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
       u8 e[13];
       fetch_edges4(W.yws, x0, y0, e);
-      const int m = W.bmodes[i];
-      i32 pr[16], c[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        pr[k] = predict4_pixel(e, m, k, ptab);
-        c[k] = (i32)W.src_y[(sby * 4 + (k >> 2)) * 16 + sbx * 4 + (k & 3)] - pr[k];
-      }
-      fdct4x4(c);
-      if (lane < 16) {
-        i32 v = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (k == lane) v = c[k];
-        W.coef[0][lane] = v;
-        simple_any |= quantize_coeff(v, SP.y1, lane) != 0;
-      }
+      const i32 pr = predict4_pixel(e, W.bmodes[i], n16, ptab);
+      const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane);
+      simple_any |= quantize_coeff(cf, SP.y1, n16) != 0;
+      __syncwarp();
+      if (lane < 16) W.coef[0][lane] = cf;
       __syncwarp();
       const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
       const bool nzh = trellis_half(lane < 16, W.coef[0], W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane);
@@ -673,15 +758,8 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
       lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
       ynz |= (u32)nz << i;
-#pragma unroll
-      for (int k = 0; k < 16; k++) c[k] = W.coef[0][k];
-      idct4x4(c);
-      if (lane < 16) {
-        i32 v = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (k == lane) v = clip255(pr[k] + c[k]);
-        W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)v;
-      }
+      const i32 rec = clip255(pr + coop_idct(W.coef[0][n16], lane));
+      if (lane < 16) W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)rec;
       __syncwarp();
     }
     simple_any = __any_sync(FULL, simple_any);
