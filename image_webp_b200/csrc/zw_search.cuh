@@ -92,7 +92,59 @@ __device__ __forceinline__ int pred_big(const u8* ws, int cofs, int mode, int x,
   return clip255((int)ws[(1 + y) * 32 + cofs] + (int)ws[cofs + 1 + x] - (int)ws[cofs]);
 }
 
+// The same for a whole 4x4 block (bx,by) of the 16x16 / 8x8 prediction: 4 top + 4 left + corner
+// loads, then selects.
+__device__ __forceinline__ void pred_block(const u8* ws, int cofs, int mode, int bx, int by, int dcv, i32* pr) {
+  i32 T[4], L[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    T[k] = ws[cofs + 1 + bx * 4 + k];
+    L[k] = ws[(1 + by * 4 + k) * 32 + cofs];
+  }
+  const i32 P = ws[cofs];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const i32 t = T[k & 3], l = L[k >> 2];
+    const i32 tm = clip255(l + t - P);
+    pr[k] = mode == 0 ? dcv : (mode == 1 ? t : (mode == 2 ? l : tm));
+  }
+}
+
 __device__ const u16 d_pred_tab[8][16] = ZW_PRED_TABLE_INIT;
+
+// One out-of-line copy of the (fully unrolled) lane-private residual cost: the kernels are
+// instruction-cache bound, so the three call sites share it.  Levels travel in registers.
+struct Lv16 { i32 v[16]; };
+__device__ __noinline__ u32 residual_cost_ol(Lv16 L, int ctype, int first, int ctx0, const u8* probs, const u16* level_cost) {
+  CostCtx cc;
+  cc.probs = probs;
+  cc.level_cost = level_cost;
+  return residual_cost(L.v, ctype, first, ctx0, cc);
+}
+__device__ __forceinline__ u32 residual_cost_call(const i32* lv, int ctype, int first, int ctx0, const CostCtx& cc) {
+  Lv16 L;
+#pragma unroll
+  for (int k = 0; k < 16; k++) L.v[k] = lv[k];
+  return residual_cost_ol(L, ctype, first, ctx0, cc.probs, cc.level_cost);
+}
+
+// One pixel of 4x4 predictor `mode` read straight from the bordered work buffer (same taps as
+// predict4_pixel in zw_prims.cuh, without staging the 13 edge pixels in registers).
+__device__ __forceinline__ i32 pred4_px(const u8* yws, int x0, int y0, int mode, int n, const u16 (*tab)[16]) {
+  const u8* top = yws + (y0 - 1) * 32 + x0;   // top[-1] = P, top[0..7] = A0..A7
+  const u8* left = yws + y0 * 32 + x0 - 1;    // left[32*i] = L_i
+  if (mode == 0) {
+    const i32 v = 4 + top[0] + top[1] + top[2] + top[3] + left[0] + left[32] + left[64] + left[96];
+    return v >> 3;
+  }
+  if (mode == 1) return clip255((i32)left[32 * (n >> 2)] - (i32)top[-1] + (i32)top[n & 3]);
+  const u32 t = tab[mode - 2][n];
+  const int i0 = t & 15, i1 = (t >> 4) & 15, i2 = (t >> 8) & 15;
+  const i32 e0 = i0 < 4 ? left[32 * (3 - i0)] : top[i0 - 5];
+  const i32 e1 = i1 < 4 ? left[32 * (3 - i1)] : top[i1 - 5];
+  const i32 e2 = i2 < 4 ? left[32 * (3 - i2)] : top[i2 - 5];
+  return (e0 + 2 * e1 + e2 + 2) >> 2;
+}
 
 __device__ __forceinline__ void fetch_edges4(const u8* yws, int x0, int y0, u8* e) {
   e[0] = yws[(y0 + 3) * 32 + x0 - 1];
@@ -203,8 +255,9 @@ __device__ __forceinline__ u32 coop_residual_cost(i32 lv, int ctype, int first, 
 // and the unwinding then follow the reference's tie rules.  Both half-warps always execute the
 // function (shuffles / ballots are warp-wide); `active` gates the stores.
 // ---------------------------------------------------------------------------------------------
-constexpr i64 T_INF = (i64)1 << 62;
-__device__ __forceinline__ i64 tadd(i64 a, i64 b) { return (a >= T_INF || b >= T_INF) ? T_INF : a + b; }
+// "Invalid" is a large finite score: up to 16 of them may add up inside the scan (2^58 * 16 = 2^62
+// still fits i64) while every real score stays far below 2^50, so plain adds need no saturation.
+constexpr i64 T_INF = (i64)1 << 58;
 __device__ __forceinline__ i64 tmin(i64 a, i64 b) { return a < b ? a : b; }
 __device__ __forceinline__ i64 shfl_up64_16(i64 v, int d) {
   int lo = __shfl_up_sync(FULL, (int)(v & 0xffffffff), d, 16);
@@ -219,7 +272,7 @@ __device__ __forceinline__ i64 shfl_xor64(i64 v, int m) {
 
 // coef: the block's 16 natural-order coefficients in shared memory (overwritten with the
 // dequantised levels); zz_out: 16 zig-zag levels.  Returns has_nz (uniform inside the half-warp).
-__device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
+__device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
                              const CostCtx& cc, int ctype, int ctx0, int lane) {
   const int n = lane & 15, h = lane >> 4;
   const int j = ZW_TAB(kZigzag)[n];
@@ -237,6 +290,12 @@ __device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& 
   const i32 cs = iabs(c) + (i32)sharpen[j];
   const i32 level0 = imin(quantdiv((u32)cs, iq, 0), 2047);
   const i32 thresh_level = imin(quantdiv((u32)cs, iq, 1u << 16), 2047);
+  // Fast path: a terminal node needs level != 0.  If no position of either block of this warp can
+  // reach level 1 the result is "all zero, no coefficients" without running the search.
+  if (!__any_sync(FULL, inrange && thresh_level >= 1)) {
+    if (active && n >= first) { zz_out[n] = 0; coef[j] = 0; }
+    return false;
+  }
   const u8* PR = cc.probs + ctype * (8 * 3 * 11);
   const u16* LC = cc.level_cost + ctype * (8 * 3 * 68);
   const int band = ZW_TAB(kEncBands)[n];
@@ -266,7 +325,7 @@ __device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& 
     rate[0][d] = (i64)(fx[d] + (u32)LC[(band * 3 + pcx0) * 68 + lc[d]]) * lam;
     rate[1][d] = (i64)(fx[d] + (u32)LC[(band * 3 + pcx1) * 68 + lc[d]]) * lam;
   }
-  i64 P00, P01, P10, P11;  // prefix product, [from node of first-1 chain][to node]
+  i64 P00, P01, P10, P11;  // prefix product, [virtual start node][this node]
   if (inrange) {
     P00 = valid[0] ? rate[0][0] + base[0] : T_INF;
     P01 = valid[1] ? rate[0][1] + base[1] : T_INF;
@@ -279,10 +338,10 @@ __device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& 
   for (int d = 1; d < 16; d <<= 1) {
     const i64 L00 = shfl_up64_16(P00, d), L01 = shfl_up64_16(P01, d), L10 = shfl_up64_16(P10, d), L11 = shfl_up64_16(P11, d);
     if (n >= d) {
-      const i64 n00 = tmin(tadd(L00, P00), tadd(L01, P10));
-      const i64 n01 = tmin(tadd(L00, P01), tadd(L01, P11));
-      const i64 n10 = tmin(tadd(L10, P00), tadd(L11, P10));
-      const i64 n11 = tmin(tadd(L10, P01), tadd(L11, P11));
+      const i64 n00 = tmin(L00 + P00, L01 + P10);
+      const i64 n01 = tmin(L00 + P01, L01 + P11);
+      const i64 n10 = tmin(L10 + P00, L11 + P10);
+      const i64 n11 = tmin(L10 + P01, L11 + P11);
       P00 = n00; P01 = n01; P10 = n10; P11 = n11;
     }
   }
@@ -291,46 +350,46 @@ __device__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& 
   const i64 init = (ctx0 == 0 ? (i64)bit_cost(1, p0first) : 0) * lam;
   const i64 skip_score = (i64)bit_cost(0, p0first) * lam;
   i64 s[2];
-  s[0] = tadd(init, tmin(P00, P10));
-  s[1] = tadd(init, tmin(P01, P11));
+  s[0] = init + tmin(P00, P10);
+  s[1] = init + tmin(P01, P11);
   // back pointers (ties keep predecessor 0, cost.rs:927)
   i64 sp0 = shfl_up64_16(s[0], 1), sp1 = shfl_up64_16(s[1], 1);
   if (n == first) { sp0 = init; sp1 = init; }
-  const bool bp0 = tadd(sp1, rate[1][0]) < tadd(sp0, rate[0][0]);
-  const bool bp1 = tadd(sp1, rate[1][1]) < tadd(sp0, rate[0][1]);
-  const u32 bpm0 = (__ballot_sync(FULL, inrange && bp0) >> (16 * h)) & 0xffffu;
-  const u32 bpm1 = (__ballot_sync(FULL, inrange && bp1) >> (16 * h)) & 0xffffu;
-  // terminal candidates in (n, delta) order
-  i64 best = T_INF;
-  int bidx = 64;
+  const bool bp0 = sp1 + rate[1][0] < sp0 + rate[0][0];
+  const bool bp1 = sp1 + rate[1][1] < sp0 + rate[0][1];
+  u32 bpm0 = (__ballot_sync(FULL, inrange && bp0) >> (16 * h)) & 0xffffu;
+  u32 bpm1 = (__ballot_sync(FULL, inrange && bp1) >> (16 * h)) & 0xffffu;
+  // terminal candidates in (n, delta) order: key = score * 32 + (2n + delta) keeps that order on ties
+  i64 best = I64_MAX;
 #pragma unroll
   for (int d = 0; d < 2; d++) {
     if (inrange && valid[d] && (level0 + d) != 0) {
       const i64 eob = n < 15 ? (i64)bit_cost(0, PR[(ZW_TAB(kEncBands)[n + 1] * 3 + cx[d]) * 11]) : 0;
-      const i64 term = tadd(s[d], eob * lam);
-      if (term < best) { best = term; bidx = n * 2 + d; }
+      const i64 key = (s[d] + eob * lam) * 32 + (n * 2 + d);
+      best = tmin(best, key);
     }
   }
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    const i64 ob = shfl_xor64(best, o);
-    const int oi = __shfl_xor_sync(FULL, bidx, o);
-    if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-  }
-  const bool have = best < skip_score;
+  for (int o = 8; o > 0; o >>= 1) best = tmin(best, shfl_xor64(best, o));
+  const int bidx = (int)(best & 31);
+  const bool have = (best >> 5) < skip_score;  // arithmetic shift == floor division by 32
   const int best_n = have ? (bidx >> 1) : -1;
-  // unwind: node chosen at my position
-  int delta = bidx & 1, mine = 0;
+  // unwind (uniform per half-warp): delta mask of the chosen path
+  u32 dm = 0;
+  {
+    const u32 low = best_n >= 0 ? ((2u << best_n) - 1u) : 0u;
+    bpm0 &= low;
+    bpm1 = (bpm1 & low) | (0xffffu & ~low);  // identity above best_n
+    int dl = bidx & 1;
 #pragma unroll
-  for (int k = 15; k >= 0; k--) {
-    if (k <= best_n) {
-      if (k == n) mine = delta;
-      delta = (int)(((delta ? bpm1 : bpm0) >> k) & 1);
+    for (int k = 15; k >= 0; k--) {
+      dm |= (u32)dl << k;
+      dl = (int)(((dl ? bpm1 : bpm0) >> k) & 1);
     }
   }
   i32 level = 0;
   if (have && inrange && n <= best_n) {
-    level = level0 + mine;
+    level = level0 + (int)((dm >> n) & 1);
     if (sign) level = -level;
   }
   if (active && n >= first) {
@@ -444,10 +503,10 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     const int mode = round * 2 + hb;  // 0 DC, 1 V, 2 H, 3 TM (MODES order, vp8.rs:1509)
     const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
     i32 c[16], pr[16];
+    pred_block(W.yws, 0, mode, bx, by, dc16, pr);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
-      pr[k] = pred_big(W.yws, 0, mode, x, y, dc16);
       c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
     }
     fdct4x4(c);
@@ -460,7 +519,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     wht4x4(y2);
 #pragma unroll
     for (int k = 0; k < 16; k++) y2[k] = quantize_coeff(y2[k], SP.y2, k);
-    const u32 cost_y2 = residual_cost(y2, 1, 0, 0, cc);
+    const u32 cost_y2 = residual_cost_call(y2, 1, 0, 0, cc);
 #pragma unroll
     for (int k = 0; k < 16; k++) y2[k] = dequantize(y2[k], SP.y2, k);
     iwht4x4(y2);
@@ -472,7 +531,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     int nzc = 0;
 #pragma unroll
     for (int k = 1; k < 16; k++) { lv[k] = quantize_coeff(c[k], SP.y1, k); nzc += lv[k] != 0; }
-    int cost_ac = (int)residual_cost(lv, 0, 1, 0, cc);
+    int cost_ac = (int)residual_cost_call(lv, 0, 1, 0, cc);
 #pragma unroll
     for (int k = 1; k < 16; k++) c[k] = dequantize(lv[k], SP.y1, k);
     c[0] = mydc;
@@ -531,14 +590,12 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       const int top_ctx = sby == 0 ? 0 : W.bmodes[i - 4];
       const int left_ctx = sbx == 0 ? 0 : W.bmodes[i - 1];
       const int ctx0 = (sby == 0 ? 0 : (int)((tnz4 >> sbx) & 1)) + (sbx == 0 ? 0 : (int)((lnz4 >> sby) & 1));
-      u8 e[13];
-      fetch_edges4(W.yws, x0, y0, e);
       const i32 srcpx = W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)];
       // prediction SSE of the ten modes, two modes per step
 #pragma unroll 1
       for (int r = 0; r < 5; r++) {
         const int m = 2 * r + hb;
-        const i32 df = srcpx - predict4_pixel(e, m, n16, ptab);
+        const i32 df = srcpx - pred4_px(W.yws, x0, y0, m, n16, ptab);
         const int sse = half_sum(df * df);
         if (n16 == 0) W.psse[m] = (u32)sse;
       }
@@ -564,7 +621,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
         const int rank = r + hb;
         const bool act = rank < max_modes;
         const int m = W.cand_mode[act ? rank : 0];
-        const i32 pr = predict4_pixel(e, m, n16, ptab);
+        const i32 pr = pred4_px(W.yws, x0, y0, m, n16, ptab);
         const i32 cf = coop_fdct(srcpx - pr, lane);
         const i32 q = quantize_coeff(cf, SP.y1, n16);
         bool nz;
@@ -612,10 +669,10 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
   if (!use_i4) {
     // ---- transform_luma_block (vp8.rs:2647-2780) ----
     i32 c[16], pr[16];
+    pred_block(W.yws, 0, best16_mode, bx, by, dc16, pr);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const int x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
-      pr[k] = pred_big(W.yws, 0, best16_mode, x, y, dc16);
       c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
     }
     fdct4x4(c);
@@ -743,9 +800,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
-      u8 e[13];
-      fetch_edges4(W.yws, x0, y0, e);
-      const i32 pr = predict4_pixel(e, W.bmodes[i], n16, ptab);
+      const i32 pr = pred4_px(W.yws, x0, y0, W.bmodes[i], n16, ptab);
       const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane);
       simple_any |= quantize_coeff(cf, SP.y1, n16) != 0;
       __syncwarp();
@@ -807,17 +862,17 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
     const int mode = lane >> 3;  // lane = mode*8 + block (0..3 U, 4..7 V); MODES order DC,V,H,TM
     const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
     i32 c[16], pr[16], q[16];
+    pred_block(W.uvws, cofs, mode, cbx, cby, ch ? dcV : dcU, pr);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
-      pr[k] = pred_big(W.uvws, cofs, mode, x, y, ch ? dcV : dcU);
       c[k] = (i32)src[y * 8 + x] - pr[k];
     }
     fdct4x4(c);
     int nzac = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.uv, k); if (k > 0) nzac += q[k] != 0; }
-    int cost = (int)residual_cost(q, 2, 0, 0, cc);
+    int cost = (int)residual_cost_call(q, 2, 0, 0, cc);
 #pragma unroll
     for (int k = 0; k < 16; k++) c[k] = dequantize(q[k], SP.uv, k);
     idct4x4(c);
@@ -842,10 +897,10 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
   }
   // ---- transform_chroma_blocks ----
   i32 c[16], pr[16];
+  pred_block(W.uvws, cofs, uv_mode, cbx, cby, ch ? dcV : dcU, pr);
 #pragma unroll
   for (int k = 0; k < 16; k++) {
     const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
-    pr[k] = pred_big(W.uvws, cofs, uv_mode, x, y, ch ? dcV : dcU);
     c[k] = (i32)src[y * 8 + x] - pr[k];
   }
   fdct4x4(c);
