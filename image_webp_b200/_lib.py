@@ -70,9 +70,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if _stale():
-        build()
-    L = C.CDLL(SO)
+    override = os.environ.get("ZW_LIB_PATH")  # tuning experiments: load an alternative build
+    if override:
+        L = C.CDLL(override)
+    else:
+        if _stale():
+            build()
+        L = C.CDLL(SO)
     L.zw_create.restype = C.c_void_p
     L.zw_create.argtypes = [C.c_int, C.POINTER(ZwLimits)]
     L.zw_destroy.argtypes = [C.c_void_p]

@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
   const bool active = rp * 2 < ph;
   const int ccy = min(rp, chh - 1);
   const int rowA = 2 * ccy, rowB = min(2 * ccy + 1, h - 1);
-  const u8* rgb = P.rgb + d.rgb_off;
   int skew[2] = {0, 0};
   if (active) {
 #pragma unroll
@@ -51,7 +50,6 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
       for (int i = threadIdx.x; i < nvec; i += YUV_THREADS) dst[i] = __ldg(src + i);
     }
   }
-  (void)rgb;
   __syncthreads();
   if (!active) return;
   const u8* sA = sm + (size_t)(threadIdx.y * 2 + 0) * row_slots * 16 + skew[0];

@@ -27,6 +27,9 @@
 namespace zw {
 
 constexpr int SEARCH_WARPS = 4;  // warps per CTA (each independent)
+#ifndef ZW_SEARCH_MIN_BLOCKS
+#define ZW_SEARCH_MIN_BLOCKS 6   // CTAs per SM the wavefront kernels are register-budgeted for
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
 
@@ -991,7 +994,7 @@ __device__ __forceinline__ void complexity_after(bool is_b, bool skip, int y2nz,
 // The wavefront kernel.  PASS 1: luma only (see file header).  PASS 2: luma + chroma.
 // ---------------------------------------------------------------------------------------------
 template <int PASS>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(ChunkParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_search(ChunkParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
   for (int i = threadIdx.x; i < 128; i += blockDim.x) (&SH.pred_tab[0][0])[i] = (&d_pred_tab[0][0])[i];
