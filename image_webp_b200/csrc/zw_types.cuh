@@ -16,7 +16,7 @@ struct SegParams {
 };
 
 // Per-macroblock record: the interface between the search passes, the statistics kernel and
-// the tokeniser, and the P1MB / P2MB parity dump (same POD layout as the oracle's zwo_mb_record).
+// the tokeniser, and the P1MB / P2MB parity dump (832-byte POD, the layout tests/ compare against their CPU checker).
 struct MbRecord {
   u8 ymode;   // 0 DC 1 V 2 H 3 TM 4 B_PRED
   u8 uvmode;  // 0 DC 1 V 2 H 3 TM

@@ -1,0 +1,94 @@
+// zenwebp_b200.hpp -- C++ host-side mirror of the reference's encoder API for the lossy path,
+// header-only on top of the C ABI (zenwebp_b200.h).  Mirrors imazen/image-webp `zenwebp` 0.2.0:
+//   ColorType      src/encoder/api.rs:83-92      EncodingError  src/encoder/api.rs:35-48
+//   EncoderParams  src/encoder/api.rs:419-459    WebPEncoder    src/encoder/api.rs:1244-1398
+// plus the batch entry point.  The reference is Rust; with no Rust toolchain in the build image
+// this header (and the Python mirror) stand where the wrapper crate of rust/zenwebp-b200 would.
+#ifndef ZENWEBP_B200_HPP
+#define ZENWEBP_B200_HPP
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "zenwebp_b200.h"
+
+namespace zenwebp_b200 {
+
+enum class ColorType { L8 = ZW_COLOR_L8, La8 = ZW_COLOR_LA8, Rgb8 = ZW_COLOR_RGB8, Rgba8 = ZW_COLOR_RGBA8 };
+
+struct EncodingError : std::runtime_error {
+  int code;
+  EncodingError(int c) : std::runtime_error(zw_strerror(c)), code(c) {}
+};
+struct InvalidDimensions : EncodingError { InvalidDimensions() : EncodingError(ZW_ERR_INVALID_DIMENSIONS) {} };
+struct InvalidBufferSize : EncodingError { InvalidBufferSize() : EncodingError(ZW_ERR_INVALID_BUFFER_SIZE) {} };
+
+struct EncoderParams {
+  bool use_predictor_transform = true;
+  bool use_lossy = false;
+  uint8_t lossy_quality = 95;
+  uint8_t method = 4;
+  static EncoderParams lossless() { return EncoderParams(); }
+  static EncoderParams lossy(uint8_t quality) { EncoderParams p; p.use_lossy = true; p.lossy_quality = quality; return p; }
+  EncoderParams with_method(uint8_t m) const { EncoderParams p = *this; p.method = m; return p; }
+};
+
+inline void raise_for(int status) {
+  if (status == ZW_OK) return;
+  if (status == ZW_ERR_INVALID_DIMENSIONS) throw InvalidDimensions();
+  if (status == ZW_ERR_INVALID_BUFFER_SIZE) throw InvalidBufferSize();
+  throw EncodingError(status);
+}
+
+// One context per (host thread, GPU).
+class Context {
+ public:
+  explicit Context(int device = 0) : h_(zw_create(device, nullptr)) { if (!h_) throw EncodingError(zw_last_error()); }
+  ~Context() { zw_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  struct ImageRef { const uint8_t* data; size_t len; uint32_t width, height; ColorType color; };
+  // Batch entry: n images -> n .webp files (per-image errors throw for the first failing image).
+  std::vector<std::vector<uint8_t>> encode_batch(const std::vector<ImageRef>& imgs, const EncoderParams& p, zw_timing* t = nullptr) {
+    if (!p.use_lossy) throw std::logic_error("only the lossy VP8 path is implemented on the GPU");
+    std::vector<zw_image> in(imgs.size());
+    std::vector<zw_output> out(imgs.size());
+    for (size_t i = 0; i < imgs.size(); i++) {
+      in[i] = zw_image{imgs[i].data, imgs[i].len, imgs[i].width, imgs[i].height, (uint32_t)imgs[i].color, 0};
+      out[i] = zw_output{nullptr, 0, 0, 0, 0};
+    }
+    raise_for(zw_encode_webp_batch(h_, in.data(), in.size(), p.lossy_quality, p.method, out.data(), t));
+    std::vector<std::vector<uint8_t>> res(imgs.size());
+    int first_err = 0;
+    for (size_t i = 0; i < imgs.size(); i++) {
+      if (out[i].status == ZW_OK) res[i].assign(out[i].data, out[i].data + out[i].len);
+      else if (!first_err) first_err = out[i].status;
+      zw_free(out[i].data);
+    }
+    raise_for(first_err);
+    return res;
+  }
+  zw_ctx* handle() { return h_; }
+ private:
+  zw_ctx* h_;
+};
+
+// WebPEncoder::new(&mut Vec<u8>) / set_params / encode: appends the .webp bytes to `writer`.
+class WebPEncoder {
+ public:
+  explicit WebPEncoder(std::vector<uint8_t>& writer, Context& ctx) : w_(writer), ctx_(ctx) {}
+  void set_params(const EncoderParams& p) { params_ = p; }
+  void encode(const uint8_t* data, size_t len, uint32_t width, uint32_t height, ColorType color) {
+    if (width > 65535 || height > 65535) throw InvalidDimensions();
+    auto out = ctx_.encode_batch({Context::ImageRef{data, len, width, height, color}}, params_);
+    w_.insert(w_.end(), out[0].begin(), out[0].end());
+  }
+ private:
+  std::vector<uint8_t>& w_;
+  Context& ctx_;
+  EncoderParams params_;
+};
+
+}  // namespace zenwebp_b200
+#endif
