@@ -167,54 +167,69 @@ struct DevBuf {
 
 }  // namespace
 
-struct zw_ctx {
+// One "lane": a stream with its own chunk buffers.  A context owns several lanes and splits
+// every staged chunk between them so that the low-parallelism kernels of one lane (pass-1 chroma
+// chain, boolean coder) and its host round trip overlap the wavefront kernels / copies of the other.
+struct Lane {
   int device = 0;
-  int sm_count = 0;
-  size_t budget = 0;
-  int warps_per_sm_hint = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[16];
-  // constant tables
-  DevBuf d_segtab, d_lut;
-  // chunk buffers
+  const SegParams* segtab = nullptr;  // shared constant tables (owned by the context)
+  const u8* lut = nullptr;
   DevBuf d_img, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
-      d_derr1, d_derr2, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
+      d_derr1, d_derr2, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
       d_part, d_out, d_outoff;
-  // host mirrors of the staged chunk
   std::vector<ImageDesc> img;
   std::vector<ImageState> st;
   std::vector<RowRef> rows;
   std::vector<u64> out_off;
-  std::vector<int> img_status;  // host-side validation result per image of the chunk (0 = staged)
-  std::vector<int> slot_of;     // chunk image index -> position among staged (valid) images, or -1
-  std::vector<u8> h_out;
+  std::vector<int> img_status;  // host-side validation result per image handed to this lane (0 = staged)
+  std::vector<int> slot_of;     // image index within the lane -> position among staged (valid) images, or -1
   u8* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   u32 n_valid = 0, n_rows = 0, n_mb = 0, max_pw = 0, max_ph = 0, max_mb = 0;
   u64 layout_key = 0;
   bool staged = false, encoded = false;
   int quality = -1, method = -1, base_qidx = 0;
-  int search_blocks1 = 0, search_blocks2 = 0, chroma_blocks = 0;
+  int search_blocks1 = 0, search_blocks2 = 0, chroma_blocks = 0, chroma2_blocks = 0;
+  u64 launches = 0;
+  dim3 tok_grid;
   ChunkParams P;
   zw_timing last;
 };
 
-static void fill_params(zw_ctx* c) {
+struct zw_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t budget = 0;
+  DevBuf d_segtab, d_lut;
+  std::vector<Lane*> lanes;
+  std::vector<size_t> lane_begin;  // image ranges of the staged chunk: lane k owns [lane_begin[k], lane_begin[k+1])
+  size_t n_staged = 0;
+  int active_lanes = 0;
+  bool staged = false, encoded = false;
+  int base_qidx = 0;
+  zw_timing last;
+};
+
+static void fill_params(Lane* c) {
   ChunkParams& P = c->P;
   memset(&P, 0, sizeof(P));
   P.img = c->d_img.as<ImageDesc>(); P.st = c->d_st.as<ImageState>(); P.rows = c->d_rows.as<RowRef>();
-  P.segtab = c->d_segtab.as<SegParams>(); P.segquant_lut = c->d_lut.as<u8>();
+  P.segtab = c->segtab; P.segquant_lut = c->lut;
   P.n_img = c->n_valid; P.n_rows = c->n_rows; P.n_mb = c->n_mb;
   P.rgb = c->d_rgb.as<u8>(); P.planes = c->d_planes.as<u8>();
   P.alpha_hist = c->d_alpha_hist.as<u32>(); P.map256 = c->d_map256.as<u8>();
   P.alpha = c->d_alpha.as<u8>(); P.segmap = c->d_segmap.as<u8>();
   P.rec1 = c->d_rec1.as<MbRecord>(); P.rec2 = c->d_rec2.as<MbRecord>(); P.bottom = c->d_bottom.as<MbBottom>();
-  P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>();
+  P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>(); P.uvflags = c->d_uvflags.as<u8>();
   P.progress = c->d_progress.as<int>(); P.ticket = c->d_ticket.as<u32>(); P.rowstats = c->d_rowstats.as<u32>();
   P.stats = c->d_stats.as<u32>(); P.probs = c->d_probs.as<u8>(); P.lcost = c->d_lcost.as<u16>();
   P.mb_hdr_cnt = c->d_hcnt.as<u32>(); P.mb_tok_cnt = c->d_tcnt.as<u32>();
   P.hdr_tokens = c->d_htok.as<Token>(); P.tok_tokens = c->d_ttok.as<Token>();
   P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
+  P.method = (u32)c->method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = c->method >= 4;
+  P.filter_level = (u8)compute_filter_level(c->base_qidx);
 }
 
 static int validate_image(const zw_image& im) {
@@ -236,6 +251,300 @@ static size_t image_footprint(u32 w, u32 h, u32 bpp) {
   b += 1056 * 7 + 6528 * 2 + 2048;             // per-image tables
   b += nmb * 256 * 10 + nmb * 256;             // token streams (estimate: 5 symbols/px) + bitstream
   return b;
+}
+
+static void lane_destroy(Lane* c) {
+  if (!c) return;
+  DevBuf* all[] = {&c->d_img, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
+                   &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_uvflags, &c->d_progress,
+                   &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_htok,
+                   &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
+  for (DevBuf* b : all) b->release();
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto& ev : c->ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
+  Lane* c = new Lane();
+  c->device = ctx->device;
+  c->segtab = ctx->d_segtab.as<SegParams>();
+  c->lut = ctx->d_lut.as<u8>();
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  if (c->d_ticket.reserve(64) != cudaSuccess) { lane_destroy(c); return nullptr; }
+  int b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_chroma1, SEARCH_WARPS * 32, sizeof(SearchShared));
+  if (warps_hint > 0) {
+    const int cap = std::max(1, warps_hint / SEARCH_WARPS);
+    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b3 = std::min(b3, cap); b4 = std::min(b4, cap);
+  }
+  c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
+  c->search_blocks1 = std::max(1, b1) * ctx->sm_count;
+  c->search_blocks2 = std::max(1, b2) * ctx->sm_count;
+  c->chroma_blocks = std::max(1, b3) * ctx->sm_count;
+  return c;
+}
+
+// Validate + lay out + start the H2D copies of one lane's images (asynchronous on its stream).
+static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
+  c->staged = false; c->encoded = false;
+  c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
+  u64 rgb_bytes = 0, plane_bytes = 0, key = 1469598103934665603ull;
+  u32 n_mb = 0, n_rows = 0, max_pw = 0, max_ph = 0, max_mb = 0, max_mbh = 0;
+  for (size_t i = 0; i < n; i++) {
+    const int v = validate_image(imgs[i]);
+    c->img_status[i] = v;
+    if (v != ZW_OK) continue;
+    ImageDesc d;
+    memset(&d, 0, sizeof(d));
+    d.width = imgs[i].width; d.height = imgs[i].height;
+    d.mbw = (d.width + 15) / 16; d.mbh = (d.height + 15) / 16;
+    d.bpp = imgs[i].color == ZW_COLOR_RGB8 ? 3 : 4;
+    d.mb_off = n_mb; d.row_off = n_rows;
+    d.use_segments = (d.mbw * d.mbh >= 256) ? 1 : 0;
+    d.rgb_off = rgb_bytes; d.y_off = plane_bytes;
+    rgb_bytes += ((u64)imgs[i].len + 15) & ~15ull;
+    plane_bytes += (u64)d.mbw * d.mbh * 384;
+    n_mb += d.mbw * d.mbh; n_rows += d.mbh;
+    max_pw = std::max(max_pw, d.mbw * 16); max_ph = std::max(max_ph, d.mbh * 16);
+    max_mb = std::max(max_mb, d.mbw * d.mbh); max_mbh = std::max(max_mbh, d.mbh);
+    c->slot_of[i] = (int)c->img.size();
+    c->img.push_back(d);
+    key = (key ^ (((u64)d.width << 32) | ((u64)d.height << 8) | d.bpp)) * 1099511628211ull;
+  }
+  c->n_valid = (u32)c->img.size(); c->n_mb = n_mb; c->n_rows = n_rows;
+  c->max_pw = max_pw; c->max_ph = max_ph; c->max_mb = max_mb;
+  c->last = zw_timing();
+  if (c->n_valid == 0) { c->staged = true; return ZW_OK; }
+  const u32 ni = c->n_valid;
+  CK(c->d_img.reserve(ni * sizeof(ImageDesc))); CK(c->d_st.reserve(ni * sizeof(ImageState)));
+  CK(c->d_rows.reserve((size_t)n_rows * sizeof(RowRef))); CK(c->d_rgb.reserve(rgb_bytes + 64)); CK(c->d_planes.reserve(plane_bytes + 64));
+  CK(c->d_alpha_hist.reserve((size_t)ni * 1024)); CK(c->d_map256.reserve((size_t)ni * 256));
+  CK(c->d_alpha.reserve(n_mb)); CK(c->d_segmap.reserve(n_mb));
+  CK(c->d_rec1.reserve((size_t)n_mb * sizeof(MbRecord))); CK(c->d_rec2.reserve((size_t)n_mb * sizeof(MbRecord)));
+  CK(c->d_bottom.reserve((size_t)n_mb * sizeof(MbBottom))); CK(c->d_nz.reserve((size_t)n_mb * 2));
+  CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4)); CK(c->d_uvflags.reserve(n_mb));
+  CK(c->d_progress.reserve((size_t)n_rows * 3 * sizeof(int))); CK(c->d_rowstats.reserve((size_t)n_rows * 2112 * 4));
+  CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
+  CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
+  CK(c->d_outoff.reserve(((size_t)ni + 1) * 8));
+  // ticket order: macroblock row y of every image before row y+1 of any image ("many images
+  // interleaved"): each image has at most a couple of rows in flight, so rows rarely wait.
+  if (key != c->layout_key || c->rows.size() != n_rows) {
+    c->rows.resize(n_rows);
+    size_t k = 0;
+    for (u32 y = 0; y < max_mbh; y++)
+      for (u32 i = 0; i < ni; i++)
+        if (y < c->img[i].mbh) { c->rows[k].img = i; c->rows[k].mby = y; k++; }
+    CK(cudaMemcpyAsync(c->d_rows.p, c->rows.data(), (size_t)n_rows * sizeof(RowRef), cudaMemcpyHostToDevice, c->stream));
+    c->layout_key = key;
+  }
+  CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  for (size_t i = 0; i < n; i++) {
+    if (c->slot_of[i] < 0) continue;
+    const ImageDesc& d = c->img[c->slot_of[i]];
+    CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + d.rgb_off, imgs[i].data, imgs[i].len, cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  c->last.h2d_bytes = rgb_bytes;
+  for (const ImageDesc& d : c->img) c->last.pixels += (u64)d.width * d.height;
+  c->staged = true;
+  return ZW_OK;
+}
+
+// Phase A: everything up to the symbol counts (asynchronous; ends with the D2H of ImageState).
+static int lane_encode_a(Lane* c, int quality, int method) {
+  c->encoded = false;
+  c->launches = 0;
+  if (c->n_valid == 0) return ZW_OK;
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
+  fill_params(c);
+  ChunkParams& P = c->P;
+  CK(cudaEventRecord(c->ev[2], s));
+  CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
+  CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
+  CK(cudaMemsetAsync(c->d_progress.p, 0, (size_t)c->n_rows * 3 * sizeof(int), s));
+  CK(cudaMemsetAsync(c->d_ticket.p, 0, 64, s));
+  {  // (1) RGB -> YUV420
+    dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + YUV_ROWPAIRS * 2 - 1) / (YUV_ROWPAIRS * 2), ni);
+    dim3 block(YUV_THREADS, YUV_ROWPAIRS);
+    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * ((YUV_TILE_W * 4 + 32) / 16) * 16;
+    k_yuv<<<grid, block, sm, s>>>(P);
+    c->launches++;
+  }
+  CK(cudaEventRecord(c->ev[3], s));
+  {  // (2) analysis + segments
+    bool any_seg = false;
+    for (const ImageDesc& d : c->img) any_seg |= d.use_segments != 0;
+    if (any_seg) {
+      dim3 grid((c->max_mb + AN_WARPS - 1) / AN_WARPS, ni);
+      k_analysis<<<grid, AN_WARPS * 32, 0, s>>>(P);
+      c->launches++;
+    }
+    k_segments<<<ni, 256, 0, s>>>(P);
+    c->launches++;
+  }
+  CK(cudaEventRecord(c->ev[4], s));
+  {  // (3) pass 1: luma wavefront, then the chroma chain
+    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    const int g3 = (int)std::min<u64>((u64)c->chroma_blocks, ((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    c->launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[5], s));
+  {  // (4) token statistics -> probabilities, level costs, skip probability
+    k_rowstats<<<(c->n_rows + STAT_WARPS - 1) / STAT_WARPS, STAT_WARPS * 32, 0, s>>>(P);
+    k_probs<<<ni, 256, 0, s>>>(P);
+    c->launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[6], s));
+  {  // (3') pass 2: chroma wavefront first (independent of luma), then the luma wavefront
+    const int g4 = (int)std::min<u64>((u64)c->chroma2_blocks, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_search<2><<<g2, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    c->launches += 2;
+  }
+  CK(cudaEventRecord(c->ev[7], s));
+  {  // (5a) count symbols, scan
+    c->tok_grid = dim3((c->max_mb + TOK_WARPS - 1) / TOK_WARPS, ni);
+    k_tokenize<0><<<c->tok_grid, TOK_WARPS * 32, 0, s>>>(P);
+    k_tokscan<<<ni, 256, 0, s>>>(P);
+    c->launches += 2;
+    c->st.resize(ni);
+    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
+  }
+  return ZW_OK;
+}
+
+// Phase B: wait for the symbol counts, size the streams, emit + code + assemble (asynchronous).
+static int lane_encode_b(Lane* c) {
+  if (c->n_valid == 0) return ZW_OK;
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  CK(cudaStreamSynchronize(s));
+  u64 hoff = 0, toff = 0, poff = 0;
+  for (u32 i = 0; i < ni; i++) {
+    ImageDesc& d = c->img[i];
+    d.hdr_off = hoff; d.tok_off = toff; d.part_off = poff;
+    d.p0_cap = (u32)(((u64)c->st[i].hdr_tokens * 7) / 8 + 16);
+    d.p1_cap = (u32)(((u64)c->st[i].tok_tokens * 7) / 8 + 16);
+    hoff += ((u64)c->st[i].hdr_tokens + 7) & ~7ull;
+    toff += ((u64)c->st[i].tok_tokens + 7) & ~7ull;
+    poff += ((u64)d.p0_cap + d.p1_cap + 15) & ~15ull;
+  }
+  CK(c->d_htok.reserve(hoff * sizeof(Token) + 64)); CK(c->d_ttok.reserve(toff * sizeof(Token) + 64));
+  CK(c->d_part.reserve(poff + 64)); CK(c->d_out.reserve(poff + (u64)ni * 32 + 64));
+  fill_params(c);
+  ChunkParams& P = c->P;
+  CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, s));
+  k_tokenize<1><<<c->tok_grid, TOK_WARPS * 32, 0, s>>>(P);
+  k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
+  c->launches += 2;
+  CK(cudaEventRecord(c->ev[8], s));
+  k_boolcode<<<(2 * ni + 127) / 128, 128, 0, s>>>(P);
+  c->launches++;
+  CK(cudaEventRecord(c->ev[9], s));
+  k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
+  k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
+  c->launches += 2;
+  CK(cudaEventRecord(c->ev[10], s));
+  return ZW_OK;
+}
+
+static int lane_encode_finish(Lane* c) {
+  if (c->n_valid == 0) { c->encoded = true; return ZW_OK; }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  zw_timing T = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
+  T.h2d_bytes = c->last.h2d_bytes; T.pixels = c->last.pixels;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); T.pass1_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); T.stats_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); T.pass2_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[10]); T.device_total_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms = ms;
+  T.kernel_launches = c->launches;
+  c->last = T;
+  c->encoded = true;
+  return ZW_OK;
+}
+
+static int lane_download(Lane* c, zw_output* outs, size_t n, int container) {
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  if (ni) {
+    c->st.resize(ni); c->out_off.resize(ni + 1);
+    CK(cudaEventRecord(c->ev[11], s));
+    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->out_off.data(), c->d_outoff.p, ((size_t)ni + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const size_t total = (size_t)c->out_off[ni];
+    if (total > c->h_pinned_cap) {
+      if (c->h_pinned) cudaFreeHost(c->h_pinned);
+      c->h_pinned = nullptr; c->h_pinned_cap = 0;
+      CK(cudaMallocHost((void**)&c->h_pinned, total + total / 4 + 4096));
+      c->h_pinned_cap = total + total / 4 + 4096;
+    }
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c->ev[12], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]);
+    c->last.d2h_ms = ms;
+    c->last.d2h_bytes = total + ni * sizeof(ImageState) + ((size_t)ni + 1) * 8;
+  }
+  for (size_t i = 0; i < n; i++) {
+    zw_output& o = outs[i];
+    o.len = 0;
+    if (c->slot_of[i] < 0) { o.status = c->img_status[i]; continue; }
+    const u32 k = (u32)c->slot_of[i];
+    const ImageState& st = c->st[k];
+    if (st.status != 0) { o.status = (int)st.status; continue; }
+    const size_t payload = st.vp8_bytes;
+    const size_t need = container ? 20 + payload + (payload & 1) : payload;
+    if (o.data == nullptr) {
+      o.data = (uint8_t*)malloc(need ? need : 1);
+      o.cap = need;
+      if (!o.data) { o.status = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; continue; }
+    } else if (o.cap < need) { o.status = ZW_ERR_OUTPUT_TOO_SMALL; o.len = need; continue; }
+    uint8_t* w = o.data;
+    if (container) {  // api.rs:1325-1329 + write_chunk :1232-1241
+      const u32 chunk = (u32)(payload + (payload & 1)) + 8;
+      const u32 riff = chunk + 4;
+      memcpy(w, "RIFF", 4); w[4] = (u8)riff; w[5] = (u8)(riff >> 8); w[6] = (u8)(riff >> 16); w[7] = (u8)(riff >> 24);
+      memcpy(w + 8, "WEBP", 4); memcpy(w + 12, "VP8 ", 4);
+      const u32 pl = (u32)payload;
+      w[16] = (u8)pl; w[17] = (u8)(pl >> 8); w[18] = (u8)(pl >> 16); w[19] = (u8)(pl >> 24);
+      w += 20;
+    }
+    memcpy(w, c->h_pinned + c->out_off[k], payload);
+    if (container && (payload & 1)) w[payload] = 0;
+    o.len = need;
+    o.status = ZW_OK;
+  }
+  return ZW_OK;
+}
+
+static void add_timing(zw_timing& a, const zw_timing& L) {
+  a.h2d_ms += L.h2d_ms; a.yuv_ms += L.yuv_ms; a.analysis_ms += L.analysis_ms; a.pass1_ms += L.pass1_ms;
+  a.stats_ms += L.stats_ms; a.pass2_ms += L.pass2_ms; a.token_ms += L.token_ms; a.boolcode_ms += L.boolcode_ms;
+  a.assemble_ms += L.assemble_ms; a.d2h_ms += L.d2h_ms;
+  a.kernel_launches += L.kernel_launches; a.h2d_bytes += L.h2d_bytes; a.d2h_bytes += L.d2h_bytes; a.pixels += L.pixels;
 }
 
 extern "C" {
@@ -274,9 +583,12 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
   cudaGetDeviceProperties(&prop, device);
   c->sm_count = prop.multiProcessorCount;
   c->budget = (limits && limits->max_device_bytes) ? limits->max_device_bytes : ((size_t)32 << 30);
-  c->warps_per_sm_hint = limits ? limits->persistent_warps_per_sm : 0;
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; delete c; return nullptr; }
-  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  int warps_hint = limits ? limits->persistent_warps_per_sm : 0;
+  if (const char* env = getenv("ZW_WARPS_PER_SM")) warps_hint = atoi(env);
+  int n_lanes = limits ? limits->reserved[0] : 0;  // reserved[0]: number of lanes (0 = default)
+  if (const char* env = getenv("ZW_LANES")) n_lanes = atoi(env);
+  if (n_lanes <= 0) n_lanes = 1;  // measured: >1 lane does not help while the wavefront kernels are persistent and fill the SMs
+  n_lanes = std::min(n_lanes, 8);
   // constant tables
   std::vector<SegParams> segtab(128);
   for (int i = 0; i < 128; i++) segtab[i] = make_segparams(i);
@@ -284,22 +596,17 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
   for (int b = 0; b < 128; b++)
     for (int a = -127; a <= 127; a++) lut[b * 255 + (a + 127)] = (u8)compute_segment_quant(b, a, 50);
   const TokenTables tt = make_token_tables();
-  if (c->d_segtab.reserve(segtab.size() * sizeof(SegParams)) != cudaSuccess || c->d_lut.reserve(lut.size()) != cudaSuccess ||
-      c->d_ticket.reserve(64) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr; }
+  if (c->d_segtab.reserve(segtab.size() * sizeof(SegParams)) != cudaSuccess || c->d_lut.reserve(lut.size()) != cudaSuccess) {
+    g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr;
+  }
   cudaMemcpy(c->d_segtab.p, segtab.data(), segtab.size() * sizeof(SegParams), cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice);
   cudaMemcpyToSymbol(c_tok, &tt, sizeof(tt));
-  int b1 = 0, b2 = 0, b3 = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_chroma1, SEARCH_WARPS * 32, sizeof(SearchShared));
-  if (c->warps_per_sm_hint > 0) {
-    const int cap = std::max(1, c->warps_per_sm_hint / SEARCH_WARPS);
-    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b3 = std::min(b3, cap);
+  for (int k = 0; k < n_lanes; k++) {
+    Lane* l = lane_create(c, warps_hint);
+    if (!l) { g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr; }
+    c->lanes.push_back(l);
   }
-  c->search_blocks1 = std::max(1, b1) * c->sm_count;
-  c->search_blocks2 = std::max(1, b2) * c->sm_count;
-  c->chroma_blocks = std::max(1, b3) * c->sm_count;
   e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; zw_destroy(c); return nullptr; }
   g_last_error = 0;
@@ -309,84 +616,39 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
 void zw_destroy(zw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->d_segtab, &c->d_lut, &c->d_img, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist,
-                   &c->d_map256, &c->d_alpha, &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1,
-                   &c->d_derr2, &c->d_progress, &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost,
-                   &c->d_hcnt, &c->d_tcnt, &c->d_htok, &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
-  for (DevBuf* b : all) b->release();
-  if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  for (auto& ev : c->ev) cudaEventDestroy(ev);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  for (Lane* l : c->lanes) lane_destroy(l);
+  c->d_segtab.release(); c->d_lut.release();
   delete c;
 }
 
 int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
   if (!c || (!imgs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
-  if (n > 65535) return g_last_error = ZW_ERR_INVALID_PARAM;  // grid.y / grid.z limit; the batch API chunks below this
+  if (n > 65535 * c->lanes.size()) return g_last_error = ZW_ERR_INVALID_PARAM;  // grid.y / grid.z limit per lane
   CK(cudaSetDevice(c->device));
   c->staged = false; c->encoded = false;
-  c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
-  u64 rgb_bytes = 0, plane_bytes = 0, key = 1469598103934665603ull;
-  u32 n_mb = 0, n_rows = 0, max_pw = 0, max_ph = 0, max_mb = 0, max_mbh = 0;
-  for (size_t i = 0; i < n; i++) {
-    const int v = validate_image(imgs[i]);
-    c->img_status[i] = v;
-    if (v != ZW_OK) continue;
-    ImageDesc d;
-    memset(&d, 0, sizeof(d));
-    d.width = imgs[i].width; d.height = imgs[i].height;
-    d.mbw = (d.width + 15) / 16; d.mbh = (d.height + 15) / 16;
-    d.bpp = imgs[i].color == ZW_COLOR_RGB8 ? 3 : 4;
-    d.mb_off = n_mb; d.row_off = n_rows;
-    d.use_segments = (d.mbw * d.mbh >= 256) ? 1 : 0;
-    d.rgb_off = rgb_bytes; d.y_off = plane_bytes;
-    rgb_bytes += ((u64)imgs[i].len + 15) & ~15ull;
-    plane_bytes += (u64)d.mbw * d.mbh * 384;
-    n_mb += d.mbw * d.mbh; n_rows += d.mbh;
-    max_pw = std::max(max_pw, d.mbw * 16); max_ph = std::max(max_ph, d.mbh * 16);
-    max_mb = std::max(max_mb, d.mbw * d.mbh); max_mbh = std::max(max_mbh, d.mbh);
-    c->slot_of[i] = (int)c->img.size();
-    c->img.push_back(d);
-    key = (key ^ (((u64)d.width << 32) | ((u64)d.height << 8) | d.bpp)) * 1099511628211ull;
+  // split the chunk between the lanes by pixel count (contiguous image ranges)
+  const int L = (int)std::max<size_t>(1, std::min<size_t>(c->lanes.size(), n / 2 > 0 ? n / 2 : 1));
+  u64 total_px = 0;
+  for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
+  c->lane_begin.assign(L + 1, n);
+  c->lane_begin[0] = 0;
+  {
+    u64 acc = 0;
+    int k = 1;
+    for (size_t i = 0; i < n && k < L; i++) {
+      acc += (u64)imgs[i].width * imgs[i].height;
+      if (acc * L >= total_px * k) { c->lane_begin[k++] = i + 1; }
+    }
+    for (; k < L; k++) c->lane_begin[k] = n;
   }
-  c->n_valid = (u32)c->img.size(); c->n_mb = n_mb; c->n_rows = n_rows;
-  c->max_pw = max_pw; c->max_ph = max_ph; c->max_mb = max_mb;
-  if (c->n_valid == 0) { c->staged = true; return g_last_error = ZW_OK; }
-  const u32 ni = c->n_valid;
-  CK(c->d_img.reserve(ni * sizeof(ImageDesc))); CK(c->d_st.reserve(ni * sizeof(ImageState)));
-  CK(c->d_rows.reserve((size_t)n_rows * sizeof(RowRef))); CK(c->d_rgb.reserve(rgb_bytes + 64)); CK(c->d_planes.reserve(plane_bytes + 64));
-  CK(c->d_alpha_hist.reserve((size_t)ni * 1024)); CK(c->d_map256.reserve((size_t)ni * 256));
-  CK(c->d_alpha.reserve(n_mb)); CK(c->d_segmap.reserve(n_mb));
-  CK(c->d_rec1.reserve((size_t)n_mb * sizeof(MbRecord))); CK(c->d_rec2.reserve((size_t)n_mb * sizeof(MbRecord)));
-  CK(c->d_bottom.reserve((size_t)n_mb * sizeof(MbBottom))); CK(c->d_nz.reserve((size_t)n_mb * 2));
-  CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4));
-  CK(c->d_progress.reserve((size_t)n_rows * 2 * sizeof(int))); CK(c->d_rowstats.reserve((size_t)n_rows * 2112 * 4));
-  CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
-  CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
-  CK(c->d_outoff.reserve(((size_t)ni + 1) * 8));
-  // ticket order: macroblock row y of every image before row y+1 of any image ("many images
-  // interleaved"): each image has at most a couple of rows in flight, so rows rarely wait.
-  if (key != c->layout_key || c->rows.size() != n_rows) {
-    c->rows.resize(n_rows);
-    size_t k = 0;
-    for (u32 y = 0; y < max_mbh; y++)
-      for (u32 i = 0; i < ni; i++)
-        if (y < c->img[i].mbh) { c->rows[k].img = i; c->rows[k].mby = y; k++; }
-    CK(cudaMemcpyAsync(c->d_rows.p, c->rows.data(), (size_t)n_rows * sizeof(RowRef), cudaMemcpyHostToDevice, c->stream));
-    c->layout_key = key;
+  c->active_lanes = L;
+  c->n_staged = n;
+  for (int k = 0; k < L; k++) {
+    const size_t b = c->lane_begin[k], e = c->lane_begin[k + 1];
+    if (e - b > 65535) return g_last_error = ZW_ERR_INVALID_PARAM;
+    int rc = lane_stage(c->lanes[k], imgs + b, e - b);
+    if (rc != ZW_OK) return g_last_error = rc;
   }
-  CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaEventRecord(c->ev[0], c->stream));
-  for (size_t i = 0; i < n; i++) {
-    if (c->slot_of[i] < 0) continue;
-    const ImageDesc& d = c->img[c->slot_of[i]];
-    CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + d.rgb_off, imgs[i].data, imgs[i].len, cudaMemcpyHostToDevice, c->stream));
-  }
-  CK(cudaEventRecord(c->ev[1], c->stream));
-  fill_params(c);
-  c->last = zw_timing();
-  c->last.h2d_bytes = rgb_bytes;
-  for (const ImageDesc& d : c->img) c->last.pixels += (u64)d.width * d.height;
   c->staged = true;
   return g_last_error = ZW_OK;
 }
@@ -397,115 +659,26 @@ int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
   if (quality < 0 || quality > 100 || method < 0) return g_last_error = ZW_ERR_INVALID_PARAM;
   CK(cudaSetDevice(c->device));
   c->encoded = false;
-  if (c->n_valid == 0) { c->encoded = true; return g_last_error = ZW_OK; }
   method = std::min(method, 6);  // vp8.rs:1291
-  const u32 ni = c->n_valid;
-  cudaStream_t s = c->stream;
-  fill_params(c);
-  ChunkParams& P = c->P;
-  P.method = (u32)method;
-  P.base_qidx = (u32)quality_to_quant_index(quality);
-  P.do_trellis = method >= 4;
-  P.filter_level = (u8)compute_filter_level((int)P.base_qidx);
-  c->quality = quality; c->method = method; c->base_qidx = (int)P.base_qidx;
-  u64 launches = 0;
-  CK(cudaEventRecord(c->ev[2], s));
-  CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
-  CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
-  CK(cudaMemsetAsync(c->d_progress.p, 0, (size_t)c->n_rows * 2 * sizeof(int), s));
-  CK(cudaMemsetAsync(c->d_ticket.p, 0, 64, s));
-  {  // (1) RGB -> YUV420
-    dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + YUV_ROWPAIRS * 2 - 1) / (YUV_ROWPAIRS * 2), ni);
-    dim3 block(YUV_THREADS, YUV_ROWPAIRS);
-    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * ((YUV_TILE_W * 4 + 32) / 16) * 16;
-    k_yuv<<<grid, block, sm, s>>>(P);
-    launches++;
-  }
-  CK(cudaEventRecord(c->ev[3], s));
-  {  // (2) analysis + segments
-    bool any_seg = false;
-    for (const ImageDesc& d : c->img) any_seg |= d.use_segments != 0;
-    if (any_seg) {
-      dim3 grid((c->max_mb + AN_WARPS - 1) / AN_WARPS, ni);
-      k_analysis<<<grid, AN_WARPS * 32, 0, s>>>(P);
-      launches++;
+  c->base_qidx = quality_to_quant_index(quality);
+  const int L = c->active_lanes;
+  int rc;
+  for (int k = 0; k < L; k++) if ((rc = lane_encode_a(c->lanes[k], quality, method)) != ZW_OK) return g_last_error = rc;
+  for (int k = 0; k < L; k++) if ((rc = lane_encode_b(c->lanes[k])) != ZW_OK) return g_last_error = rc;
+  for (int k = 0; k < L; k++) if ((rc = lane_encode_finish(c->lanes[k])) != ZW_OK) return g_last_error = rc;
+  // device span over all lanes: first "start" event to last "end" event
+  zw_timing T = zw_timing();
+  float span = 0;
+  for (int a = 0; a < L; a++) {
+    if (c->lanes[a]->n_valid == 0) continue;
+    add_timing(T, c->lanes[a]->last);
+    for (int b = 0; b < L; b++) {
+      if (c->lanes[b]->n_valid == 0) continue;
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->lanes[a]->ev[2], c->lanes[b]->ev[10]) == cudaSuccess) span = std::max(span, ms);
     }
-    k_segments<<<ni, 256, 0, s>>>(P);
-    launches++;
   }
-  CK(cudaEventRecord(c->ev[4], s));
-  {  // (3) pass 1: luma wavefront, then the chroma chain
-    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    const int g3 = (int)std::min<u64>((u64)c->chroma_blocks, ((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    launches += 2;
-  }
-  CK(cudaEventRecord(c->ev[5], s));
-  {  // (4) token statistics -> probabilities, level costs, skip probability
-    k_rowstats<<<(c->n_rows + STAT_WARPS - 1) / STAT_WARPS, STAT_WARPS * 32, 0, s>>>(P);
-    k_probs<<<ni, 256, 0, s>>>(P);
-    launches += 2;
-  }
-  CK(cudaEventRecord(c->ev[6], s));
-  {  // (3') pass 2
-    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_search<2><<<g2, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    launches++;
-  }
-  CK(cudaEventRecord(c->ev[7], s));
-  {  // (5a) count symbols, scan, size the streams
-    dim3 grid((c->max_mb + TOK_WARPS - 1) / TOK_WARPS, ni);
-    k_tokenize<0><<<grid, TOK_WARPS * 32, 0, s>>>(P);
-    k_tokscan<<<ni, 256, 0, s>>>(P);
-    launches += 2;
-    c->st.resize(ni);
-    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    u64 hoff = 0, toff = 0, poff = 0;
-    for (u32 i = 0; i < ni; i++) {
-      ImageDesc& d = c->img[i];
-      d.hdr_off = hoff; d.tok_off = toff; d.part_off = poff;
-      d.p0_cap = (u32)(((u64)c->st[i].hdr_tokens * 7) / 8 + 16);
-      d.p1_cap = (u32)(((u64)c->st[i].tok_tokens * 7) / 8 + 16);
-      hoff += ((u64)c->st[i].hdr_tokens + 7) & ~7ull;
-      toff += ((u64)c->st[i].tok_tokens + 7) & ~7ull;
-      poff += ((u64)d.p0_cap + d.p1_cap + 15) & ~15ull;
-    }
-    CK(c->d_htok.reserve(hoff * sizeof(Token) + 64)); CK(c->d_ttok.reserve(toff * sizeof(Token) + 64));
-    CK(c->d_part.reserve(poff + 64)); CK(c->d_out.reserve(poff + (u64)ni * 32 + 64));
-    fill_params(c);
-    P.method = (u32)method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = method >= 4;
-    P.filter_level = (u8)compute_filter_level(c->base_qidx);
-    CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, s));
-    k_tokenize<1><<<grid, TOK_WARPS * 32, 0, s>>>(P);
-    k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
-    launches += 2;
-  }
-  CK(cudaEventRecord(c->ev[8], s));
-  k_boolcode<<<(2 * ni + 127) / 128, 128, 0, s>>>(P);
-  launches++;
-  CK(cudaEventRecord(c->ev[9], s));
-  k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
-  k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
-  launches += 2;
-  CK(cudaEventRecord(c->ev[10], s));
-  CK(cudaStreamSynchronize(s));
-  CK(cudaGetLastError());
-  zw_timing T = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
-  T.h2d_bytes = c->last.h2d_bytes; T.pixels = c->last.pixels;
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); T.pass1_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); T.stats_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); T.pass2_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[2], c->ev[10]); T.device_total_ms += ms;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms += ms;
-  T.kernel_launches += launches;
+  T.device_total_ms = span;
   c->last = T;
   if (timing) *timing = T;
   c->encoded = true;
@@ -515,59 +688,14 @@ int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
 int zw_download(zw_ctx* c, zw_output* outs, size_t n, int container, zw_timing* timing) {
   if (!c || (!outs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
   if (!c->staged || !c->encoded) return g_last_error = ZW_ERR_NOT_STAGED;
-  if (n != c->img_status.size()) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (n != c->n_staged) return g_last_error = ZW_ERR_INVALID_PARAM;
   CK(cudaSetDevice(c->device));
-  const u32 ni = c->n_valid;
-  cudaStream_t s = c->stream;
-  if (ni) {
-    c->st.resize(ni); c->out_off.resize(ni + 1);
-    CK(cudaEventRecord(c->ev[11], s));
-    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c->out_off.data(), c->d_outoff.p, ((size_t)ni + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const size_t total = (size_t)c->out_off[ni];
-    if (total > c->h_pinned_cap) {
-      if (c->h_pinned) cudaFreeHost(c->h_pinned);
-      c->h_pinned = nullptr; c->h_pinned_cap = 0;
-      CK(cudaMallocHost((void**)&c->h_pinned, total + total / 4 + 4096));
-      c->h_pinned_cap = total + total / 4 + 4096;
-    }
-    CK(cudaMemcpyAsync(c->h_pinned, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(c->ev[12], s));
-    CK(cudaStreamSynchronize(s));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]);
-    c->last.d2h_ms += ms;
-    c->last.d2h_bytes += total + ni * sizeof(ImageState) + ((size_t)ni + 1) * 8;
-  }
-  for (size_t i = 0; i < n; i++) {
-    zw_output& o = outs[i];
-    o.len = 0;
-    if (c->slot_of[i] < 0) { o.status = c->img_status[i]; continue; }
-    const u32 k = (u32)c->slot_of[i];
-    const ImageState& st = c->st[k];
-    if (st.status != 0) { o.status = (int)st.status; continue; }
-    const size_t payload = st.vp8_bytes;
-    const size_t need = container ? 20 + payload + (payload & 1) : payload;
-    if (o.data == nullptr) {
-      o.data = (uint8_t*)malloc(need ? need : 1);
-      o.cap = need;
-      if (!o.data) { o.status = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; continue; }
-    } else if (o.cap < need) { o.status = ZW_ERR_OUTPUT_TOO_SMALL; o.len = need; continue; }
-    uint8_t* w = o.data;
-    if (container) {  // api.rs:1325-1329 + write_chunk :1232-1241
-      const u32 chunk = (u32)(payload + (payload & 1)) + 8;
-      const u32 riff = chunk + 4;
-      memcpy(w, "RIFF", 4); w[4] = (u8)riff; w[5] = (u8)(riff >> 8); w[6] = (u8)(riff >> 16); w[7] = (u8)(riff >> 24);
-      memcpy(w + 8, "WEBP", 4); memcpy(w + 12, "VP8 ", 4);
-      const u32 pl = (u32)payload;
-      w[16] = (u8)pl; w[17] = (u8)(pl >> 8); w[18] = (u8)(pl >> 16); w[19] = (u8)(pl >> 24);
-      w += 20;
-    }
-    memcpy(w, c->h_pinned + c->out_off[k], payload);
-    if (container && (payload & 1)) w[payload] = 0;
-    o.len = need;
-    o.status = ZW_OK;
+  for (int k = 0; k < c->active_lanes; k++) {
+    const size_t b = c->lane_begin[k], e = c->lane_begin[k + 1];
+    int rc = lane_download(c->lanes[k], outs + b, e - b, container);
+    if (rc != ZW_OK) return g_last_error = rc;
+    c->last.d2h_ms += c->lanes[k]->last.d2h_ms;
+    c->last.d2h_bytes += c->lanes[k]->last.d2h_bytes;
   }
   if (timing) *timing = c->last;
   return g_last_error = ZW_OK;
@@ -593,11 +721,8 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
     if (rc != ZW_OK) return rc;
     rc = zw_download(c, outs + i0, i1 - i0, container, nullptr);
     if (rc != ZW_OK) return rc;
-    const zw_timing& L = c->last;
-    acc.h2d_ms += L.h2d_ms; acc.yuv_ms += L.yuv_ms; acc.analysis_ms += L.analysis_ms; acc.pass1_ms += L.pass1_ms;
-    acc.stats_ms += L.stats_ms; acc.pass2_ms += L.pass2_ms; acc.token_ms += L.token_ms; acc.boolcode_ms += L.boolcode_ms;
-    acc.assemble_ms += L.assemble_ms; acc.d2h_ms += L.d2h_ms; acc.device_total_ms += L.device_total_ms;
-    acc.kernel_launches += L.kernel_launches; acc.h2d_bytes += L.h2d_bytes; acc.d2h_bytes += L.d2h_bytes; acc.pixels += L.pixels;
+    add_timing(acc, c->last);
+    acc.device_total_ms += c->last.device_total_ms;
     i0 = i1;
   }
   acc.wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -612,10 +737,15 @@ int zw_encode_webp_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality,
   return encode_batch(c, imgs, n, quality, method, outs, timing, 1);
 }
 
-int zw_dump_stage(zw_ctx* c, size_t index, const char* stage, void* dst, size_t cap, size_t* len) {
-  if (!c || !stage || !len) return g_last_error = ZW_ERR_INVALID_PARAM;
-  if (!c->staged || !c->encoded || index >= c->slot_of.size() || c->slot_of[index] < 0) return g_last_error = ZW_ERR_NOT_STAGED;
-  CK(cudaSetDevice(c->device));
+int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len) {
+  if (!ctx || !stage || !len) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (!ctx->staged || !ctx->encoded || index >= ctx->n_staged) return g_last_error = ZW_ERR_NOT_STAGED;
+  CK(cudaSetDevice(ctx->device));
+  int lk = 0;
+  while (lk + 1 < ctx->active_lanes && index >= ctx->lane_begin[lk + 1]) lk++;
+  Lane* c = ctx->lanes[lk];
+  index -= ctx->lane_begin[lk];
+  if (c->slot_of[index] < 0) return g_last_error = ZW_ERR_NOT_STAGED;
   const u32 k = (u32)c->slot_of[index];
   const ImageDesc& d = c->img[k];
   const size_t nmb = (size_t)d.mbw * d.mbh, ysz = nmb * 256, csz = nmb * 64;

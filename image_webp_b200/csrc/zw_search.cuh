@@ -1016,10 +1016,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
     const ImageDesc d = P.img[rr.img];
     const ImageState& IS = P.st[rr.img];
     const int mbw = d.mbw, mby = rr.mby;
-    const int pw = mbw * 16, cwid = mbw * 8;
+    const int pw = mbw * 16;
     const u8* yp = P.planes + d.y_off;
-    const u8* up = yp + (size_t)pw * d.mbh * 16;
-    const u8* vp = up + (size_t)cwid * d.mbh * 8;
     const u32 row_mb0 = d.mb_off + mby * mbw;
     const u32 up_mb0 = row_mb0 - mbw;  // only dereferenced when mby > 0
     CostCtx cc;
@@ -1029,9 +1027,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
 
     // row-start state (vp8.rs:1339-1344 / :1423-1429)
     u32 left_nz = 0;
-    u32 left_derr = 0;  // pass 2 resets it per row (:1425)
     if (lane < 17) W.left_y[lane] = 129;
-    if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
     __syncwarp();
 
     for (int mbx = 0; mbx < mbw; mbx++) {
@@ -1045,72 +1041,60 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
       const u32 gmb = row_mb0 + mbx;
       const int seg = seg_on ? P.segmap[gmb] : 0;
       const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
-      u32 top_nz = 0, top_derr = 0;
-      if (PASS == 2) {
-        if (mby > 0) {
-          top_nz = __ldcg(&P.nz_after[up_mb0 + mbx]);
-          top_derr = __ldcg(&P.derr2[up_mb0 + mbx]);
-        } else {
-          // Q4: top_derr is not reset between passes -> row 0 of pass 2 starts from pass 1's last row
-          top_derr = __ldcg(&P.derr1[d.mb_off + (d.mbh - 1) * mbw + mbx]);
-        }
-      }
+      u32 top_nz = 0;
+      if (PASS == 2 && mby > 0) top_nz = __ldcg(&P.nz_after[up_mb0 + mbx]);
       load_luma_mb(W, P, yp, pw, mbw, mbx, mby, up_mb0, lane);
-      if (PASS == 2) load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
-      for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;
+      for (int k = lane; k < 136; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;  // luma levels [0..16]
       __syncwarp();
 
       const LumaOut L = luma_mb(W, ptab, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane);
-      ChromaOut C;
-      C.uv_mode = 0; C.uvnz = 0;
       bool skip = false;
       u32 out_top = 0, out_left = 0;
       if (PASS == 2) {
-        C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
-        skip = !(L.simple_nz || C.uvnz != 0);
-        complexity_after(L.use_i4, skip, L.y2nz, L.ynz, C.uvnz, top_nz, left_nz, out_top, out_left);
+        // chroma of this macroblock was coded by k_chroma2 (it does not depend on luma)
+        const u32 uvnz = P.uvflags[gmb];
+        skip = !(L.simple_nz || uvnz != 0);
+        complexity_after(L.use_i4, skip, L.y2nz, L.ynz, uvnz, top_nz, left_nz, out_top, out_left);
       }
       if (lane == 0) {
         W.rec.ymode = L.use_i4 ? 4 : (u8)L.mode16;
-        W.rec.uvmode = (u8)C.uv_mode;
         W.rec.segment = (u8)seg;
         W.rec.skip = skip;
         if (PASS == 2) {
           W.rec.top_nz = (u16)top_nz;
           W.rec.left_nz = (u16)left_nz;
+          // chroma-owned header fields: keep what k_chroma2 stored
+          W.rec.uvmode = recs[gmb].uvmode;
+          *reinterpret_cast<u32*>(W.rec.derr_left) = *reinterpret_cast<const u32*>(recs[gmb].derr_left);
+          *reinterpret_cast<u32*>(W.rec.derr_top) = *reinterpret_cast<const u32*>(recs[gmb].derr_top);
         } else {
           // pass 1: luma flags parked here until k_chroma1 completes the record
+          W.rec.uvmode = 0;
           W.rec.top_nz = (u16)L.ynz;
           W.rec.left_nz = (u16)((L.y2nz ? 1 : 0) | (L.simple_nz ? 2 : 0));
+          *reinterpret_cast<u32*>(W.rec.derr_left) = 0;
+          *reinterpret_cast<u32*>(W.rec.derr_top) = 0;
         }
-        *reinterpret_cast<u32*>(W.rec.derr_left) = left_derr;
-        *reinterpret_cast<u32*>(W.rec.derr_top) = top_derr;
       }
       if (lane < 16) W.rec.bmodes[lane] = L.use_i4 ? W.bmodes[lane] : 0;
       __syncwarp();
-      if (PASS == 2 && skip) {  // the reference codes nothing for a skipped MB; keep the dump canonical
-        for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;
-        __syncwarp();
-      }
       {
+        // header (8 words) + luma levels (136 words); a skipped MB codes nothing: zero all 200 level words
         const u32* s = reinterpret_cast<const u32*>(&W.rec);
         u32* g = reinterpret_cast<u32*>(&recs[gmb]);
-        for (int k = lane; k < 208; k += 32) g[k] = s[k];
+        if (PASS == 2 && skip) {
+          for (int k = lane; k < 208; k += 32) g[k] = k < 8 ? s[k] : 0u;
+        } else {
+          const int nw = PASS == 1 ? 208 : 144;  // pass 1 also clears the chroma levels for k_chroma1
+          for (int k = lane; k < nw; k += 32) g[k] = (PASS == 1 && k >= 144) ? 0u : s[k];
+        }
       }
       left_nz = out_left;
       // borders for the neighbours
       if (lane < 17) W.left_y[lane] = W.yws[lane * 32 + 16];
       MbBottom* bo = &P.bottom[gmb];
       if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
-      if (PASS == 2) {
-        if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
-        if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
-        if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
-        if (lane == 0) {
-          P.nz_after[gmb] = (u16)out_top;
-          P.derr2[gmb] = top_derr;
-        }
-      }
+      if (PASS == 2 && lane == 0) P.nz_after[gmb] = (u16)out_top;
       __threadfence();
       __syncwarp();
       if (lane == 0) st_release(&progress[d.row_off + mby], mbx + 1);
@@ -1195,6 +1179,77 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_chroma1(ChunkParams P) {
       }
     }
     if (lane == 0) IS.n_skip1 = nskip;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass-2 chroma: wavefront over rows (pass 2 resets left_derr per row, so rows only depend on
+// the row above).  Runs BEFORE k_search<2>: chroma never depends on luma, while the luma kernel
+// needs the chroma non-zero flags for the skip decision and the complexity contexts.  Keeping
+// chroma out of the luma kernel also keeps both instruction working sets small.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_chroma2(ChunkParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  WarpScratch& W = SH.w[threadIdx.x >> 5];
+  int* progress = P.progress + 2 * P.n_rows;
+  for (;;) {
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(&P.ticket[3], 1u);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= P.n_rows) break;
+    const RowRef rr = P.rows[t];
+    const ImageDesc d = P.img[rr.img];
+    const ImageState& IS = P.st[rr.img];
+    const int mbw = d.mbw, mby = rr.mby, pw = mbw * 16, cwid = mbw * 8;
+    const u8* yp = P.planes + d.y_off;
+    const u8* up = yp + (size_t)pw * d.mbh * 16;
+    const u8* vp = up + (size_t)cwid * d.mbh * 8;
+    const u32 row_mb0 = d.mb_off + mby * mbw, up_mb0 = row_mb0 - mbw;
+    CostCtx cc;
+    cc.probs = P.probs + (size_t)rr.img * 1056;
+    cc.level_cost = P.lcost + (size_t)rr.img * 6528;
+    const bool seg_on = IS.seg_enabled != 0;
+    u32 left_derr = 0;  // reset per row in pass 2 (vp8.rs:1425)
+    if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
+    __syncwarp();
+    for (int mbx = 0; mbx < mbw; mbx++) {
+      if (mby > 0) {  // chroma needs the macroblock above only (no top-right)
+        if (lane == 0) {
+          while (ld_acquire(&progress[d.row_off + mby - 1]) < mbx + 1) __nanosleep(100);
+        }
+        __syncwarp();
+      }
+      const u32 gmb = row_mb0 + mbx;
+      const int seg = seg_on ? P.segmap[gmb] : 0;
+      const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
+      // Q4: top_derr is not reset between passes -> row 0 of pass 2 starts from pass 1's last row
+      u32 top_derr = mby > 0 ? __ldcg(&P.derr2[up_mb0 + mbx]) : __ldcg(&P.derr1[d.mb_off + (d.mbh - 1) * mbw + mbx]);
+      load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
+      const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
+      MbRecord* r = &P.rec2[gmb];
+      if (lane < 8) {
+        u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
+        const u32* s = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[k] = s[k];
+      }
+      if (lane == 0) {
+        r->uvmode = (u8)C.uv_mode;
+        *reinterpret_cast<u32*>(r->derr_left) = left_derr;
+        *reinterpret_cast<u32*>(r->derr_top) = top_derr;
+        P.derr2[gmb] = top_derr;
+        P.uvflags[gmb] = (u8)C.uvnz;
+      }
+      if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+      MbBottom* bo = &P.bottom[gmb];
+      if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
+      if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(&progress[d.row_off + mby], mbx + 1);
+    }
   }
 }
 

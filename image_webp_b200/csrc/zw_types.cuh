@@ -105,7 +105,8 @@ struct ChunkParams {
   u16* nz_after;     // [n_mb] top complexity left behind by each MB
   u32* derr1;        // [n_mb] packed top_derr after pass 1
   u32* derr2;        // [n_mb] same, pass 2
-  int* progress;     // [2][n_rows] macroblocks completed per row, per pass
+  u8* uvflags;       // [n_mb] pass-2 chroma has_coeffs bits (4 U | 4 V), k_chroma2 -> k_search<2>
+  int* progress;     // [3][n_rows] macroblocks completed per row: pass-1 luma, pass-2 luma, pass-2 chroma
   u32* ticket;       // [4] work counters
   u32* rowstats;     // [n_rows][1056][2] per-row (total, ones)
   u32* stats;        // [n_img][1056] packed ProbaStats

@@ -94,9 +94,11 @@ def _raise_for(status, lib):
 class Context:
     """One encoder context per (host thread, GPU) -- wraps zw_create / zw_destroy."""
 
-    def __init__(self, device=0, max_device_bytes=0, persistent_warps_per_sm=0):
+    def __init__(self, device=0, max_device_bytes=0, persistent_warps_per_sm=0, lanes=0):
         self.lib = _lib.load()
-        lim = _lib.ZwLimits(max_device_bytes, persistent_warps_per_sm, (C.c_int * 5)())
+        res = (C.c_int * 5)()
+        res[0] = lanes  # streams the context pipelines a chunk over (0 = library default)
+        lim = _lib.ZwLimits(max_device_bytes, persistent_warps_per_sm, res)
         self.h = self.lib.zw_create(device, C.byref(lim))
         if not self.h:
             code = self.lib.zw_last_error()
