@@ -359,12 +359,16 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
 }
 
 // Phase A: everything up to the symbol counts (asynchronous; ends with the D2H of ImageState).
-static int lane_encode_a(Lane* c, int quality, int method) {
+static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   c->encoded = false;
   c->launches = 0;
   if (c->n_valid == 0) return ZW_OK;
   const u32 ni = c->n_valid;
   cudaStream_t s = c->stream;
+  // Lanes run their wavefront kernels one after the other (two persistent kernels competing for the
+  // SMs only slow each other down); what overlaps is the previous lane's tokeniser / boolean coder /
+  // D2H and this lane's H2D copy.
+  if (after && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[7], 0));
   c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
   fill_params(c);
   ChunkParams& P = c->P;
@@ -663,7 +667,7 @@ int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
   c->base_qidx = quality_to_quant_index(quality);
   const int L = c->active_lanes;
   int rc;
-  for (int k = 0; k < L; k++) if ((rc = lane_encode_a(c->lanes[k], quality, method)) != ZW_OK) return g_last_error = rc;
+  for (int k = 0; k < L; k++) if ((rc = lane_encode_a(c->lanes[k], quality, method, k ? c->lanes[k - 1] : nullptr)) != ZW_OK) return g_last_error = rc;
   for (int k = 0; k < L; k++) if ((rc = lane_encode_b(c->lanes[k])) != ZW_OK) return g_last_error = rc;
   for (int k = 0; k < L; k++) if ((rc = lane_encode_finish(c->lanes[k])) != ZW_OK) return g_last_error = rc;
   // device span over all lanes: first "start" event to last "end" event
