@@ -547,8 +547,15 @@ __device__ __forceinline__ void bool_carry(u8* out, u32 pos, u32 cap) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_boolcode(ChunkParams P) {
-  const u32 sid = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per (image, partition) stream: the 32 lanes fetch 32 symbols with one coalesced load and
+// then all run the (strictly serial) range-coder recurrence in lock step on identical state -- no
+// divergence between different streams, symbol fetch latency off the critical path -- while lane 0
+// owns the output bytes.  Streams 0..n_img-1 are the token partitions, n_img..2n_img-1 the first
+// partitions.
+constexpr int BC_WARPS = 4;
+__global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
+  const int lane = threadIdx.x & 31;
+  const u32 sid = blockIdx.x * BC_WARPS + (threadIdx.x >> 5);
   if (sid >= 2 * P.n_img) return;
   const bool is_hdr = sid >= P.n_img;
   const u32 img = is_hdr ? sid - P.n_img : sid;
@@ -565,42 +572,37 @@ __global__ void __launch_bounds__(128) k_boolcode(ChunkParams P) {
   // write_bool (arithmetic.rs:67-95) with the bit-at-a-time renormalisation loop collapsed: the
   // `s` shifts a symbol needs are applied in at most two steps around the byte boundary.  Bits
   // reaching bit 31 are carries into the bytes already written (at most one per symbol).
-  const uint4* tk4 = reinterpret_cast<const uint4*>(tk);  // streams start 16-byte aligned
-  uint4 cur = n ? __ldg(tk4) : make_uint4(0, 0, 0, 0);
-  for (u32 i0 = 0; i0 < n; i0 += 8) {
-    const uint4 nxt = (i0 + 8 < n) ? __ldg(tk4 + (i0 >> 3) + 1) : make_uint4(0, 0, 0, 0);  // prefetch
-    const u32 w4[4] = {cur.x, cur.y, cur.z, cur.w};
-    const u32 cnt = n - i0 < 8 ? n - i0 : 8;
-#pragma unroll
-    for (u32 k = 0; k < 8; k++) {
-      if (k < cnt) {
-        const u32 t = (w4[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-        const u32 split = 1 + (((range - 1) * (t & 255)) >> 8);
-        if (t >> 8) { bottom += split; range -= split; } else { range = split; }
-        int s2 = __clz(range) - 24;  // shifts needed to bring range back to >= 128
-        if (s2 > 0) {
-          range <<= s2;
-          if (s2 >= bit_num) {  // a byte completes inside this renormalisation
-            if (bottom >> (32 - bit_num)) bool_carry(out, pos, cap);
-            bottom <<= bit_num;
-            if (pos < cap) out[pos] = (u8)(bottom >> 24); else overflow = true;
-            pos++;
-            bottom &= 0xffffffu;
-            s2 -= bit_num;
-            bit_num = 8;
-          }
-          if (s2 > 0) {
-            if (bottom >> (32 - s2)) bool_carry(out, pos, cap);
-            bottom <<= s2;
-            bit_num -= s2;
-          }
-        }
+  u32 mine = lane < n ? tk[lane] : 0;
+  for (u32 i0 = 0; i0 < n; i0 += 32) {
+    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
+    const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
+#pragma unroll 4
+    for (int k = 0; k < cnt; k++) {
+      const u32 t = __shfl_sync(FULL, mine, k);
+      const u32 split = 1 + (((range - 1) * (t & 255)) >> 8);
+      const bool bit = (t >> 8) != 0;
+      bottom += bit ? split : 0u;
+      range = bit ? range - split : split;
+      int s2 = __clz(range) - 24;  // shifts needed to bring range back to >= 128
+      range <<= s2;
+      if (s2 >= bit_num) {  // a byte completes inside this renormalisation (bit_num <= 7 here)
+        if (bottom >> (32 - bit_num)) { if (lane == 0) bool_carry(out, pos, cap); }
+        bottom <<= bit_num;
+        if (lane == 0) { if (pos < cap) out[pos] = (u8)(bottom >> 24); else overflow = true; }
+        pos++;
+        bottom &= 0xffffffu;
+        s2 -= bit_num;
+        bit_num = 8;
       }
+      const u64 w = (u64)bottom << s2;  // s2 may be 0
+      if ((u32)(w >> 32)) { if (lane == 0) bool_carry(out, pos, cap); }
+      bottom = (u32)w;
+      bit_num -= s2;
     }
-    cur = nxt;
+    mine = nxt;
   }
   // flush_and_get_buffer (arithmetic.rs:176-195)
-  {
+  if (lane == 0) {
     int c = bit_num;
     u32 v = bottom;
     if (bottom & (1u << (32 - bit_num))) bool_carry(out, pos, cap);
@@ -612,9 +614,9 @@ __global__ void __launch_bounds__(128) k_boolcode(ChunkParams P) {
       pos++;
       v <<= 8;
     }
+    if (is_hdr) IS.part0_bytes = pos; else IS.part1_bytes = pos;
+    if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
   }
-  if (is_hdr) IS.part0_bytes = pos; else IS.part1_bytes = pos;
-  if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
 }
 
 // ---------------------------------------------------------------------------------------------
