@@ -118,11 +118,31 @@ __device__ const u16 d_pred_tab[8][16] = ZW_PRED_TABLE_INIT;
 // One out-of-line copy of the (fully unrolled) lane-private residual cost: the kernels are
 // instruction-cache bound, so the three call sites share it.  Levels travel in registers.
 struct Lv16 { i32 v[16]; };
+// Rolled loop on purpose (the levels sit in local memory, L1-resident): ~16x less code than the
+// unrolled form, same arithmetic as residual_cost() in zw_cost.cuh.
 __device__ __noinline__ u32 residual_cost_ol(Lv16 L, int ctype, int first, int ctx0, const u8* probs, const u16* level_cost) {
-  CostCtx cc;
-  cc.probs = probs;
-  cc.level_cost = level_cost;
-  return residual_cost(L.v, ctype, first, ctx0, cc);
+  int last = -1;
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    if (L.v[i] != 0) last = i;
+  const u8* pp = probs + ctype * (8 * 3 * 11);
+  const u32 p0 = pp[(ZW_TAB(kEncBands)[first] * 3 + ctx0) * 11];
+  if (last < 0) return bit_cost(0, p0);
+  u32 cost = ctx0 == 0 ? bit_cost(1, p0) : 0;
+  int ctx = ctx0;
+  const u16* lc = level_cost ? level_cost + ctype * (8 * 3 * 68) : nullptr;
+#pragma unroll 1
+  for (int n = first; n <= last; n++) {
+    const int v = iabs(L.v[n]);
+    cost += ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
+    if (lc) cost += lc[(ZW_TAB(kEncBands)[n] * 3 + ctx) * 68 + imin(v, 67)];
+    ctx = v >= 2 ? 2 : v;
+  }
+  if (last < 15) {
+    const int v = iabs(L.v[last]);
+    cost += bit_cost(0, pp[(ZW_TAB(kEncBands)[last + 1] * 3 + (v == 1 ? 1 : 2)) * 11]);
+  }
+  return cost;
 }
 __device__ __forceinline__ u32 residual_cost_call(const i32* lv, int ctype, int first, int ctx0, const CostCtx& cc) {
   Lv16 L;
