@@ -357,8 +357,11 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
   } else {
     P00 = 0; P11 = 0; P01 = T_INF; P10 = T_INF;  // identity
   }
-#pragma unroll
-  for (int d = 1; d < 16; d <<= 1) {
+  // Hillis-Steele inclusive scan; positions beyond `last` are never read, so log2(last+1) steps do
+  // (rolled loop, bound uniform across the warp: keeps the code small and skips dead steps)
+  const int span = max(last, __shfl_xor_sync(FULL, last, 16));
+#pragma unroll 1
+  for (int d = 1; d <= span; d <<= 1) {
     const i64 L00 = shfl_up64_16(P00, d), L01 = shfl_up64_16(P01, d), L10 = shfl_up64_16(P10, d), L11 = shfl_up64_16(P11, d);
     if (n >= d) {
       const i64 n00 = tmin(L00 + P00, L01 + P10);
@@ -392,7 +395,7 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
       best = tmin(best, key);
     }
   }
-#pragma unroll
+#pragma unroll 1
   for (int o = 8; o > 0; o >>= 1) best = tmin(best, shfl_xor64(best, o));
   const int bidx = (int)(best & 31);
   const bool have = (best >> 5) < skip_score;  // arithmetic shift == floor division by 32
@@ -400,12 +403,9 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
   // unwind (uniform per half-warp): delta mask of the chosen path
   u32 dm = 0;
   {
-    const u32 low = best_n >= 0 ? ((2u << best_n) - 1u) : 0u;
-    bpm0 &= low;
-    bpm1 = (bpm1 & low) | (0xffffu & ~low);  // identity above best_n
     int dl = bidx & 1;
-#pragma unroll
-    for (int k = 15; k >= 0; k--) {
+#pragma unroll 1
+    for (int k = best_n; k >= first; k--) {
       dm |= (u32)dl << k;
       dl = (int)(((dl ? bpm1 : bpm0) >> k) & 1);
     }
