@@ -207,6 +207,8 @@ struct zw_ctx {
   std::vector<size_t> lane_begin;  // image ranges of the staged chunk: lane k owns [lane_begin[k], lane_begin[k+1])
   size_t n_staged = 0;
   int active_lanes = 0;
+  int resident_lanes = 1;  // lanes used by zw_stage_batch (inputs already resident: nothing to overlap)
+  int batch_lanes = 1;     // lanes used by the host-buffer batch entry points
   bool staged = false, encoded = false;
   int base_qidx = 0;
   zw_timing last;
@@ -365,10 +367,10 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   if (c->n_valid == 0) return ZW_OK;
   const u32 ni = c->n_valid;
   cudaStream_t s = c->stream;
-  // Lanes run their wavefront kernels one after the other (two persistent kernels competing for the
-  // SMs only slow each other down); what overlaps is the previous lane's tokeniser / boolean coder /
-  // D2H and this lane's H2D copy.
-  if (after && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[7], 0));
+  // Lanes run their kernels strictly one after the other (measured: concurrent persistent kernels
+  // only slow each other down); what overlaps is this lane's H2D copy with the previous lane's
+  // kernels, and the previous lane's D2H with this lane's kernels.
+  if (after && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[10], 0));
   c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
   fill_params(c);
   ChunkParams& P = c->P;
@@ -589,10 +591,12 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
   c->budget = (limits && limits->max_device_bytes) ? limits->max_device_bytes : ((size_t)32 << 30);
   int warps_hint = limits ? limits->persistent_warps_per_sm : 0;
   if (const char* env = getenv("ZW_WARPS_PER_SM")) warps_hint = atoi(env);
-  int n_lanes = limits ? limits->reserved[0] : 0;  // reserved[0]: number of lanes (0 = default)
+  int n_lanes = limits ? limits->reserved[0] : 0;  // reserved[0]: lanes of the host-buffer batch path (0 = default 2)
   if (const char* env = getenv("ZW_LANES")) n_lanes = atoi(env);
-  if (n_lanes <= 0) n_lanes = 1;  // measured: >1 lane does not help while the wavefront kernels are persistent and fill the SMs
+  if (n_lanes <= 0) n_lanes = 1;  // measured on B200: extra lanes cost more (tails, per-lane syncs) than the copy overlap returns
   n_lanes = std::min(n_lanes, 8);
+  c->batch_lanes = n_lanes;
+  if (const char* env = getenv("ZW_RESIDENT_LANES")) c->resident_lanes = std::max(1, std::min(atoi(env), n_lanes));
   // constant tables
   std::vector<SegParams> segtab(128);
   for (int i = 0; i < 128; i++) segtab[i] = make_segparams(i);
@@ -625,13 +629,13 @@ void zw_destroy(zw_ctx* c) {
   delete c;
 }
 
-int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
+static int stage_internal(zw_ctx* c, const zw_image* imgs, size_t n, int use_lanes) {
   if (!c || (!imgs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
   if (n > 65535 * c->lanes.size()) return g_last_error = ZW_ERR_INVALID_PARAM;  // grid.y / grid.z limit per lane
   CK(cudaSetDevice(c->device));
   c->staged = false; c->encoded = false;
   // split the chunk between the lanes by pixel count (contiguous image ranges)
-  const int L = (int)std::max<size_t>(1, std::min<size_t>(c->lanes.size(), n / 2 > 0 ? n / 2 : 1));
+  const int L = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(c->lanes.size(), (size_t)use_lanes), n / 2 > 0 ? n / 2 : 1));
   u64 total_px = 0;
   for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
   c->lane_begin.assign(L + 1, n);
@@ -657,6 +661,10 @@ int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
   return g_last_error = ZW_OK;
 }
 
+int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
+  return stage_internal(c, imgs, n, c ? c->resident_lanes : 1);
+}
+
 int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
   if (!c) return g_last_error = ZW_ERR_INVALID_PARAM;
   if (!c->staged) return g_last_error = ZW_ERR_NOT_STAGED;
@@ -667,8 +675,10 @@ int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
   c->base_qidx = quality_to_quant_index(quality);
   const int L = c->active_lanes;
   int rc;
-  for (int k = 0; k < L; k++) if ((rc = lane_encode_a(c->lanes[k], quality, method, k ? c->lanes[k - 1] : nullptr)) != ZW_OK) return g_last_error = rc;
-  for (int k = 0; k < L; k++) if ((rc = lane_encode_b(c->lanes[k])) != ZW_OK) return g_last_error = rc;
+  for (int k = 0; k < L; k++) {
+    if ((rc = lane_encode_a(c->lanes[k], quality, method, k ? c->lanes[k - 1] : nullptr)) != ZW_OK) return g_last_error = rc;
+    if ((rc = lane_encode_b(c->lanes[k])) != ZW_OK) return g_last_error = rc;
+  }
   for (int k = 0; k < L; k++) if ((rc = lane_encode_finish(c->lanes[k])) != ZW_OK) return g_last_error = rc;
   // device span over all lanes: first "start" event to last "end" event
   zw_timing T = zw_timing();
@@ -719,7 +729,8 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
       if (i1 > i0 && bytes + f > c->budget) break;
       bytes += f; i1++;
     }
-    int rc = zw_stage_batch(c, imgs + i0, i1 - i0);
+    // host-buffer path: two lanes so that the second half's H2D copy hides behind the first half's kernels
+    int rc = stage_internal(c, imgs + i0, i1 - i0, (i1 - i0) >= 16 ? c->batch_lanes : 1);
     if (rc != ZW_OK) return rc;
     rc = zw_encode_resident(c, quality, method, nullptr);
     if (rc != ZW_OK) return rc;

@@ -42,8 +42,9 @@ typedef struct zw_ctx zw_ctx;
 typedef struct zw_limits {
   size_t max_device_bytes; /* working-set budget per chunk of a batch; 0 = default (32 GiB)     */
   int persistent_warps_per_sm; /* 0 = default; tuning knob of the wavefront kernels            */
-  int reserved[5];         /* reserved[0]: number of lanes (streams) a chunk is pipelined over;
-                              0 = default (1).  Others must be 0.                               */
+  int reserved[5];         /* reserved[0]: lanes (streams) the host-buffer batch entry points split a
+                              chunk over so H2D/D2H copies hide behind kernels; 0 = default (1).
+                              Others must be 0.                                                  */
 } zw_limits;
 
 /* One input image: caller-owned, tightly packed rows (stride = width * bpp), host memory
