@@ -374,15 +374,17 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
   fill_params(c);
   ChunkParams& P = c->P;
-  CK(cudaEventRecord(c->ev[2], s));
+  CK(cudaEventRecord(c->ev[13], s));
   CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
   CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
   CK(cudaMemsetAsync(c->d_progress.p, 0, (size_t)c->n_rows * 3 * sizeof(int), s));
   CK(cudaMemsetAsync(c->d_ticket.p, 0, 64, s));
+  CK(cudaEventRecord(c->ev[2], s));  // yuv_ms times k_yuv alone; device_total_ms starts at ev[13]
   {  // (1) RGB -> YUV420
-    dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + YUV_ROWPAIRS * 2 - 1) / (YUV_ROWPAIRS * 2), ni);
+    const int rows_per_cta = YUV_ROWPAIRS * YUV_STEPS * 2;
+    dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + rows_per_cta - 1) / rows_per_cta, ni);
     dim3 block(YUV_THREADS, YUV_ROWPAIRS);
-    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * ((YUV_TILE_W * 4 + 32) / 16) * 16;
+    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * YUV_ROW_SLOTS * 16;
     k_yuv<<<grid, block, sm, s>>>(P);
     c->launches++;
   }
@@ -482,7 +484,7 @@ static int lane_encode_finish(Lane* c) {
   cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[2], c->ev[10]); T.device_total_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[13], c->ev[10]); T.device_total_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms = ms;
   T.kernel_launches = c->launches;
   c->last = T;
@@ -689,7 +691,7 @@ int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
     for (int b = 0; b < L; b++) {
       if (c->lanes[b]->n_valid == 0) continue;
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, c->lanes[a]->ev[2], c->lanes[b]->ev[10]) == cudaSuccess) span = std::max(span, ms);
+      if (cudaEventElapsedTime(&ms, c->lanes[a]->ev[13], c->lanes[b]->ev[10]) == cudaSuccess) span = std::max(span, ms);
     }
   }
   T.device_total_ms = span;

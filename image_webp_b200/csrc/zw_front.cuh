@@ -10,35 +10,43 @@ namespace zw {
 //     (rgb_to_y :859, rgb_to_u/v_avg :866-886, raw :889-899), 16-bit fixed point, 2x2 box
 //     average with edge duplication, replicate padding to 16*mbw x 16*mbh.
 //
-// One CTA converts a strip of 2 source rows x YUV_TILE_W pixels.  The packed RGB bytes of both rows
-// are staged in shared memory with 128-bit loads (3 B/px is never 16-byte aligned per pixel, so
-// threads pick their pixels out of the staged span); each thread then produces an 8x2 luma patch
-// (two 64-bit stores) and 4 U + 4 V samples (two 32-bit stores).  HBM-bound: 3 B/px read,
-// 1.5 B/px written.
+// One warp converts a strip of 2 source rows x YUV_TILE_W pixels per step (8 warps per CTA, 2 steps).
+// The packed RGB bytes of both rows are staged in shared memory with 128-bit loads (3 B/px is never
+// 16-byte aligned per pixel, so threads pick their pixels out of the staged span); each thread then
+// produces an 8x2 luma patch (two 64-bit stores) and 4 U + 4 V samples (two 32-bit stores).
+// HBM-bound: 3 B/px read, 1.5 B/px written.
 // ---------------------------------------------------------------------------------------------
-constexpr int YUV_TILE_W = 512;                 // luma pixels per CTA strip
-constexpr int YUV_THREADS = YUV_TILE_W / 8;     // 64 threads, 8 px each
-constexpr int YUV_ROWPAIRS = 4;                 // row pairs per CTA (blockDim.y)
+constexpr int YUV_TILE_W = 256;                 // luma pixels per CTA strip
+constexpr int YUV_THREADS = YUV_TILE_W / 8;     // 32 threads (one warp) per row pair, 8 px each
+constexpr int YUV_ROWPAIRS = 8;                 // row pairs per CTA step (blockDim.y)
+constexpr int YUV_STEPS = 2;                    // steps per CTA: 32 source rows x 256 px = 36 KB of RGB per CTA
+constexpr int YUV_ROW_SLOTS = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row (RGBA worst case + skew)
 
 __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P) {
   const ImageDesc d = P.img[blockIdx.z];
   const int pw = d.mbw * 16, ph = d.mbh * 16;
   const int x0 = blockIdx.x * YUV_TILE_W;
-  const int rp = blockIdx.y * YUV_ROWPAIRS + threadIdx.y;  // row pair index in the padded plane
-  if (x0 >= pw || blockIdx.y * YUV_ROWPAIRS * 2 >= ph) return;
+  if (x0 >= pw || (int)blockIdx.y * YUV_ROWPAIRS * YUV_STEPS * 2 >= ph) return;
   const int w = d.width, h = d.height, bpp = d.bpp;
   const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
   // span of source columns this strip needs (always non-empty: x0 < w because padding < 16)
   const int xs = x0, xe = min(x0 + YUV_TILE_W, w);
   const int span_bytes = (xe - xs) * bpp;
   extern __shared__ uint4 smem4[];
-  const int row_slots = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row
   u8* sm = reinterpret_cast<u8*>(smem4);
-  const bool active = rp * 2 < ph;
-  const int ccy = min(rp, chh - 1);
-  const int rowA = 2 * ccy, rowB = min(2 * ccy + 1, h - 1);
-  int skew[2] = {0, 0};
-  if (active) {
+  u8* yp = P.planes + d.y_off;
+  u8* up = yp + (size_t)pw * ph;
+  u8* vp = up + (size_t)(pw >> 1) * (ph >> 1);
+  const int tx = x0 + threadIdx.x * 8;
+  // every warp (threadIdx.y) owns its two staged rows: no CTA-wide barrier, just __syncwarp
+  uint4* stage = smem4 + (threadIdx.y * 2) * YUV_ROW_SLOTS;
+#pragma unroll 1
+  for (int step = 0; step < YUV_STEPS; step++) {
+    const int rp = (blockIdx.y * YUV_STEPS + step) * YUV_ROWPAIRS + threadIdx.y;  // row pair in the padded plane
+    if (rp * 2 >= ph) break;
+    const int ccy = min(rp, chh - 1);
+    const int rowA = 2 * ccy, rowB = min(2 * ccy + 1, h - 1);
+    int skew[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
@@ -46,49 +54,82 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
       skew[r] = (int)((d.rgb_off + byte0) - al);
       const int nvec = (skew[r] + span_bytes + 15) >> 4;
       const uint4* src = reinterpret_cast<const uint4*>(P.rgb + al);
-      uint4* dst = smem4 + (threadIdx.y * 2 + r) * row_slots;
+      uint4* dst = stage + r * YUV_ROW_SLOTS;
       for (int i = threadIdx.x; i < nvec; i += YUV_THREADS) dst[i] = __ldg(src + i);
     }
-  }
-  __syncthreads();
-  if (!active) return;
-  const u8* sA = sm + (size_t)(threadIdx.y * 2 + 0) * row_slots * 16 + skew[0];
-  const u8* sB = sm + (size_t)(threadIdx.y * 2 + 1) * row_slots * 16 + skew[1];
-  const int tx = x0 + threadIdx.x * 8;
-  if (tx >= pw) return;
-  // luma rows 2rp and 2rp+1: source rows min(2rp,h-1) and min(2rp+1,h-1)
-  const bool lumaA_is_A = (rp <= chh - 1);  // else row h-1 == rowB
-  u8* yp = P.planes + d.y_off;
-  u8* up = yp + (size_t)pw * ph;
-  u8* vp = up + (size_t)(pw >> 1) * (ph >> 1);
-  u32 y0w[2] = {0, 0}, y1w[2] = {0, 0}, uw = 0, vw = 0;
+    __syncwarp();
+    if (tx < pw) {
+      const u8* sA = sm + (size_t)(threadIdx.y * 2 + 0) * YUV_ROW_SLOTS * 16 + skew[0];
+      const u8* sB = sm + (size_t)(threadIdx.y * 2 + 1) * YUV_ROW_SLOTS * 16 + skew[1];
+      // luma rows 2rp and 2rp+1: source rows min(2rp,h-1) and min(2rp+1,h-1)
+      const bool lumaA_is_A = (rp <= chh - 1);  // else row h-1 == rowB
+      u32 y0w[2] = {0, 0}, y1w[2] = {0, 0}, uw = 0, vw = 0;
+      if (bpp == 3 && tx + 8 <= w && 2 * rp + 1 < h) {
+        // interior fast path: the thread's 8 pixels of both rows are 24 contiguous bytes each; fetch
+        // them as 32-bit words (7 per row, funnel-shifted to byte alignment) instead of 96 byte loads
+        u32 a[2][6];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int sx = min(tx + k, w - 1) - xs;
-    const u8* pa = (lumaA_is_A ? sA : sB) + sx * bpp;
-    const u8* pb = sB + sx * bpp;
-    const int ya = (16839 * pa[0] + 33059 * pa[1] + 6420 * pa[2] + 32768 + (16 << 16)) >> 16;
-    const int yb = (16839 * pb[0] + 33059 * pb[1] + 6420 * pb[2] + 32768 + (16 << 16)) >> 16;
-    y0w[k >> 2] |= (u32)ya << (8 * (k & 3));
-    y1w[k >> 2] |= (u32)yb << (8 * (k & 3));
-  }
+        for (int r = 0; r < 2; r++) {
+          const u8* base = r == 0 ? sA : sB;
+          const u32 o = (u32)(base - sm) + 24u * threadIdx.x;
+          const u32* wp = reinterpret_cast<const u32*>(sm) + (o >> 2);
+          const u32 sh = (o & 3u) * 8u;
+          u32 wv[7];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int ccx = min((tx >> 1) + k, cw - 1);
-    const int c0 = 2 * ccx - xs, c1 = min(2 * ccx + 1, w - 1) - xs;
-    const u8 *p1 = sA + c0 * bpp, *p2 = sA + c1 * bpp, *p3 = sB + c0 * bpp, *p4 = sB + c1 * bpp;
-    const int r = p1[0] + p2[0] + p3[0] + p4[0];
-    const int g = p1[1] + p2[1] + p3[1] + p4[1];
-    const int b = p1[2] + p2[2] + p3[2] + p4[2];
-    const int u = (-9719 * r - 19081 * g + 28800 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
-    const int v = (28800 * r - 24116 * g - 4684 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
-    uw |= (u32)u << (8 * k);
-    vw |= (u32)v << (8 * k);
+          for (int k = 0; k < 7; k++) wv[k] = wp[k];
+#pragma unroll
+          for (int k = 0; k < 6; k++) a[r][k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+        }
+        auto byte_at = [&](int r, int j) -> int { return (int)((a[r][j >> 2] >> (8 * (j & 3))) & 255u); };
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int ya = (16839 * byte_at(0, 3 * k) + 33059 * byte_at(0, 3 * k + 1) + 6420 * byte_at(0, 3 * k + 2) + 32768 + (16 << 16)) >> 16;
+          const int yb = (16839 * byte_at(1, 3 * k) + 33059 * byte_at(1, 3 * k + 1) + 6420 * byte_at(1, 3 * k + 2) + 32768 + (16 << 16)) >> 16;
+          y0w[k >> 2] |= (u32)ya << (8 * (k & 3));
+          y1w[k >> 2] |= (u32)yb << (8 * (k & 3));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int r = byte_at(0, 6 * k) + byte_at(0, 6 * k + 3) + byte_at(1, 6 * k) + byte_at(1, 6 * k + 3);
+          const int g = byte_at(0, 6 * k + 1) + byte_at(0, 6 * k + 4) + byte_at(1, 6 * k + 1) + byte_at(1, 6 * k + 4);
+          const int b = byte_at(0, 6 * k + 2) + byte_at(0, 6 * k + 5) + byte_at(1, 6 * k + 2) + byte_at(1, 6 * k + 5);
+          const int u = (-9719 * r - 19081 * g + 28800 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+          const int v = (28800 * r - 24116 * g - 4684 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+          uw |= (u32)u << (8 * k);
+          vw |= (u32)v << (8 * k);
+        }
+      } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int sx = min(tx + k, w - 1) - xs;
+        const u8* pa = (lumaA_is_A ? sA : sB) + sx * bpp;
+        const u8* pb = sB + sx * bpp;
+        const int ya = (16839 * pa[0] + 33059 * pa[1] + 6420 * pa[2] + 32768 + (16 << 16)) >> 16;
+        const int yb = (16839 * pb[0] + 33059 * pb[1] + 6420 * pb[2] + 32768 + (16 << 16)) >> 16;
+        y0w[k >> 2] |= (u32)ya << (8 * (k & 3));
+        y1w[k >> 2] |= (u32)yb << (8 * (k & 3));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int ccx = min((tx >> 1) + k, cw - 1);
+        const int c0 = 2 * ccx - xs, c1 = min(2 * ccx + 1, w - 1) - xs;
+        const u8 *p1 = sA + c0 * bpp, *p2 = sA + c1 * bpp, *p3 = sB + c0 * bpp, *p4 = sB + c1 * bpp;
+        const int r = p1[0] + p2[0] + p3[0] + p4[0];
+        const int g = p1[1] + p2[1] + p3[1] + p4[1];
+        const int b = p1[2] + p2[2] + p3[2] + p4[2];
+        const int u = (-9719 * r - 19081 * g + 28800 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+        const int v = (28800 * r - 24116 * g - 4684 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
+        uw |= (u32)u << (8 * k);
+        vw |= (u32)v << (8 * k);
+      }
+      }
+      *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp) * pw + tx) = make_uint2(y0w[0], y0w[1]);
+      *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp + 1) * pw + tx) = make_uint2(y1w[0], y1w[1]);
+      *reinterpret_cast<u32*>(up + (size_t)rp * (pw >> 1) + (tx >> 1)) = uw;
+      *reinterpret_cast<u32*>(vp + (size_t)rp * (pw >> 1) + (tx >> 1)) = vw;
+    }
+    __syncwarp();
   }
-  *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp) * pw + tx) = make_uint2(y0w[0], y0w[1]);
-  *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp + 1) * pw + tx) = make_uint2(y1w[0], y1w[1]);
-  *reinterpret_cast<u32*>(up + (size_t)rp * (pw >> 1) + (tx >> 1)) = uw;
-  *reinterpret_cast<u32*>(vp + (size_t)rp * (pw >> 1) + (tx >> 1)) = vw;
 }
 
 // ---------------------------------------------------------------------------------------------
