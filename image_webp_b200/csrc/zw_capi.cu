@@ -293,7 +293,7 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
 }
 
 // Validate + lay out + start the H2D copies of one lane's images (asynchronous on its stream).
-static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
+static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after) {
   c->staged = false; c->encoded = false;
   c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
   u64 rgb_bytes = 0, plane_bytes = 0, key = 1469598103934665603ull;
@@ -347,6 +347,9 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
     c->layout_key = key;
   }
   CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
+  // copies of consecutive lanes go one after the other over the link (sharing it would only delay
+  // the first lane's kernels); the second lane's copy then runs under the first lane's kernels
+  if (copy_after && copy_after->n_valid) CK(cudaStreamWaitEvent(c->stream, copy_after->ev[1], 0));
   CK(cudaEventRecord(c->ev[0], c->stream));
   for (size_t i = 0; i < n; i++) {
     if (c->slot_of[i] < 0) continue;
@@ -656,7 +659,7 @@ static int stage_internal(zw_ctx* c, const zw_image* imgs, size_t n, int use_lan
   for (int k = 0; k < L; k++) {
     const size_t b = c->lane_begin[k], e = c->lane_begin[k + 1];
     if (e - b > 65535) return g_last_error = ZW_ERR_INVALID_PARAM;
-    int rc = lane_stage(c->lanes[k], imgs + b, e - b);
+    int rc = lane_stage(c->lanes[k], imgs + b, e - b, k ? c->lanes[k - 1] : nullptr);
     if (rc != ZW_OK) return g_last_error = rc;
   }
   c->staged = true;
