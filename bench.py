@@ -26,9 +26,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, QUALITY, METHOD = 768, 512, 75, 4
 WORKLOAD = "batch of %d x 768x512 RGB, q75 method 4"
-# algorithmic HBM bytes per pixel of the dominant kernel (pass-2 search): read Y+U+V planes
-# (1.5 B/px) + write one 832-byte macroblock record per 256 px (3.25 B/px).  DESIGN.md §Roofline.
-SEARCH_BYTES_PER_PX = 1.5 + 832.0 / 256.0
+# algorithmic HBM bytes per pixel of the dominant kernel (pass-2 luma search k_search<2>): read the Y
+# plane (1 B/px) + write the 32-byte header and 17 luma blocks (544 B) of one macroblock record per
+# 256 px (2.25 B/px).  DESIGN.md §Measurement.
+SEARCH_BYTES_PER_PX = 1.0 + 576.0 / 256.0  # luma kernel: Y plane read + header and luma part of the record written
 
 
 def rank_env():
@@ -200,7 +201,7 @@ def main():
         t = ctx.encode_resident(params)
         dev_ms += t["device_total_ms"]
         launches += t["kernel_launches"]
-        for k in ("yuv_ms", "analysis_ms", "pass1_ms", "stats_ms", "pass2_ms", "token_ms", "boolcode_ms", "assemble_ms"):
+        for k in ("yuv_ms", "analysis_ms", "pass1_ms", "chroma1_ms", "stats_ms", "chroma2_ms", "pass2_ms", "token_ms", "boolcode_ms", "assemble_ms"):
             stage_ms[k] = stage_ms.get(k, 0.0) + t[k]
     barrier()
     wall_kernel_s = time.perf_counter() - t0
@@ -243,9 +244,19 @@ def main():
     if rank == 0:
         peaks, how = measured_peaks()
         dom = max(("pass1_ms", "pass2_ms", "boolcode_ms", "token_ms", "stats_ms", "yuv_ms", "analysis_ms"), key=lambda k: stage_ms[k])
-        dom_s = stage_ms["pass2_ms"] / args.steps / 1e3
+        dom_s = stage_ms["pass2_ms"] / args.steps / 1e3   # k_search<2> alone (CUDA events around that launch)
         achieved = pix * SEARCH_BYTES_PER_PX / dom_s / 1e9
         yuv_s = stage_ms["yuv_ms"] / args.steps / 1e3
+        traffic = traffic_yuv = None
+        try:  # DRAM bytes per pixel from the committed ncu --set full capture (profiles/r1_traffic.json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+            for kname, v in tj.items():
+                if "k_search<(int)2>" in kname:
+                    traffic = v["dram_bytes_per_pixel"] * pix
+                if "k_yuv" in kname:
+                    traffic_yuv = v["dram_bytes_per_pixel"] * pix
+        except Exception:
+            pass
         line = {
             "metric": "lossy encode MPix/s (q75 m4, byte-identical)", "value": value, "unit": "MPix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
@@ -257,11 +268,11 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_search<2> (pass-2 mode search + transform)", "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                          "peak_source": how, "ms_per_launch": 1e3 * dom_s,
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md and profiles/ for the ALU pipe figures"},
             "roofline_yuv": {"bound": "hbm", "kernel": "k_yuv", "achieved": pix * 4.5 / yuv_s / 1e9, "peak": peaks["hbm_gbs"],
-                             "unit": "GB/s", "frac": pix * 4.5 / yuv_s / 1e9 / peaks["hbm_gbs"], "ms_per_launch": 1e3 * yuv_s},
+                             "unit": "GB/s", "frac": pix * 4.5 / yuv_s / 1e9 / peaks["hbm_gbs"], "ms_per_launch": 1e3 * yuv_s, "traffic": traffic_yuv},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "dominant_stage": dom,
             "kernel_wall_ms_per_step": 1e3 * wall_kernel_s / args.steps,

@@ -407,6 +407,7 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   {  // (3) pass 1: luma wavefront, then the chroma chain
     const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    CK(cudaEventRecord(c->ev[15], s));
     const int g3 = (int)std::min<u64>((u64)c->chroma_blocks, ((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     c->launches += 2;
@@ -421,6 +422,7 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   {  // (3') pass 2: chroma wavefront first (independent of luma), then the luma wavefront
     const int g4 = (int)std::min<u64>((u64)c->chroma2_blocks, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    CK(cudaEventRecord(c->ev[14], s));
     const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_search<2><<<g2, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     c->launches += 2;
@@ -481,9 +483,11 @@ static int lane_encode_finish(Lane* c) {
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); T.pass1_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[15]); T.pass1_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[15], c->ev[5]); T.chroma1_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); T.stats_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); T.pass2_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[14]); T.chroma2_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[14], c->ev[7]); T.pass2_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms = ms;
@@ -554,7 +558,7 @@ static int lane_download(Lane* c, zw_output* outs, size_t n, int container) {
 static void add_timing(zw_timing& a, const zw_timing& L) {
   a.h2d_ms += L.h2d_ms; a.yuv_ms += L.yuv_ms; a.analysis_ms += L.analysis_ms; a.pass1_ms += L.pass1_ms;
   a.stats_ms += L.stats_ms; a.pass2_ms += L.pass2_ms; a.token_ms += L.token_ms; a.boolcode_ms += L.boolcode_ms;
-  a.assemble_ms += L.assemble_ms; a.d2h_ms += L.d2h_ms;
+  a.assemble_ms += L.assemble_ms; a.d2h_ms += L.d2h_ms; a.chroma1_ms += L.chroma1_ms; a.chroma2_ms += L.chroma2_ms;
   a.kernel_launches += L.kernel_launches; a.h2d_bytes += L.h2d_bytes; a.d2h_bytes += L.d2h_bytes; a.pixels += L.pixels;
 }
 

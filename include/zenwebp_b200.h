@@ -76,6 +76,8 @@ typedef struct zw_timing {
   uint64_t kernel_launches;
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t pixels;
+  float chroma1_ms, chroma2_ms; /* pass-1 chroma chain / pass-2 chroma wavefront (pass1_ms and
+                                   pass2_ms time the luma wavefront kernels alone)             */
 } zw_timing;
 
 /* Create / destroy an encoder context bound to one CUDA device.  One context per (host thread,

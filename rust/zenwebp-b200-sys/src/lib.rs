@@ -20,6 +20,7 @@ pub struct zw_timing {
     pub h2d_ms: f32, pub yuv_ms: f32, pub analysis_ms: f32, pub pass1_ms: f32, pub stats_ms: f32, pub pass2_ms: f32,
     pub token_ms: f32, pub boolcode_ms: f32, pub assemble_ms: f32, pub d2h_ms: f32, pub device_total_ms: f32, pub wall_ms: f32,
     pub kernel_launches: u64, pub h2d_bytes: u64, pub d2h_bytes: u64, pub pixels: u64,
+    pub chroma1_ms: f32, pub chroma2_ms: f32,
 }
 
 pub const ZW_COLOR_RGB8: u32 = 2;
