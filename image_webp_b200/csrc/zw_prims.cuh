@@ -261,5 +261,34 @@ ZW_HD i32 predict4_pixel(const u8* e, int mode, int k, const u16 (*tab)[16]) {
   return avg3(e[t & 15], e[(t >> 4) & 15], e[(t >> 8) & 15]);
 }
 
+// The same predictors as two-level lookups (used by the cooperative I4 search in zw_search.cuh):
+// the pixels of the eight directional modes take only 23 distinct 3-tap values of the edges;
+// ZW_DTAPS_INIT[k] = taps (a | b << 4 | c << 8) of value k = (e[a] + 2 e[b] + e[c] + 2) >> 2,
+// slot 23 holds the DC prediction, ZW_PRED_IDX_INIT[mode][pixel] selects the slot.
+#define ZW_DTAPS_INIT                                                                                          \
+  {528, 801, 1074, 1347, 1620, 1893, 2166, 2439, 2712, 2985, 3258, 3275, 256, 16, 289, 562,                    \
+   835, 1108, 1381, 1654, 1927, 2200, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define ZW_PRED_IDX_INIT                                                                \
+  {                                                                                     \
+    {23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23}, /* DC */          \
+    {23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23, 23}, /* TM: computed */ \
+    {4, 5, 6, 7, 4, 5, 6, 7, 4, 5, 6, 7, 4, 5, 6, 7},                 /* VE */          \
+    {2, 2, 2, 2, 1, 1, 1, 1, 0, 0, 0, 0, 12, 12, 12, 12},             /* HE */          \
+    {5, 6, 7, 8, 6, 7, 8, 9, 7, 8, 9, 10, 8, 9, 10, 11},              /* LD */          \
+    {3, 4, 5, 6, 2, 3, 4, 5, 1, 2, 3, 4, 0, 1, 2, 3},                 /* RD */          \
+    {17, 18, 19, 20, 3, 4, 5, 6, 2, 17, 18, 19, 1, 3, 4, 5},          /* VR */          \
+    {18, 19, 20, 21, 5, 6, 7, 8, 19, 20, 21, 9, 6, 7, 8, 10},         /* VL */          \
+    {16, 3, 4, 5, 15, 2, 16, 3, 14, 1, 15, 2, 13, 0, 14, 1},          /* HD */          \
+    {15, 1, 14, 0, 14, 0, 13, 12, 13, 12, 22, 22, 22, 22, 22, 22},    /* HU */          \
+  }
+// Host-checkable statement of the lookup form (tests/hostcheck compares it with predict4_pixel).
+ZW_HD i32 predict4_pixel_lut(const u8* e, int mode, int k, const u16* dtaps, const u8 (*pidx)[16]) {
+  if (mode == 1) return clip255((i32)e[3 - (k >> 2)] - (i32)e[4] + (i32)e[5 + (k & 3)]);
+  const int slot = pidx[mode][k];
+  if (slot == 23) return (4 + e[5] + e[6] + e[7] + e[8] + e[0] + e[1] + e[2] + e[3]) >> 3;
+  const u32 t = dtaps[slot];
+  return avg3(e[t & 15], e[(t >> 4) & 15], e[(t >> 8) & 15]);
+}
+
 }  // namespace zw
 #endif  // ZW_PRIMS_CUH

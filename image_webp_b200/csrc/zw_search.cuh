@@ -50,12 +50,14 @@ struct __align__(16) WarpScratch {
   u32 psse[10];         // I4 search: prediction SSE per mode
   u8 cand_mode[12];     // I4 search: mode with rank r
   u8 bmodes[16];
+  u8 dtab[32];       // I4: the 23 distinct 3-tap edge filters of the current sub-block + its DC ([23])
   u8 nzflag[32];     // per-block non-zero flags (scratch)
   MbRecord rec;      // staged record
 };
 
 struct SearchShared {
-  u16 pred_tab[8][16];
+  u8 pred_idx[10][16];  // (mode, pixel) -> index into WarpScratch::dtab
+  u16 dtaps[32];        // lane k -> the three edge taps of dtab[k]
   WarpScratch w[SEARCH_WARPS];
 };
 
@@ -72,7 +74,21 @@ __device__ __forceinline__ i64 shfl64(i64 v, int src) {
   int hi = __shfl_sync(FULL, (int)(v >> 32), src);
   return (i64)(((u64)(u32)hi << 32) | (u64)(u32)lo);
 }
-__device__ __forceinline__ int red16_add(int v) {  // sum over each aligned group of 16 lanes
+// Sums over aligned groups of 16 / 8 lanes: one redux.sync per group mask (integer adds: exact).
+__device__ __forceinline__ unsigned lane_id() {
+  unsigned l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+#ifdef ZW_USE_REDUX
+__device__ __forceinline__ int red16_add(int v) {
+  return __reduce_add_sync(0xffffu << (lane_id() & 16), v);
+}
+__device__ __forceinline__ int red8_add(int v) {
+  return __reduce_add_sync(0xffu << (lane_id() & 24), v);
+}
+#else  // measured on B200: redux.sync on sub-warp masks is slower than the xor-shuffle butterfly
+__device__ __forceinline__ int red16_add(int v) {
   v += __shfl_xor_sync(FULL, v, 8);
   v += __shfl_xor_sync(FULL, v, 4);
   v += __shfl_xor_sync(FULL, v, 2);
@@ -85,6 +101,7 @@ __device__ __forceinline__ int red8_add(int v) {
   v += __shfl_xor_sync(FULL, v, 1);
   return v;
 }
+#endif
 
 // 16x16 / 8x8 whole-block predictors evaluated per pixel from the bordered work buffer
 // (predict_vpred/hpred/dcpred/tmpred, prediction.rs:164-324).  mode: 0 DC 1 V 2 H 3 TM.
@@ -113,7 +130,14 @@ __device__ __forceinline__ void pred_block(const u8* ws, int cofs, int mode, int
   }
 }
 
-__device__ const u16 d_pred_tab[8][16] = ZW_PRED_TABLE_INIT;
+// 4x4 predictors (prediction.rs:326-554) as lookups.  Every pixel of the eight directional modes
+// is one of 23 distinct 3-tap filters (x + 2y + z + 2) >> 2 of the 13 edge pixels
+// e[0..12] = L3 L2 L1 L0 P A0..A7 (avg2(x,y) == taps (x,y,x); a copy == taps (x,x,x)): lane k
+// evaluates filter k once per sub-block into WarpScratch::dtab, [23] holds the DC value, and a
+// predicted pixel is dtab[d_pred_idx[mode][pixel]] (TM is computed per pixel).
+// Same values as predict4_pixel() / ZW_PRED_TABLE_INIT in zw_prims.cuh (checked by tests/hostcheck).
+__device__ const u16 d_dtaps[32] = ZW_DTAPS_INIT;
+__device__ const u8 d_pred_idx[10][16] = ZW_PRED_IDX_INIT;
 
 // One out-of-line copy of the (fully unrolled) lane-private residual cost: the kernels are
 // instruction-cache bound, so the three call sites share it.  Levels travel in registers.
@@ -151,31 +175,30 @@ __device__ __forceinline__ u32 residual_cost_call(const i32* lv, int ctype, int 
   return residual_cost_ol(L, ctype, first, ctx0, cc.probs, cc.level_cost);
 }
 
-// One pixel of 4x4 predictor `mode` read straight from the bordered work buffer (same taps as
-// predict4_pixel in zw_prims.cuh, without staging the 13 edge pixels in registers).
-__device__ __forceinline__ i32 pred4_px(const u8* yws, int x0, int y0, int mode, int n, const u16 (*tab)[16]) {
-  const u8* top = yws + (y0 - 1) * 32 + x0;   // top[-1] = P, top[0..7] = A0..A7
-  const u8* left = yws + y0 * 32 + x0 - 1;    // left[32*i] = L_i
-  if (mode == 0) {
-    const i32 v = 4 + top[0] + top[1] + top[2] + top[3] + left[0] + left[32] + left[64] + left[96];
-    return v >> 3;
-  }
-  if (mode == 1) return clip255((i32)left[32 * (n >> 2)] - (i32)top[-1] + (i32)top[n & 3]);
-  const u32 t = tab[mode - 2][n];
-  const int i0 = t & 15, i1 = (t >> 4) & 15, i2 = (t >> 8) & 15;
-  const i32 e0 = i0 < 4 ? left[32 * (3 - i0)] : top[i0 - 5];
-  const i32 e1 = i1 < 4 ? left[32 * (3 - i1)] : top[i1 - 5];
-  const i32 e2 = i2 < 4 ? left[32 * (3 - i2)] : top[i2 - 5];
-  return (e0 + 2 * e1 + e2 + 2) >> 2;
+// Per sub-block set-up of the predictor lookups: gathers the 13 edge pixels (one per lane), fills
+// W.dtab and returns this lane's DC / TM predictions (n = lane & 15 is the lane's pixel).
+struct Pred4 {
+  i32 dc, tm;
+};
+__device__ __forceinline__ Pred4 pred4_prepare(WarpScratch& W, int x0, int y0, u32 taps, int lane) {
+  // lane k < 4: L(3-k) = yws[(y0+3-k)][x0-1]; k = 4: P; k = 5..12: A(k-5) on the row above
+  const int k = imin(lane, 12);
+  const int off = k < 4 ? (y0 + 3 - k) * 32 + x0 - 1 : (y0 - 1) * 32 + x0 - 5 + k;
+  const i32 e = W.yws[off];
+  const i32 a = __shfl_sync(FULL, e, taps & 15), b = __shfl_sync(FULL, e, (taps >> 4) & 15), c = __shfl_sync(FULL, e, (taps >> 8) & 15);
+  const bool in_dc = lane < 4 || (lane >= 5 && lane < 9);
+  Pred4 r;
+  r.dc = (__reduce_add_sync(FULL, in_dc ? e : 0) + 4) >> 3;
+  W.dtab[lane] = (u8)(lane == 23 ? r.dc : ((a + 2 * b + c + 2) >> 2));
+  const int n = lane & 15;
+  const i32 l = __shfl_sync(FULL, e, 3 - (n >> 2)), t = __shfl_sync(FULL, e, 5 + (n & 3)), p = __shfl_sync(FULL, e, 4);
+  r.tm = clip255(l + t - p);
+  __syncwarp();
+  return r;
 }
-
-__device__ __forceinline__ void fetch_edges4(const u8* yws, int x0, int y0, u8* e) {
-  e[0] = yws[(y0 + 3) * 32 + x0 - 1];
-  e[1] = yws[(y0 + 2) * 32 + x0 - 1];
-  e[2] = yws[(y0 + 1) * 32 + x0 - 1];
-  e[3] = yws[(y0 + 0) * 32 + x0 - 1];
-#pragma unroll
-  for (int k = 0; k < 9; k++) e[4 + k] = yws[(y0 - 1) * 32 + x0 - 1 + k];
+__device__ __forceinline__ i32 pred4_get(const WarpScratch& W, const u8 (*pidx)[16], int mode, int n, const Pred4& p) {
+  const i32 v = W.dtab[pidx[mode][n]];
+  return mode == 1 ? p.tm : v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,11 +263,7 @@ __device__ __forceinline__ i32 coop_idct(i32 v, int lane) {
 }
 
 __device__ __forceinline__ int half_sum(int v) {  // sum over the 16 lanes of each half-warp
-  v += __shfl_xor_sync(FULL, v, 8);
-  v += __shfl_xor_sync(FULL, v, 4);
-  v += __shfl_xor_sync(FULL, v, 2);
-  v += __shfl_xor_sync(FULL, v, 1);
-  return v;
+  return red16_add(v);
 }
 
 // residual_cost with one level per lane (natural order n = lane & 15).  Uniform per half-warp.
@@ -489,10 +508,11 @@ struct LumaOut {
   bool simple_nz;  // any SIMPLE-quantised luma level non-zero (skip test, Q13)
 };
 
-__device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParams& SP, const CostCtx& cc, int method,
+__device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegParams& SP, const CostCtx& cc, int method,
                            bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane) {
   LumaOut R;
   const int hb = lane >> 4, blk = lane & 15, bx = blk & 3, by = blk >> 2;
+  const u8(*pidx)[16] = SH.pred_idx;
   // ===== pick_best_intra16 (vp8.rs:1504-1681) =====
   int dc16;
   {
@@ -604,6 +624,9 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     use_i4 = true;
     const int max_modes = method <= 3 ? 3 : (method == 4 ? 4 : 10);
     const int n16 = lane & 15;
+    const u32 taps = SH.dtaps[lane];
+    // table indices of this lane's pixel for the modes 2r + hb of SSE steps r = 1..4, one per byte
+    const u32 pk = (u32)pidx[2 + hb][n16] | ((u32)pidx[4 + hb][n16] << 8) | ((u32)pidx[6 + hb][n16] << 16) | ((u32)pidx[8 + hb][n16] << 24);
     u64 running = 211ull * (u64)SP.lambda_mode;
     u32 total_mode_cost = 0;
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
@@ -614,28 +637,31 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
       const int left_ctx = sbx == 0 ? 0 : W.bmodes[i - 1];
       const int ctx0 = (sby == 0 ? 0 : (int)((tnz4 >> sbx) & 1)) + (sbx == 0 ? 0 : (int)((lnz4 >> sby) & 1));
       const i32 srcpx = W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)];
-      // prediction SSE of the ten modes, two modes per step
-#pragma unroll 1
-      for (int r = 0; r < 5; r++) {
-        const int m = 2 * r + hb;
-        const i32 df = srcpx - pred4_px(W.yws, x0, y0, m, n16, ptab);
-        const int sse = half_sum(df * df);
-        if (n16 == 0) W.psse[m] = (u32)sse;
-      }
-      __syncwarp();
-      // stable ascending rank by prediction SSE (sort_unstable_by_key is an insertion sort here, Q11)
-      if (lane < 10) {
-        const u32 mine = W.psse[lane];
-        int rank = 0;
+      const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
+      // prediction SSE of the ten modes, two modes per step; lane m < 10 ends up with the sort key
+      // (sse << 4 | m) of mode m: ascending key order == stable ascending SSE order
+      // (sort_unstable_by_key is an insertion sort at this length, Q11)
+      {
+        const i32 d0 = srcpx - (hb ? P4.tm : P4.dc);
+        const int s0 = half_sum(d0 * d0);
+        if (n16 == 0) W.psse[hb] = (u32)s0;
 #pragma unroll
-        for (int o = 0; o < 10; o++) {
-          const u32 os = W.psse[o];
-          rank += (os < mine) || (os == mine && o < lane);
+        for (int r = 1; r < 5; r++) {
+          const i32 df = srcpx - (i32)W.dtab[(pk >> (8 * (r - 1))) & 255];
+          const int sse = half_sum(df * df);
+          if (n16 == 0) W.psse[2 * r + hb] = (u32)sse;
         }
-        W.cand_mode[rank] = (u8)lane;
       }
       __syncwarp();
-      // evaluate the best `max_modes` candidates in rank order, two per step
+      u32 skey = lane < 10 ? ((W.psse[lane] << 4) | (u32)lane) : 0xffffffffu;
+#pragma unroll 1
+      for (int r = 0; r < max_modes; r++) {  // extract the `max_modes` smallest keys in order
+        const u32 kmin = __reduce_min_sync(FULL, skey);
+        if (skey == kmin) { skey = 0xffffffffu; W.cand_mode[r] = (u8)lane; }
+      }
+      __syncwarp();
+      // evaluate the best `max_modes` candidates in rank order, two per step; each half-warp keeps
+      // the best of its own candidates (the rank in the key makes keys unique: min == first best)
       u64 best_key = ~0ull;
       u32 best_sse = 0, best_rate = 0;
       int best_nz = 0;
@@ -644,7 +670,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
         const int rank = r + hb;
         const bool act = rank < max_modes;
         const int m = W.cand_mode[act ? rank : 0];
-        const i32 pr = pred4_px(W.yws, x0, y0, m, n16, ptab);
+        const i32 pr = pred4_get(W, pidx, m, n16, P4);
         const i32 cf = coop_fdct(srcpx - pr, lane);
         const i32 q = quantize_coeff(cf, SP.y1, n16);
         bool nz;
@@ -659,14 +685,13 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
         const u32 rate = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m] + coeff_cost;
         const u64 score = (u64)sse * 256ull + (u64)(rate & 0xffffu) * (u64)SP.lambda_i4;  // u16 truncation (Q8)
         const u64 key = act ? ((score << 4) | (u64)rank) : ~0ull;
-        // both halves in rank order; strict < keeps the earlier candidate on ties
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          const u64 k2 = (u64)shfl64((i64)key, hh * 16);
-          const u32 s2 = __shfl_sync(FULL, sse, hh * 16), r2 = __shfl_sync(FULL, rate, hh * 16);
-          const int z2 = __shfl_sync(FULL, (int)nz, hh * 16);
-          if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
-        }
+        if (key < best_key) { best_key = key; best_sse = sse; best_rate = rate; best_nz = (int)nz; }
+      }
+      {  // merge the two halves
+        const u64 k2 = (u64)shfl_xor64((i64)best_key, 16);
+        const u32 s2 = __shfl_xor_sync(FULL, best_sse, 16), r2 = __shfl_xor_sync(FULL, best_rate, 16);
+        const int z2 = __shfl_xor_sync(FULL, best_nz, 16);
+        if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
       }
       __syncwarp();
       const int wrank = (int)(best_key & 15);
@@ -820,10 +845,12 @@ __device__ LumaOut luma_mb(WarpScratch& W, const u16 (*ptab)[16], const SegParam
     u32 tnz = (in_top_nz >> 1) & 15, lnz = (in_left_nz >> 1) & 15;
     bool simple_any = false;
     const int n16 = lane & 15;
+    const u32 taps = SH.dtaps[lane];
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
-      const i32 pr = pred4_px(W.yws, x0, y0, W.bmodes[i], n16, ptab);
+      const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
+      const i32 pr = pred4_get(W, pidx, W.bmodes[i], n16, P4);
       const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane);
       simple_any |= quantize_coeff(cf, SP.y1, n16) != 0;
       __syncwarp();
@@ -1017,11 +1044,11 @@ template <int PASS>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_search(ChunkParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) (&SH.pred_tab[0][0])[i] = (&d_pred_tab[0][0])[i];
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
+  if (threadIdx.x < 32) SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   WarpScratch& W = SH.w[threadIdx.x >> 5];
-  const u16(*ptab)[16] = SH.pred_tab;
   int* progress = P.progress + (PASS - 1) * P.n_rows;
   MbRecord* recs = PASS == 1 ? P.rec1 : P.rec2;
   const bool trellis = (PASS == 2) && P.do_trellis;
@@ -1067,7 +1094,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
       for (int k = lane; k < 136; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;  // luma levels [0..16]
       __syncwarp();
 
-      const LumaOut L = luma_mb(W, ptab, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane);
+      const LumaOut L = luma_mb(W, SH, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane);
       bool skip = false;
       u32 out_top = 0, out_left = 0;
       if (PASS == 2) {

@@ -6,12 +6,15 @@
 #include "../../image_webp_b200/csrc/zw_cost.cuh"
 using namespace zw;
 static const u16 kPredTab[8][16] = ZW_PRED_TABLE_INIT;
+static const u16 kDTaps[32] = ZW_DTAPS_INIT;
+static const u8 kPredIdx[10][16] = ZW_PRED_IDX_INIT;
 extern "C" {
 void hc_fdct(i32* b) { fdct4x4(b); }
 void hc_idct(i32* b) { idct4x4(b); }
 void hc_wht(i32* b) { wht4x4(b); }
 void hc_iwht(i32* b) { iwht4x4(b); }
 int hc_ttransform(const i32* px) { return t_transform16(px, host::kWeightY); }
+void hc_predict4_lut(const u8* e, int mode, u8* out) { for (int k = 0; k < 16; k++) out[k] = (u8)predict4_pixel_lut(e, mode, k, kDTaps, kPredIdx); }
 void hc_predict4(const u8* e, int mode, u8* out) { for (int k = 0; k < 16; k++) out[k] = (u8)predict4_pixel(e, mode, k, kPredTab); }
 static Matrix mk(const u16* q, const u32* iq, const u32* bias) { Matrix m; for (int i = 0; i < 2; i++) { m.q[i] = q[i]; m.iq[i] = iq[i]; m.bias[i] = bias[i]; } return m; }
 int hc_quantize(int coeff, const u16* q, const u32* iq, const u32* bias, int pos) { return quantize_coeff(coeff, mk(q, iq, bias), pos); }

@@ -76,6 +76,9 @@ def test_predictors_match_oracle():
             out = (C.c_uint8 * 16)()
             H.hc_predict4(e.ctypes.data_as(C.c_void_p), m, out)
             assert list(out) == list(allp[m * 16:(m + 1) * 16]), m
+            out2 = (C.c_uint8 * 16)()  # the two-level lookup form the cooperative I4 search uses
+            H.hc_predict4_lut(e.ctypes.data_as(C.c_void_p), m, out2)
+            assert list(out2) == list(allp[m * 16:(m + 1) * 16]), ("lut", m)
 
 
 def test_ttransform_matches_oracle_tdisto():
