@@ -547,6 +547,7 @@ __device__ __forceinline__ void bool_carry(u8* out, u32 pos, u32 cap) {
   }
 }
 
+#ifdef ZW_BOOLCODE_SERIAL
 // One WARP per (image, partition) stream: the 32 lanes fetch 32 symbols with one coalesced load and
 // then all run the (strictly serial) range-coder recurrence in lock step on identical state -- no
 // divergence between different streams, symbol fetch latency off the critical path -- while lane 0
@@ -618,6 +619,145 @@ __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
     if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
   }
 }
+
+#else
+// One WARP per (image, partition) stream.  Streams 0..n_img-1 are the token partitions,
+// n_img..2n_img-1 the first partitions.
+//
+// The coder is split into its strictly serial part and a parallel part.  write_bool
+// (arithmetic.rs:67-95) does, per symbol, `bottom += bit ? split : 0; bottom <<= s` with
+// split = 1 + (((range - 1) * prob) >> 8) and s = the renormalisation shift of the new range:
+//   * (range, split, s) depend only on the previous range and the symbol -- a short dependent
+//     chain (multiply, shift, select, count-leading-zeros, shift) that all lanes run in lock step
+//     over the 32 symbols the warp fetched with one coalesced load;
+//   * `bottom` with its carries is a long binary number: symbol k contributes its 8-bit `split`
+//     with the most significant bit at stream bit P_k = s_0 + .. + s_(k-1) (byte 0 = stream bits
+//     0..7: the initial bit_num = 24 aligns the first addend with the first byte).  Lane k adds its
+//     symbol's contribution into a shared-memory window of 16-bit cells, the cells are carry-
+//     normalised with a ballot-based carry look-ahead, completed cells are flushed as bytes and the
+//     window slides.  A carry out of the window ripples into bytes already written exactly like
+//     add_one_to_output (arithmetic.rs:47-60).
+// The flush (arithmetic.rs:176-195) emits the pending bits and pads to pos + 4 bytes, where
+// pos = 0 if T < 24 else 1 + (T - 24) / 8 for T total shifts: the first pos + 4 bytes of the number.
+constexpr int BC_WARPS = 4;
+__global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
+  __shared__ u32 s_cells[BC_WARPS][32];
+  __shared__ u32 s_range[BC_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 sid = blockIdx.x * BC_WARPS + warp;
+  if (sid >= 2 * P.n_img) return;
+  const bool is_hdr = sid >= P.n_img;
+  const u32 img = is_hdr ? sid - P.n_img : sid;
+  const ImageDesc d = P.img[img];
+  ImageState& IS = P.st[img];
+  const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
+  const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
+  u8* out = P.part_bytes + d.part_off + (is_hdr ? 0 : d.p0_cap);  // partition scratch: [first | token]
+  const u32 cap = is_hdr ? d.p0_cap : d.p1_cap;
+  u32* cells = s_cells[warp];
+  u32* rsave = s_range[warp];
+  cells[lane] = 0;
+  __syncwarp();
+  u32 range = 255;  // uniform across the warp
+  u32 T = 0;        // total renormalisation shifts so far == stream bit of the next addend's MSB
+  u32 base = 0;     // stream bit of cell 0 (multiple of 16); base / 8 bytes are already written
+  bool overflow = false;
+  u32 mine = lane < n ? tk[lane] : 0;
+  for (u32 i0 = 0; i0 < n; i0 += 32) {
+    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
+    const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
+    // ---- serial part: the range recurrence; lane 0 parks the range each symbol starts from ----
+    if (cnt == 32) {
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        const u32 t = __shfl_sync(FULL, mine, k);
+        if (lane == 0) rsave[k] = range;
+        const u32 x = ((range - 1) * (t & 255)) >> 8;  // split - 1
+        const u32 r2 = (t >> 8) ? range - 1 - x : x + 1;
+        range = r2 << (__clz(r2) - 24);
+      }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < cnt; k++) {
+        const u32 t = __shfl_sync(FULL, mine, k);
+        if (lane == 0) rsave[k] = range;
+        const u32 x = ((range - 1) * (t & 255)) >> 8;
+        const u32 r2 = (t >> 8) ? range - 1 - x : x + 1;
+        range = r2 << (__clz(r2) - 24);
+      }
+    }
+    __syncwarp();
+    // ---- parallel part: lane k redoes symbol k from its parked range ----
+    u32 add = 0, sh = 0;
+    if (lane < cnt) {
+      const u32 r = rsave[lane];
+      const u32 x = ((r - 1) * (mine & 255)) >> 8;
+      const bool bit = (mine >> 8) != 0;
+      const u32 r2 = bit ? r - 1 - x : x + 1;
+      add = bit ? x + 1 : 0;
+      sh = (u32)(__clz(r2) - 24);
+    }
+    u32 incl = sh;  // inclusive prefix sum of the shifts
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const u32 v = __shfl_up_sync(FULL, incl, dlt);
+      if (lane >= dlt) incl += v;
+    }
+    const u32 total = __shfl_sync(FULL, incl, 31);
+    if (add) {
+      const u32 o = T + incl - sh - base;  // window offset of the addend's MSB
+      const u32 c = o >> 4, b = o & 15;
+      const u32 f = add << (24 - b);       // two-cell field: cell c in the high half, c + 1 in the low half
+      atomicAdd(&cells[c], f >> 16);
+      if (f & 0xffffu) atomicAdd(&cells[c + 1], f & 0xffffu);
+    }
+    T += total;
+    __syncwarp();
+    // ---- carry normalisation: cell c keeps 16 bits, the excess moves to cell c - 1 ----
+    const u32 v = cells[lane];
+    const u32 from_next = __shfl_down_sync(FULL, v >> 16, 1);
+    const u32 v1 = (v & 0xffffu) + (lane < 31 ? from_next : 0u);  // <= 0xffff + 31
+    // look-ahead on the reversed cell order (bit i <-> cell 31 - i) so that carries move up
+    const u32 G = __brev(__ballot_sync(FULL, v1 > 0xffffu)), Pm = __brev(__ballot_sync(FULL, v1 == 0xffffu));
+    const u64 sum = (u64)Pm + ((u64)G << 1);
+    const u32 cin = ((u32)sum ^ Pm);  // carry into reversed position i
+    const u32 my_cin = (cin >> (31 - lane)) & 1;
+    const u32 fin = (v1 + my_cin) & 0xffffu;
+    // carry out of cell 0 (reversed position 31): generated there or propagated through it
+    u32 carry0 = (__shfl_sync(FULL, v, 0) >> 16) + (u32)((sum >> 32) & 1);
+    if (lane == 0) {
+      for (; carry0 > 0; carry0--) bool_carry(out, base >> 3, cap);
+    }
+    // ---- flush the cells no later symbol can reach (only carries can, through bool_carry) ----
+    const u32 nf = (T - base) >> 4;
+    if ((u32)lane < nf) {
+      const u32 bp = (base >> 3) + 2 * lane;
+      if (bp + 1 < cap) { out[bp] = (u8)(fin >> 8); out[bp + 1] = (u8)fin; } else overflow = true;
+    }
+    const u32 moved = __shfl_sync(FULL, fin, (lane + nf) & 31);
+    __syncwarp();
+    cells[lane] = (lane + nf < 32) ? moved : 0u;
+    base += 16 * nf;
+    __syncwarp();
+    mine = nxt;
+  }
+  // flush_and_get_buffer (arithmetic.rs:176-195): the first pos + 4 bytes of the number
+  const u32 pos = T < 24 ? 0u : 1u + (T - 24) / 8;
+  const u32 total_bytes = pos + 4;
+  {
+    const u32 fin = cells[lane];  // already normalised
+    const u32 bp = (base >> 3) + 2 * lane;
+    if (bp < total_bytes) { if (bp < cap) out[bp] = (u8)(fin >> 8); else overflow = true; }
+    if (bp + 1 < total_bytes) { if (bp + 1 < cap) out[bp + 1] = (u8)fin; else overflow = true; }
+  }
+  overflow = __any_sync(FULL, overflow);
+  if (lane == 0) {
+    if (is_hdr) IS.part0_bytes = total_bytes; else IS.part1_bytes = total_bytes;
+    if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
+  }
+}
+
+#endif  // ZW_BOOLCODE_SERIAL
 
 // ---------------------------------------------------------------------------------------------
 // (6) Assembly: frame tag + start code + dimensions + first partition + token partition, packed

@@ -30,6 +30,9 @@ constexpr int SEARCH_WARPS = 4;  // warps per CTA (each independent)
 #ifndef ZW_SEARCH_MIN_BLOCKS
 #define ZW_SEARCH_MIN_BLOCKS 6   // CTAs per SM the wavefront kernels are register-budgeted for
 #endif
+#ifndef ZW_EXP_ROUNDS
+#define ZW_EXP_ROUNDS 2
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 constexpr i64 I64_MAX = 0x7fffffffffffffffLL;
 
@@ -542,7 +545,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
   u32 best16_cc = 0, best16_mc = 0, best16_d = 0;
   i32 best16_sd = 0;
 #pragma unroll 1
-  for (int round = 0; round < 2; round++) {
+  for (int round = 0; round < ZW_EXP_ROUNDS; round++) {
     const int mode = round * 2 + hb;  // 0 DC, 1 V, 2 H, 3 TM (MODES order, vp8.rs:1509)
     const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
     i32 c[16], pr[16];
