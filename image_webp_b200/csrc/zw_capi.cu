@@ -173,11 +173,11 @@ struct DevBuf {
 struct Lane {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[16], ev2[2];
   const SegParams* segtab = nullptr;  // shared constant tables (owned by the context)
   const u8* lut = nullptr;
   DevBuf d_img, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
-      d_derr1, d_derr2, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
+      d_derr1, d_derr2, d_c1, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
       d_part, d_out, d_outoff;
   std::vector<ImageDesc> img;
   std::vector<ImageState> st;
@@ -191,7 +191,7 @@ struct Lane {
   u64 layout_key = 0;
   bool staged = false, encoded = false;
   int quality = -1, method = -1, base_qidx = 0;
-  int search_blocks1 = 0, search_blocks2 = 0, chroma_blocks = 0, chroma2_blocks = 0;
+  int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0;
   u64 launches = 0;
   dim3 tok_grid;
   ChunkParams P;
@@ -224,7 +224,7 @@ static void fill_params(Lane* c) {
   P.alpha_hist = c->d_alpha_hist.as<u32>(); P.map256 = c->d_map256.as<u8>();
   P.alpha = c->d_alpha.as<u8>(); P.segmap = c->d_segmap.as<u8>();
   P.rec1 = c->d_rec1.as<MbRecord>(); P.rec2 = c->d_rec2.as<MbRecord>(); P.bottom = c->d_bottom.as<MbBottom>();
-  P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>(); P.uvflags = c->d_uvflags.as<u8>();
+  P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>(); P.c1info = c->d_c1.as<u32>(); P.uvflags = c->d_uvflags.as<u8>();
   P.progress = c->d_progress.as<int>(); P.ticket = c->d_ticket.as<u32>(); P.rowstats = c->d_rowstats.as<u32>();
   P.stats = c->d_stats.as<u32>(); P.probs = c->d_probs.as<u8>(); P.lcost = c->d_lcost.as<u16>();
   P.mb_hdr_cnt = c->d_hcnt.as<u32>(); P.mb_tok_cnt = c->d_tcnt.as<u32>();
@@ -248,7 +248,7 @@ static size_t image_footprint(u32 w, u32 h, u32 bpp) {
   const size_t mbw = (w + 15) / 16, mbh = (h + 15) / 16, nmb = mbw * mbh;
   size_t b = (size_t)w * h * bpp + 64;        // RGB
   b += nmb * 384;                              // planes
-  b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8);
+  b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8 + 8);
   b += mbh * (2112 * 4 + 8 + 8);               // row statistics, progress, row table
   b += 1056 * 7 + 6528 * 2 + 2048;             // per-image tables
   b += nmb * 256 * 10 + nmb * 256;             // token streams (estimate: 5 symbols/px) + bitstream
@@ -258,13 +258,15 @@ static size_t image_footprint(u32 w, u32 h, u32 bpp) {
 static void lane_destroy(Lane* c) {
   if (!c) return;
   DevBuf* all[] = {&c->d_img, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
-                   &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_uvflags, &c->d_progress,
+                   &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_c1, &c->d_uvflags, &c->d_progress,
                    &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_htok,
                    &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
   for (DevBuf* b : all) b->release();
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto& ev : c->ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev2) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
+
   delete c;
 }
 
@@ -275,20 +277,19 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   c->lut = ctx->d_lut.as<u8>();
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
+  for (auto& ev : c->ev2) cudaEventCreate(&ev);
   if (c->d_ticket.reserve(64) != cudaSuccess) { lane_destroy(c); return nullptr; }
-  int b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+  int b1 = 0, b2 = 0, b4 = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_chroma1, SEARCH_WARPS * 32, sizeof(SearchShared));
   if (warps_hint > 0) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
-    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b3 = std::min(b3, cap); b4 = std::min(b4, cap);
+    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b4 = std::min(b4, cap);
   }
   c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
   c->search_blocks1 = std::max(1, b1) * ctx->sm_count;
   c->search_blocks2 = std::max(1, b2) * ctx->sm_count;
-  c->chroma_blocks = std::max(1, b3) * ctx->sm_count;
   return c;
 }
 
@@ -330,7 +331,7 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after)
   CK(c->d_alpha.reserve(n_mb)); CK(c->d_segmap.reserve(n_mb));
   CK(c->d_rec1.reserve((size_t)n_mb * sizeof(MbRecord))); CK(c->d_rec2.reserve((size_t)n_mb * sizeof(MbRecord)));
   CK(c->d_bottom.reserve((size_t)n_mb * sizeof(MbBottom))); CK(c->d_nz.reserve((size_t)n_mb * 2));
-  CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4)); CK(c->d_uvflags.reserve(n_mb));
+  CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4)); CK(c->d_c1.reserve((size_t)n_mb * 8)); CK(c->d_uvflags.reserve(n_mb));
   CK(c->d_progress.reserve((size_t)n_rows * 3 * sizeof(int))); CK(c->d_rowstats.reserve((size_t)n_rows * 2112 * 4));
   CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
   CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
@@ -404,13 +405,17 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
     c->launches++;
   }
   CK(cudaEventRecord(c->ev[4], s));
-  {  // (3) pass 1: luma wavefront, then the chroma chain
+  {  // (3) pass 1: luma wavefront, then the per-image chroma chains, then the bookkeeping.  (Running the
+     // chains on a side stream UNDER the wavefront was measured: they starve -- 43 ms instead of 8.8 ms,
+     // instruction-cache contention with the wavefront's code -- so the kernels stay back to back.)
     const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     CK(cudaEventRecord(c->ev[15], s));
-    const int g3 = (int)std::min<u64>((u64)c->chroma_blocks, ((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    c->launches += 2;
+    CK(cudaEventRecord(c->ev2[0], s));
+    k_finish1<<<ni, 256, 0, s>>>(P);
+    c->launches += 3;
   }
   CK(cudaEventRecord(c->ev[5], s));
   {  // (4) token statistics -> probabilities, level costs, skip probability
@@ -484,8 +489,8 @@ static int lane_encode_finish(Lane* c) {
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[15]); T.pass1_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[15], c->ev[5]); T.chroma1_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); T.stats_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[15], c->ev2[0]); T.chroma1_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev2[0], c->ev[6]); T.stats_ms = ms;  // k_finish1 + statistics + probabilities
   cudaEventElapsedTime(&ms, c->ev[6], c->ev[14]); T.chroma2_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[14], c->ev[7]); T.pass2_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms = ms;

@@ -1041,6 +1041,58 @@ __device__ __forceinline__ void complexity_after(bool is_b, bool skip, int y2nz,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pass-1 chroma chain: one warp per image, raster order (see file header).  A latency-bound
+// chain (1024 warps for 1024 images).  It reads nothing luma produces: it writes the chroma levels
+// of rec1, the chroma borders, derr1 and c1info; k_finish1 then derives the skip flags and the
+// complexity contexts from both halves.  (Measured: running it UNDER the luma wavefront, as extra
+// tickets of k_search<1> or on a side stream, starves the chains -- instruction-cache contention --
+// and is slower than running the two kernels back to back.)
+// ---------------------------------------------------------------------------------------------
+__device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int lane) {
+  const ImageDesc d = P.img[img];
+  const ImageState& IS = P.st[img];
+  const int mbw = d.mbw, mbh = d.mbh, pw = mbw * 16, cwid = mbw * 8;
+  const u8* yp = P.planes + d.y_off;
+  const u8* up = yp + (size_t)pw * mbh * 16;
+  const u8* vp = up + (size_t)cwid * mbh * 8;
+  CostCtx cc;
+  cc.probs = ZW_TAB(kCoeffProbs);
+  cc.level_cost = nullptr;
+  const bool seg_on = IS.seg_enabled != 0;
+  u32 left_derr = 0;  // carried across rows in pass 1 (Q5)
+  for (int mby = 0; mby < mbh; mby++) {
+    const u32 row_mb0 = d.mb_off + mby * mbw, up_mb0 = row_mb0 - mbw;
+    if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
+    __syncwarp();
+    for (int mbx = 0; mbx < mbw; mbx++) {
+      const u32 gmb = row_mb0 + mbx;
+      const int seg = seg_on ? P.segmap[gmb] : 0;
+      const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
+      u32 top_derr = mby > 0 ? P.derr1[up_mb0 + mbx] : 0u;
+      load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
+      const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
+      MbRecord* r = &P.rec1[gmb];
+      if (lane < 8) {
+        u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
+        const u32* sl = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[k] = sl[k];
+      }
+      if (lane == 0) {
+        P.derr1[gmb] = top_derr;
+        P.c1info[2 * gmb] = left_derr;
+        P.c1info[2 * gmb + 1] = (u32)C.uv_mode | (C.uvnz << 8);
+      }
+      if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+      MbBottom* bo = &P.bottom[gmb];
+      if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
+      if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The wavefront kernel.  PASS 1: luma only (see file header).  PASS 2: luma + chroma.
 // ---------------------------------------------------------------------------------------------
 template <int PASS>
@@ -1135,8 +1187,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
         if (PASS == 2 && skip) {
           for (int k = lane; k < 208; k += 32) g[k] = k < 8 ? s[k] : 0u;
         } else {
-          const int nw = PASS == 1 ? 208 : 144;  // pass 1 also clears the chroma levels for k_chroma1
-          for (int k = lane; k < nw; k += 32) g[k] = (PASS == 1 && k >= 144) ? 0u : s[k];
+          for (int k = lane; k < 144; k += 32) g[k] = s[k];  // chroma levels: k_chroma2 / the pass-1 chroma chain
         }
       }
       left_nz = out_left;
@@ -1152,10 +1203,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Pass-1 chroma chain: one warp per image, raster order (see file header).  Completes rec1.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_chroma1(ChunkParams P) {
+#ifndef ZW_CHROMA1_MIN_BLOCKS
+#define ZW_CHROMA1_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_CHROMA1_MIN_BLOCKS) k_chroma1(ChunkParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -1165,71 +1216,77 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_chroma1(ChunkParams P) {
     if (lane == 0) img = atomicAdd(&P.ticket[2], 1u);
     img = __shfl_sync(FULL, img, 0);
     if (img >= P.n_img) break;
-    const ImageDesc d = P.img[img];
-    ImageState& IS = P.st[img];
-    const int mbw = d.mbw, mbh = d.mbh, pw = mbw * 16, cwid = mbw * 8;
-    const u8* yp = P.planes + d.y_off;
-    const u8* up = yp + (size_t)pw * mbh * 16;
-    const u8* vp = up + (size_t)cwid * mbh * 8;
-    CostCtx cc;
-    cc.probs = ZW_TAB(kCoeffProbs);
-    cc.level_cost = nullptr;
-    const bool seg_on = IS.seg_enabled != 0;
-    u32 left_derr = 0;  // carried across rows in pass 1 (Q5)
-    u32 nskip = 0;
-    for (int mby = 0; mby < mbh; mby++) {
-      const u32 row_mb0 = d.mb_off + mby * mbw, up_mb0 = row_mb0 - mbw;
-      u32 left_nz = 0;
-      if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
-      __syncwarp();
-      for (int mbx = 0; mbx < mbw; mbx++) {
-        const u32 gmb = row_mb0 + mbx;
-        const int seg = seg_on ? P.segmap[gmb] : 0;
-        const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
-        u32 top_nz = 0, top_derr = 0;
-        if (mby > 0) {
-          top_nz = P.nz_after[up_mb0 + mbx];
-          top_derr = P.derr1[up_mb0 + mbx];
-        }
-        load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
-        const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
-        MbRecord* r = &P.rec1[gmb];
-        const u32 ynz = r->top_nz;
-        const u32 lf = r->left_nz;
-        const bool is_b = r->ymode == 4;
-        const bool skip = !((lf & 2) || C.uvnz != 0);
-        u32 out_top, out_left;
-        complexity_after(is_b, skip, (int)(lf & 1), ynz, C.uvnz, top_nz, left_nz, out_top, out_left);
-        __syncwarp();
-        if (skip) {
-          for (int k = lane; k < 200; k += 32) reinterpret_cast<u32*>(r->levels)[k] = 0;
-        } else if (lane < 8) {
-          u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
-          const u32* s = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
-#pragma unroll
-          for (int k = 0; k < 8; k++) g[k] = s[k];
-        }
-        if (lane == 0) {
-          r->uvmode = (u8)C.uv_mode;
-          r->skip = skip;
-          r->top_nz = (u16)top_nz;
-          r->left_nz = (u16)left_nz;
-          *reinterpret_cast<u32*>(r->derr_left) = left_derr;
-          *reinterpret_cast<u32*>(r->derr_top) = top_derr;
-          P.nz_after[gmb] = (u16)out_top;
-          P.derr1[gmb] = top_derr;
-        }
-        nskip += skip;
-        left_nz = out_left;
-        if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
-        MbBottom* bo = &P.bottom[gmb];
-        if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
-        if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
-        __syncwarp();
+    chroma_chain1(W, P, img, lane);
+  }
+}
+
+// Completes rec1 after k_search<1>: skip flags, incoming complexity contexts (the bookkeeping of
+// encode_residual_data / record_residual_stats, vp8.rs:1367-1374, :1468-1474), chroma header
+// fields, zeroed levels of skipped macroblocks, the pass-1 skip count.  One CTA per image:
+//   A  per MB: skip + the complexity it leaves behind, Y2 bit of I4 macroblocks left open
+//   B  the Y2 bit passes through I4 macroblocks: one thread per column (top) / per row (left)
+//   C  per MB: contexts = what the neighbours left behind; finish the record
+// Scratch: two u16 per MB in derr2 (free until k_chroma2), bit 15 = is_b, bit 14 = skip.
+__global__ void __launch_bounds__(256) k_finish1(ChunkParams P) {
+  const u32 img = blockIdx.x;
+  const ImageDesc d = P.img[img];
+  const u32 mbw = d.mbw, mbh = d.mbh, nmb = mbw * mbh;
+  u16* sc = reinterpret_cast<u16*>(P.derr2) + 2 * (size_t)d.mb_off;
+  MbRecord* recs = P.rec1 + d.mb_off;
+  const u32* ci = P.c1info + 2 * (size_t)d.mb_off;
+  __shared__ u32 s_nskip;
+  if (threadIdx.x == 0) s_nskip = 0;
+  for (u32 i = threadIdx.x; i < nmb; i += blockDim.x) {
+    const MbRecord& r = recs[i];
+    const u32 ynz = r.top_nz, lf = r.left_nz;  // parked by k_search<1>
+    const bool is_b = r.ymode == 4;
+    const u32 uvnz = (ci[2 * i + 1] >> 8) & 0xffu;
+    const bool skip = !((lf & 2) || uvnz != 0);
+    u32 ot, ol;
+    complexity_after(is_b, skip, (int)(lf & 1), ynz, uvnz, 0, 0, ot, ol);
+    const u32 fl = (is_b ? 0x8000u : 0u) | (skip ? 0x4000u : 0u);
+    sc[2 * i] = (u16)(ot | fl);
+    sc[2 * i + 1] = (u16)(ol | fl);
+  }
+  __syncthreads();
+  for (u32 j = threadIdx.x; j < mbw + mbh; j += blockDim.x) {
+    u32 y2 = 0;
+    if (j < mbw) {
+      for (u32 y = 0; y < mbh; y++) {
+        const u32 k = 2 * (y * mbw + j);
+        const u32 v = sc[k];
+        if (v & 0x8000u) sc[k] = (u16)((v & ~1u) | y2); else y2 = v & 1;
+      }
+    } else {
+      const u32 y = j - mbw;
+      for (u32 x = 0; x < mbw; x++) {
+        const u32 k = 2 * (y * mbw + x) + 1;
+        const u32 v = sc[k];
+        if (v & 0x8000u) sc[k] = (u16)((v & ~1u) | y2); else y2 = v & 1;
       }
     }
-    if (lane == 0) IS.n_skip1 = nskip;
   }
+  __syncthreads();
+  u32 nskip = 0;
+  for (u32 i = threadIdx.x; i < nmb; i += blockDim.x) {
+    const u32 x = i % mbw, y = i / mbw;
+    MbRecord& r = recs[i];
+    const bool skip = (sc[2 * i] & 0x4000u) != 0;
+    r.top_nz = (u16)(y > 0 ? (sc[2 * (i - mbw)] & 0x1ffu) : 0u);
+    r.left_nz = (u16)(x > 0 ? (sc[2 * (i - 1) + 1] & 0x1ffu) : 0u);
+    r.skip = skip;
+    r.uvmode = (u8)(ci[2 * i + 1] & 0xffu);
+    *reinterpret_cast<u32*>(r.derr_left) = ci[2 * i];
+    *reinterpret_cast<u32*>(r.derr_top) = P.derr1[d.mb_off + i];
+    if (skip) {
+      uint4* lv = reinterpret_cast<uint4*>(r.levels);
+      for (int k = 0; k < 50; k++) lv[k] = make_uint4(0, 0, 0, 0);
+    }
+    nskip += skip;
+  }
+  atomicAdd(&s_nskip, nskip);
+  __syncthreads();
+  if (threadIdx.x == 0) P.st[img].n_skip1 = s_nskip;
 }
 
 // ---------------------------------------------------------------------------------------------

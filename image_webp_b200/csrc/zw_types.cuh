@@ -104,7 +104,8 @@ struct ChunkParams {
   MbBottom* bottom;  // [n_mb]
   u16* nz_after;     // [n_mb] top complexity left behind by each MB
   u32* derr1;        // [n_mb] packed top_derr after pass 1
-  u32* derr2;        // [n_mb] same, pass 2
+  u32* derr2;        // [n_mb] same, pass 2 (k_finish1 borrows it as scratch before)
+  u32* c1info;       // [n_mb][2] pass-1 chroma chain -> k_finish1: left_derr after the MB, uv_mode | uvnz << 8
   u8* uvflags;       // [n_mb] pass-2 chroma has_coeffs bits (4 U | 4 V), k_chroma2 -> k_search<2>
   int* progress;     // [3][n_rows] macroblocks completed per row: pass-1 luma, pass-2 luma, pass-2 chroma
   u32* ticket;       // [4] work counters
