@@ -1,8 +1,8 @@
 """image_webp_b200 -- B200-native lossy WebP (VP8 key-frame) encoder core behind the C ABI of
 include/zenwebp_b200.h; a drop-in for the WebPEncoder / EncoderParams::lossy(q) + method path of
 imazen/image-webp (`zenwebp` 0.2.0).  Hand-written CUDA for sm_100a, no CPU fallback."""
-from .encoder import (ColorType, Context, DeviceError, EncoderParams, EncodingError, InvalidBufferSize,
+from .encoder import (BatchPipeline, ColorType, Context, DeviceError, EncoderParams, EncodingError, InvalidBufferSize,
                       InvalidDimensions, WebPEncoder, default_context, encode_batch)
 
-__all__ = ["ColorType", "Context", "DeviceError", "EncoderParams", "EncodingError", "InvalidBufferSize",
+__all__ = ["BatchPipeline", "ColorType", "Context", "DeviceError", "EncoderParams", "EncodingError", "InvalidBufferSize",
            "InvalidDimensions", "WebPEncoder", "default_context", "encode_batch"]

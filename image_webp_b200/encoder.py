@@ -12,8 +12,10 @@ header include/zenwebp_b200.hpp) stand where the `zenwebp-b200` wrapper crate wo
 INTEGRATION.md for the -sys crate a maintainer would add.  Only the lossy VP8 path is provided:
 lossless parameters raise NotImplementedError (out of scope).  No CPU fallback.
 """
+import concurrent.futures
 import ctypes as C
 import enum
+import queue
 
 import numpy as np
 
@@ -193,6 +195,51 @@ class Context:
         if rc != 0:
             _raise_for(rc, self.lib)
         return buf[:n.value].view(dtype) if n.value else buf[:0].view(dtype)
+
+
+class BatchPipeline:
+    """Streaming batch entry: `depth` contexts on one GPU, each driven by its own host thread, so
+    that the H2D copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of
+    the next (the C ABI is thread-safe across contexts; ctypes drops the GIL during the call).
+    `submit` returns a concurrent.futures.Future of (list of .webp bytes, timing dict); batches are
+    independent, results are bit-identical to `Context.encode_batch`."""
+
+    def __init__(self, device=0, depth=2, **ctx_kwargs):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.depth = depth
+        self._free = queue.Queue()
+        self._ctxs = [Context(device, **ctx_kwargs) for _ in range(depth)]
+        for c in self._ctxs:
+            self._free.put(c)
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=depth, thread_name_prefix="zw-pipe")
+
+    def _run(self, images, params, color, container):
+        ctx = self._free.get()
+        try:
+            return ctx.encode_batch(images, params, color, container)
+        finally:
+            self._free.put(ctx)
+
+    def submit(self, images, params, color=ColorType.Rgb8, container=True):
+        return self._pool.submit(self._run, images, params, color, container)
+
+    def encode_batches(self, batches, params, color=ColorType.Rgb8, container=True):
+        """Encode an iterable of batches; returns the list of per-batch outputs, in order."""
+        futs = [self.submit(b, params, color, container) for b in batches]
+        return [f.result()[0] for f in futs]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for c in self._ctxs:
+            c.close()
+        self._ctxs = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 _default_ctx = {}

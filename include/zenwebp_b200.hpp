@@ -7,8 +7,12 @@
 #ifndef ZENWEBP_B200_HPP
 #define ZENWEBP_B200_HPP
 #include <cstdint>
+#include <future>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "zenwebp_b200.h"
@@ -72,6 +76,33 @@ class Context {
   zw_ctx* handle() { return h_; }
  private:
   zw_ctx* h_;
+};
+
+// Streaming batch entry: `depth` contexts on one GPU, one host thread per in-flight batch, so that the
+// H2D copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of the next.
+// Contexts are independent (the C ABI is thread-safe across contexts); results equal encode_batch's.
+// The caller keeps at most `depth` futures outstanding and must keep the image memory alive until get().
+class BatchPipeline {
+ public:
+  explicit BatchPipeline(int device = 0, int depth = 2) {
+    for (int i = 0; i < depth; i++) free_.push_back(std::unique_ptr<Context>(new Context(device)));
+  }
+  std::future<std::vector<std::vector<uint8_t>>> submit(std::vector<Context::ImageRef> imgs, EncoderParams p) {
+    return std::async(std::launch::async, [this, imgs, p]() {
+      std::unique_ptr<Context> c;
+      for (;;) {  // take a free context (at most `depth` batches run at once)
+        std::unique_lock<std::mutex> l(m_);
+        if (!free_.empty()) { c = std::move(free_.back()); free_.pop_back(); break; }
+        l.unlock();
+        std::this_thread::yield();
+      }
+      struct Return { BatchPipeline* p; std::unique_ptr<Context>& c; ~Return() { std::lock_guard<std::mutex> l(p->m_); p->free_.push_back(std::move(c)); } } ret{this, c};
+      return c->encode_batch(imgs, p);
+    });
+  }
+ private:
+  std::mutex m_;
+  std::vector<std::unique_ptr<Context>> free_;
 };
 
 // WebPEncoder::new(&mut Vec<u8>) / set_params / encode: appends the .webp bytes to `writer`.

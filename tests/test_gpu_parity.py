@@ -149,3 +149,18 @@ def test_resident_split_api_matches_batch_api(ctx):
     c, _ = ctx.encode_batch(imgs, _params(75, 4))
     assert a == b == c
     assert t2["kernel_launches"] >= 10
+
+
+def test_batch_pipeline_matches_oracle_and_single_context(ctx):
+    """The streaming entry point (several contexts / host threads on one GPU) returns, per batch and
+    in order, the bytes the oracle produces."""
+    import image_webp_b200 as Z
+    batches = [[synth.photo_like(160 + 16 * k, 96 + 16 * j, 40 + 5 * k + j) for j in range(3)] for k in range(5)]
+    with Z.BatchPipeline(0, depth=2) as pipe:
+        got = pipe.encode_batches(batches, _params(75, 4))
+    assert len(got) == len(batches)
+    for b, outs in zip(batches, got):
+        assert len(outs) == len(b)
+        for img, o in zip(b, outs):
+            rc, ref, _ = O.encode(img, 75, 4)
+            assert rc == 0 and o == ref
