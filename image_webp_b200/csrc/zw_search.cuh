@@ -64,13 +64,20 @@ struct SearchShared {
   WarpScratch w[SEARCH_WARPS];
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
+// Progress flags.  On sm_100a an acquire load / fence.sc / fence.acq_rel each end in CCTL.IVALL -- an
+// invalidation of the SM's whole L1 -- which, issued per poll and per macroblock by 24 warps, keeps
+// the rate tables out of L1.  None of it is needed here: everything a waiting row reads from its
+// producer goes through ld.global.cg (L2 only: MbBottom, nz_after, derr2), so the consumer polls with
+// a relaxed gpu-scope load (the dependent loads issue after the branch on its value) and the
+// producer orders its data stores with fence.release (MEMBAR, no L1 invalidation) + a relaxed store.
+__device__ __forceinline__ int ld_flag(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void fence_release() { asm volatile("fence.release.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_flag(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ i64 shfl64(i64 v, int src) {
   int lo = __shfl_sync(FULL, (int)(v & 0xffffffff), src);
@@ -1136,7 +1143,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
       if (mby > 0) {  // wait for the top / top-right neighbours
         const int need = min(mbx + 2, mbw);
         if (lane == 0) {
-          while (ld_acquire(&progress[d.row_off + mby - 1]) < need) __nanosleep(100);
+          while (ld_flag(&progress[d.row_off + mby - 1]) < need) __nanosleep(100);
         }
         __syncwarp();
       }
@@ -1196,9 +1203,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
       MbBottom* bo = &P.bottom[gmb];
       if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
       if (PASS == 2 && lane == 0) P.nz_after[gmb] = (u16)out_top;
-      __threadfence();
+      fence_release();
       __syncwarp();
-      if (lane == 0) st_release(&progress[d.row_off + mby], mbx + 1);
+      if (lane == 0) st_flag(&progress[d.row_off + mby], mbx + 1);
     }
   }
 }
@@ -1324,7 +1331,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_chr
     for (int mbx = 0; mbx < mbw; mbx++) {
       if (mby > 0) {  // chroma needs the macroblock above only (no top-right)
         if (lane == 0) {
-          while (ld_acquire(&progress[d.row_off + mby - 1]) < mbx + 1) __nanosleep(100);
+          while (ld_flag(&progress[d.row_off + mby - 1]) < mbx + 1) __nanosleep(100);
         }
         __syncwarp();
       }
@@ -1353,9 +1360,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_chr
       MbBottom* bo = &P.bottom[gmb];
       if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
       if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
-      __threadfence();
+      fence_release();
       __syncwarp();
-      if (lane == 0) st_release(&progress[d.row_off + mby], mbx + 1);
+      if (lane == 0) st_flag(&progress[d.row_off + mby], mbx + 1);
     }
   }
 }

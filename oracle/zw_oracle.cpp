@@ -219,7 +219,18 @@ static inline const u8* coeff_probs_default() { return kCoeffProbs; }
 // ---------------------------------------------------------------------------------------------
 // src/common/transform.rs
 // ---------------------------------------------------------------------------------------------
+// ---- primitive-invocation counters (measurement only; SURVEY.md 8(d) "ALGORITHMIC int-ops") ----
+// Active only inside the mode-search / transform functions of both passes (OpsGate), i.e. not for
+// the re-quantisation the reference repeats for statistics and token emission.
+enum { OPC_FDCT, OPC_IDCT, OPC_WHT, OPC_IWHT, OPC_TTRANSFORM, OPC_QUANT_COEFF, OPC_SSE_PX, OPC_COST_COEFF,
+       OPC_TRELLIS_POS, OPC_I4_PREDSET, OPC_ADD_RESIDUE, OPC_TRELLIS_BLOCK, OPC_N };
+static thread_local int g_ops_gate = 0;
+static thread_local u64 g_ops[OPC_N];
+struct OpsGate { OpsGate() { g_ops_gate++; } ~OpsGate() { g_ops_gate--; } };
+#define OPC(i, n) do { if (g_ops_gate) g_ops[i] += (u64)(n); } while (0)
+
 static void idct4x4(i32* block) {  // transform.rs:35-79 (scalar; SIMD twin is equivalent, Q16)
+  OPC(OPC_IDCT, 1);
   const i64 CONST1 = 20091, CONST2 = 35468;
   for (int i = 0; i < 4; i++) {
     i64 a1 = (i64)block[i] + (i64)block[8 + i];
@@ -252,6 +263,7 @@ static void idct4x4(i32* block) {  // transform.rs:35-79 (scalar; SIMD twin is e
 }
 
 static void iwht4x4(i32* block) {  // transform.rs:82-114
+  OPC(OPC_IWHT, 1);
   for (int i = 0; i < 4; i++) {
     i32 a1 = block[i] + block[12 + i];
     i32 b1 = block[4 + i] + block[8 + i];
@@ -277,6 +289,7 @@ static void iwht4x4(i32* block) {  // transform.rs:82-114
 }
 
 static void wht4x4(i32* block) {  // transform.rs:116-158
+  OPC(OPC_WHT, 1);
   for (int i = 0; i < 4; i++) {
     i64 a = (i64)block[i * 4] + (i64)block[i * 4 + 3];
     i64 b = (i64)block[i * 4 + 1] + (i64)block[i * 4 + 2];
@@ -306,6 +319,7 @@ static void wht4x4(i32* block) {  // transform.rs:116-158
 }
 
 static void dct4x4(i32* block) {  // transform.rs:176-207 (scalar; SIMD twin is equivalent, Q16)
+  OPC(OPC_FDCT, 1);
   for (int i = 0; i < 4; i++) {
     i64 a = ((i64)block[i * 4] + (i64)block[i * 4 + 3]) * 8;
     i64 b = ((i64)block[i * 4 + 1] + (i64)block[i * 4 + 2]) * 8;
@@ -394,6 +408,7 @@ static ChromaBuf create_border_chroma(size_t mbx, size_t mby, const u8* top, siz
 }
 
 static void add_residue(u8* pblock, const i32* rblock, size_t y0, size_t x0, size_t stride) {
+  OPC(OPC_ADD_RESIDUE, 1);
   // prediction.rs:138-152
   size_t pos = y0 * stride + x0;
   for (int r = 0; r < 4; r++) {
@@ -552,6 +567,7 @@ static void apply_intra4_prediction(u8* ws, int mode, size_t x0, size_t y0, size
 // I4Predictions::compute (prediction.rs:568-780)
 struct I4Predictions { u8 data[10][16]; };
 static I4Predictions i4_predictions_compute(const u8* src, size_t x0, size_t y0, size_t stride) {
+  OPC(OPC_I4_PREDSET, 1);
   I4Predictions r;
   Edges e = fetch_edges(src, x0, y0, stride);
   for (int m = 0; m < 10; m++) predict4x4_block(e, m, r.data[m]);
@@ -687,6 +703,7 @@ static inline i32 quantdiv(u32 coeff, u32 iq, u32 bias) {                       
 }
 
 static i32 t_transform(const u8* in, size_t stride, const u16* w) {  // cost.rs:73-107
+  OPC(OPC_TTRANSFORM, 1);
   i32 tmp[16];
   for (int i = 0; i < 4; i++) {
     size_t row = i * stride;
@@ -788,6 +805,7 @@ struct VP8Matrix {  // cost.rs:386-486
     return m;
   }
   i32 quantize_coeff(i32 coeff, size_t pos) const {  // cost.rs:457
+    OPC(OPC_QUANT_COEFF, 1);
     bool sign = coeff < 0;
     u32 abs_coeff = (u32)(sign ? -coeff : coeff);
     i32 level = quantdiv(abs_coeff, iq[pos], bias[pos]);
@@ -900,6 +918,8 @@ static bool trellis_quantize_block(i32* coeffs, i32* out, const VP8Matrix& mtx, 
     if (err > thresh) { last = n; break; }
   }
   if (last < 15) last += 1;
+  OPC(OPC_TRELLIS_BLOCK, 1);
+  OPC(OPC_TRELLIS_POS, last - (i32)first + 1);
 
   i32 best_path[3] = {-1, -1, -1};
   i64 skip_cost = level_costs.get_skip_eob_cost(ctype, first, ctx0);
@@ -1098,6 +1118,7 @@ static u32 get_residual_cost(size_t ctx0, const i32* coeffs, size_t ctype, size_
   size_t ctx = ctx0;
   u32 cost = ctx0 == 0 ? (u32)vp8_bit_cost(true, p0) : 0;
   if (last < 0) return (u32)vp8_bit_cost(false, p0);
+  OPC(OPC_COST_COEFF, last - (i32)first + 1);
   while ((i32)n < last) {
     size_t v = (size_t)std::abs(coeffs[n]);
     cost += costs.get_level_cost(ctype, n, ctx, v);
@@ -2068,6 +2089,7 @@ struct Vp8Encoder {
   }
 
   static u32 sse_16x16_luma(const u8* src_y, size_t src_width, size_t mbx, size_t mby, const LumaBuf& pred) {  // vp8.rs:66
+    OPC(OPC_SSE_PX, 256);
     u32 sse = 0;
     size_t src_base = mby * 16 * src_width + mbx * 16;
     for (size_t y = 0; y < 16; y++)
@@ -2078,6 +2100,7 @@ struct Vp8Encoder {
     return sse;
   }
   static u32 sse_8x8_chroma(const u8* src_uv, size_t src_width, size_t mbx, size_t mby, const ChromaBuf& pred) {  // vp8.rs:97
+    OPC(OPC_SSE_PX, 64);
     u32 sse = 0;
     size_t src_base = mby * 8 * src_width + mbx * 8;
     for (size_t y = 0; y < 8; y++)
@@ -2202,6 +2225,7 @@ struct Vp8Encoder {
         const VP8Matrix& y1_matrix = segment.y1_matrix;
         size_t max_modes_to_try = method <= 3 ? 3 : (method == 4 ? 4 : 10);
         std::pair<u32, size_t> mode_sse[10];
+        OPC(OPC_SSE_PX, 160);
         for (size_t m = 0; m < 10; m++) {
           u32 sse = 0;
           for (int k = 0; k < 16; k++) { i32 d = (i32)src_block[k] - (i32)preds.data[m][k]; sse += (u32)(d * d); }
@@ -2222,6 +2246,8 @@ struct Vp8Encoder {
           i32 dequantized[16];
           for (size_t idx = 0; idx < 16; idx++) dequantized[idx] = y1_matrix.dequantize(quantized[idx], idx);
           idct4x4(dequantized);
+          OPC(OPC_SSE_PX, 16);
+          OPC(OPC_ADD_RESIDUE, 1);
           u32 sse = 0;
           for (int t = 0; t < 16; t++) {
             i32 rec = std::min(std::max((i32)pred[t] + dequantized[t], 0), 255);
@@ -2310,6 +2336,7 @@ struct Vp8Encoder {
   }
 
   MacroblockInfo choose_macroblock_info(size_t mbx, size_t mby) const {  // vp8.rs:2202-2246
+    OpsGate ops_gate_;
     u64 i16_score;
     int luma_mode = pick_best_intra16(mbx, mby, i16_score);
     MacroblockInfo info;
@@ -2335,6 +2362,7 @@ struct Vp8Encoder {
 
   // ---- final transforms -------------------------------------------------------------------
   void transform_luma_blocks_4x4(const int* bpred_modes, size_t mbx, size_t mby, i32* luma_blocks) {  // vp8.rs:2785-2916
+    OpsGate ops_gate_;
     memset(luma_blocks, 0, 256 * sizeof(i32));
     size_t stride = LUMA_STRIDE, mbw = macroblock_width, w = mbw * 16;
     LumaBuf y_with_border = create_border_luma(mbx, mby, mbw, top_border_y.data(), left_border_y);
@@ -2380,6 +2408,7 @@ struct Vp8Encoder {
   }
 
   void transform_luma_block(size_t mbx, size_t mby, const MacroblockInfo& info, i32* luma_blocks) {  // vp8.rs:2647-2780
+    OpsGate ops_gate_;
     if (info.luma_mode == LM_B) {
       assert(info.has_bpred);
       transform_luma_blocks_4x4(info.luma_bpred, mbx, mby, luma_blocks);
@@ -2439,6 +2468,7 @@ struct Vp8Encoder {
   }
 
   void transform_chroma_blocks(size_t mbx, size_t mby, int chroma_mode, i32* u_blocks, i32* v_blocks) {  // vp8.rs:3039-3121
+    OpsGate ops_gate_;
     size_t stride = CHROMA_STRIDE;
     ChromaBuf predicted_u = get_predicted_chroma_block(chroma_mode, mbx, mby, top_border_u, left_border_u);
     ChromaBuf predicted_v = get_predicted_chroma_block(chroma_mode, mbx, mby, top_border_v, left_border_v);
@@ -2729,6 +2759,12 @@ int zwo_encode_webp(const uint8_t* data, size_t data_len, uint32_t width, uint32
 }
 
 void zwo_free(void* p) { free(p); }
+// Counters of the calling thread: reset, then run zwo_encode_* on this thread, then read.
+void zwo_opcounts_reset(void) { memset(g_ops, 0, sizeof(g_ops)); }
+size_t zwo_opcounts_get(uint64_t* out, size_t cap) {
+  for (size_t i = 0; i < (size_t)OPC_N && i < cap; i++) out[i] = g_ops[i];
+  return (size_t)OPC_N;
+}
 
 size_t zwo_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32_t height, int quality, int method,
                            int threads) {

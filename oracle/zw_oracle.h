@@ -112,6 +112,13 @@ uint16_t zwo_fixed_cost_i4(int top, int left, int mode);
 uint16_t zwo_entropy_cost(int p);
 uint16_t zwo_level_fixed_cost(int level);
 
+/* Primitive-invocation counters of the calling thread (measurement: SURVEY.md 8(d) algorithmic
+   int-ops).  Order: fdct, idct, wht, iwht, ttransform, quantised coefficients, sse pixels,
+   residual-cost coefficients visited, trellis positions, I4 predictor sets, add_residue blocks,
+   trellis blocks.  Counted inside the mode-search / transform functions of both passes only. */
+void zwo_opcounts_reset(void);
+size_t zwo_opcounts_get(uint64_t* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
