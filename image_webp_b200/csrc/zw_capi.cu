@@ -192,6 +192,7 @@ struct Lane {
   bool staged = false, encoded = false;
   int quality = -1, method = -1, base_qidx = 0;
   int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0;
+  u32 start_slack = 0;  // measured: rows wait 1.1-1.4 % of their time at 1024 images; extra start slack only idles warps
   u64 launches = 0;
   dim3 tok_grid;
   ChunkParams P;
@@ -232,6 +233,7 @@ static void fill_params(Lane* c) {
   P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
   P.method = (u32)c->method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = c->method >= 4;
   P.filter_level = (u8)compute_filter_level(c->base_qidx);
+  P.start_slack = c->start_slack;
 }
 
 static int validate_image(const zw_image& im) {
@@ -287,6 +289,7 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
     b1 = std::min(b1, cap); b2 = std::min(b2, cap); b4 = std::min(b4, cap);
   }
+  if (const char* env = getenv("ZW_START_SLACK")) c->start_slack = (u32)std::max(0, atoi(env));
   c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
   c->search_blocks1 = std::max(1, b1) * ctx->sm_count;
   c->search_blocks2 = std::max(1, b2) * ctx->sm_count;
@@ -499,6 +502,14 @@ static int lane_encode_finish(Lane* c) {
   cudaEventElapsedTime(&ms, c->ev[13], c->ev[10]); T.device_total_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms = ms;
   T.kernel_launches = c->launches;
+#ifdef ZW_WAIT_STATS
+  {
+    unsigned long long w[8];
+    cudaMemcpy(w, c->d_ticket.p, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "wait stats: pass1 wait %.1f%% of row time, pass2 wait %.1f%%\n", 100.0 * (double)w[3] / (double)(w[5] ? w[5] : 1),
+            100.0 * (double)w[4] / (double)(w[6] ? w[6] : 1));
+  }
+#endif
   c->last = T;
   c->encoded = true;
   return ZW_OK;

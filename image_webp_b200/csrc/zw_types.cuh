@@ -92,6 +92,7 @@ struct ChunkParams {
   const u8* segquant_lut;   // [128][255]: compute_segment_quant(base, alpha-127..127)
   u32 n_img, n_rows, n_mb;
   u32 method, base_qidx, do_trellis;
+  u32 start_slack;   // a wavefront row starts once the row above is this many macroblocks ahead
   u8 filter_level;
   const u8* rgb;
   u8* planes;

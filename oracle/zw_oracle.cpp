@@ -224,10 +224,11 @@ static inline const u8* coeff_probs_default() { return kCoeffProbs; }
 // the re-quantisation the reference repeats for statistics and token emission.
 enum { OPC_FDCT, OPC_IDCT, OPC_WHT, OPC_IWHT, OPC_TTRANSFORM, OPC_QUANT_COEFF, OPC_SSE_PX, OPC_COST_COEFF,
        OPC_TRELLIS_POS, OPC_I4_PREDSET, OPC_ADD_RESIDUE, OPC_TRELLIS_BLOCK, OPC_N };
-static thread_local int g_ops_gate = 0;
-static thread_local u64 g_ops[OPC_N];
+static thread_local int g_ops_gate = 0, g_ops_pass = 0, g_ops_chroma = 0;
+static thread_local u64 g_ops[4][OPC_N];  // [pass-1 luma, pass-1 chroma, pass-2 luma, pass-2 chroma]
 struct OpsGate { OpsGate() { g_ops_gate++; } ~OpsGate() { g_ops_gate--; } };
-#define OPC(i, n) do { if (g_ops_gate) g_ops[i] += (u64)(n); } while (0)
+struct OpsChroma { int prev; OpsChroma() : prev(g_ops_chroma) { g_ops_chroma = 1; } ~OpsChroma() { g_ops_chroma = prev; } };
+#define OPC(i, n) do { if (g_ops_gate) g_ops[2 * g_ops_pass + g_ops_chroma][i] += (u64)(n); } while (0)
 
 static void idct4x4(i32* block) {  // transform.rs:35-79 (scalar; SIMD twin is equivalent, Q16)
   OPC(OPC_IDCT, 1);
@@ -2282,6 +2283,7 @@ struct Vp8Encoder {
   }
 
   int pick_best_uv(size_t mbx, size_t mby) const {  // vp8.rs:2050-2200
+    OpsChroma ops_chroma_;
     size_t mbw = macroblock_width, chroma_width = mbw * 8;
     const int MODES[4] = {LM_DC, LM_V, LM_H, LM_TM};
     const Segment& segment = get_segment_for_mb(mbx, mby);
@@ -2469,6 +2471,7 @@ struct Vp8Encoder {
 
   void transform_chroma_blocks(size_t mbx, size_t mby, int chroma_mode, i32* u_blocks, i32* v_blocks) {  // vp8.rs:3039-3121
     OpsGate ops_gate_;
+    OpsChroma ops_chroma_;
     size_t stride = CHROMA_STRIDE;
     ChromaBuf predicted_u = get_predicted_chroma_block(chroma_mode, mbx, mby, top_border_u, left_border_u);
     ChromaBuf predicted_v = get_predicted_chroma_block(chroma_mode, mbx, mby, top_border_v, left_border_v);
@@ -2611,6 +2614,7 @@ struct Vp8Encoder {
     if (dump) { rec_p1.assign(nmb, zwo_mb_record()); rec_p2.assign(nmb, zwo_mb_record()); }
 
     // ===== PASS 1 =====
+    g_ops_pass = 0;
     {
       bool trellis_during_pass2 = do_trellis;
       do_trellis = false;
@@ -2664,6 +2668,7 @@ struct Vp8Encoder {
     encode_compressed_frame_header();
 
     // ===== PASS 2 =====
+    g_ops_pass = 1;
     for (size_t mby = 0; mby < macroblock_height; mby++) {
       size_t partition_index = mby % partitions.size();
       left_complexity = Complexity();
@@ -2762,7 +2767,7 @@ void zwo_free(void* p) { free(p); }
 // Counters of the calling thread: reset, then run zwo_encode_* on this thread, then read.
 void zwo_opcounts_reset(void) { memset(g_ops, 0, sizeof(g_ops)); }
 size_t zwo_opcounts_get(uint64_t* out, size_t cap) {
-  for (size_t i = 0; i < (size_t)OPC_N && i < cap; i++) out[i] = g_ops[i];
+  for (size_t i = 0; i < (size_t)(4 * OPC_N) && i < cap; i++) out[i] = g_ops[i / OPC_N][i % OPC_N];
   return (size_t)OPC_N;
 }
 

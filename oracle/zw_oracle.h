@@ -115,7 +115,9 @@ uint16_t zwo_level_fixed_cost(int level);
 /* Primitive-invocation counters of the calling thread (measurement: SURVEY.md 8(d) algorithmic
    int-ops).  Order: fdct, idct, wht, iwht, ttransform, quantised coefficients, sse pixels,
    residual-cost coefficients visited, trellis positions, I4 predictor sets, add_residue blocks,
-   trellis blocks.  Counted inside the mode-search / transform functions of both passes only. */
+   trellis blocks.  Counted inside the mode-search / transform functions of both passes only.
+   zwo_opcounts_get fills out[set * n + i], set = pass-1 luma, pass-1 chroma, pass-2 luma, pass-2
+   chroma, and returns n (the number of counters per set). */
 void zwo_opcounts_reset(void);
 size_t zwo_opcounts_get(uint64_t* out, size_t cap);
 

@@ -105,3 +105,28 @@ def encode_raw(data: bytes, w, h, quality, method, color="Rgb8", container=True)
         res = C.string_at(out, n.value)
         L.zwo_free(out)
     return rc, res
+
+
+# ---- algorithmic int-op model: oracle-counted primitive invocations x fixed costs ----
+OP_NAMES = ["fdct", "idct", "wht", "iwht", "ttransform", "quant_coeff", "sse_px", "cost_coeff", "trellis_pos", "i4_predset",
+            "add_residue", "trellis_block"]
+# 32-bit integer operations per invocation, loads/stores excluded: FDCT incl. the residual 190, IDCT 176, WHT 112,
+# IWHT 96, TTransform 112, quantise+dequantise 8 per coefficient, SSE 3 per pixel, residual cost 10 per coefficient
+# visited, trellis 60 i64 ops (counted x2.5) per position, the ten 4x4 predictors 100 per set, add_residue 48.
+OP_COST = [190, 176, 112, 96, 112, 8, 3, 10, 150, 100, 48, 0]
+OP_SETS = ["pass1_luma", "pass1_chroma", "pass2_luma", "pass2_chroma"]
+
+
+def count_ops(img, quality, method):
+    """Encode `img` with the oracle on this thread; return {set: {primitive: count}} and {set: int ops}."""
+    import ctypes as C
+    L = lib()
+    L.zwo_opcounts_reset()
+    rc, _, _ = encode(img, quality, method)
+    assert rc == 0
+    buf = (C.c_uint64 * 64)()
+    L.zwo_opcounts_get.restype = C.c_size_t
+    n = L.zwo_opcounts_get(buf, 64)
+    counts = {s: {OP_NAMES[i]: int(buf[k * n + i]) for i in range(n)} for k, s in enumerate(OP_SETS)}
+    ops = {s: sum(counts[s][OP_NAMES[i]] * OP_COST[i] for i in range(n)) for s in OP_SETS}
+    return counts, ops
