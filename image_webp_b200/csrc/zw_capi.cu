@@ -284,10 +284,11 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   int b1 = 0, b2 = 0, b4 = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2)));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2)));
   if (warps_hint > 0) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
-    b1 = std::min(b1, cap); b2 = std::min(b2, cap); b4 = std::min(b4, cap);
+    b1 = std::min(b1, cap); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
   }
   if (const char* env = getenv("ZW_START_SLACK")) c->start_slack = (u32)std::max(0, atoi(env));
   c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
@@ -431,8 +432,9 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
     const int g4 = (int)std::min<u64>((u64)c->chroma2_blocks, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     CK(cudaEventRecord(c->ev[14], s));
-    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_search<2><<<g2, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    const int w2 = search_warps(2);
+    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);
+    k_search<2><<<g2, w2 * 32, search_smem_bytes(w2), s>>>(P);
     c->launches += 2;
   }
   CK(cudaEventRecord(c->ev[7], s));

@@ -26,7 +26,19 @@
 
 namespace zw {
 
-constexpr int SEARCH_WARPS = 4;  // warps per CTA (each independent)
+constexpr int SEARCH_WARPS = 4;  // warps per CTA of the free-running wavefront kernels (each warp independent)
+// Pass-2 luma kernel: the warps of a CTA step through the three phases of a macroblock (I16 search,
+// I4 search, final transform) in lock step, one barrier per phase.  The kernel is bound by
+// instruction supply (97 KB of code, every warp somewhere else in it: 42 % of the stall samples were
+// "no instruction"); warps that share a scheduler now run the same code at the same time.  Measured:
+// pass 2 78 -> 67 ms in spite of the idle time at the barriers.  0 = free-running like pass 1.
+#ifndef ZW_LS_WARPS
+#define ZW_LS_WARPS 12
+#endif
+constexpr int LS_WARPS = ZW_LS_WARPS;
+#ifndef ZW_LS_I4SYNC
+#define ZW_LS_I4SYNC 0
+#endif
 #ifndef ZW_SEARCH_MIN_BLOCKS
 #define ZW_SEARCH_MIN_BLOCKS 6   // CTAs per SM the wavefront kernels are register-budgeted for
 #endif
@@ -518,13 +530,19 @@ struct LumaOut {
   bool simple_nz;  // any SIMPLE-quantised luma level non-zero (skip test, Q13)
 };
 
+// LS: the CTA's warps run the three phases in lock step (a CTA barrier between them); `work` is
+// false for a warp that only keeps the barriers company this round (no row / dependency not ready).
+template <bool LS>
 __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegParams& SP, const CostCtx& cc, int method,
-                           bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane) {
+                           bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane, bool work) {
   LumaOut R;
   const int hb = lane >> 4, blk = lane & 15, bx = blk & 3, by = blk >> 2;
   const u8(*pidx)[16] = SH.pred_idx;
   // ===== pick_best_intra16 (vp8.rs:1504-1681) =====
-  int dc16;
+  int dc16 = 0;
+  int best16_mode = 0;
+  u64 i16_score = 0;
+  if (work) {
   {
     int s = 0;
     if (lane < 16) s = (mby != 0 ? W.yws[1 + lane] : 0) + (mbx != 0 ? W.yws[(1 + lane) * 32] : 0);
@@ -547,7 +565,6 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     is_flat = __all_sync(FULL, same);
     tsrc = t_transform16(px, ZW_TAB(kWeightY));
   }
-  int best16_mode = 0;
   i64 best16_score = I64_MAX;
   u32 best16_cc = 0, best16_mc = 0, best16_d = 0;
   i32 best16_sd = 0;
@@ -621,17 +638,19 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       }
     }
   }
-  u64 i16_score;
   {
     const i64 fs = ((i64)best16_mc + (i64)best16_cc) * (i64)SP.lambda_mode + 256 * ((i64)best16_d + (i64)best16_sd);
     i16_score = (u64)(fs > 0 ? fs : 0);
   }
+  }  // work (I16 search)
 
   // ===== pick_best_intra4 (vp8.rs:1790-2036), gated as in choose_macroblock_info (:2210-2231) =====
   // Cooperative: each half-warp evaluates one prediction mode at a time, one pixel per lane.
   bool use_i4 = false;
-  if (method > 1 && (method >= 5 || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0)) {
-    use_i4 = true;
+  if (LS) __syncthreads();
+  bool i4_go = work && method > 1 && (method >= 5 || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0);
+  use_i4 = i4_go;
+  {
     const int max_modes = method <= 3 ? 3 : (method == 4 ? 4 : 10);
     const int n16 = lane & 15;
     const u32 taps = SH.dtaps[lane];
@@ -642,6 +661,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
+      if (LS && ZW_LS_I4SYNC) __syncthreads();  // optional finer lock step: one barrier per sub-block
+      if (!i4_go) {
+        if (LS && ZW_LS_I4SYNC) continue;
+        break;
+      }
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
       const int top_ctx = sby == 0 ? 0 : W.bmodes[i - 4];
       const int left_ctx = sbx == 0 ? 0 : W.bmodes[i - 1];
@@ -716,15 +740,17 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       lnz4 = (lnz4 & ~(1u << sby)) | ((u32)best_nz << sby);
       total_mode_cost += ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + wmode];
       running += (u64)best_sse * 256ull + (u64)(best_rate & 0xffffu) * (u64)SP.lambda_mode;
-      if (running >= i16_score || total_mode_cost > 16384u) { use_i4 = false; break; }
+      if (running >= i16_score || total_mode_cost > 16384u) { use_i4 = false; i4_go = false; }
     }
   }
 
   // ===== final luma transform -> coded levels + reconstruction =====
+  if (LS) __syncthreads();
   bool any_simple_nz = false;
   u32 ynz = 0;
   int y2nz = 0;
-  if (!use_i4) {
+  if (!work) {
+  } else if (!use_i4) {
     // ---- transform_luma_block (vp8.rs:2647-2780) ----
     i32 c[16], pr[16];
     pred_block(W.yws, 0, best16_mode, bx, by, dc16, pr);
@@ -1102,12 +1128,23 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
 // ---------------------------------------------------------------------------------------------
 // The wavefront kernel.  PASS 1: luma only (see file header).  PASS 2: luma + chroma.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr bool search_lockstep(int pass) { return pass == 2 && LS_WARPS > 0; }
+__host__ __device__ constexpr int search_warps(int pass) { return search_lockstep(pass) ? LS_WARPS : SEARCH_WARPS; }
+__host__ __device__ constexpr int search_min_blocks(int pass) {
+  return search_lockstep(pass) ? (ZW_SEARCH_MIN_BLOCKS * SEARCH_WARPS) / (LS_WARPS > 0 ? LS_WARPS : 1) : ZW_SEARCH_MIN_BLOCKS;
+}
+// dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
+__host__ __device__ constexpr size_t search_smem_bytes(int nwarps) { return sizeof(SearchShared) + (size_t)(nwarps - SEARCH_WARPS) * sizeof(WarpScratch); }
+
 template <int PASS>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_search(ChunkParams P) {
+__global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PASS)) k_search(ChunkParams P) {
+  constexpr bool LS = search_lockstep(PASS);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
+  __shared__ int s_active;  // LS: warps of this CTA that still have (or may get) a row
   for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
   if (threadIdx.x < 32) SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x];
+  if (threadIdx.x == 0) s_active = (int)(blockDim.x >> 5);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   WarpScratch& W = SH.w[threadIdx.x >> 5];
@@ -1116,113 +1153,148 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_sea
   const bool trellis = (PASS == 2) && P.do_trellis;
   const int method = P.method;
 
-  for (;;) {
-    u32 t = 0;
-    if (lane == 0) t = atomicAdd(&P.ticket[PASS - 1], 1u);
-    t = __shfl_sync(FULL, t, 0);
-    if (t >= P.n_rows) break;
+  // state of the row this warp owns
+  bool have_row = false, done = false;
+  u32 img = 0, row_mb0 = 0, up_mb0 = 0, left_nz = 0, mb_off = 0, row_off = 0;
+  int mbw = 0, mby = 0, mbx = 0, seen = 0;
+  const u8* yp = nullptr;
+  bool seg_on = false;
+  CostCtx cc;
+  cc.probs = nullptr; cc.level_cost = nullptr;
 #ifdef ZW_WAIT_STATS
-    const long long r0 = clock64();
+  long long r0 = 0;
 #endif
-    const RowRef rr = P.rows[t];
-    const ImageDesc d = P.img[rr.img];
-    const ImageState& IS = P.st[rr.img];
-    const int mbw = d.mbw, mby = rr.mby;
-    const int pw = mbw * 16;
-    const u8* yp = P.planes + d.y_off;
-    const u32 row_mb0 = d.mb_off + mby * mbw;
-    const u32 up_mb0 = row_mb0 - mbw;  // only dereferenced when mby > 0
-    CostCtx cc;
-    cc.probs = PASS == 1 ? ZW_TAB(kCoeffProbs) : P.probs + (size_t)rr.img * 1056;
-    cc.level_cost = PASS == 1 ? nullptr : P.lcost + (size_t)rr.img * 6528;
-    const bool seg_on = IS.seg_enabled != 0;
 
-    // row-start state (vp8.rs:1339-1344 / :1423-1429)
-    u32 left_nz = 0;
-    if (lane < 17) W.left_y[lane] = 129;
-    __syncwarp();
-
-    int seen = 0;  // last observed progress of the row above (lane 0)
-    for (int mbx = 0; mbx < mbw; mbx++) {
-      if (mby > 0) {  // wait for the top / top-right neighbours
-        // start_slack > 2 makes a row START only once the row above is that many macroblocks ahead
-        // (tuning knob, default off: measured with ZW_WAIT_STATS, rows wait ~1 % of their time).
-        const int need = min(mbx == 0 ? max(2, (int)P.start_slack) : mbx + 2, mbw);
+  for (;;) {
+    if (!have_row && !done) {
+      u32 t = 0;
+      if (lane == 0) t = atomicAdd(&P.ticket[PASS - 1], 1u);
+      t = __shfl_sync(FULL, t, 0);
+      if (t >= P.n_rows) {
+        if (!LS) break;
+        done = true;
+        if (lane == 0) atomicSub(&s_active, 1);
+      } else {
+#ifdef ZW_WAIT_STATS
+        r0 = clock64();
+#endif
+        const RowRef rr = P.rows[t];
+        const ImageDesc d = P.img[rr.img];
+        img = rr.img;
+        mbw = d.mbw; mby = rr.mby; mb_off = d.mb_off; row_off = d.row_off;
+        yp = P.planes + d.y_off;
+        row_mb0 = d.mb_off + mby * mbw;
+        up_mb0 = row_mb0 - mbw;  // only dereferenced when mby > 0
+        cc.probs = PASS == 1 ? ZW_TAB(kCoeffProbs) : P.probs + (size_t)img * 1056;
+        cc.level_cost = PASS == 1 ? nullptr : P.lcost + (size_t)img * 6528;
+        seg_on = P.st[img].seg_enabled != 0;
+        // row-start state (vp8.rs:1339-1344 / :1423-1429)
+        left_nz = 0; mbx = 0; seen = 0;
+        if (lane < 17) W.left_y[lane] = 129;
+        __syncwarp();
+        have_row = true;
+      }
+    }
+    // ---- dependency: the top / top-right neighbours (row above finished mbx + 1) ----
+    bool work = have_row;
+    if (work && mby > 0) {
+      // start_slack > 2 makes a row START only once the row above is that many macroblocks ahead
+      // (tuning knob, default off: measured with ZW_WAIT_STATS, rows wait ~1 % of their time).
+      const int need = min(mbx == 0 ? max(2, (int)P.start_slack) : mbx + 2, mbw);
+      if (LS) {  // never block inside a lock-step round: look once, sit the round out if not ready
+        int ok = 1;
+        if (lane == 0 && seen < need) { seen = ld_flag(&progress[row_off + mby - 1]); ok = seen >= need; }
+        work = __shfl_sync(FULL, ok, 0) != 0;
+      } else {
         if (lane == 0 && seen < need) {
 #ifdef ZW_WAIT_STATS
           const long long w0 = clock64();
 #endif
-          while ((seen = ld_flag(&progress[d.row_off + mby - 1])) < need) __nanosleep(100);
+          while ((seen = ld_flag(&progress[row_off + mby - 1])) < need) __nanosleep(100);
 #ifdef ZW_WAIT_STATS
           atomicAdd(reinterpret_cast<unsigned long long*>(P.ticket) + 2 + PASS, (unsigned long long)(clock64() - w0));
 #endif
         }
         __syncwarp();
       }
-      const u32 gmb = row_mb0 + mbx;
-      const int seg = seg_on ? P.segmap[gmb] : 0;
-      const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
-      u32 top_nz = 0;
+    }
+    if (LS) {
+      __syncthreads();            // phase barrier 1 (s_active only changes at ticket time, i.e. before it)
+      if (s_active == 0) break;   // every warp reads the same value: the next change comes after barrier 3
+    }
+    const u32 gmb = row_mb0 + mbx;
+    int seg = 0;
+    u32 top_nz = 0;
+    const SegParams* SPp = &P.segtab[P.base_qidx];
+    if (work) {
+      seg = seg_on ? P.segmap[gmb] : 0;
+      SPp = &P.segtab[seg_on ? P.st[img].seg_qidx[seg] : P.base_qidx];
       if (PASS == 2 && mby > 0) top_nz = __ldcg(&P.nz_after[up_mb0 + mbx]);
-      load_luma_mb(W, P, yp, pw, mbw, mbx, mby, up_mb0, lane);
+      load_luma_mb(W, P, yp, mbw * 16, mbw, mbx, mby, up_mb0, lane);
       for (int k = lane; k < 136; k += 32) reinterpret_cast<u32*>(W.rec.levels)[k] = 0;  // luma levels [0..16]
       __syncwarp();
-
-      const LumaOut L = luma_mb(W, SH, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane);
-      bool skip = false;
-      u32 out_top = 0, out_left = 0;
-      if (PASS == 2) {
-        // chroma of this macroblock was coded by k_chroma2 (it does not depend on luma)
-        const u32 uvnz = P.uvflags[gmb];
-        skip = !(L.simple_nz || uvnz != 0);
-        complexity_after(L.use_i4, skip, L.y2nz, L.ynz, uvnz, top_nz, left_nz, out_top, out_left);
-      }
-      if (lane == 0) {
-        W.rec.ymode = L.use_i4 ? 4 : (u8)L.mode16;
-        W.rec.segment = (u8)seg;
-        W.rec.skip = skip;
-        if (PASS == 2) {
-          W.rec.top_nz = (u16)top_nz;
-          W.rec.left_nz = (u16)left_nz;
-          // chroma-owned header fields: keep what k_chroma2 stored
-          W.rec.uvmode = recs[gmb].uvmode;
-          *reinterpret_cast<u32*>(W.rec.derr_left) = *reinterpret_cast<const u32*>(recs[gmb].derr_left);
-          *reinterpret_cast<u32*>(W.rec.derr_top) = *reinterpret_cast<const u32*>(recs[gmb].derr_top);
-        } else {
-          // pass 1: luma flags parked here until k_chroma1 completes the record
-          W.rec.uvmode = 0;
-          W.rec.top_nz = (u16)L.ynz;
-          W.rec.left_nz = (u16)((L.y2nz ? 1 : 0) | (L.simple_nz ? 2 : 0));
-          *reinterpret_cast<u32*>(W.rec.derr_left) = 0;
-          *reinterpret_cast<u32*>(W.rec.derr_top) = 0;
-        }
-      }
-      if (lane < 16) W.rec.bmodes[lane] = L.use_i4 ? W.bmodes[lane] : 0;
-      __syncwarp();
-      {
-        // header (8 words) + luma levels (136 words); a skipped MB codes nothing: zero all 200 level words
-        const u32* s = reinterpret_cast<const u32*>(&W.rec);
-        u32* g = reinterpret_cast<u32*>(&recs[gmb]);
-        if (PASS == 2 && skip) {
-          for (int k = lane; k < 208; k += 32) g[k] = k < 8 ? s[k] : 0u;
-        } else {
-          for (int k = lane; k < 144; k += 32) g[k] = s[k];  // chroma levels: k_chroma2 / the pass-1 chroma chain
-        }
-      }
-      left_nz = out_left;
-      // borders for the neighbours
-      if (lane < 17) W.left_y[lane] = W.yws[lane * 32 + 16];
-      MbBottom* bo = &P.bottom[gmb];
-      if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
-      if (PASS == 2 && lane == 0) P.nz_after[gmb] = (u16)out_top;
-      fence_release();
-      __syncwarp();
-      if (lane == 0) st_flag(&progress[d.row_off + mby], mbx + 1);
     }
+    const SegParams& SP = *SPp;
+    const LumaOut L = luma_mb<LS>(W, SH, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane, work);
+    if (!work) continue;
+    bool skip = false;
+    u32 out_top = 0, out_left = 0;
+    if (PASS == 2) {
+      // chroma of this macroblock was coded by k_chroma2 (it does not depend on luma)
+      const u32 uvnz = P.uvflags[gmb];
+      skip = !(L.simple_nz || uvnz != 0);
+      complexity_after(L.use_i4, skip, L.y2nz, L.ynz, uvnz, top_nz, left_nz, out_top, out_left);
+    }
+    if (lane == 0) {
+      W.rec.ymode = L.use_i4 ? 4 : (u8)L.mode16;
+      W.rec.segment = (u8)seg;
+      W.rec.skip = skip;
+      if (PASS == 2) {
+        W.rec.top_nz = (u16)top_nz;
+        W.rec.left_nz = (u16)left_nz;
+        // chroma-owned header fields: keep what k_chroma2 stored
+        W.rec.uvmode = recs[gmb].uvmode;
+        *reinterpret_cast<u32*>(W.rec.derr_left) = *reinterpret_cast<const u32*>(recs[gmb].derr_left);
+        *reinterpret_cast<u32*>(W.rec.derr_top) = *reinterpret_cast<const u32*>(recs[gmb].derr_top);
+      } else {
+        // pass 1: luma flags parked here until k_finish1 completes the record
+        W.rec.uvmode = 0;
+        W.rec.top_nz = (u16)L.ynz;
+        W.rec.left_nz = (u16)((L.y2nz ? 1 : 0) | (L.simple_nz ? 2 : 0));
+        *reinterpret_cast<u32*>(W.rec.derr_left) = 0;
+        *reinterpret_cast<u32*>(W.rec.derr_top) = 0;
+      }
+    }
+    if (lane < 16) W.rec.bmodes[lane] = L.use_i4 ? W.bmodes[lane] : 0;
+    __syncwarp();
+    {
+      // header (8 words) + luma levels (136 words); a skipped MB codes nothing: zero all 200 level words
+      const u32* sr = reinterpret_cast<const u32*>(&W.rec);
+      u32* g = reinterpret_cast<u32*>(&recs[gmb]);
+      if (PASS == 2 && skip) {
+        for (int k = lane; k < 208; k += 32) g[k] = k < 8 ? sr[k] : 0u;
+      } else {
+        for (int k = lane; k < 144; k += 32) g[k] = sr[k];  // chroma levels: k_chroma2 / the pass-1 chroma chain
+      }
+    }
+    left_nz = out_left;
+    // borders for the neighbours
+    if (lane < 17) W.left_y[lane] = W.yws[lane * 32 + 16];
+    MbBottom* bo = &P.bottom[gmb];
+    if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
+    if (PASS == 2 && lane == 0) P.nz_after[gmb] = (u16)out_top;
+    fence_release();
+    __syncwarp();
+    if (lane == 0) st_flag(&progress[row_off + mby], mbx + 1);
+    mbx++;
+    if (mbx == mbw) {
+      have_row = false;
 #ifdef ZW_WAIT_STATS
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.ticket) + 4 + PASS, (unsigned long long)(clock64() - r0));
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.ticket) + 4 + PASS, (unsigned long long)(clock64() - r0));
 #endif
+    }
   }
+  (void)mb_off;
 }
 
 #ifndef ZW_CHROMA1_MIN_BLOCKS
