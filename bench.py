@@ -235,6 +235,8 @@ def main():
     e2e_s = time.perf_counter() - t0
     pipe.close()
 
+    int_peak = ctx.measure_int_peak()  # thread-level integer instructions / s (microbenchmark, outside the timed regions)
+
     # ---- parity spot check (after the timed regions) -----------------------------------------
     parity = None
     if rank == 0 and args.check > 0:
@@ -296,6 +298,30 @@ def main():
             "kernel_wall_ms_per_step": 1e3 * wall_kernel_s / args.steps,
             "parity": parity,
         }
+        # Integer roofline of the mode search (north_star: "ALU/IMAD pipe utilisation against the sm_100a integer issue
+        # peak"): algorithmic int-ops = primitive invocations counted by the instrumented oracle on sample images of this
+        # workload x fixed per-primitive costs (tests/oracle_lib.py OP_COST), per pass and plane.
+        try:
+            import oracle_lib as O
+            ops = {}
+            n_s = 4
+            for i in range(n_s):
+                _, o = O.count_ops(imgs[i * (n // n_s)], QUALITY, METHOD)
+                for k, v in o.items():
+                    ops[k] = ops.get(k, 0.0) + v / (n_s * W * H)
+            p2_s = stage_ms["pass2_ms"] / args.steps / 1e3
+            p1_s = stage_ms["pass1_ms"] / args.steps / 1e3
+            all_s = dev_s / args.steps
+            line["roofline_int"] = {
+                "bound": "int-issue", "unit": "Tint-op/s", "peak": int_peak / 1e12, "peak_source": "zw_measure_int_peak (IMAD + LOP3/IADD3 chains, this run)",
+                "ops_per_px": ops,
+                "kernel": "k_search<2> (pass-2 luma)", "achieved": ops["pass2_luma"] * pix / p2_s / 1e12,
+                "frac": ops["pass2_luma"] * pix / p2_s / int_peak,
+                "pass1_luma": {"achieved": ops["pass1_luma"] * pix / p1_s / 1e12, "frac": ops["pass1_luma"] * pix / p1_s / int_peak},
+                "whole_step": {"achieved": sum(ops.values()) * pix / all_s / 1e12, "frac": sum(ops.values()) * pix / all_s / int_peak},
+                "note": "1 algorithmic op counted as 1 instruction slot; sample = %d images of the batch" % n_s}
+        except Exception as e:  # the figure is informative; never fail the bench on it
+            line["roofline_int"] = {"error": str(e)}
         if not args.no_cpu and world == 1:
             lib = native_oracle()
             cores = os.cpu_count() or 1

@@ -62,7 +62,7 @@ class ZwTiming(C.Structure):
 # Every symbol include/zenwebp_b200.h declares.
 EXPORTS = ["zw_create", "zw_destroy", "zw_last_error", "zw_strerror", "zw_free", "zw_max_output_size",
            "zw_encode_vp8_batch", "zw_encode_webp_batch", "zw_stage_batch", "zw_encode_resident", "zw_download",
-           "zw_dump_stage", "zw_version"]
+           "zw_dump_stage", "zw_version", "zw_measure_int_peak"]
 
 _lib = None
 
@@ -93,5 +93,6 @@ def load():
     L.zw_encode_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ZwTiming)]
     L.zw_download.argtypes = [C.c_void_p, C.POINTER(ZwOutput), C.c_size_t, C.c_int, C.POINTER(ZwTiming)]
     L.zw_dump_stage.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zw_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L

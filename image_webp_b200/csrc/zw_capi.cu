@@ -236,11 +236,13 @@ static void fill_params(Lane* c) {
   P.start_slack = c->start_slack;
 }
 
+static inline u32 color_bpp(u32 color) { return color + 1; }  // L8 1, La8 2, Rgb8 3, Rgba8 4 (api.rs:83-92)
+
 static int validate_image(const zw_image& im) {
-  if (im.color != ZW_COLOR_RGB8 && im.color != ZW_COLOR_RGBA8) return ZW_ERR_INVALID_PARAM;
+  if (im.color > ZW_COLOR_RGBA8) return ZW_ERR_INVALID_PARAM;
   if (im.width == 0 || im.height == 0 || im.width > 16383 || im.height > 16383) return ZW_ERR_INVALID_DIMENSIONS;
   if (im.data == nullptr) return im.len == 0 ? ZW_ERR_INVALID_BUFFER_SIZE : ZW_ERR_INVALID_PARAM;
-  const u64 bpp = im.color == ZW_COLOR_RGB8 ? 3 : 4;
+  const u64 bpp = color_bpp(im.color);
   if ((u64)im.width * im.height * bpp != (u64)im.len) return ZW_ERR_INVALID_BUFFER_SIZE;
   return ZW_OK;
 }
@@ -311,7 +313,7 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after)
     memset(&d, 0, sizeof(d));
     d.width = imgs[i].width; d.height = imgs[i].height;
     d.mbw = (d.width + 15) / 16; d.mbh = (d.height + 15) / 16;
-    d.bpp = imgs[i].color == ZW_COLOR_RGB8 ? 3 : 4;
+    d.bpp = color_bpp(imgs[i].color);
     d.mb_off = n_mb; d.row_off = n_rows;
     d.use_segments = (d.mbw * d.mbh >= 256) ? 1 : 0;
     d.rgb_off = rgb_bytes; d.y_off = plane_bytes;
@@ -573,6 +575,22 @@ static int lane_download(Lane* c, zw_output* outs, size_t n, int container) {
   return ZW_OK;
 }
 
+// Integer issue peak (measurement only, SURVEY.md 8(d) "INT peak: measure, don't assume"): eight
+// independent chains per thread, alternating the fma pipe (IMAD) and the alu pipe (LOP3 / IADD3),
+// 48 integer instructions per thread and outer iteration, full occupancy.
+__global__ void __launch_bounds__(256) k_intpeak(u32* out, int iters) {
+  u32 a = threadIdx.x, b = blockIdx.x + 1, c = 3, d = 5, e = 7, f = 11, g = 13, h = 17;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      a = a * 5 + b;  c = c * 3 + d;  e = e * 7 + f;  g = g * 9 + h;    // 4 IMAD
+      b = (b ^ c) + 1; d = (d ^ e) + 3; f = (f ^ g) + 5; h = (h ^ a) + 7; // 4 (LOP3, IADD) pairs; may fuse
+    }
+  }
+  if ((a ^ b ^ c ^ d ^ e ^ f ^ g ^ h) == 0x12345678u) out[0] = a;
+}
+
 static void add_timing(zw_timing& a, const zw_timing& L) {
   a.h2d_ms += L.h2d_ms; a.yuv_ms += L.yuv_ms; a.analysis_ms += L.analysis_ms; a.pass1_ms += L.pass1_ms;
   a.stats_ms += L.stats_ms; a.pass2_ms += L.pass2_ms; a.token_ms += L.token_ms; a.boolcode_ms += L.boolcode_ms;
@@ -752,7 +770,7 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
   while (i0 < n) {
     size_t i1 = i0, bytes = 0;
     while (i1 < n && (i1 - i0) < 32768) {
-      const size_t f = validate_image(imgs[i1]) == ZW_OK ? image_footprint(imgs[i1].width, imgs[i1].height, imgs[i1].color == ZW_COLOR_RGB8 ? 3 : 4) : 0;
+      const size_t f = validate_image(imgs[i1]) == ZW_OK ? image_footprint(imgs[i1].width, imgs[i1].height, color_bpp(imgs[i1].color)) : 0;
       if (i1 > i0 && bytes + f > c->budget) break;
       bytes += f; i1++;
     }
@@ -777,6 +795,34 @@ int zw_encode_vp8_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
 }
 int zw_encode_webp_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing) {
   return encode_batch(c, imgs, n, quality, method, outs, timing, 1);
+}
+
+int zw_measure_int_peak(zw_ctx* c, double* int_instr_per_s) {
+  if (!c || !int_instr_per_s) return g_last_error = ZW_ERR_INVALID_PARAM;
+  CK(cudaSetDevice(c->device));
+  Lane* l = c->lanes[0];
+  CK(l->d_ticket.reserve(64));
+  const int iters = 20000, grid = c->sm_count * 8;
+  // instructions per thread and outer iteration, read off the SASS of k_intpeak (cuobjdump -sass):
+  // 16 IMAD (fma pipe) + 16 LOP3 + 16 IADD3/VIADD (alu pipe) = 48; loop overhead not counted
+  const double per_iter = 48.0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_intpeak<<<grid, 256, 0, l->stream>>>(l->d_ticket.as<u32>() + 15, 100);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    CK(cudaEventRecord(e0, l->stream));
+    k_intpeak<<<grid, 256, 0, l->stream>>>(l->d_ticket.as<u32>() + 15, iters);
+    CK(cudaEventRecord(e1, l->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *int_instr_per_s = (double)grid * 256.0 * (double)iters * per_iter / ((double)best * 1e-3);
+  return g_last_error = ZW_OK;
 }
 
 int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len) {

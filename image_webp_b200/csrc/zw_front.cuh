@@ -98,6 +98,16 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
           uw |= (u32)u << (8 * k);
           vw |= (u32)v << (8 * k);
         }
+      } else if (bpp <= 2) {
+        // L8 / La8 (convert_image_y, src/decoder/yuv.rs:806-845): Y = the grey sample, U = V = 127
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int sx = min(tx + k, w - 1) - xs;
+          y0w[k >> 2] |= (u32)((lumaA_is_A ? sA : sB)[sx * bpp]) << (8 * (k & 3));
+          y1w[k >> 2] |= (u32)(sB[sx * bpp]) << (8 * (k & 3));
+        }
+        uw = 0x7f7f7f7fu;
+        vw = 0x7f7f7f7fu;
       } else {
 #pragma unroll
       for (int k = 0; k < 8; k++) {

@@ -153,6 +153,9 @@ class Context:
         Returns (outputs, timing dict)."""
         if not params.use_lossy:
             raise NotImplementedError("only the lossy VP8 path is implemented on the GPU (SURVEY.md §2)")
+        if container and color.has_alpha():
+            # the reference wraps lossy + alpha in VP8X with a lossless ALPH chunk (api.rs:1330-1394): not built
+            raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f); container=False returns the VP8 payload")
         arr, keep = self._as_images(images, color)
         outs = (_lib.ZwOutput * len(images))()
         t = _lib.ZwTiming()
@@ -184,6 +187,14 @@ class Context:
         if rc != 0:
             _raise_for(rc, self.lib)
         return self._collect(outs, raise_errors), t.as_dict()
+
+    def measure_int_peak(self):
+        """Thread-level integer instructions per second of this GPU (issue-rate microbenchmark)."""
+        x = C.c_double(0)
+        rc = self.lib.zw_measure_int_peak(self.h, C.byref(x))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return x.value
 
     def dump_stage(self, index, name, dtype=np.uint8):
         n = C.c_size_t(0)
@@ -265,8 +276,6 @@ class WebPEncoder:
     def encode(self, data, width, height, color):
         if not self.params.use_lossy:
             raise NotImplementedError("lossless VP8L encoding is out of scope of the GPU path (SURVEY.md §2)")
-        if color not in (ColorType.Rgb8, ColorType.Rgba8):
-            raise NotImplementedError("L8/La8 input is a 'next' row (SURVEY.md §8f)")
         if color.has_alpha():
             raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f)")
         if width > 65535 or height > 65535:

@@ -110,6 +110,12 @@ int zw_stage_batch(zw_ctx* ctx, const zw_image* imgs, size_t n);
 int zw_encode_resident(zw_ctx* ctx, int quality, int method, zw_timing* timing);
 int zw_download(zw_ctx* ctx, zw_output* outs, size_t n, int container, zw_timing* timing);
 
+/* Measurement helper (no reference counterpart; SURVEY.md 8(d) "INT peak: measure, don't assume"):
+ * runs an integer-issue microbenchmark (IMAD + LOP3/IADD3 chains, full occupancy) on the context's
+ * GPU and returns thread-level integer instructions per second -- the denominator of the
+ * mode-search kernels' integer roofline in bench.py. */
+int zw_measure_int_peak(zw_ctx* ctx, double* int_instr_per_s);
+
 /* Parity/debug: copy a named intermediate stage of image `index` of the last encoded chunk to
  * host memory (names follow SURVEY.md Appendix F: "YUV_Y","YUV_U","YUV_V","ALPHA","ALPHA_HIST",
  * "SEG_MAP","SEG_QIDX","SEG_TREE_PROBS","SEG_UPDATE_MAP","P1MB","STATS","PROBS","SKIP_PROB",

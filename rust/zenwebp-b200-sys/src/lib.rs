@@ -42,4 +42,5 @@ extern "C" {
     pub fn zw_download(ctx: *mut zw_ctx, outs: *mut zw_output, n: usize, container: c_int, timing: *mut zw_timing) -> c_int;
     pub fn zw_dump_stage(ctx: *mut zw_ctx, index: usize, stage: *const c_char, dst: *mut c_void, cap: usize, len: *mut usize) -> c_int;
     pub fn zw_version() -> *const c_char;
+    pub fn zw_measure_int_peak(ctx: *mut zw_ctx, int_instr_per_s: *mut f64) -> c_int;
 }

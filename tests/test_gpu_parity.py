@@ -96,6 +96,31 @@ def test_rgba_input_ignores_alpha(ctx):
     assert outs[0] == ref
 
 
+@pytest.mark.parametrize("w,h,q,m", [(320, 272, 75, 4), (99, 87, 50, 2), (17, 33, 90, 6), (768, 512, 75, 4)])
+def test_grey_input_l8_la8(ctx, w, h, q, m):
+    # L8 / La8 go through convert_image_y (yuv.rs:806): Y = the grey sample, U = V = 127
+    import image_webp_b200 as Z
+    grey = synth.photo_like(w, h, 50 + w)[:, :, 1:2].copy()
+    outs, _ = ctx.encode_batch([grey], _params(q, m), color=Z.ColorType.L8)
+    rc, ref, dump = O.encode(grey, q, m, color="L8", want_dump=True)
+    assert rc == 0
+    if outs[0] != ref:
+        pytest.fail("L8 differs:\n" + "\n".join(PU.compare_stages(ctx, 0, dump, (w + 15) // 16)[:4]))
+    la = np.concatenate([grey, np.full((h, w, 1), 200, np.uint8)], axis=2)
+    outs, _ = ctx.encode_batch([la], _params(q, m), color=Z.ColorType.La8, container=False)
+    rc, ref2, _ = O.encode(la, q, m, color="La8", container=False)
+    assert rc == 0 and outs[0] == ref2
+    assert ref2 == ref[20:20 + len(ref2)]  # same VP8 payload as the L8 file: alpha is ignored by the VP8 path
+    # WebPEncoder drop-in: L8 accepted, alpha colours rejected (lossy+alpha needs VP8X/ALPH, not built)
+    out = bytearray()
+    enc = Z.WebPEncoder(out)
+    enc.set_params(_params(q, m))
+    enc.encode(grey.tobytes(), w, h, Z.ColorType.L8)
+    assert bytes(out) == ref
+    with pytest.raises(NotImplementedError):
+        Z.WebPEncoder(bytearray()).encode(la.tobytes(), w, h, Z.ColorType.La8)
+
+
 def test_decodes_with_libwebp_and_psnr(ctx):
     # the reference's own acceptance test: libwebp decodes our output, PSNR thresholds
     # (tests/lossy_encoder_quality.rs:160-198, :345-380)
