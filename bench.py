@@ -121,7 +121,7 @@ def run_reference(args):
     from image_webp_b200 import synth
     cores = os.cpu_count() or 1
     lib = native_oracle()
-    n_sample = max(cores * 4, 64)
+    n_sample = max(cores * 16, 128)  # ~2-4 s of all-core CPU work per step
     imgs = synth.batch_photo_like(n_sample, W, H, 0)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_run(imgs[:cores], cores, lib)
@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight in the end-to-end leg (BatchPipeline depth)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end leg (BatchPipeline depth)")
     ap.add_argument("--check", type=int, default=8, help="images per step byte-compared with the oracle after timing")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -325,7 +325,7 @@ def main():
         if not args.no_cpu and world == 1:
             lib = native_oracle()
             cores = os.cpu_count() or 1
-            ns = max(cores * 4, 64)
+            ns = max(cores * 32, 256)  # ~5-10 s of all-core CPU work
             sample = host.numpy()[:ns]
             cpu_run(sample[:cores], cores, lib)
             ts = cpu_run(sample, cores, lib)
