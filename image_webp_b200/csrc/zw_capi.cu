@@ -285,12 +285,13 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   if (c->d_ticket.reserve(64) != cudaSuccess) { lane_destroy(c); return nullptr; }
   int b1 = 0, b2 = 0, b4 = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, SEARCH_WARPS * 32, sizeof(SearchShared));
+  cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(1)));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, search_warps(1) * 32, search_smem_bytes(search_warps(1)));
   cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2)));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2)));
   if (warps_hint > 0) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
-    b1 = std::min(b1, cap); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
+    b1 = std::min(b1, std::max(1, warps_hint / search_warps(1))); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
   }
   if (const char* env = getenv("ZW_START_SLACK")) c->start_slack = (u32)std::max(0, atoi(env));
   c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
@@ -414,8 +415,9 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
   {  // (3) pass 1: luma wavefront, then the per-image chroma chains, then the bookkeeping.  (Running the
      // chains on a side stream UNDER the wavefront was measured: they starve -- 43 ms instead of 8.8 ms,
      // instruction-cache contention with the wavefront's code -- so the kernels stay back to back.)
-    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_search<1><<<g1, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    const int w1 = search_warps(1);
+    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + w1 - 1) / w1);
+    k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
     CK(cudaEventRecord(c->ev[15], s));
     const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);

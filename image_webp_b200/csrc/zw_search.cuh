@@ -1128,10 +1128,17 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
 // ---------------------------------------------------------------------------------------------
 // The wavefront kernel.  PASS 1: luma only (see file header).  PASS 2: luma + chroma.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr bool search_lockstep(int pass) { return pass == 2 && LS_WARPS > 0; }
+#ifndef ZW_LS_PASS1
+#define ZW_LS_PASS1 0  // measured: pass 1 (9-14 % "no instruction" stalls) does not gain from the lock step
+#endif
+__host__ __device__ constexpr bool search_lockstep(int pass) { return (pass == 2 || ZW_LS_PASS1) && LS_WARPS > 0; }
 __host__ __device__ constexpr int search_warps(int pass) { return search_lockstep(pass) ? LS_WARPS : SEARCH_WARPS; }
 __host__ __device__ constexpr int search_min_blocks(int pass) {
+#ifdef ZW_LS_MIN_BLOCKS
+  return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
+#else
   return search_lockstep(pass) ? (ZW_SEARCH_MIN_BLOCKS * SEARCH_WARPS) / (LS_WARPS > 0 ? LS_WARPS : 1) : ZW_SEARCH_MIN_BLOCKS;
+#endif
 }
 // dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
 __host__ __device__ constexpr size_t search_smem_bytes(int nwarps) { return sizeof(SearchShared) + (size_t)(nwarps - SEARCH_WARPS) * sizeof(WarpScratch); }

@@ -106,6 +106,7 @@ struct ArithmeticEncoder {
   u32 bottom = 0;
   u32 range = 255;
   i32 bit_num = 24;
+  std::vector<u16>* log = nullptr;  // dump only: every (bit << 8 | probability) handed to write_bool
 
   void add_one_to_output() {  // arithmetic.rs:47-60
     size_t i = writer.size();
@@ -121,6 +122,7 @@ struct ArithmeticEncoder {
   }
   void write_flag(bool f) { write_bool(f, 128); }  // arithmetic.rs:63
   void write_bool(bool b, u8 probability) {        // arithmetic.rs:67-95
+    if (log) log->push_back((u16)(((u16)b << 8) | probability));
     u32 split = 1 + (((range - 1) * (u32)probability) >> 8);
     if (b) {
       bottom += split;
@@ -2665,6 +2667,8 @@ struct Vp8Encoder {
     }
     if (level_costs.dirty) level_costs.calculate(token_probs);
 
+    std::vector<u16> sym_hdr, sym_tok;  // dump only: the symbol streams of the two boolean coders
+    if (dump) { encoder.log = &sym_hdr; partitions[0].log = &sym_tok; }
     encode_compressed_frame_header();
 
     // ===== PASS 2 =====
@@ -2695,6 +2699,8 @@ struct Vp8Encoder {
     std::vector<u8> compressed_header_bytes = encoder.flush_and_get_buffer();
     encoder = ArithmeticEncoder();
     if (dump) {
+      dump->put("HDR_TOKENS", sym_hdr.data(), sym_hdr.size());
+      dump->put("TOK_TOKENS", sym_tok.data(), sym_tok.size());
       dump->put("P2MB", rec_p2.data(), rec_p2.size());
       dump->put("PART0", compressed_header_bytes.data(), compressed_header_bytes.size());
       dump->put("TOKEN_PROBS_FINAL", &token_probs[0][0][0][0], 1056);

@@ -62,8 +62,8 @@ COLOR = {"L8": 0, "La8": 1, "Rgb8": 2, "Rgba8": 3}
 
 STAGES = ["YUV_Y", "YUV_U", "YUV_V", "BASE_QIDX", "SEG_ENABLED", "ALPHA", "ALPHA_HIST", "SEG_CENTERS", "SEG_MAP256",
           "SEG_MID", "SEG_MAP", "SEG_QIDX", "SEG_TREE_PROBS", "SEG_UPDATE_MAP", "P1MB", "STATS", "PROBS",
-          "PROBS_UPDATED", "SKIP_PROB", "LCOST", "P2MB", "PART0", "PART1", "TOKEN_PROBS_FINAL", "VP8"]
-_STAGE_DTYPES = {"ALPHA_HIST": "<u4", "SEG_MID": "<i4", "STATS": "<u4", "LCOST": "<u2", "P1MB": MB_DTYPE, "P2MB": MB_DTYPE}
+          "PROBS_UPDATED", "SKIP_PROB", "LCOST", "P2MB", "HDR_TOKENS", "TOK_TOKENS", "PART0", "PART1", "TOKEN_PROBS_FINAL", "VP8"]
+_STAGE_DTYPES = {"HDR_TOKENS": "<u2", "TOK_TOKENS": "<u2", "ALPHA_HIST": "<u4", "SEG_MID": "<i4", "STATS": "<u4", "LCOST": "<u2", "P1MB": MB_DTYPE, "P2MB": MB_DTYPE}
 
 
 def encode(img, quality, method, color="Rgb8", container=True, want_dump=False):
