@@ -137,19 +137,18 @@ __device__ __forceinline__ int pred_big(const u8* ws, int cofs, int mode, int x,
 // The same for a whole 4x4 block (bx,by) of the 16x16 / 8x8 prediction: 4 top + 4 left + corner
 // loads, then selects.
 __device__ __forceinline__ void pred_block(const u8* ws, int cofs, int mode, int bx, int by, int dcv, i32* pr) {
+  // one formula for the four modes: clip255(T'[x] + L'[y] + base) with T' = T for V / TM (else 0),
+  // L' = L for H / TM (else 0), base = dc for DC, -P for TM (else 0); the clip only acts for TM
+  const bool useT = (mode & 1) != 0, useL = mode >= 2;
   i32 T[4], L[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    T[k] = ws[cofs + 1 + bx * 4 + k];
-    L[k] = ws[(1 + by * 4 + k) * 32 + cofs];
+    T[k] = useT ? (i32)ws[cofs + 1 + bx * 4 + k] : 0;
+    L[k] = useL ? (i32)ws[(1 + by * 4 + k) * 32 + cofs] : 0;
   }
-  const i32 P = ws[cofs];
+  const i32 base = mode == 0 ? dcv : (mode == 3 ? -(i32)ws[cofs] : 0);
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const i32 t = T[k & 3], l = L[k >> 2];
-    const i32 tm = clip255(l + t - P);
-    pr[k] = mode == 0 ? dcv : (mode == 1 ? t : (mode == 2 ? l : tm));
-  }
+  for (int k = 0; k < 16; k++) pr[k] = clip255(T[k & 3] + L[k >> 2] + base);
 }
 
 // 4x4 predictors (prediction.rs:326-554) as lookups.  Every pixel of the eight directional modes
@@ -282,6 +281,29 @@ __device__ __forceinline__ i32 coop_idct(i32 v, int lane) {
   else if (x == 1) o = p + t;
   else o = t - p;
   return (o + 4) >> 3;
+}
+
+// Y2 transforms with one coefficient per lane (n = lane & 15 = block index in raster order).  Both are
+// the same +-1 butterflies (wht4x4 / iwht4x4 in zw_prims.cuh; transform.rs:116-158, :82-114) with
+// different rounding: the lane pattern is that of coop_fdct (outputs land in 0,2,1,3 order per pass).
+template <bool FORWARD>
+__device__ __forceinline__ i32 coop_wht_any(i32 v, int lane) {
+  const int x = lane & 3, y = (lane >> 2) & 3;
+  // FORWARD runs rows then columns, the inverse columns then rows; the arithmetic per pass is the same
+  const int m1a = FORWARD ? 3 : 12, m1b = FORWARD ? 1 : 4, m2a = FORWARD ? 12 : 3, m2b = FORWARD ? 4 : 1;
+  const int i1 = FORWARD ? x : y, i2 = FORWARD ? y : x;
+  i32 p = __shfl_xor_sync(FULL, v, m1a);
+  i32 t = i1 < 2 ? v + p : p - v;          // a b c d
+  p = __shfl_xor_sync(FULL, t, m1b);
+  i32 r = (i1 == 0 || i1 == 2) ? t + p : (i1 == 1 ? p - t : t - p);  // y0 y2 y1 y3
+  p = __shfl_xor_sync(FULL, r, m2a);
+  t = i2 < 2 ? r + p : p - r;
+  p = __shfl_xor_sync(FULL, t, m2b);
+  i32 o = (i2 == 0 || i2 == 2) ? t + p : (i2 == 1 ? p - t : t - p);
+  o = FORWARD ? (o + (o > 0 ? 1 : 0)) / 2 : (o + 3) >> 3;
+  // lane (x,y) holds output (R[x], R[y]), R = {0,2,1,3}: un-permute
+  const int rx = ((x & 1) << 1) | (x >> 1), ry = ((y & 1) << 1) | (y >> 1);
+  return __shfl_sync(FULL, o, (lane & 16) | (ry * 4 + rx));
 }
 
 __device__ __forceinline__ int half_sum(int v) {  // sum over the 16 lanes of each half-warp
@@ -580,22 +602,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
     }
     fdct4x4(c);
-    W.dcbuf[lane] = c[0];
-    __syncwarp();
-    i32 y2[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) y2[k] = W.dcbuf[hb * 16 + k];
-    __syncwarp();
-    wht4x4(y2);
-#pragma unroll
-    for (int k = 0; k < 16; k++) y2[k] = quantize_coeff(y2[k], SP.y2, k);
-    const u32 cost_y2 = residual_cost_call(y2, 1, 0, 0, cc);
-#pragma unroll
-    for (int k = 0; k < 16; k++) y2[k] = dequantize(y2[k], SP.y2, k);
-    iwht4x4(y2);
-    i32 mydc = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) if (k == blk) mydc = y2[k];
+    // Y2: the DC of this lane's block is coefficient `blk` (raster order) of its mode's Y2 block
+    const i32 y2q = quantize_coeff(coop_wht_any<true>(c[0], lane), SP.y2, blk);
+    bool y2_any;
+    const u32 cost_y2 = coop_residual_cost(y2q, 1, 0, 0, cc, lane, y2_any);
+    const i32 mydc = coop_wht_any<false>(dequantize(y2q, SP.y2, blk), lane);
     i32 lv[16];
     lv[0] = 0;
     int nzc = 0;
@@ -760,32 +771,16 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       c[k] = (i32)W.src_y[y * 16 + x] - pr[k];
     }
     fdct4x4(c);
-    if (lane < 16) W.dcbuf[lane] = c[0];
-    __syncwarp();
-    i32 mydc = 0;
-    {
-      i32 y2[16];
+    // both half-warps hold the same 16 blocks here, so the cooperative Y2 transforms agree in both
+    const i32 y2q = quantize_coeff(coop_wht_any<true>(c[0], lane), SP.y2, blk);
+    y2nz = (__ballot_sync(FULL, y2q != 0) & 0xffffu) != 0;
+    if (lane < 16) {
+      int zp = 0;  // zig-zag position of natural index `lane`
 #pragma unroll
-      for (int k = 0; k < 16; k++) y2[k] = W.dcbuf[k];
-      wht4x4(y2);
-#pragma unroll
-      for (int k = 0; k < 16; k++) { y2[k] = quantize_coeff(y2[k], SP.y2, k); y2nz |= y2[k] != 0; }
-      if (lane < 16) {
-        // zig-zag position p of natural index `lane`: scatter y2[lane] to levels[0][p]
-        int p = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (ZW_TAB(kZigzag)[k] == lane) p = k;
-        i32 v = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (k == lane) v = y2[k];
-        W.rec.levels[0][p] = (i16)v;
-      }
-#pragma unroll
-      for (int k = 0; k < 16; k++) y2[k] = dequantize(y2[k], SP.y2, k);
-      iwht4x4(y2);
-#pragma unroll
-      for (int k = 0; k < 16; k++) if (k == blk) mydc = y2[k];
+      for (int k = 0; k < 16; k++) if (ZW_TAB(kZigzag)[k] == lane) zp = k;
+      W.rec.levels[0][zp] = (i16)y2q;
     }
+    const i32 mydc = coop_wht_any<false>(dequantize(y2q, SP.y2, blk), lane);
     any_simple_nz |= y2nz != 0;
     bool my_simple = false;
     i32 lv[16];
