@@ -71,6 +71,7 @@ struct __align__(16) WarpScratch {
 };
 
 struct SearchShared {
+  int4 lk[6][32];       // per-lane butterfly constants of coop_fdct / coop_idct (fill_lane_consts)
   u8 pred_idx[10][16];  // (mode, pixel) -> index into WarpScratch::dtab
   u16 dtaps[32];        // lane k -> the three edge taps of dtab[k]
   WarpScratch w[SEARCH_WARPS];
@@ -228,58 +229,65 @@ __device__ __forceinline__ i32 pred4_get(const WarpScratch& W, const u8 (*pidx)[
 // warp works on two blocks per step.  Same arithmetic as fdct4x4 / idct4x4 / residual_cost in
 // zw_prims.cuh / zw_cost.cuh (reference transform.rs:35-79,176-207; cost.rs:1670-1729).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ i32 coop_fdct(i32 v, int lane) {
-  const int x = lane & 3, y = (lane >> 2) & 3;
-  // rows: lanes x=0..3 end up holding outputs 0,2,1,3 of their row
-  i32 p = __shfl_xor_sync(FULL, v, 3);
-  i32 t = (x < 2 ? v + p : p - v) * 8;
-  i32 p2 = __shfl_xor_sync(FULL, t, 1);
-  i32 r;
-  if (x == 0) r = t + p2;
-  else if (x == 1) r = p2 - t;
-  else if (x == 2) r = (t * 2217 + p2 * 5352 + 14500) >> 12;
-  else r = (t * 2217 - p2 * 5352 + 7500) >> 12;
-  // columns: lanes y=0..3 end up holding outputs 0,2,1,3 of their column
-  p = __shfl_xor_sync(FULL, r, 12);
-  t = y < 2 ? r + p : p - r;
-  p2 = __shfl_xor_sync(FULL, t, 4);
-  i32 o;
-  if (y == 0) o = (t + p2 + 7) >> 4;
-  else if (y == 1) o = (p2 - t + 7) >> 4;
-  else if (y == 2) o = ((t * 2217 + p2 * 5352 + 12000) >> 16) + (p2 != 0 ? 1 : 0);
-  else o = (t * 2217 - p2 * 5352 + 51000) >> 16;
-  // lane (x,y) holds coefficient (R[x], R[y]), R = {0,2,1,3} (an involution): un-permute
+// Per-lane constants of the butterflies below (SearchShared::lk, filled by fill_lane_consts): the four
+// cases per stage (which output a lane produces) become one multiply-add form, so a stage costs two
+// or three instructions instead of computing all cases and selecting.
+//   lk[0] = {8*sA, A, B, C}      fdct rows:    t = 8p + 8sA*v;  r = (t*A + p2*B + C) >> S
+//   lk[1] = {S, sC, A', B'}      fdct columns: t = p + sC*r;    o = ((t*A' + p2*B' + C') >> S') + (E & (p2 != 0))
+//   lk[2] = {C', S', E, src}     src: lane holding this lane's natural-order output (un-permute)
+//   lk[3] = {KA, KB, sg, s1}     idct pass:    t = ((v*KA) >> 16) + sg*(p + ((p*KB) >> 16));  r = s1*t + s2*p
+//   lk[4] = {s2, KA', KB', sg'}  (primed: the horizontal pass, indexed by x instead of y)
+//   lk[5] = {s1', s2', 0, 0}
+__device__ __forceinline__ void fill_lane_consts(int4 (*lk)[32], int t) {
+  const int x = t & 3, y = (t >> 2) & 3;
+  // (selects, not indexed local arrays: keeps the kernels' stack frames small)
+  auto A4 = [](int i) { return i == 0 ? 1 : (i == 1 ? -1 : 2217); };
+  auto B4 = [](int i) { return i < 2 ? 1 : (i == 2 ? 5352 : -5352); };
   const int rx = ((x & 1) << 1) | (x >> 1), ry = ((y & 1) << 1) | (y >> 1);
-  return __shfl_sync(FULL, o, (lane & 16) | (ry * 4 + rx));
+  lk[0][t] = make_int4(x < 2 ? 8 : -8, A4(x), B4(x), x < 2 ? 0 : (x == 2 ? 14500 : 7500));
+  lk[1][t] = make_int4(x < 2 ? 0 : 12, y < 2 ? 1 : -1, A4(y), B4(y));
+  lk[2][t] = make_int4(y < 2 ? 7 : (y == 2 ? 12000 : 51000), y < 2 ? 4 : 16, y == 2 ? 1 : 0, ry * 4 + rx);
+  // idct case tables by index i (y for the vertical pass, x for the horizontal one):
+  //   i=0: t = v + p      i=2: t = p - v      i=1: t = mulA(v) - mulB(p)      i=3: t = mulA(v) + mulB(p)
+  //   then                i=0: r = t + p      i=3: r = p - t      i=1: r = p + t      i=2: r = t - p
+  auto KA = [](int i) { return (i & 1) ? 35468 : (i == 0 ? 65536 : -65536); };
+  auto KB = [](int i) { return (i & 1) ? 20091 : 0; };
+  auto SG = [](int i) { return i == 1 ? -1 : 1; };
+  auto S1 = [](int i) { return i == 3 ? -1 : 1; };
+  auto S2 = [](int i) { return i == 2 ? -1 : 1; };
+  lk[3][t] = make_int4(KA(y), KB(y), SG(y), S1(y));
+  lk[4][t] = make_int4(S2(y), KA(x), KB(x), SG(x));
+  lk[5][t] = make_int4(S1(x), S2(x), 0, 0);
 }
 
-__device__ __forceinline__ i32 coop_idct(i32 v, int lane) {
-  const int x = lane & 3, y = (lane >> 2) & 3;
+__device__ __forceinline__ i32 coop_fdct(i32 v, int lane, const int4 (*lk)[32]) {
+  const int4 k0 = lk[0][lane], k1 = lk[1][lane], k2 = lk[2][lane];
+  // rows: lanes x=0..3 end up holding outputs 0,2,1,3 of their row
+  i32 p = __shfl_xor_sync(FULL, v, 3);
+  i32 t = v * k0.x + (p << 3);
+  i32 p2 = __shfl_xor_sync(FULL, t, 1);
+  const i32 r = (t * k0.y + p2 * k0.z + k0.w) >> k1.x;
+  // columns: lanes y=0..3 end up holding outputs 0,2,1,3 of their column
+  p = __shfl_xor_sync(FULL, r, 12);
+  t = r * k1.y + p;
+  p2 = __shfl_xor_sync(FULL, t, 4);
+  const i32 o = ((t * k1.z + p2 * k1.w + k2.x) >> k2.y) + ((p2 != 0) ? k2.z : 0);
+  // lane (x,y) holds coefficient (R[x], R[y]), R = {0,2,1,3} (an involution): un-permute
+  return __shfl_sync(FULL, o, (lane & 16) | k2.w);
+}
+
+__device__ __forceinline__ i32 coop_idct(i32 v, int lane, const int4 (*lk)[32]) {
+  const int4 k3 = lk[3][lane], k4 = lk[4][lane], k5 = lk[5][lane];
   // vertical pass: rows 0/2 form a1,b1; rows 1/3 form c1,d1
   i32 p = __shfl_xor_sync(FULL, v, 8);
-  i32 t;
-  if (y == 0) t = v + p;                                                    // a1
-  else if (y == 2) t = p - v;                                               // b1
-  else if (y == 1) t = ((v * 35468) >> 16) - (p + ((p * 20091) >> 16));     // c1
-  else t = (p + ((p * 20091) >> 16)) + ((v * 35468) >> 16);                 // d1
+  i32 t = ((v * k3.x) >> 16) + k3.z * (p + ((p * k3.y) >> 16));
   p = __shfl_xor_sync(FULL, t, 12);
-  i32 r;
-  if (y == 0) r = t + p;       // a1 + d1
-  else if (y == 3) r = p - t;  // a1 - d1
-  else if (y == 1) r = p + t;  // b1 + c1
-  else r = t - p;              // b1 - c1
+  const i32 r = k3.w * t + k4.x * p;
   // horizontal pass with the final rounding
   p = __shfl_xor_sync(FULL, r, 2);
-  if (x == 0) t = r + p;
-  else if (x == 2) t = p - r;
-  else if (x == 1) t = ((r * 35468) >> 16) - (p + ((p * 20091) >> 16));
-  else t = (p + ((p * 20091) >> 16)) + ((r * 35468) >> 16);
+  t = ((r * k4.y) >> 16) + k4.w * (p + ((p * k4.z) >> 16));
   p = __shfl_xor_sync(FULL, t, 3);
-  i32 o;
-  if (x == 0) o = t + p;
-  else if (x == 3) o = p - t;
-  else if (x == 1) o = p + t;
-  else o = t - p;
+  const i32 o = k5.x * t + k5.y * p;
   return (o + 4) >> 3;
 }
 
@@ -716,11 +724,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
         const bool act = rank < max_modes;
         const int m = W.cand_mode[act ? rank : 0];
         const i32 pr = pred4_get(W, pidx, m, n16, P4);
-        const i32 cf = coop_fdct(srcpx - pr, lane);
+        const i32 cf = coop_fdct(srcpx - pr, lane, SH.lk);
         const i32 q = quantize_coeff(cf, SP.y1, n16);
         bool nz;
         const u32 coeff_cost = coop_residual_cost(q, 3, 0, ctx0, cc, lane, nz);
-        const i32 rec = clip255(pr + coop_idct(dequantize(q, SP.y1, n16), lane));
+        const i32 rec = clip255(pr + coop_idct(dequantize(q, SP.y1, n16), lane, SH.lk));
         const i32 df = srcpx - rec;
         const u32 sse = (u32)half_sum(df * df);
         if (act) {
@@ -882,7 +890,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
       const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
       const i32 pr = pred4_get(W, pidx, W.bmodes[i], n16, P4);
-      const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane);
+      const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane, SH.lk);
       simple_any |= quantize_coeff(cf, SP.y1, n16) != 0;
       __syncwarp();
       if (lane < 16) W.coef[0][lane] = cf;
@@ -894,7 +902,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
       lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
       ynz |= (u32)nz << i;
-      const i32 rec = clip255(pr + coop_idct(W.coef[0][n16], lane));
+      const i32 rec = clip255(pr + coop_idct(W.coef[0][n16], lane, SH.lk));
       if (lane < 16) W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)rec;
       __syncwarp();
     }
@@ -1145,7 +1153,7 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
   __shared__ int s_active;  // LS: warps of this CTA that still have (or may get) a row
   for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
-  if (threadIdx.x < 32) SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x];
+  if (threadIdx.x < 32) { SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x]; fill_lane_consts(SH.lk, threadIdx.x); }
   if (threadIdx.x == 0) s_active = (int)(blockDim.x >> 5);
   __syncthreads();
   const int lane = threadIdx.x & 31;
