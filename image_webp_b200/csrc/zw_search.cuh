@@ -71,7 +71,7 @@ struct __align__(16) WarpScratch {
 };
 
 struct SearchShared {
-  int4 lk[6][32];       // per-lane butterfly constants of coop_fdct / coop_idct (fill_lane_consts)
+  int4 lk[7][32];       // per-lane constants: butterflies of coop_fdct / coop_idct, coefficient bands (fill_lane_consts)
   u8 pred_idx[10][16];  // (mode, pixel) -> index into WarpScratch::dtab
   u16 dtaps[32];        // lane k -> the three edge taps of dtab[k]
   WarpScratch w[SEARCH_WARPS];
@@ -238,6 +238,7 @@ __device__ __forceinline__ i32 pred4_get(const WarpScratch& W, const u8 (*pidx)[
 //   lk[3] = {KA, KB, sg, s1}     idct pass:    t = ((v*KA) >> 16) + sg*(p + ((p*KB) >> 16));  r = s1*t + s2*p
 //   lk[4] = {s2, KA', KB', sg'}  (primed: the horizontal pass, indexed by x instead of y)
 //   lk[5] = {s1', s2', 0, 0}
+//   lk[6] = {band(n), band(n+1), zigzag(n), trellis weight of zigzag(n)}   n = lane & 15
 __device__ __forceinline__ void fill_lane_consts(int4 (*lk)[32], int t) {
   const int x = t & 3, y = (t >> 2) & 3;
   // (selects, not indexed local arrays: keeps the kernels' stack frames small)
@@ -258,6 +259,9 @@ __device__ __forceinline__ void fill_lane_consts(int4 (*lk)[32], int t) {
   lk[3][t] = make_int4(KA(y), KB(y), SG(y), S1(y));
   lk[4][t] = make_int4(S2(y), KA(x), KB(x), SG(x));
   lk[5][t] = make_int4(S1(x), S2(x), 0, 0);
+  // position n = t & 15: band of n, band of n + 1, natural index of zig-zag position n, its trellis weight
+  const int n = t & 15, zz = ZW_TAB(kZigzag)[n];
+  lk[6][t] = make_int4(ZW_TAB(kEncBands)[n], ZW_TAB(kEncBands)[n + 1], zz, (int)ZW_TAB(kWeightTrellis)[zz]);
 }
 
 __device__ __forceinline__ i32 coop_fdct(i32 v, int lane, const int4 (*lk)[32]) {
@@ -319,19 +323,23 @@ __device__ __forceinline__ int half_sum(int v) {  // sum over the 16 lanes of ea
 }
 
 // residual_cost with one level per lane (natural order n = lane & 15).  Uniform per half-warp.
-__device__ __forceinline__ u32 coop_residual_cost(i32 lv, int ctype, int first, int ctx0, const CostCtx& cc, int lane, bool& has_nz) {
+__device__ __forceinline__ u32 coop_residual_cost(i32 lv, int ctype, int first, int ctx0, const CostCtx& cc, int lane, bool& has_nz,
+                                                  const int4 (*lk)[32]) {
   const int n = lane & 15, h = lane >> 4;
+  const int4 kb = lk[6][lane];  // band(n), band(n + 1)
   const int v = iabs(lv);
   const u32 nzm = (__ballot_sync(FULL, lv != 0) >> (16 * h)) & 0xffffu;
   const int last = nzm ? 31 - __clz(nzm) : -1;
   has_nz = nzm != 0;
-  const u32 p0 = cc.probs[((ctype * 8 + ZW_TAB(kEncBands)[first]) * 3 + ctx0) * 11];
+  const u8* pr = cc.probs + ctype * 264;  // [band][ctx][11]
+  const u32 p0 = pr[(first /* band(0) = 0, band(1) = 1 */ * 3 + ctx0) * 11];
   const int pv = __shfl_up_sync(FULL, v, 1, 16);
   const int ctx = n == first ? ctx0 : imin(pv, 2);
   u32 c = 0;
   if (n >= first && n <= last) {
-    c = level_cost_at(cc, ctype, n, ctx, v);
-    if (n == last && n < 15) c += bit_cost(0, cc.probs[((ctype * 8 + ZW_TAB(kEncBands)[n + 1]) * 3 + (v == 1 ? 1 : 2)) * 11]);
+    c = ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
+    if (cc.level_cost) c += cc.level_cost[ctype * 1632 + (kb.x * 3 + ctx) * 68 + imin(v, 67)];
+    if (n == last && n < 15) c += bit_cost(0, pr[(kb.y * 3 + (v == 1 ? 1 : 2)) * 11]);
     if (n == first && ctx0 == 0) c += bit_cost(1, p0);
   }
   const u32 sum = (u32)half_sum((int)c);
@@ -367,9 +375,10 @@ __device__ __forceinline__ i64 shfl_xor64(i64 v, int m) {
 // coef: the block's 16 natural-order coefficients in shared memory (overwritten with the
 // dequantised levels); zz_out: 16 zig-zag levels.  Returns has_nz (uniform inside the half-warp).
 __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
-                             const CostCtx& cc, int ctype, int ctx0, int lane) {
+                             const CostCtx& cc, int ctype, int ctx0, int lane, const int4 (*lk)[32]) {
   const int n = lane & 15, h = lane >> 4;
-  const int j = ZW_TAB(kZigzag)[n];
+  const int4 kb = lk[6][lane];  // band(n), band(n + 1), zigzag(n), trellis weight
+  const int j = kb.z;
   const int kq = j > 0;
   const i32 q = m.q[kq];
   const u32 iq = m.iq[kq];
@@ -392,12 +401,12 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
   }
   const u8* PR = cc.probs + ctype * (8 * 3 * 11);
   const u16* LC = cc.level_cost + ctype * (8 * 3 * 68);
-  const int band = ZW_TAB(kEncBands)[n];
+  const int band = kb.x;
   i64 base[2];
   u32 fx[2];
   int lc[2], cx[2];
   bool valid[2];
-  const i64 wgt = ZW_TAB(kWeightTrellis)[j];
+  const i64 wgt = kb.w;
   const i64 orig_sq = (i64)(cs * cs);
 #pragma unroll
   for (int d = 0; d < 2; d++) {
@@ -442,7 +451,7 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
       P00 = n00; P01 = n01; P10 = n10; P11 = n11;
     }
   }
-  const int band0 = ZW_TAB(kEncBands)[first];
+  const int band0 = first;  // band(0) = 0, band(1) = 1
   const u32 p0first = PR[(band0 * 3 + ctx0) * 11];
   const i64 init = (ctx0 == 0 ? (i64)bit_cost(1, p0first) : 0) * lam;
   const i64 skip_score = (i64)bit_cost(0, p0first) * lam;
@@ -461,7 +470,7 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
 #pragma unroll
   for (int d = 0; d < 2; d++) {
     if (inrange && valid[d] && (level0 + d) != 0) {
-      const i64 eob = n < 15 ? (i64)bit_cost(0, PR[(ZW_TAB(kEncBands)[n + 1] * 3 + cx[d]) * 11]) : 0;
+      const i64 eob = n < 15 ? (i64)bit_cost(0, PR[(kb.y * 3 + cx[d]) * 11]) : 0;
       const i64 key = (s[d] + eob * lam) * 32 + (n * 2 + d);
       best = tmin(best, key);
     }
@@ -613,7 +622,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     // Y2: the DC of this lane's block is coefficient `blk` (raster order) of its mode's Y2 block
     const i32 y2q = quantize_coeff(coop_wht_any<true>(c[0], lane), SP.y2, blk);
     bool y2_any;
-    const u32 cost_y2 = coop_residual_cost(y2q, 1, 0, 0, cc, lane, y2_any);
+    const u32 cost_y2 = coop_residual_cost(y2q, 1, 0, 0, cc, lane, y2_any, SH.lk);
     const i32 mydc = coop_wht_any<false>(dequantize(y2q, SP.y2, blk), lane);
     i32 lv[16];
     lv[0] = 0;
@@ -675,7 +684,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     const u32 taps = SH.dtaps[lane];
     // table indices of this lane's pixel for the modes 2r + hb of SSE steps r = 1..4, one per byte
     const u32 pk = (u32)pidx[2 + hb][n16] | ((u32)pidx[4 + hb][n16] << 8) | ((u32)pidx[6 + hb][n16] << 16) | ((u32)pidx[8 + hb][n16] << 24);
-    u64 running = 211ull * (u64)SP.lambda_mode;
+    // this lane's quantiser entry, hoisted out of the sub-block loop (the compiler cannot: SP lives in global memory)
+    const u32 lq_iq = SP.y1.iq[n16 > 0], lq_bias = SP.y1.bias[n16 > 0];
+    const i32 lq_q = SP.y1.q[n16 > 0];
+    const u32 lam_i4 = SP.lambda_i4, lam_mode = SP.lambda_mode;
+    u64 running = 211ull * (u64)lam_mode;
     u32 total_mode_cost = 0;
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
 #pragma unroll 1
@@ -725,10 +738,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
         const int m = W.cand_mode[act ? rank : 0];
         const i32 pr = pred4_get(W, pidx, m, n16, P4);
         const i32 cf = coop_fdct(srcpx - pr, lane, SH.lk);
-        const i32 q = quantize_coeff(cf, SP.y1, n16);
+        const i32 ql = quantdiv((u32)iabs(cf), lq_iq, lq_bias);
+        const i32 q = cf < 0 ? -ql : ql;  // quantize_coeff
         bool nz;
-        const u32 coeff_cost = coop_residual_cost(q, 3, 0, ctx0, cc, lane, nz);
-        const i32 rec = clip255(pr + coop_idct(dequantize(q, SP.y1, n16), lane, SH.lk));
+        const u32 coeff_cost = coop_residual_cost(q, 3, 0, ctx0, cc, lane, nz, SH.lk);
+        const i32 rec = clip255(pr + coop_idct(q * lq_q, lane, SH.lk));
         const i32 df = srcpx - rec;
         const u32 sse = (u32)half_sum(df * df);
         if (act) {
@@ -736,7 +750,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           W.cand_lv[rank][n16] = (i16)q;
         }
         const u32 rate = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m] + coeff_cost;
-        const u64 score = (u64)sse * 256ull + (u64)(rate & 0xffffu) * (u64)SP.lambda_i4;  // u16 truncation (Q8)
+        const u64 score = (u64)sse * 256ull + (u64)(rate & 0xffffu) * (u64)lam_i4;  // u16 truncation (Q8)
         const u64 key = act ? ((score << 4) | (u64)rank) : ~0ull;
         if (key < best_key) { best_key = key; best_sse = sse; best_rate = rate; best_nz = (int)nz; }
       }
@@ -758,7 +772,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       tnz4 = (tnz4 & ~(1u << sbx)) | ((u32)best_nz << sbx);
       lnz4 = (lnz4 & ~(1u << sby)) | ((u32)best_nz << sby);
       total_mode_cost += ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + wmode];
-      running += (u64)best_sse * 256ull + (u64)(best_rate & 0xffffu) * (u64)SP.lambda_mode;
+      running += (u64)best_sse * 256ull + (u64)(best_rate & 0xffffu) * (u64)lam_mode;
       if (running >= i16_score || total_mode_cost > 16384u) { use_i4 = false; i4_go = false; }
     }
   }
@@ -832,7 +846,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           const int bb = act ? b : 0;
           const int tbx = bb & 3, tby = bb >> 2;
           const int ctx0 = imin((int)W.nzflag[20 + tby] + (int)W.nzflag[16 + tbx], 2);
-          const bool nz = trellis_half(act, W.coef[bb], W.rec.levels[1 + bb], SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0, lane);
+          const bool nz = trellis_half(act, W.coef[bb], W.rec.levels[1 + bb], SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0, lane, SH.lk);
           __syncwarp();
           if (act && (lane & 15) == 0) {
             W.nzflag[bb] = nz;
@@ -896,7 +910,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       if (lane < 16) W.coef[0][lane] = cf;
       __syncwarp();
       const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
-      const bool nzh = trellis_half(lane < 16, W.coef[0], W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane);
+      const bool nzh = trellis_half(lane < 16, W.coef[0], W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane, SH.lk);
       const bool nz = __shfl_sync(FULL, (int)nzh, 0) != 0;
       __syncwarp();
       tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
