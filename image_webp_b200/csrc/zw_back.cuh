@@ -354,22 +354,32 @@ __device__ __forceinline__ int ctx_bmode(const MbRecord& r, int sub) {
   return r.ymode == 0 ? 0 : (r.ymode == 1 ? 2 : (r.ymode == 2 ? 3 : 1));
 }
 
-// write_macroblock_header (vp8.rs:498-560)
+// write_macroblock_header (vp8.rs:498-560), split into 18 independent pieces so that 18 lanes share the
+// (for B_PRED macroblocks long) header instead of one lane walking 16 mode trees alone:
+//   slot 0: segment id (if update_map), skip flag, ymode      slots 1..16: sub-block mode i = slot - 1
+//   slot 17: uv mode.                                          Concatenated in slot order == reference order.
+template <class S>
+__device__ __forceinline__ void mb_header_slot(S& s, int slot, const ImageState& IS, const MbRecord& r, const MbRecord* top,
+                                               const MbRecord* left) {
+  if (slot == 0) {
+    if (IS.seg_enabled && IS.update_map) put_tree(s, c_tok.tree_seg, c_tok.seg, IS.tree_probs, r.segment, 0);
+    s.put(r.skip, IS.skip_prob);
+    put_tree(s, c_tok.tree_ymode, c_tok.ymode, ZW_TAB(kKfYmodeProbs), r.ymode, 0);
+  } else if (slot <= 16) {
+    if (r.ymode == 4) {
+      const int i = slot - 1, x = i & 3, y = i >> 2;
+      const int t = y > 0 ? r.bmodes[(y - 1) * 4 + x] : (top ? ctx_bmode(*top, 12 + x) : 0);
+      const int l = x > 0 ? r.bmodes[y * 4 + x - 1] : (left ? ctx_bmode(*left, y * 4 + 3) : 0);
+      put_tree(s, c_tok.tree_bmode, c_tok.bmode, &ZW_TAB(kKfBmodeProbs)[(t * 10 + l) * 9], r.bmodes[i], 0);
+    }
+  } else if (slot == 17) {
+    put_tree(s, c_tok.tree_uv, c_tok.uv, ZW_TAB(kKfUvModeProbs), r.uvmode, 0);
+  }
+}
 template <class S>
 __device__ __forceinline__ void mb_header_tokens(S& s, const ImageState& IS, const MbRecord& r, const MbRecord* top,
                                                  const MbRecord* left) {
-  if (IS.seg_enabled && IS.update_map) put_tree(s, c_tok.tree_seg, c_tok.seg, IS.tree_probs, r.segment, 0);
-  s.put(r.skip, IS.skip_prob);
-  put_tree(s, c_tok.tree_ymode, c_tok.ymode, ZW_TAB(kKfYmodeProbs), r.ymode, 0);
-  if (r.ymode == 4) {
-    for (int y = 0; y < 4; y++)
-      for (int x = 0; x < 4; x++) {
-        const int t = y > 0 ? r.bmodes[(y - 1) * 4 + x] : (top ? ctx_bmode(*top, 12 + x) : 0);
-        const int l = x > 0 ? r.bmodes[y * 4 + x - 1] : (left ? ctx_bmode(*left, y * 4 + 3) : 0);
-        put_tree(s, c_tok.tree_bmode, c_tok.bmode, &ZW_TAB(kKfBmodeProbs)[(t * 10 + l) * 9], r.bmodes[y * 4 + x], 0);
-      }
-  }
-  put_tree(s, c_tok.tree_uv, c_tok.uv, ZW_TAB(kKfUvModeProbs), r.uvmode, 0);
+  for (int slot = 0; slot < 18; slot++) mb_header_slot(s, slot, IS, r, top, left);
 }
 
 // encode_compressed_frame_header (vp8.rs:332-372) incl. segment header (:393-437), quantiser
@@ -422,7 +432,7 @@ __device__ void frame_header_tokens(S& s, const ChunkParams& P, const ImageState
 }
 
 // MODE 0: count tokens per macroblock.  MODE 1: emit them at the scanned offsets.
-// One warp per macroblock: lanes 0..24 = residual blocks, lane 25 = macroblock header.
+// One warp per macroblock: lanes 0..24 = residual blocks; the macroblock header is shared by lanes 0..17.
 constexpr int TOK_WARPS = 8;
 template <int MODE>
 __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
@@ -452,10 +462,13 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
     if (lane == 0) P.mb_tok_cnt[gmb] = tot;
-    if (lane == 25) {
+    {
       CountSink s;
-      mb_header_tokens(s, IS, r, mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr, mbx > 0 ? &P.rec2[gmb - 1] : nullptr);
-      P.mb_hdr_cnt[gmb] = s.n;
+      if (lane < 18) mb_header_slot(s, lane, IS, r, mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr, mbx > 0 ? &P.rec2[gmb - 1] : nullptr);
+      u32 ht = s.n;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ht += __shfl_xor_sync(FULL, ht, o);
+      if (lane == 0) P.mb_hdr_cnt[gmb] = ht;
     }
   } else {
     // recount to get the per-block offsets inside the macroblock (cheap; avoids a per-block array)
@@ -475,10 +488,22 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
       s.p = P.tok_tokens + d.tok_off + P.mb_tok_cnt[gmb] + (incl - cnt);
       block_tokens(s, r.levels[lane], I.type, I.first, I.ctx, probs);
     }
-    if (lane == 25) {
-      WriteSink s;
-      s.p = P.hdr_tokens + d.hdr_off + P.mb_hdr_cnt[gmb];  // frame-header length is folded into the scan
-      mb_header_tokens(s, IS, r, mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr, mbx > 0 ? &P.rec2[gmb - 1] : nullptr);
+    {
+      const MbRecord* top = mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr;
+      const MbRecord* left = mbx > 0 ? &P.rec2[gmb - 1] : nullptr;
+      CountSink c;
+      if (lane < 18) mb_header_slot(c, lane, IS, r, top, left);
+      u32 hincl = c.n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(FULL, hincl, o);
+        if (lane >= o) hincl += a;
+      }
+      if (lane < 18) {
+        WriteSink s;
+        s.p = P.hdr_tokens + d.hdr_off + P.mb_hdr_cnt[gmb] + (hincl - c.n);  // frame-header length is folded into the scan
+        mb_header_slot(s, lane, IS, r, top, left);
+      }
     }
   }
 }
