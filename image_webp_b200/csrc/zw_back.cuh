@@ -664,61 +664,89 @@ __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
 //     add_one_to_output (arithmetic.rs:47-60).
 // The flush (arithmetic.rs:176-195) emits the pending bits and pads to pos + 4 bytes, where
 // pos = 0 if T < 24 else 1 + (T - 24) / 8 for T total shifts: the first pos + 4 bytes of the number.
-constexpr int BC_WARPS = 4;
+// Two warps per stream, software-pipelined over the groups of 32 symbols: the CHAIN warp runs the range
+// recurrence of group g + 1 (parking the range every symbol starts from in a double-buffered shared
+// slot) while the SUM warp does the parallel part of group g; one named barrier per group and pair.
+constexpr int BC_STREAMS = 2;            // streams per CTA
+constexpr int BC_WARPS = 2 * BC_STREAMS;  // warp 2s: chain, warp 2s + 1: sum
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
-  __shared__ u32 s_cells[BC_WARPS][32];
-  __shared__ u32 s_range[BC_WARPS][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 sid = blockIdx.x * BC_WARPS + warp;
-  if (sid >= 2 * P.n_img) return;
+  __shared__ u32 s_cells[BC_STREAMS][32];
+  __shared__ u32 s_range[BC_STREAMS][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1;
+  const bool chain_warp = (warp & 1) == 0;
+  const u32 sid = blockIdx.x * BC_STREAMS + pair;
+  if (sid >= 2 * P.n_img) return;  // both warps of a pair leave together
   const bool is_hdr = sid >= P.n_img;
   const u32 img = is_hdr ? sid - P.n_img : sid;
   const ImageDesc d = P.img[img];
   ImageState& IS = P.st[img];
   const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
   const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
+  const u32 groups = (n + 31) / 32;
+  if (chain_warp) {
+    // ---- serial part: the range recurrence; lane 0 parks range - 1 of every symbol ----
+    u32 rm1 = 254;  // range - 1, uniform across the warp (the recurrence is shortest in this form)
+    u32 mine = lane < n ? tk[lane] : 0;
+    for (u32 g = 0; g <= groups; g++) {
+      if (g < groups) {
+        const u32 i0 = g * 32;
+        const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
+        const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
+        const u32 mine24 = ((mine & 255u) << 24) | (mine >> 8);  // prob in the top byte, bit in bit 0
+        u32* rsave = s_range[pair][g & 1];
+        if (cnt == 32) {
+#pragma unroll
+          for (int k = 0; k < 32; k++) {
+            const u32 t = __shfl_sync(FULL, mine24, k);
+            if (lane == 0) rsave[k] = rm1;
+            const u32 x = __umulhi(rm1, t & 0xff000000u);  // ((range - 1) * prob) >> 8 = split - 1
+            const u32 r2 = (t & 1) ? rm1 - x : x + 1;
+            const u32 r2m1 = (t & 1) ? rm1 - x - 1 : x;
+            rm1 = __funnelshift_l(0xffffffffu, r2m1, __clz(r2) - 24);  // (r2 << s) - 1
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < cnt; k++) {
+            const u32 t = __shfl_sync(FULL, mine24, k);
+            if (lane == 0) rsave[k] = rm1;
+            const u32 x = __umulhi(rm1, t & 0xff000000u);
+            const u32 r2 = (t & 1) ? rm1 - x : x + 1;
+            const u32 r2m1 = (t & 1) ? rm1 - x - 1 : x;
+            rm1 = __funnelshift_l(0xffffffffu, r2m1, __clz(r2) - 24);
+          }
+        }
+        mine = nxt;
+      }
+      pair_barrier(1 + pair);  // barrier g: slot g & 1 is complete and slot (g + 1) & 1 has been consumed
+    }
+    return;
+  }
+  // ---- SUM warp: the parallel part, one group behind the chain ----
   u8* out = P.part_bytes + d.part_off + (is_hdr ? 0 : d.p0_cap);  // partition scratch: [first | token]
   const u32 cap = is_hdr ? d.p0_cap : d.p1_cap;
-  u32* cells = s_cells[warp];
-  u32* rsave = s_range[warp];
+  u32* cells = s_cells[pair];
   cells[lane] = 0;
   __syncwarp();
-  u32 range = 255;  // uniform across the warp
   u32 T = 0;        // total renormalisation shifts so far == stream bit of the next addend's MSB
   u32 base = 0;     // stream bit of cell 0 (multiple of 16); base / 8 bytes are already written
   bool overflow = false;
   u32 mine = lane < n ? tk[lane] : 0;
-  for (u32 i0 = 0; i0 < n; i0 += 32) {
-    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
+  for (u32 g = 0; g <= groups; g++) {
+    pair_barrier(1 + pair);  // barrier g: slot g & 1 is complete; the chain now fills slot (g + 1) & 1
+    if (g == groups) break;  // the chain's last barrier
+    const u32 i0 = g * 32;
+    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;
     const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
-    // ---- serial part: the range recurrence; lane 0 parks the range each symbol starts from ----
-    if (cnt == 32) {
-#pragma unroll
-      for (int k = 0; k < 32; k++) {
-        const u32 t = __shfl_sync(FULL, mine, k);
-        if (lane == 0) rsave[k] = range;
-        const u32 x = ((range - 1) * (t & 255)) >> 8;  // split - 1
-        const u32 r2 = (t >> 8) ? range - 1 - x : x + 1;
-        range = r2 << (__clz(r2) - 24);
-      }
-    } else {
-#pragma unroll 1
-      for (int k = 0; k < cnt; k++) {
-        const u32 t = __shfl_sync(FULL, mine, k);
-        if (lane == 0) rsave[k] = range;
-        const u32 x = ((range - 1) * (t & 255)) >> 8;
-        const u32 r2 = (t >> 8) ? range - 1 - x : x + 1;
-        range = r2 << (__clz(r2) - 24);
-      }
-    }
-    __syncwarp();
-    // ---- parallel part: lane k redoes symbol k from its parked range ----
+    const u32* rsave = s_range[pair][g & 1];
+    // lane k redoes symbol k from its parked range
     u32 add = 0, sh = 0;
     if (lane < cnt) {
-      const u32 r = rsave[lane];
-      const u32 x = ((r - 1) * (mine & 255)) >> 8;
+      const u32 r1 = rsave[lane];  // range - 1 this symbol starts from
+      const u32 x = (r1 * (mine & 255)) >> 8;
       const bool bit = (mine >> 8) != 0;
-      const u32 r2 = bit ? r - 1 - x : x + 1;
+      const u32 r2 = bit ? r1 - x : x + 1;
       add = bit ? x + 1 : 0;
       sh = (u32)(__clz(r2) - 24);
     }

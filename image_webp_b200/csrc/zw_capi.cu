@@ -478,7 +478,7 @@ static int lane_encode_b(Lane* c) {
   k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
   c->launches += 2;
   CK(cudaEventRecord(c->ev[8], s));
-  k_boolcode<<<(2 * ni + BC_WARPS - 1) / BC_WARPS, BC_WARPS * 32, 0, s>>>(P);
+  k_boolcode<<<(2 * ni + BC_STREAMS - 1) / BC_STREAMS, BC_WARPS * 32, 0, s>>>(P);
   c->launches++;
   CK(cudaEventRecord(c->ev[9], s));
   k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
