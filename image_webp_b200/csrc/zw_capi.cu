@@ -232,6 +232,8 @@ static void fill_params(Lane* c) {
   P.hdr_tokens = c->d_htok.as<Token>(); P.tok_tokens = c->d_ttok.as<Token>();
   P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
   P.method = (u32)c->method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = c->method >= 4;
+  P.i4_modes = c->method <= 1 ? 0u : (c->method <= 3 ? 3u : (c->method == 4 ? 4u : 10u));
+  P.i4_always = c->method >= 5;
   P.filter_level = (u8)compute_filter_level(c->base_qidx);
   P.start_slack = c->start_slack;
 }

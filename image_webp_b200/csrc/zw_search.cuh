@@ -66,6 +66,8 @@ struct __align__(16) WarpScratch {
   u8 cand_mode[12];     // I4 search: mode with rank r
   u8 bmodes[16];
   u8 dtab[32];       // I4: the 23 distinct 3-tap edge filters of the current sub-block + its DC ([23])
+  u32 eob_pack[16];  // per row: I4 end-of-block cost after position n: ctx 1 in the low half, ctx 2 in the high half
+  u32 p0c[4];        // per row: I4 bit_cost(0, p0) for ctx0 = 0, 1, 2 and bit_cost(1, p0) for ctx0 = 0
   u8 nzflag[32];     // per-block non-zero flags (scratch)
   MbRecord rec;      // staged record
 };
@@ -346,6 +348,27 @@ __device__ __forceinline__ u32 coop_residual_cost(i32 lv, int ctype, int first, 
   return last < 0 ? bit_cost(0, p0) : sum;
 }
 
+// The same for the I4 search (ctype 3, first 0), with everything that only depends on the image's
+// probabilities precomputed once per row (WarpScratch::eob_pack / p0c): c0 = bit_cost(0, p0),
+// c1 = bit_cost(1, p0) if ctx0 == 0 else 0.
+__device__ __forceinline__ u32 coop_cost_i4(i32 lv, int ctx0, const CostCtx& cc, u32 eob_pack, u32 c0, u32 c1, int band, int lane,
+                                            bool& has_nz) {
+  const int n = lane & 15, h = lane >> 4;
+  const int v = iabs(lv);
+  const u32 nzm = (__ballot_sync(FULL, lv != 0) >> (16 * h)) & 0xffffu;
+  const int last = nzm ? 31 - __clz(nzm) : -1;
+  has_nz = nzm != 0;
+  const int pv = __shfl_up_sync(FULL, v, 1, 16);
+  const int ctx = n == 0 ? ctx0 : imin(pv, 2);
+  u32 c = ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
+  if (cc.level_cost) c += cc.level_cost[3 * 1632 + (band * 3 + ctx) * 68 + imin(v, 67)];
+  if (n == last) c += v == 1 ? (eob_pack & 0xffffu) : (eob_pack >> 16);  // eob_pack is 0 for n = 15
+  if (n == 0) c += c1;
+  if (n > last) c = 0;
+  const u32 sum = (u32)half_sum((int)c);
+  return last < 0 ? c0 : sum;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cooperative trellis: the 16 lanes of a half-warp own the 16 zig-zag positions of one block.
 // Same result as the serial trellis_quantize (zw_cost.cuh; reference cost.rs:788-1006), computed
@@ -572,8 +595,8 @@ struct LumaOut {
 // LS: the CTA's warps run the three phases in lock step (a CTA barrier between them); `work` is
 // false for a warp that only keeps the barriers company this round (no row / dependency not ready).
 template <bool LS>
-__device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegParams& SP, const CostCtx& cc, int method,
-                           bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane, bool work) {
+__device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegParams& SP, const CostCtx& cc, int i4_modes,
+                           bool i4_always, bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane, bool work) {
   LumaOut R;
   const int hb = lane >> 4, blk = lane & 15, bx = blk & 3, by = blk >> 2;
   const u8(*pidx)[16] = SH.pred_idx;
@@ -676,10 +699,10 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
   // Cooperative: each half-warp evaluates one prediction mode at a time, one pixel per lane.
   bool use_i4 = false;
   if (LS) __syncthreads();
-  bool i4_go = work && method > 1 && (method >= 5 || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0);
+  bool i4_go = work && i4_modes > 0 && (i4_always || i16_score > 211ull * (u64)SP.lambda_mode || best16_mode != 0);
   use_i4 = i4_go;
   {
-    const int max_modes = method <= 3 ? 3 : (method == 4 ? 4 : 10);
+    const int max_modes = i4_modes;
     const int n16 = lane & 15;
     const u32 taps = SH.dtaps[lane];
     // table indices of this lane's pixel for the modes 2r + hb of SSE steps r = 1..4, one per byte
@@ -688,6 +711,8 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     const u32 lq_iq = SP.y1.iq[n16 > 0], lq_bias = SP.y1.bias[n16 > 0];
     const i32 lq_q = SP.y1.q[n16 > 0];
     const u32 lam_i4 = SP.lambda_i4, lam_mode = SP.lambda_mode;
+    const u32 eobp = W.eob_pack[n16];
+    const int band_n = SH.lk[6][lane].x;
     u64 running = 211ull * (u64)lam_mode;
     u32 total_mode_cost = 0;
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
@@ -741,7 +766,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
         const i32 ql = quantdiv((u32)iabs(cf), lq_iq, lq_bias);
         const i32 q = cf < 0 ? -ql : ql;  // quantize_coeff
         bool nz;
-        const u32 coeff_cost = coop_residual_cost(q, 3, 0, ctx0, cc, lane, nz, SH.lk);
+        const u32 coeff_cost = coop_cost_i4(q, ctx0, cc, eobp, W.p0c[ctx0], ctx0 == 0 ? W.p0c[3] : 0u, band_n, lane, nz);
         const i32 rec = clip255(pr + coop_idct(q * lq_q, lane, SH.lk));
         const i32 df = srcpx - rec;
         const u32 sse = (u32)half_sum(df * df);
@@ -1175,7 +1200,6 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
   int* progress = P.progress + (PASS - 1) * P.n_rows;
   MbRecord* recs = PASS == 1 ? P.rec1 : P.rec2;
   const bool trellis = (PASS == 2) && P.do_trellis;
-  const int method = P.method;
 
   // state of the row this warp owns
   bool have_row = false, done = false;
@@ -1215,6 +1239,16 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
         // row-start state (vp8.rs:1339-1344 / :1423-1429)
         left_nz = 0; mbx = 0; seen = 0;
         if (lane < 17) W.left_y[lane] = 129;
+        {  // the image's I4 (type 3) end-of-block / first-branch costs, see coop_cost_i4
+          const u8* pr3 = cc.probs + 3 * 264;
+          if (lane < 16) {
+            const int nb = SH.lk[6][lane].y;  // band(n + 1)
+            W.eob_pack[lane] = lane < 15 ? (bit_cost(0, pr3[(nb * 3 + 1) * 11]) | (bit_cost(0, pr3[(nb * 3 + 2) * 11]) << 16)) : 0u;
+          } else if (lane < 20) {
+            const int k = lane - 16;
+            W.p0c[k] = k < 3 ? bit_cost(0, pr3[k * 11]) : bit_cost(1, pr3[0]);
+          }
+        }
         __syncwarp();
         have_row = true;
       }
@@ -1259,7 +1293,7 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
       __syncwarp();
     }
     const SegParams& SP = *SPp;
-    const LumaOut L = luma_mb<LS>(W, SH, SP, cc, method, trellis, mbx, mby, top_nz, left_nz, lane, work);
+    const LumaOut L = luma_mb<LS>(W, SH, SP, cc, (int)P.i4_modes, P.i4_always != 0, trellis, mbx, mby, top_nz, left_nz, lane, work);
     if (!work) continue;
     bool skip = false;
     u32 out_top = 0, out_left = 0;

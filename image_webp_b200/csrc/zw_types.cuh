@@ -92,6 +92,8 @@ struct ChunkParams {
   const u8* segquant_lut;   // [128][255]: compute_segment_quant(base, alpha-127..127)
   u32 n_img, n_rows, n_mb;
   u32 method, base_qidx, do_trellis;
+  u32 i4_modes;      // I4 candidates evaluated per sub-block: 0 (method <= 1: no I4), 3, 4 or 10 (vp8.rs:1836)
+  u32 i4_always;     // method >= 5: I4 is tried for every macroblock (vp8.rs:2210-2231)
   u32 start_slack;   // a wavefront row starts once the row above is this many macroblocks ahead
   u8 filter_level;
   const u8* rgb;
