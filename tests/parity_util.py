@@ -8,7 +8,7 @@ STAGE_ORDER = [("YUV_Y", np.uint8), ("YUV_U", np.uint8), ("YUV_V", np.uint8), ("
                ("SEG_MAP256", np.uint8), ("SEG_CENTERS", np.uint8), ("SEG_MID", np.int32), ("SEG_QIDX", np.uint8),
                ("SEG_MAP", np.uint8), ("SEG_TREE_PROBS", np.uint8), ("SEG_UPDATE_MAP", np.uint8),
                ("P1MB", O.MB_DTYPE), ("STATS", np.uint32), ("PROBS", np.uint8), ("SKIP_PROB", np.uint8), ("LCOST", np.uint16),
-               ("P2MB", O.MB_DTYPE), ("PART0", np.uint8), ("PART1", np.uint8), ("VP8", np.uint8)]
+               ("P2MB", O.MB_DTYPE), ("HDR_TOKENS", np.uint16), ("TOK_TOKENS", np.uint16), ("PART0", np.uint8), ("PART1", np.uint8), ("VP8", np.uint8)]
 
 
 def describe_mb_mismatch(name, a, b, mbw):

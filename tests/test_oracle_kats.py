@@ -331,3 +331,36 @@ def test_yuv_formula_and_padding():
     uavg = (urp[0::2, 0::2] + urp[0::2, 1::2] + urp[1::2, 0::2] + urp[1::2, 1::2] + (32768 << 2)) >> 18
     assert (u[:3, :10] == uavg).all()
     assert (u[:3, 10:] == u[:3, 9:10]).all() and (u[3:, :] == u[2, :]).all()
+
+
+def test_symbol_log_reproduces_the_partitions():
+    """The dumped (bit, probability) streams, pushed through the oracle's stand-alone boolean coder, give the
+    dumped partitions back: pins the symbol dump the GPU tokeniser is compared against."""
+    from image_webp_b200 import synth
+    for img, q, m in ((synth.photo_like(96, 64, 3), 75, 4), (synth.noise(48, 48, 1), 90, 6), (synth.solid(32, 32), 50, 0)):
+        rc, ref, d = O.encode(img, q, m, want_dump=True)
+        assert rc == 0
+        for sym, part in (("HDR_TOKENS", "PART0"), ("TOK_TOKENS", "PART1")):
+            s = d[sym]
+            bits = np.ascontiguousarray((s >> 8).astype(np.uint8))
+            probs = np.ascontiguousarray((s & 255).astype(np.uint8))
+            out = np.zeros(s.size + 16, np.uint8)
+            L.zwo_bool_encode.restype = C.c_size_t
+            n = L.zwo_bool_encode(bits.ctypes.data_as(C.c_void_p), probs.ctypes.data_as(C.c_void_p), C.c_size_t(s.size),
+                                  out.ctypes.data_as(C.c_void_p))
+            assert bytes(out[:n]) == bytes(d[part]), (sym, q, m)
+
+
+def test_op_counters_are_consistent():
+    """Primitive counters (measurement only): every coded macroblock runs 16 luma + 8 chroma forward DCTs in the
+    final transform of each pass, trellis blocks only exist in pass 2 at method >= 4, and the counters are per thread."""
+    from image_webp_b200 import synth
+    img = synth.photo_like(64, 48, 5)
+    nmb = 4 * 3
+    counts, ops = O.count_ops(img, 75, 4)
+    assert counts["pass1_luma"]["trellis_block"] == 0 and counts["pass2_luma"]["trellis_block"] > 0
+    assert counts["pass1_chroma"]["fdct"] >= 8 * nmb and counts["pass2_chroma"]["fdct"] >= 8 * nmb
+    assert counts["pass1_luma"]["fdct"] >= 16 * nmb
+    assert all(v > 0 for v in ops.values())
+    counts0, _ = O.count_ops(img, 75, 0)
+    assert counts0["pass2_luma"]["trellis_block"] == 0 and counts0["pass1_luma"]["i4_predset"] == 0
