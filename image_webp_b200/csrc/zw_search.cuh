@@ -163,40 +163,32 @@ __device__ __forceinline__ void pred_block(const u8* ws, int cofs, int mode, int
 __device__ const u16 d_dtaps[32] = ZW_DTAPS_INIT;
 __device__ const u8 d_pred_idx[10][16] = ZW_PRED_IDX_INIT;
 
-// One out-of-line copy of the (fully unrolled) lane-private residual cost: the kernels are
-// instruction-cache bound, so the three call sites share it.  Levels travel in registers.
-struct Lv16 { i32 v[16]; };
-// Rolled loop on purpose (the levels sit in local memory, L1-resident): ~16x less code than the
-// unrolled form, same arithmetic as residual_cost() in zw_cost.cuh.
-__device__ __noinline__ u32 residual_cost_ol(Lv16 L, int ctype, int first, int ctx0, const u8* probs, const u16* level_cost) {
-  int last = -1;
+// Lane-private residual cost (get_residual_cost, cost.rs:1670-1729) in flat form.  The "context
+// chain" is no chain: the context of position n is min(|level[n-1]|, 2), known up front, so the 16
+// terms are independent loads (the rolled per-coefficient loop this replaces kept the levels in local
+// memory and serialised 16 dependent iterations -- the latency of the pass-1 chroma chain).
+// TYPE / FIRST are compile-time: the band of every position folds to a constant.
+__device__ __forceinline__ constexpr int enc_band(int n) { return n < 4 ? n : (n == 4 ? 6 : (n == 5 ? 4 : (n == 6 ? 5 : (n < 15 ? 6 : (n == 15 ? 7 : 0))))); }
+template <int TYPE, int FIRST>
+__device__ __forceinline__ u32 residual_cost_flat(const i32* lv, int ctx0, const CostCtx& cc) {
+  int last = -1, vlast = 0;
 #pragma unroll
-  for (int i = 0; i < 16; i++)
-    if (L.v[i] != 0) last = i;
-  const u8* pp = probs + ctype * (8 * 3 * 11);
-  const u32 p0 = pp[(ZW_TAB(kEncBands)[first] * 3 + ctx0) * 11];
-  if (last < 0) return bit_cost(0, p0);
+  for (int i = FIRST; i < 16; i++)
+    if (lv[i] != 0) { last = i; vlast = iabs(lv[i]); }
+  const u8* pp = cc.probs + TYPE * 264;
+  const u32 p0 = pp[(enc_band(FIRST) * 3 + ctx0) * 11];
+  const u16* lc = cc.level_cost ? cc.level_cost + TYPE * 1632 : nullptr;
   u32 cost = ctx0 == 0 ? bit_cost(1, p0) : 0;
-  int ctx = ctx0;
-  const u16* lc = level_cost ? level_cost + ctype * (8 * 3 * 68) : nullptr;
-#pragma unroll 1
-  for (int n = first; n <= last; n++) {
-    const int v = iabs(L.v[n]);
-    cost += ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
-    if (lc) cost += lc[(ZW_TAB(kEncBands)[n] * 3 + ctx) * 68 + imin(v, 67)];
-    ctx = v >= 2 ? 2 : v;
-  }
-  if (last < 15) {
-    const int v = iabs(L.v[last]);
-    cost += bit_cost(0, pp[(ZW_TAB(kEncBands)[last + 1] * 3 + (v == 1 ? 1 : 2)) * 11]);
-  }
-  return cost;
-}
-__device__ __forceinline__ u32 residual_cost_call(const i32* lv, int ctype, int first, int ctx0, const CostCtx& cc) {
-  Lv16 L;
 #pragma unroll
-  for (int k = 0; k < 16; k++) L.v[k] = lv[k];
-  return residual_cost_ol(L, ctype, first, ctx0, cc.probs, cc.level_cost);
+  for (int n = FIRST; n < 16; n++) {
+    const int v = iabs(lv[n]);
+    const int ctx = n == FIRST ? ctx0 : imin(iabs(lv[n - 1]), 2);
+    u32 c = ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
+    if (lc) c += lc[(enc_band(n) * 3 + ctx) * 68 + imin(v, 67)];
+    cost += n <= last ? c : 0u;
+  }
+  if (last < 15 && last >= 0) cost += bit_cost(0, pp[(ZW_TAB(kEncBands)[last + 1] * 3 + (vlast == 1 ? 1 : 2)) * 11]);
+  return last < 0 ? bit_cost(0, p0) : cost;
 }
 
 // Per sub-block set-up of the predictor lookups: gathers the 13 edge pixels (one per lane), fills
@@ -652,7 +644,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     int nzc = 0;
 #pragma unroll
     for (int k = 1; k < 16; k++) { lv[k] = quantize_coeff(c[k], SP.y1, k); nzc += lv[k] != 0; }
-    int cost_ac = (int)residual_cost_call(lv, 0, 1, 0, cc);
+    int cost_ac = (int)residual_cost_flat<0, 1>(lv, 0, cc);
 #pragma unroll
     for (int k = 1; k < 16; k++) c[k] = dequantize(lv[k], SP.y1, k);
     c[0] = mydc;
@@ -1000,7 +992,7 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
     int nzac = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.uv, k); if (k > 0) nzac += q[k] != 0; }
-    int cost = (int)residual_cost_call(q, 2, 0, 0, cc);
+    int cost = (int)residual_cost_flat<2, 0>(q, 0, cc);
 #pragma unroll
     for (int k = 0; k < 16; k++) c[k] = dequantize(q[k], SP.uv, k);
     idct4x4(c);
