@@ -1119,6 +1119,7 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
   const ImageDesc d = P.img[img];
   const ImageState& IS = P.st[img];
   const int mbw = d.mbw, mbh = d.mbh, pw = mbw * 16, cwid = mbw * 8;
+  const u32 nmb = (u32)mbw * mbh;
   const u8* yp = P.planes + d.y_off;
   const u8* up = yp + (size_t)pw * mbh * 16;
   const u8* vp = up + (size_t)cwid * mbh * 8;
@@ -1127,35 +1128,75 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
   cc.level_cost = nullptr;
   const bool seg_on = IS.seg_enabled != 0;
   u32 left_derr = 0;  // carried across rows in pass 1 (Q5)
-  for (int mby = 0; mby < mbh; mby++) {
-    const u32 row_mb0 = d.mb_off + mby * mbw, up_mb0 = row_mb0 - mbw;
-    if (lane < 9) { W.left_u[lane] = 129; W.left_v[lane] = 129; }
-    __syncwarp();
-    for (int mbx = 0; mbx < mbw; mbx++) {
-      const u32 gmb = row_mb0 + mbx;
-      const int seg = seg_on ? P.segmap[gmb] : 0;
-      const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[seg] : P.base_qidx];
-      u32 top_derr = mby > 0 ? P.derr1[up_mb0 + mbx] : 0u;
-      load_chroma_mb(W, P, up, vp, cwid, mbx, mby, up_mb0, lane);
-      const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
-      MbRecord* r = &P.rec1[gmb];
-      if (lane < 8) {
-        u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
-        const u32* sl = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
-#pragma unroll
-        for (int k = 0; k < 8; k++) g[k] = sl[k];
-      }
-      if (lane == 0) {
-        P.derr1[gmb] = top_derr;
-        P.c1info[2 * gmb] = left_derr;
-        P.c1info[2 * gmb + 1] = (u32)C.uv_mode | (C.uvnz << 8);
-      }
-      if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
-      MbBottom* bo = &P.bottom[gmb];
-      if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
-      if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
-      __syncwarp();
+  // Everything a macroblock needs from global memory except its left neighbour (source rows, the
+  // bottom row / diffusion state of the macroblock above, its segment) is known one step ahead: it is
+  // fetched while the previous macroblock is processed -- the chain is latency bound and these were
+  // three exposed L2 round trips per macroblock.  Not possible when the macroblock above IS the previous
+  // one (mbw == 1).
+  const bool ahead = mbw > 1;
+  uint2 n_src = make_uint2(0, 0);
+  u32 n_top = 127, n_derr = 0, n_seg = 0;
+  auto fetch = [&](u32 i, uint2& o_src, u32& o_top, u32& o_derr, u32& o_seg) {
+    const int fy = (int)(i / (u32)mbw), fx = (int)(i % (u32)mbw);
+    const u32 g = d.mb_off + i;
+    if (lane < 16) {
+      const u8* pl = lane < 8 ? up : vp;
+      o_src = __ldg(reinterpret_cast<const uint2*>(pl + (size_t)(fy * 8 + (lane & 7)) * cwid + fx * 8));
     }
+    o_top = 127; o_derr = 0;
+    if (fy > 0) {
+      const MbBottom* bt = &P.bottom[g - mbw];
+      if (lane < 16) o_top = lane < 8 ? __ldcg(&bt->u[lane]) : __ldcg(&bt->v[lane - 8]);
+      o_derr = __ldcg(&P.derr1[g - mbw]);
+    }
+    o_seg = seg_on ? (u32)P.segmap[g] : 0u;
+  };
+  if (ahead) fetch(0, n_src, n_top, n_derr, n_seg);
+  for (u32 i = 0; i < nmb; i++) {
+    const int mby = (int)(i / (u32)mbw), mbx = (int)(i % (u32)mbw);
+    const u32 gmb = d.mb_off + i;
+    uint2 c_src = n_src;
+    u32 c_top = n_top, top_derr = n_derr, c_seg = n_seg;
+    if (!ahead) fetch(i, c_src, c_top, top_derr, c_seg);
+    else if (i + 1 < nmb) fetch(i + 1, n_src, n_top, n_derr, n_seg);
+    const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[c_seg] : P.base_qidx];
+    // stage the macroblock (load_chroma_mb with the prefetched values)
+    if (lane < 8) *reinterpret_cast<uint2*>(&W.src_u[lane * 8]) = c_src;
+    else if (lane < 16) *reinterpret_cast<uint2*>(&W.src_v[(lane - 8) * 8]) = c_src;
+    if (mby == 0) {
+      W.uvws[lane] = 127;
+    } else {
+      if (lane < 8) W.uvws[1 + lane] = (u8)c_top;
+      else if (lane < 16) W.uvws[17 + (lane - 8)] = (u8)c_top;
+    }
+    __syncwarp();
+    if (lane < 8) {
+      W.uvws[(1 + lane) * 32] = (mbx == 0) ? 129 : W.left_u[1 + lane];
+      W.uvws[(1 + lane) * 32 + 16] = (mbx == 0) ? 129 : W.left_v[1 + lane];
+    }
+    if (lane == 0) {
+      W.uvws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_u[0]);
+      W.uvws[16] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_v[0]);
+    }
+    __syncwarp();
+    const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
+    MbRecord* r = &P.rec1[gmb];
+    if (lane < 8) {
+      u32* g = reinterpret_cast<u32*>(r->levels[17 + lane]);
+      const u32* sl = reinterpret_cast<const u32*>(W.rec.levels[17 + lane]);
+#pragma unroll
+      for (int k = 0; k < 8; k++) g[k] = sl[k];
+    }
+    if (lane == 0) {
+      P.derr1[gmb] = top_derr;
+      P.c1info[2 * gmb] = left_derr;
+      P.c1info[2 * gmb + 1] = (u32)C.uv_mode | (C.uvnz << 8);
+    }
+    if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+    MbBottom* bo = &P.bottom[gmb];
+    if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
+    if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
+    __syncwarp();
   }
 }
 
