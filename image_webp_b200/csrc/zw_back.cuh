@@ -817,16 +817,29 @@ __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
 //     back to back in the output arena in image order.  (Only the RIFF wrap stays on the host.)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_outscan(ChunkParams P, u64* out_offsets /*[n_img+1]*/) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  // one warp: exclusive scan of the 16-byte-aligned payload sizes, 32 images per step
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   u64 acc = 0;
-  for (u32 i = 0; i < P.n_img; i++) {
-    ImageState& IS = P.st[i];
-    IS.vp8_bytes = 10 + IS.part0_bytes + IS.part1_bytes;
-    if (IS.part0_bytes >= (1u << 19) && IS.status == 0) IS.status = 5;  // ZW_ERR_PARTITION_TOO_LARGE
-    out_offsets[i] = acc;
-    acc += (IS.vp8_bytes + 15u) & ~15u;
+  for (u32 i0 = 0; i0 < P.n_img; i0 += 32) {
+    const u32 i = i0 + lane;
+    u64 sz = 0;
+    if (i < P.n_img) {
+      ImageState& IS = P.st[i];
+      IS.vp8_bytes = 10 + IS.part0_bytes + IS.part1_bytes;
+      if (IS.part0_bytes >= (1u << 19) && IS.status == 0) IS.status = 5;  // ZW_ERR_PARTITION_TOO_LARGE
+      sz = (IS.vp8_bytes + 15u) & ~15u;
+    }
+    u64 incl = sz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 v = (u64)shfl_up64_full((i64)incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (i < P.n_img) out_offsets[i] = acc + incl - sz;
+    acc += (u64)shfl64((i64)incl, 31);
   }
-  out_offsets[P.n_img] = acc;
+  if (lane == 0) out_offsets[P.n_img] = acc;
 }
 
 __global__ void __launch_bounds__(256) k_assemble(ChunkParams P, const u64* out_offsets) {

@@ -552,6 +552,9 @@ static int lane_download(Lane* c, zw_output* outs, size_t n, int container) {
     o.len = 0;
     if (c->slot_of[i] < 0) { o.status = c->img_status[i]; continue; }
     const u32 k = (u32)c->slot_of[i];
+    // lossy + alpha files need VP8X + ALPH (api.rs:1330-1394), which is not built: refuse rather than
+    // emit a simple container the reference would not produce
+    if (container && (c->img[k].bpp == 2 || c->img[k].bpp == 4)) { o.status = ZW_ERR_INVALID_PARAM; continue; }
     const ImageState& st = c->st[k];
     if (st.status != 0) { o.status = (int)st.status; continue; }
     const size_t payload = st.vp8_bytes;

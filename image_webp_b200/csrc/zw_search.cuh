@@ -105,6 +105,11 @@ __device__ __forceinline__ unsigned lane_id() {
   asm("mov.u32 %0, %%laneid;" : "=r"(l));
   return l;
 }
+__device__ __forceinline__ i64 shfl_up64_full(i64 v, int d) {
+  int lo = __shfl_up_sync(FULL, (int)(v & 0xffffffff), d);
+  int hi = __shfl_up_sync(FULL, (int)(v >> 32), d);
+  return (i64)(((u64)(u32)hi << 32) | (u64)(u32)lo);
+}
 #ifdef ZW_USE_REDUX
 __device__ __forceinline__ int red16_add(int v) {
   return __reduce_add_sync(0xffffu << (lane_id() & 16), v);

@@ -98,7 +98,11 @@ int zw_encode_vp8_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality
                         zw_output* outs, zw_timing* timing);
 
 /* Same, wrapped in the simple RIFF container exactly as WebPEncoder::encode does for opaque
- * input without metadata (api.rs:1320-1329): these bytes ARE the .webp file. */
+ * input without metadata (api.rs:1320-1329): these bytes ARE the .webp file.  For the alpha colour
+ * types (ZW_COLOR_LA8 / ZW_COLOR_RGBA8) the reference writes a VP8X container with a lossless ALPH
+ * chunk instead (api.rs:1330-1394), which this library does not build: images of those types get
+ * outs[i].status = ZW_ERR_INVALID_PARAM here (zw_encode_vp8_batch accepts them: the VP8 payload ignores
+ * alpha, vp8.rs:1296). */
 int zw_encode_webp_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
                          zw_output* outs, zw_timing* timing);
 

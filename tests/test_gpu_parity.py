@@ -189,3 +189,22 @@ def test_batch_pipeline_matches_oracle_and_single_context(ctx):
         for img, o in zip(b, outs):
             rc, ref, _ = O.encode(img, 75, 4)
             assert rc == 0 and o == ref
+
+
+def test_c_abi_refuses_alpha_in_the_simple_container(ctx):
+    """zw_encode_webp_batch: lossy + alpha would need VP8X + ALPH (api.rs:1330-1394): per-image INVALID_PARAM, while
+    the opaque images of the same batch are encoded."""
+    import ctypes as C
+    from image_webp_b200 import _lib
+    L = _lib.load()
+    rgb = synth.photo_like(64, 48, 3)
+    rgba = np.concatenate([rgb, np.full((48, 64, 1), 9, np.uint8)], axis=2).copy()
+    arr = (_lib.ZwImage * 2)()
+    arr[0] = _lib.ZwImage(rgb.ctypes.data, rgb.size, 64, 48, 2, 0)
+    arr[1] = _lib.ZwImage(rgba.ctypes.data, rgba.size, 64, 48, 3, 0)
+    outs = (_lib.ZwOutput * 2)()
+    rc = L.zw_encode_webp_batch(ctx.h, arr, 2, 75, 4, outs, None)
+    assert rc == 0 and outs[0].status == 0 and outs[1].status == 3
+    rc0, ref, _ = O.encode(rgb, 75, 4)
+    assert C.string_at(outs[0].data, outs[0].len) == ref
+    L.zw_free(outs[0].data)
