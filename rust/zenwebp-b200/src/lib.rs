@@ -75,3 +75,29 @@ impl<'a> WebPEncoder<'a> {
         Ok(())
     }
 }
+
+// SAFETY: a context is only ever used by the thread that currently owns it (the C ABI is
+// thread-safe across contexts; one context must not be used from two threads at once).
+unsafe impl Send for Context {}
+
+/// Streaming batch entry: `depth` contexts on one GPU, one worker thread each, so that the H2D
+/// copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of the next
+/// (same design as `BatchPipeline` in the Python / C++ mirrors).  `encode_batches` returns the
+/// per-batch results in order.
+pub struct BatchPipeline { ctxs: Vec<Context> }
+impl BatchPipeline {
+    pub fn new(device: i32, depth: usize) -> Result<Self, EncodingError> {
+        Ok(Self { ctxs: (0..depth.max(1)).map(|_| Context::new(device)).collect::<Result<_, _>>()? })
+    }
+    pub fn encode_batches(&mut self, batches: &[Vec<ImageRef<'_>>], p: &EncoderParams) -> Vec<Vec<Result<Vec<u8>, EncodingError>>> {
+        let depth = self.ctxs.len();
+        let mut out: Vec<Option<Vec<Result<Vec<u8>, EncodingError>>>> = (0..batches.len()).map(|_| None).collect();
+        std::thread::scope(|s| {
+            let handles: Vec<_> = self.ctxs.iter_mut().enumerate().map(|(k, ctx)| {
+                s.spawn(move || (k..batches.len()).step_by(depth).map(|i| (i, ctx.encode_batch(&batches[i], p))).collect::<Vec<_>>())
+            }).collect();
+            for h in handles { for (i, r) in h.join().unwrap() { out[i] = Some(r); } }
+        });
+        out.into_iter().map(|o| o.unwrap()).collect()
+    }
+}
