@@ -68,6 +68,8 @@ struct __align__(16) WarpScratch {
   u8 dtab[32];       // I4: the 23 distinct 3-tap edge filters of the current sub-block + its DC ([23])
   u32 eob_pack[16];  // per row: I4 end-of-block cost after position n: ctx 1 in the low half, ctx 2 in the high half
   u32 p0c[4];        // per row: I4 bit_cost(0, p0) for ctx0 = 0, 1, 2 and bit_cost(1, p0) for ctx0 = 0
+  u32 eob_pack0[16]; // the same two for the I16 AC blocks (type 0, first coefficient 1: p0 of band 1)
+  u32 p0c0[4];
   u8 nzflag[32];     // per-block non-zero flags (scratch)
   MbRecord rec;      // staged record
 };
@@ -236,7 +238,7 @@ __device__ __forceinline__ i32 pred4_get(const WarpScratch& W, const u8 (*pidx)[
 //   lk[2] = {C', S', E, src}     src: lane holding this lane's natural-order output (un-permute)
 //   lk[3] = {KA, KB, sg, s1}     idct pass:    t = ((v*KA) >> 16) + sg*(p + ((p*KB) >> 16));  r = s1*t + s2*p
 //   lk[4] = {s2, KA', KB', sg'}  (primed: the horizontal pass, indexed by x instead of y)
-//   lk[5] = {s1', s2', 0, 0}
+//   lk[5] = {s1', s2', zig-zag position of natural index n, 0}
 //   lk[6] = {band(n), band(n+1), zigzag(n), trellis weight of zigzag(n)}   n = lane & 15
 __device__ __forceinline__ void fill_lane_consts(int4 (*lk)[32], int t) {
   const int x = t & 3, y = (t >> 2) & 3;
@@ -257,7 +259,9 @@ __device__ __forceinline__ void fill_lane_consts(int4 (*lk)[32], int t) {
   auto S2 = [](int i) { return i == 2 ? -1 : 1; };
   lk[3][t] = make_int4(KA(y), KB(y), SG(y), S1(y));
   lk[4][t] = make_int4(S2(y), KA(x), KB(x), SG(x));
-  lk[5][t] = make_int4(S1(x), S2(x), 0, 0);
+  int zinv = 0;  // zig-zag position of natural index n = t & 15
+  for (int z = 0; z < 16; z++) if (ZW_TAB(kZigzag)[z] == (t & 15)) zinv = z;
+  lk[5][t] = make_int4(S1(x), S2(x), zinv, 0);
   // position n = t & 15: band of n, band of n + 1, natural index of zig-zag position n, its trellis weight
   const int n = t & 15, zz = ZW_TAB(kZigzag)[n];
   lk[6][t] = make_int4(ZW_TAB(kEncBands)[n], ZW_TAB(kEncBands)[n + 1], zz, (int)ZW_TAB(kWeightTrellis)[zz]);
@@ -394,8 +398,10 @@ __device__ __forceinline__ i64 shfl_xor64(i64 v, int m) {
 
 // coef: the block's 16 natural-order coefficients in shared memory (overwritten with the
 // dequantised levels); zz_out: 16 zig-zag levels.  Returns has_nz (uniform inside the half-warp).
-__device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
-                             const CostCtx& cc, int ctype, int ctx0, int lane, const int4 (*lk)[32]) {
+// c: the block's coefficient at this lane's zig-zag position; dq: its dequantised level (0 below `first`);
+// eobp / p0c: the per-row end-of-block / first-branch cost packs of the block's type (see k_search).
+__device__ __noinline__ bool trellis_half(bool active, i32 c, i32& dq, i16* zz_out, const Matrix& m, const u16* sharpen, u32 lambda, int first,
+                             const CostCtx& cc, int ctype, int ctx0, int lane, const int4 (*lk)[32], const u32* eobp, const u32* p0c) {
   const int n = lane & 15, h = lane >> 4;
   const int4 kb = lk[6][lane];  // band(n), band(n + 1), zigzag(n), trellis weight
   const int j = kb.z;
@@ -403,7 +409,6 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
   const i32 q = m.q[kq];
   const u32 iq = m.iq[kq];
   const i64 lam = (i64)lambda;
-  const i32 c = coef[j];
   const i32 thresh = ((i32)m.q[1] * (i32)m.q[1]) / 4;
   const u32 big = (__ballot_sync(FULL, n >= first && c * c > thresh) >> (16 * h)) & 0xffffu;
   int last = big ? 31 - __clz(big) : first - 1;
@@ -416,10 +421,10 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
   // Fast path: a terminal node needs level != 0.  If no position of either block of this warp can
   // reach level 1 the result is "all zero, no coefficients" without running the search.
   if (!__any_sync(FULL, inrange && thresh_level >= 1)) {
-    if (active && n >= first) { zz_out[n] = 0; coef[j] = 0; }
+    if (active && n >= first) zz_out[n] = 0;
+    dq = 0;
     return false;
   }
-  const u8* PR = cc.probs + ctype * (8 * 3 * 11);
   const u16* LC = cc.level_cost + ctype * (8 * 3 * 68);
   const int band = kb.x;
   i64 base[2];
@@ -471,10 +476,9 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
       P00 = n00; P01 = n01; P10 = n10; P11 = n11;
     }
   }
-  const int band0 = first;  // band(0) = 0, band(1) = 1
-  const u32 p0first = PR[(band0 * 3 + ctx0) * 11];
-  const i64 init = (ctx0 == 0 ? (i64)bit_cost(1, p0first) : 0) * lam;
-  const i64 skip_score = (i64)bit_cost(0, p0first) * lam;
+  const i64 init = (ctx0 == 0 ? (i64)p0c[3] : 0) * lam;  // bit_cost(1, p0(ctx 0))
+  const i64 skip_score = (i64)p0c[ctx0] * lam;            // bit_cost(0, p0(ctx0))
+  const u32 my_eob = eobp[n];                             // end-of-block cost after position n: ctx 1 | ctx 2 << 16
   i64 s[2];
   s[0] = init + tmin(P00, P10);
   s[1] = init + tmin(P01, P11);
@@ -490,7 +494,7 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
 #pragma unroll
   for (int d = 0; d < 2; d++) {
     if (inrange && valid[d] && (level0 + d) != 0) {
-      const i64 eob = n < 15 ? (i64)bit_cost(0, PR[(kb.y * 3 + cx[d]) * 11]) : 0;
+      const i64 eob = (i64)(cx[d] == 1 ? (my_eob & 0xffffu) : (my_eob >> 16));  // 0 for n = 15; cx is 1 or 2 here
       const i64 key = (s[d] + eob * lam) * 32 + (n * 2 + d);
       best = tmin(best, key);
     }
@@ -515,10 +519,8 @@ __device__ __noinline__ bool trellis_half(bool active, i32* coef, i16* zz_out, c
     level = level0 + (int)((dm >> n) & 1);
     if (sign) level = -level;
   }
-  if (active && n >= first) {
-    zz_out[n] = (i16)level;
-    coef[j] = level * q;
-  }
+  if (active && n >= first) zz_out[n] = (i16)level;
+  dq = level * q;
   const u32 nzm = (__ballot_sync(FULL, level != 0) >> (16 * h)) & 0xffffu;
   return nzm != 0;
 }
@@ -868,7 +870,11 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           const int bb = act ? b : 0;
           const int tbx = bb & 3, tby = bb >> 2;
           const int ctx0 = imin((int)W.nzflag[20 + tby] + (int)W.nzflag[16 + tbx], 2);
-          const bool nz = trellis_half(act, W.coef[bb], W.rec.levels[1 + bb], SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0, lane, SH.lk);
+          const int zj = SH.lk[6][lane].z;  // natural index of this lane's zig-zag position
+          i32 dqv;
+          const bool nz = trellis_half(act, W.coef[bb][zj], dqv, W.rec.levels[1 + bb], SP.y1, SP.sharpen, SP.lambda_trellis_i16, 1, cc, 0, ctx0,
+                                       lane, SH.lk, W.eob_pack0, W.p0c0);
+          if (act && (lane & 15) >= 1) W.coef[bb][zj] = dqv;
           __syncwarp();
           if (act && (lane & 15) == 0) {
             W.nzflag[bb] = nz;
@@ -921,24 +927,28 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     bool simple_any = false;
     const int n16 = lane & 15;
     const u32 taps = SH.dtaps[lane];
+    const u32 tq_iq = SP.y1.iq[n16 > 0], tq_bias = SP.y1.bias[n16 > 0];
+    const int zz_nat = SH.lk[6][lane].z;  // natural index of zig-zag position n16
+    const int zz_pos = SH.lk[5][lane].z;  // zig-zag position of natural index n16
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
       const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
       const i32 pr = pred4_get(W, pidx, W.bmodes[i], n16, P4);
       const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane, SH.lk);
-      simple_any |= quantize_coeff(cf, SP.y1, n16) != 0;
-      __syncwarp();
-      if (lane < 16) W.coef[0][lane] = cf;
-      __syncwarp();
+      simple_any |= quantdiv((u32)iabs(cf), tq_iq, tq_bias) != 0;  // quantize_coeff != 0
       const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
-      const bool nzh = trellis_half(lane < 16, W.coef[0], W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane, SH.lk);
+      // coefficients travel in registers: natural order -> zig-zag order and back by shuffle
+      const i32 czz = __shfl_sync(FULL, cf, (lane & 16) | zz_nat);
+      i32 dqz;
+      const bool nzh = trellis_half(lane < 16, czz, dqz, W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane, SH.lk,
+                                    W.eob_pack, W.p0c);
       const bool nz = __shfl_sync(FULL, (int)nzh, 0) != 0;
-      __syncwarp();
+      const i32 dqn = __shfl_sync(FULL, dqz, (lane & 16) | zz_pos);
       tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
       lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
       ynz |= (u32)nz << i;
-      const i32 rec = clip255(pr + coop_idct(W.coef[0][n16], lane, SH.lk));
+      const i32 rec = clip255(pr + coop_idct(dqn, lane, SH.lk));
       if (lane < 16) W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)rec;
       __syncwarp();
     }
@@ -1285,6 +1295,16 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
           } else if (lane < 20) {
             const int k = lane - 16;
             W.p0c[k] = k < 3 ? bit_cost(0, pr3[k * 11]) : bit_cost(1, pr3[0]);
+          }
+          if (PASS == 2) {  // I16 AC blocks (type 0, first 1 -> band 1) for the trellis
+            const u8* pr0 = cc.probs;
+            if (lane < 16) {
+              const int nb = SH.lk[6][lane].y;
+              W.eob_pack0[lane] = lane < 15 ? (bit_cost(0, pr0[(nb * 3 + 1) * 11]) | (bit_cost(0, pr0[(nb * 3 + 2) * 11]) << 16)) : 0u;
+            } else if (lane < 20) {
+              const int k = lane - 16;
+              W.p0c0[k] = k < 3 ? bit_cost(0, pr0[(3 + k) * 11]) : bit_cost(1, pr0[3 * 11]);
+            }
           }
         }
         __syncwarp();
