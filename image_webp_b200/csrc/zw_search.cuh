@@ -921,35 +921,71 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     ynz = __ballot_sync(FULL, lane < 16 && W.nzflag[lane] != 0) & 0xffffu;
     any_simple_nz |= ynz != 0;
   } else {
-    // ---- transform_luma_blocks_4x4 with trellis (vp8.rs:2785-2916): strictly serial over the 16
-    //      sub-blocks; half-warp 0 works one pixel / coefficient per lane, half-warp 1 shadows it ----
+    // ---- transform_luma_blocks_4x4 with trellis (vp8.rs:2785-2916).  The reference walks the 16
+    //      sub-blocks in raster order; block (x, y) only needs its left, top and top-right neighbours
+    //      (prediction, non-zero contexts), so blocks with equal x + 2y are independent: ten rounds, the
+    //      two half-warps taking one block each in six of them (same results, 16 -> 10 steps) ----
     u32 tnz = (in_top_nz >> 1) & 15, lnz = (in_left_nz >> 1) & 15;
     bool simple_any = false;
     const int n16 = lane & 15;
-    const u32 taps = SH.dtaps[lane];
     const u32 tq_iq = SP.y1.iq[n16 > 0], tq_bias = SP.y1.bias[n16 > 0];
     const int zz_nat = SH.lk[6][lane].z;  // natural index of zig-zag position n16
     const int zz_pos = SH.lk[5][lane].z;  // zig-zag position of natural index n16
+    const int hsel = lane & 16;
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) {
+    for (int rd = 0; rd < 10; rd++) {
+      // round -> block of half 0 / half 1 (-1: idle): {0,-} {1,-} {2,4} {3,5} {6,8} {7,9} {10,12} {11,13} {14,-} {15,-}
+      const int ba = rd < 4 ? rd : (rd < 8 ? 6 + ((rd - 4) >> 1) * 4 + (rd & 1) : 6 + rd);
+      const int bb = (rd >= 2 && rd < 8) ? ba + 2 : -1;
+      const int blk_i = hb ? bb : ba;
+      const bool act = blk_i >= 0;
+      const int i = act ? blk_i : ba;  // an idle half shadows half 0's block (its stores are gated)
       const int sbx = i & 3, sby = i >> 2, x0 = 1 + 4 * sbx, y0 = 1 + 4 * sby;
-      const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
-      const i32 pr = pred4_get(W, pidx, W.bmodes[i], n16, P4);
+      const int bmode = W.bmodes[i];
+      // the one predictor this block uses, straight from its 13 edge pixels (lane k of the half holds e[k])
+      i32 pr;
+      {
+        const int k = imin(n16, 12);
+        const int off = k < 4 ? (y0 + 3 - k) * 32 + x0 - 1 : (y0 - 1) * 32 + x0 - 5 + k;
+        const i32 e = W.yws[off];
+        const u32 tp = SH.dtaps[pidx[bmode][n16]];
+        const i32 ta = __shfl_sync(FULL, e, hsel | (tp & 15)), tb = __shfl_sync(FULL, e, hsel | ((tp >> 4) & 15)),
+                  tc = __shfl_sync(FULL, e, hsel | ((tp >> 8) & 15));
+        pr = (ta + 2 * tb + tc + 2) >> 2;
+        if (__any_sync(FULL, bmode < 2)) {  // DC / TM (uniform branch)
+          const bool in_dc = n16 < 4 || (n16 >= 5 && n16 < 9);
+          const i32 dc = (half_sum(in_dc ? e : 0) + 4) >> 3;
+          const i32 l = __shfl_sync(FULL, e, hsel | (3 - (n16 >> 2))), t = __shfl_sync(FULL, e, hsel | (5 + (n16 & 3))),
+                    pp = __shfl_sync(FULL, e, hsel | 4);
+          if (bmode == 0) pr = dc;
+          if (bmode == 1) pr = clip255(l + t - pp);
+        }
+      }
       const i32 cf = coop_fdct((i32)W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)] - pr, lane, SH.lk);
-      simple_any |= quantdiv((u32)iabs(cf), tq_iq, tq_bias) != 0;  // quantize_coeff != 0
+      if (act) simple_any |= quantdiv((u32)iabs(cf), tq_iq, tq_bias) != 0;  // quantize_coeff != 0
       const int ctx0 = imin((int)((lnz >> sby) & 1) + (int)((tnz >> sbx) & 1), 2);
       // coefficients travel in registers: natural order -> zig-zag order and back by shuffle
-      const i32 czz = __shfl_sync(FULL, cf, (lane & 16) | zz_nat);
+      const i32 czz = __shfl_sync(FULL, cf, hsel | zz_nat);
       i32 dqz;
-      const bool nzh = trellis_half(lane < 16, czz, dqz, W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane, SH.lk,
+      const bool nzh = trellis_half(act, czz, dqz, W.rec.levels[1 + i], SP.y1, SP.sharpen, SP.lambda_trellis_i4, 0, cc, 3, ctx0, lane, SH.lk,
                                     W.eob_pack, W.p0c);
-      const bool nz = __shfl_sync(FULL, (int)nzh, 0) != 0;
-      const i32 dqn = __shfl_sync(FULL, dqz, (lane & 16) | zz_pos);
-      tnz = (tnz & ~(1u << sbx)) | ((u32)nz << sbx);
-      lnz = (lnz & ~(1u << sby)) | ((u32)nz << sby);
-      ynz |= (u32)nz << i;
+      const i32 dqn = __shfl_sync(FULL, dqz, hsel | zz_pos);
       const i32 rec = clip255(pr + coop_idct(dqn, lane, SH.lk));
-      if (lane < 16) W.yws[(y0 + (lane >> 2)) * 32 + x0 + (lane & 3)] = (u8)rec;
+      if (act) W.yws[(y0 + (n16 >> 2)) * 32 + x0 + (n16 & 3)] = (u8)rec;
+      // contexts: both halves learn both results (blocks of one round differ in x and in y)
+      const u32 nza = (u32)(__shfl_sync(FULL, (int)nzh, 0) != 0), nzb = (u32)(__shfl_sync(FULL, (int)nzh, 16) != 0);
+      {
+        const int ax = ba & 3, ay = ba >> 2;
+        tnz = (tnz & ~(1u << ax)) | (nza << ax);
+        lnz = (lnz & ~(1u << ay)) | (nza << ay);
+        ynz |= nza << ba;
+        if (bb >= 0) {
+          const int bx2 = bb & 3, by2 = bb >> 2;
+          tnz = (tnz & ~(1u << bx2)) | (nzb << bx2);
+          lnz = (lnz & ~(1u << by2)) | (nzb << by2);
+          ynz |= nzb << bb;
+        }
+      }
       __syncwarp();
     }
     simple_any = __any_sync(FULL, simple_any);
