@@ -36,6 +36,10 @@ constexpr int SEARCH_WARPS = 4;  // warps per CTA of the free-running wavefront 
 #define ZW_LS_WARPS 12
 #endif
 constexpr int LS_WARPS = ZW_LS_WARPS;
+#ifndef ZW_I4_LANES8
+#define ZW_I4_LANES8 1  // I4 candidates with 8 lanes x 2 values per candidate (four per step) instead of 16 lanes x 1 (two per step):
+                        // bit 0 = in pass 1, bit 1 = in pass 2 (measured: pass 1 23.0 -> 20.8 ms, pass 2 41.4 -> 42.2 ms)
+#endif
 #ifndef ZW_LS_I4SYNC
 #define ZW_LS_I4SYNC 0
 #endif
@@ -65,7 +69,7 @@ struct __align__(16) WarpScratch {
   u32 psse[10];         // I4 search: prediction SSE per mode
   u8 cand_mode[12];     // I4 search: mode with rank r
   u8 bmodes[16];
-  u8 dtab[32];       // I4: the 23 distinct 3-tap edge filters of the current sub-block + its DC ([23])
+  u8 dtab[48];       // I4: the 23 distinct 3-tap edge filters of the current sub-block, its DC ([23]), its TM pixels ([32 + n])
   u32 eob_pack[16];  // per row: I4 end-of-block cost after position n: ctx 1 in the low half, ctx 2 in the high half
   u32 p0c[4];        // per row: I4 bit_cost(0, p0) for ctx0 = 0, 1, 2 and bit_cost(1, p0) for ctx0 = 0
   u32 eob_pack0[16]; // the same two for the I16 AC blocks (type 0, first coefficient 1: p0 of band 1)
@@ -76,6 +80,7 @@ struct __align__(16) WarpScratch {
 
 struct SearchShared {
   int4 lk[7][32];       // per-lane constants: butterflies of coop_fdct / coop_idct, coefficient bands (fill_lane_consts)
+  int4 lk8[6][32];      // per-lane constants of the 8-lanes-per-candidate I4 evaluation (fill_lane_consts8)
   u8 pred_idx[10][16];  // (mode, pixel) -> index into WarpScratch::dtab
   u16 dtaps[32];        // lane k -> the three edge taps of dtab[k]
   WarpScratch w[SEARCH_WARPS];
@@ -216,12 +221,13 @@ __device__ __forceinline__ Pred4 pred4_prepare(WarpScratch& W, int x0, int y0, u
   const int n = lane & 15;
   const i32 l = __shfl_sync(FULL, e, 3 - (n >> 2)), t = __shfl_sync(FULL, e, 5 + (n & 3)), p = __shfl_sync(FULL, e, 4);
   r.tm = clip255(l + t - p);
+  if (lane < 16) W.dtab[32 + lane] = (u8)r.tm;
   __syncwarp();
   return r;
 }
 __device__ __forceinline__ i32 pred4_get(const WarpScratch& W, const u8 (*pidx)[16], int mode, int n, const Pred4& p) {
-  const i32 v = W.dtab[pidx[mode][n]];
-  return mode == 1 ? p.tm : v;
+  (void)p;
+  return W.dtab[pidx[mode][n]];  // DC at [23], TM at [32 + n], the directional modes among [0..22]
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,6 +302,68 @@ __device__ __forceinline__ i32 coop_idct(i32 v, int lane, const int4 (*lk)[32]) 
   p = __shfl_xor_sync(FULL, t, 3);
   const i32 o = k5.x * t + k5.y * p;
   return (o + 4) >> 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// I4 candidates, EIGHT lanes per candidate and two values per lane: all four method-4 candidates of a
+// sub-block in one pass instead of two.  lane = cand * 8 + j, j = 2 * r + t:
+//   pixel domain:       row r;            t = 0: columns (0, 1)     t = 1: columns (3, 2)
+//   coefficient domain: row R[r] = {0,2,1,3}[r];  t = 0: columns (0, 2)     t = 1: columns (1, 3)
+// In this layout the first stage of every butterfly pass is an exchange with lane ^ 1 (columns) or
+// lane ^ 6 / lane ^ 2 (rows) and half of the arithmetic is in-lane.  Per-lane constants (lk8):
+//   [0] = {s8, F0, F1, FC}  [1] = {G0, G1, GC, FS}   fdct rows:    u = 8 * recv + s8 * own; first = (u0*F0 + u1*F1 + FC) >> FS; second likewise with G
+//   [2] = {sv, VA, VB, VC}  [3] = {VS, VE, KA, KB}   fdct columns: t = recv + sv * own;     out = ((t*VA + recv2*VB + VC) >> VS) + (VE & (recv2 != 0))
+//   [4] = {sg, s2, HA, HB}                          idct: x = ((w*KA) >> 16) + sg * mulB'(recv);  y = recv2 + s2 * x;  first = g(y0) + f(y1), second = f(y0) - g(y1)
+//   [5] = {sh, pixel / coefficient indices, bands / previous-row source lane, 0}
+// Same arithmetic as fdct4x4 / idct4x4 (zw_prims.cuh).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fill_lane_consts8(int4 (*lk8)[32], int lane) {
+  const int j = lane & 7, r = j >> 1, t = j & 1;
+  const int R = ((r & 1) << 1) | (r >> 1);
+  lk8[0][lane] = t ? make_int4(-8, 5352, 2217, 14500) : make_int4(8, 1, 1, 0);
+  lk8[1][lane] = t ? make_int4(2217, -5352, 7500, 12) : make_int4(1, -1, 0, 0);
+  lk8[2][lane] = make_int4(r < 2 ? 1 : -1, r == 1 ? -1 : (r == 0 ? 1 : 2217), r < 2 ? 1 : (r == 2 ? 5352 : -5352), r < 2 ? 7 : (r == 2 ? 12000 : 51000));
+  lk8[3][lane] = make_int4(r < 2 ? 4 : 16, r == 2 ? 1 : 0, r == 0 ? 65536 : (r == 1 ? -65536 : 35468), r < 2 ? 0 : 20091);
+  lk8[4][lane] = make_int4(r == 2 ? -1 : 1, r < 2 ? 1 : -1, t ? 35468 : 65536, t ? 20091 : 0);
+  const int npx0 = 4 * r + (t ? 3 : 0), npx1 = 4 * r + (t ? 2 : 1);
+  const int nc0 = 4 * R + (t ? 1 : 0), nc1 = 4 * R + (t ? 3 : 2);
+  // lane (within the candidate) holding the last coefficient of the previous coefficient row: type B of row-lane Rinv[R - 1]
+  const int Rm = R > 0 ? R - 1 : 0, rprev = ((Rm & 1) << 1) | (Rm >> 1), psrc = 2 * rprev + 1;
+  lk8[5][lane] = make_int4(t ? -1 : 1, npx0 | (npx1 << 8) | (nc0 << 16) | (nc1 << 24),
+                           (int)ZW_TAB(kEncBands)[nc0] | ((int)ZW_TAB(kEncBands)[nc1] << 8) | (psrc << 16), 0);
+}
+__device__ __forceinline__ void fdct8(i32& v0, i32& v1, int lane, const int4 (*lk8)[32]) {
+  const int4 k0 = lk8[0][lane], k1 = lk8[1][lane], k2 = lk8[2][lane], k3 = lk8[3][lane];
+  const i32 r0 = __shfl_xor_sync(FULL, v0, 1), r1 = __shfl_xor_sync(FULL, v1, 1);
+  const i32 u0 = (r0 << 3) + k0.x * v0, u1 = (r1 << 3) + k0.x * v1;
+  const i32 h0 = (u0 * k0.y + u1 * k0.z + k0.w) >> k1.w, h1 = (u0 * k1.x + u1 * k1.y + k1.z) >> k1.w;
+  const i32 p0 = __shfl_xor_sync(FULL, h0, 6), p1 = __shfl_xor_sync(FULL, h1, 6);
+  const i32 t0 = p0 + k2.x * h0, t1 = p1 + k2.x * h1;
+  const i32 q0 = __shfl_xor_sync(FULL, t0, 2), q1 = __shfl_xor_sync(FULL, t1, 2);
+  v0 = ((t0 * k2.y + q0 * k2.z + k2.w) >> k3.x) + (q0 != 0 ? k3.y : 0);
+  v1 = ((t1 * k2.y + q1 * k2.z + k2.w) >> k3.x) + (q1 != 0 ? k3.y : 0);
+}
+__device__ __forceinline__ void idct8(i32& w0, i32& w1, int lane, const int4 (*lk8)[32]) {
+  const int4 k3 = lk8[3][lane], k4 = lk8[4][lane];
+  const int sh = lk8[5][lane].x;
+  const i32 p0 = __shfl_xor_sync(FULL, w0, 2), p1 = __shfl_xor_sync(FULL, w1, 2);
+  const i32 x0 = ((w0 * k3.z) >> 16) + k4.x * (p0 + ((p0 * k3.w) >> 16));
+  const i32 x1 = ((w1 * k3.z) >> 16) + k4.x * (p1 + ((p1 * k3.w) >> 16));
+  const i32 q0 = __shfl_xor_sync(FULL, x0, 6), q1 = __shfl_xor_sync(FULL, x1, 6);
+  const i32 y0 = q0 + k4.y * x0, y1 = q1 + k4.y * x1;
+  // f(x) = (x * HA) >> 16, g(x) = x + ((x * HB) >> 16): identity for t = 0, the two IDCT multipliers for t = 1
+  const i32 f0 = (y0 * k4.z) >> 16, f1 = (y1 * k4.z) >> 16;
+  const i32 g0 = y0 + ((y0 * k4.w) >> 16), g1 = y1 + ((y1 * k4.w) >> 16);
+  const i32 first = g0 + f1, second = f0 - g1;
+  const i32 e0 = __shfl_xor_sync(FULL, first, 1), e1 = __shfl_xor_sync(FULL, second, 1);
+  w0 = (e0 + sh * first + 4) >> 3;
+  w1 = (e1 + sh * second + 4) >> 3;
+}
+__device__ __forceinline__ int red8_max(int v) {
+  v = max(v, __shfl_xor_sync(FULL, v, 1));
+  v = max(v, __shfl_xor_sync(FULL, v, 2));
+  v = max(v, __shfl_xor_sync(FULL, v, 4));
+  return v;
 }
 
 // Y2 transforms with one coefficient per lane (n = lane & 15 = block index in raster order).  Both are
@@ -593,7 +661,7 @@ struct LumaOut {
 
 // LS: the CTA's warps run the three phases in lock step (a CTA barrier between them); `work` is
 // false for a warp that only keeps the barriers company this round (no row / dependency not ready).
-template <bool LS>
+template <bool LS, bool L8>
 __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegParams& SP, const CostCtx& cc, int i4_modes,
                            bool i4_always, bool trellis, int mbx, int mby, u32 in_top_nz, u32 in_left_nz, int lane, bool work) {
   LumaOut R;
@@ -712,6 +780,19 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     const u32 lam_i4 = SP.lambda_i4, lam_mode = SP.lambda_mode;
     const u32 eobp = W.eob_pack[n16];
     const int band_n = SH.lk[6][lane].x;
+    // (only used by the 8-lanes-per-candidate evaluation, L8)
+    const int4 c8k = SH.lk8[5][lane];
+    const int c8_cand = lane >> 3, c8_t = lane & 1, c8_r = (lane >> 1) & 3;
+    const int c8_px0 = c8k.y & 255, c8_px1 = (c8k.y >> 8) & 255, c8_nc0 = (c8k.y >> 16) & 255, c8_nc1 = (c8k.y >> 24) & 255;
+    const int c8_band0 = c8k.z & 255, c8_band1 = (c8k.z >> 8) & 255, c8_psrc = (c8k.z >> 16) & 255;
+    const bool c8_dc = c8_nc0 == 0;
+    const u32 c8_iq = SP.y1.iq[1], c8_bias = SP.y1.bias[1];
+    const i32 c8_q = SP.y1.q[1];
+    const u32 c8_iq0 = c8_dc ? SP.y1.iq[0] : c8_iq, c8_bias0 = c8_dc ? SP.y1.bias[0] : c8_bias;  // value 0 is the DC in one lane per group
+    const i32 c8_q0 = c8_dc ? (i32)SP.y1.q[0] : c8_q;
+    const u32 c8_eob0 = W.eob_pack[c8_nc0], c8_eob1 = W.eob_pack[c8_nc1];
+    (void)eobp; (void)band_n; (void)lq_iq; (void)lq_bias; (void)lq_q; (void)c8_cand; (void)c8_t; (void)c8_r; (void)c8_px0; (void)c8_px1;
+    (void)c8_band0; (void)c8_band1; (void)c8_psrc; (void)c8_iq0; (void)c8_bias0; (void)c8_q0; (void)c8_eob0; (void)c8_eob1;
     u64 running = 211ull * (u64)lam_mode;
     u32 total_mode_cost = 0;
     u32 tnz4 = 0, lnz4 = 0;  // MB-local non-zero context bits (Q7)
@@ -750,11 +831,71 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
         if (skey == kmin) { skey = 0xffffffffu; W.cand_mode[r] = (u8)lane; }
       }
       __syncwarp();
-      // evaluate the best `max_modes` candidates in rank order, two per step; each half-warp keeps
-      // the best of its own candidates (the rank in the key makes keys unique: min == first best)
       u64 best_key = ~0ull;
       u32 best_sse = 0, best_rate = 0;
       int best_nz = 0;
+      if constexpr (L8) {
+      // evaluate the best `max_modes` candidates in rank order, FOUR per step (eight lanes and two values
+      // per lane each, see fdct8); each lane group keeps the best of its own candidates (the rank in the
+      // key makes keys unique: min == first best), merged once at the end
+      {
+        const int s0 = W.src_y[(sby * 4 + c8_r) * 16 + sbx * 4 + (c8_px0 & 3)], s1 = W.src_y[(sby * 4 + c8_r) * 16 + sbx * 4 + (c8_px1 & 3)];
+        const u32 c0 = W.p0c[ctx0], c1 = ctx0 == 0 ? W.p0c[3] : 0u;
+#pragma unroll 1
+        for (int r = 0; r < max_modes; r += 4) {
+          const int rank = r + c8_cand;
+          const bool act = rank < max_modes;
+          const int m = W.cand_mode[act ? rank : 0];
+          const i32 pr0 = W.dtab[pidx[m][c8_px0]], pr1 = W.dtab[pidx[m][c8_px1]];
+          i32 w0 = s0 - pr0, w1 = s1 - pr1;
+          fdct8(w0, w1, lane, SH.lk8);
+          // quantize_coeff: the DC entry only for coefficient 0 (value 0 of the first lane of a group)
+          const i32 a0 = quantdiv((u32)iabs(w0), c8_iq0, c8_bias0);
+          const i32 a1 = quantdiv((u32)iabs(w1), c8_iq, c8_bias);
+          const i32 q0 = w0 < 0 ? -a0 : a0, q1 = w1 < 0 ? -a1 : a1;
+          // get_residual_cost in natural order: position n's context is min(|level[n - 1]|, 2)
+          const i32 e0 = __shfl_xor_sync(FULL, a0, 1), e1 = __shfl_xor_sync(FULL, a1, 1);
+          const i32 pl = __shfl_sync(FULL, a1, (lane & 24) | c8_psrc);  // last level of the previous coefficient row
+          const int ctxa = c8_t ? imin(e0, 2) : (c8_nc0 == 0 ? ctx0 : imin(pl, 2));
+          const int ctxb = c8_t ? imin(e1, 2) : imin(e0, 2);
+          const int last = red8_max(a1 != 0 ? c8_nc1 : (a0 != 0 ? c8_nc0 : -1));
+          const bool nz = last >= 0;
+          u32 t0 = ZW_TAB(kLevelFixedCosts)[imin(a0, 2047)], t1 = ZW_TAB(kLevelFixedCosts)[imin(a1, 2047)];
+          if (cc.level_cost) {
+            t0 += cc.level_cost[3 * 1632 + (c8_band0 * 3 + ctxa) * 68 + imin(a0, 67)];
+            t1 += cc.level_cost[3 * 1632 + (c8_band1 * 3 + ctxb) * 68 + imin(a1, 67)];
+          }
+          if (c8_nc0 == last) t0 += a0 == 1 ? (c8_eob0 & 0xffffu) : (c8_eob0 >> 16);
+          if (c8_nc1 == last) t1 += a1 == 1 ? (c8_eob1 & 0xffffu) : (c8_eob1 >> 16);
+          if (c8_nc0 == 0) t0 += c1;
+          u32 cs = (c8_nc0 <= last ? t0 : 0u) + (c8_nc1 <= last ? t1 : 0u);
+          cs = (u32)red8_add((int)cs);
+          const u32 coeff_cost = last < 0 ? c0 : cs;
+          i32 d0 = q0 * c8_q0, d1 = q1 * c8_q;
+          idct8(d0, d1, lane, SH.lk8);
+          const i32 rec0 = clip255(pr0 + d0), rec1 = clip255(pr1 + d1);
+          const i32 df0 = s0 - rec0, df1 = s1 - rec1;
+          const u32 sse = (u32)red8_add(df0 * df0 + df1 * df1);
+          if (act) {
+            W.cand_px[rank][c8_px0] = (u8)rec0; W.cand_px[rank][c8_px1] = (u8)rec1;
+            W.cand_lv[rank][c8_nc0] = (i16)q0;  W.cand_lv[rank][c8_nc1] = (i16)q1;
+          }
+          const u32 rate = ZW_TAB(kFixedCostsI4)[(top_ctx * 10 + left_ctx) * 10 + m] + coeff_cost;
+          const u64 score = (u64)sse * 256ull + (u64)(rate & 0xffffu) * (u64)lam_i4;  // u16 truncation (Q8)
+          const u64 key = act ? ((score << 4) | (u64)rank) : ~0ull;
+          if (key < best_key) { best_key = key; best_sse = sse; best_rate = rate; best_nz = (int)nz; }
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {  // merge the four lane groups
+          const u64 k2 = (u64)shfl_xor64((i64)best_key, o);
+          const u32 s2 = __shfl_xor_sync(FULL, best_sse, o), r2 = __shfl_xor_sync(FULL, best_rate, o);
+          const int z2 = __shfl_xor_sync(FULL, best_nz, o);
+          if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
+        }
+      }
+      } else {
+      // evaluate the best `max_modes` candidates in rank order, two per step; each half-warp keeps
+      // the best of its own candidates (the rank in the key makes keys unique: min == first best)
 #pragma unroll 1
       for (int r = 0; r < max_modes; r += 2) {
         const int rank = r + hb;
@@ -783,6 +924,7 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
         const u32 s2 = __shfl_xor_sync(FULL, best_sse, 16), r2 = __shfl_xor_sync(FULL, best_rate, 16);
         const int z2 = __shfl_xor_sync(FULL, best_nz, 16);
         if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
+      }
       }
       __syncwarp();
       const int wrank = (int)(best_key & 15);
@@ -1276,7 +1418,8 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
   __shared__ int s_active;  // LS: warps of this CTA that still have (or may get) a row
   for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
-  if (threadIdx.x < 32) { SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x]; fill_lane_consts(SH.lk, threadIdx.x); }
+  if (threadIdx.x < 32) { SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x]; fill_lane_consts(SH.lk, threadIdx.x); fill_lane_consts8(SH.lk8, threadIdx.x); }
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) SH.pred_idx[1][i] = (u8)(32 + i);  // TM pixels live in dtab[32 + n]
   if (threadIdx.x == 0) s_active = (int)(blockDim.x >> 5);
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -1387,7 +1530,7 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
       __syncwarp();
     }
     const SegParams& SP = *SPp;
-    const LumaOut L = luma_mb<LS>(W, SH, SP, cc, (int)P.i4_modes, P.i4_always != 0, trellis, mbx, mby, top_nz, left_nz, lane, work);
+    const LumaOut L = luma_mb<LS, (PASS == 1 ? (ZW_I4_LANES8 & 1) : (ZW_I4_LANES8 & 2)) != 0>(W, SH, SP, cc, (int)P.i4_modes, P.i4_always != 0, trellis, mbx, mby, top_nz, left_nz, lane, work);
     if (!work) continue;
     bool skip = false;
     u32 out_top = 0, out_left = 0;
