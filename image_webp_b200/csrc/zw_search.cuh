@@ -1171,10 +1171,14 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
   const int b8 = lane & 7, ch = b8 >> 2, cbx = b8 & 1, cby = (b8 >> 1) & 1, cofs = ch * 16;
   const u8* src = ch ? W.src_v : W.src_u;
   int uv_mode;
+  // The final transform reuses what the winning mode's lanes computed in the search: prediction, raw DC
+  // and the simple-quantised AC levels (transform_chroma_blocks quantises the same coefficients the same
+  // way; only the DCs change through the error diffusion) -- fetched with shuffles instead of a second
+  // prediction + FDCT + quantisation.
+  i32 c[16], pr[16], q[16];
   {
     const int mode = lane >> 3;  // lane = mode*8 + block (0..3 U, 4..7 V); MODES order DC,V,H,TM
     const bool avail = !((mode == 1 && mby == 0) || (mode == 2 && mbx == 0) || (mode == 3 && (mbx == 0 || mby == 0)));
-    i32 c[16], pr[16], q[16];
     pred_block(W.uvws, cofs, mode, cbx, cby, ch ? dcV : dcU, pr);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -1182,6 +1186,7 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
       c[k] = (i32)src[y * 8 + x] - pr[k];
     }
     fdct4x4(c);
+    const i32 rawdc = c[0];
     int nzac = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) { q[k] = quantize_coeff(c[k], SP.uv, k); if (k > 0) nzac += q[k] != 0; }
@@ -1207,16 +1212,14 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
       const i64 s = shfl64(score, mm * 8);
       if (s < best) { best = s; uv_mode = mm; }
     }
-  }
-  // ---- transform_chroma_blocks ----
-  i32 c[16], pr[16];
-  pred_block(W.uvws, cofs, uv_mode, cbx, cby, ch ? dcV : dcU, pr);
+    // ---- transform_chroma_blocks: lane b (< 8) takes over block b of the winning mode ----
+    const int from = uv_mode * 8 + b8;
+    c[0] = __shfl_sync(FULL, rawdc, from);
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const int x = cbx * 4 + (k & 3), y = cby * 4 + (k >> 2);
-    c[k] = (i32)src[y * 8 + x] - pr[k];
+    for (int k = 1; k < 16; k++) q[k] = __shfl_sync(FULL, q[k], from);
+#pragma unroll
+    for (int k = 0; k < 16; k++) pr[k] = __shfl_sync(FULL, pr[k], from);
   }
-  fdct4x4(c);
   if (lane < 8) W.dcbuf[lane] = c[0];
   __syncwarp();
   // error diffusion of the 8 DCs, computed redundantly by every lane (tiny, strictly serial)
@@ -1224,7 +1227,7 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
   u32 new_left = 0, new_top = 0;
 #pragma unroll
   for (int cch = 0; cch < 2; cch++) {
-    const i32 q = SP.uv.q[0];
+    const i32 qd = SP.uv.q[0];
     const u32 iq = SP.uv.iq[0], bias = SP.uv.bias[0];
     const i32 t0 = (i8)(top_derr >> (16 * cch)), t1 = (i8)(top_derr >> (16 * cch + 8));
     const i32 l0 = (i8)(left_derr >> (16 * cch)), l1 = (i8)(left_derr >> (16 * cch + 8));
@@ -1239,7 +1242,7 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
       const bool sign = dc < 0;
       const u32 a = (u32)iabs(dc);
       const i32 level = a > SP.uv_dc_zthresh ? (i32)((a * iq + bias) >> 17) : 0;
-      const i32 err = (i32)a - level * q;
+      const i32 err = (i32)a - level * qd;
       const i32 se = (sign ? -err : err) >> 1;
       errs[b] = imin(imax(se, -127), 127);
     }
@@ -1254,13 +1257,13 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
   if (lane < 8) {
 #pragma unroll
     for (int k = 0; k < 8; k++) if (k == lane) c[0] = ndc[k];
+    q[0] = quantize_coeff(c[0], SP.uv, 0);
     bool nz = false;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const i32 q = quantize_coeff(c[k], SP.uv, k);
-      nz |= q != 0;
-      W.nat[lane][k] = (i16)q;
-      c[k] = dequantize(q, SP.uv, k);
+      nz |= q[k] != 0;
+      W.nat[lane][k] = (i16)q[k];
+      c[k] = dequantize(q[k], SP.uv, k);
     }
     idct4x4(c);
 #pragma unroll
