@@ -33,12 +33,13 @@ constexpr int SEARCH_WARPS = 4;  // warps per CTA of the free-running wavefront 
 // "no instruction"); warps that share a scheduler now run the same code at the same time.  Measured:
 // pass 2 78 -> 67 ms in spite of the idle time at the barriers.  0 = free-running like pass 1.
 #ifndef ZW_LS_WARPS
-#define ZW_LS_WARPS 12
+#define ZW_LS_WARPS 10
 #endif
 constexpr int LS_WARPS = ZW_LS_WARPS;
 #ifndef ZW_I4_LANES8
-#define ZW_I4_LANES8 1  // I4 candidates with 8 lanes x 2 values per candidate (four per step) instead of 16 lanes x 1 (two per step):
-                        // bit 0 = in pass 1, bit 1 = in pass 2 (measured: pass 1 23.0 -> 20.8 ms, pass 2 41.4 -> 42.2 ms)
+#define ZW_I4_LANES8 3  // I4 candidates with 8 lanes x 2 values per candidate (four per step) instead of 16 lanes x 1 (two per step):
+                        // bit 0 = in pass 1, bit 1 = in pass 2.  Measured: pass 1 23.0 -> 20.6 ms; pass 2 needs the registers of
+                        // 10-warp CTAs (2 per SM, 96 registers): 41.2 -> 39.3 ms (with 12-warp CTAs / 80 registers it loses: 42.3)
 #endif
 #ifndef ZW_LS_I4SYNC
 #define ZW_LS_I4SYNC 0
@@ -1408,7 +1409,7 @@ __host__ __device__ constexpr int search_min_blocks(int pass) {
 #ifdef ZW_LS_MIN_BLOCKS
   return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
 #else
-  return search_lockstep(pass) ? (ZW_SEARCH_MIN_BLOCKS * SEARCH_WARPS) / (LS_WARPS > 0 ? LS_WARPS : 1) : ZW_SEARCH_MIN_BLOCKS;
+  return search_lockstep(pass) ? 2 : ZW_SEARCH_MIN_BLOCKS;  // lock-step CTAs: two per SM
 #endif
 }
 // dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
