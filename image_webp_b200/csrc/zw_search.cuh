@@ -1409,7 +1409,11 @@ __host__ __device__ constexpr int search_min_blocks(int pass) {
 #ifdef ZW_LS_MIN_BLOCKS
   return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
 #else
+#ifdef ZW_LS_MIN_BLOCKS
+  return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
+#else
   return search_lockstep(pass) ? 2 : ZW_SEARCH_MIN_BLOCKS;  // lock-step CTAs: two per SM
+#endif
 #endif
 }
 // dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
