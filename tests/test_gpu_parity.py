@@ -208,3 +208,28 @@ def test_c_abi_refuses_alpha_in_the_simple_container(ctx):
     rc0, ref, _ = O.encode(rgb, 75, 4)
     assert C.string_at(outs[0].data, outs[0].len) == ref
     L.zw_free(outs[0].data)
+
+
+def test_small_device_budget_splits_the_batch_into_chunks():
+    """A context with a tiny device budget encodes the batch as several chunks (and, with lanes=2, two lanes
+    per chunk): same bytes as the single-chunk context."""
+    import image_webp_b200 as Z
+    imgs = [synth.photo_like(128 + 16 * (i % 3), 96 + 16 * (i % 2), 70 + i) for i in range(12)]
+    ref = []
+    for im in imgs:
+        rc, b, _ = O.encode(im, 75, 4)
+        assert rc == 0
+        ref.append(b)
+    small = Z.Context(0, max_device_bytes=3 << 20)  # ~3 images per chunk
+    try:
+        outs, t = small.encode_batch(imgs, _params(75, 4))
+        assert outs == ref
+        assert t["kernel_launches"] > 17  # more than one chunk ran
+    finally:
+        small.close()
+    two = Z.Context(0, lanes=2)
+    try:
+        outs, _ = two.encode_batch(imgs + imgs, _params(75, 4))
+        assert outs == ref + ref
+    finally:
+        two.close()
