@@ -168,6 +168,7 @@ __device__ __forceinline__ void an_fdct_hist(const i32* res, u32* hist) {
 
 __global__ void __launch_bounds__(AN_WARPS * 32) k_analysis(ChunkParams P) {
   __shared__ u32 s_hist[AN_WARPS][4][32];  // [warp][y-dc, y-tm, uv-dc, uv-tm][bin]
+  __shared__ __align__(16) u8 s_tile[AN_WARPS][17 * 32 + 2 * 9 * 16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gmb = blockIdx.x * AN_WARPS + warp;
   const int img = blockIdx.y;
@@ -183,18 +184,46 @@ __global__ void __launch_bounds__(AN_WARPS * 32) k_analysis(ChunkParams P) {
     const u8* up = yp + (size_t)pw * d.mbh * 16;
     const u8* vp = up + (size_t)cwid * d.mbh * 8;
     const bool has_left = mbx > 0, has_top = mby > 0;
+    // stage the macroblock with its top row / left column / corner in shared memory: one 16-byte (luma) or
+    // 8-byte (chroma) row per lane instead of ~50 strided byte loads per lane from global memory
+    u8* ty = s_tile[warp];            // [17][32]: row 0 = the row above, column 15 = the column to the left, pixels at 16..31
+    u8* tu = ty + 17 * 32;            // [9][16]:  column 7 = left, pixels at 8..15
+    u8* tv = tu + 9 * 16;
+    if (lane < 17) {
+      const int r = lane - 1;         // source row relative to the macroblock
+      if (r >= 0 || has_top) {
+        const u8* src = yp + (size_t)(mby * 16 + r) * pw + mbx * 16;
+        *reinterpret_cast<uint4*>(&ty[lane * 32 + 16]) = __ldg(reinterpret_cast<const uint4*>(src));
+        if (has_left) ty[lane * 32 + 15] = __ldg(src - 1);
+      }
+    } else if (lane < 26) {
+      const int r = lane - 18;
+      if (r >= 0 || has_top) {
+        const u8* src = up + (size_t)(mby * 8 + r) * cwid + mbx * 8;
+        *reinterpret_cast<uint2*>(&tu[(lane - 17) * 16 + 8]) = __ldg(reinterpret_cast<const uint2*>(src));
+        if (has_left) tu[(lane - 17) * 16 + 7] = __ldg(src - 1);
+      }
+    }
+    if (lane < 9) {  // V rows (lanes 0..8 a second time)
+      const int r = lane - 1;
+      if (r >= 0 || has_top) {
+        const u8* src = vp + (size_t)(mby * 8 + r) * cwid + mbx * 8;
+        *reinterpret_cast<uint2*>(&tv[lane * 16 + 8]) = __ldg(reinterpret_cast<const uint2*>(src));
+        if (has_left) tv[lane * 16 + 7] = __ldg(src - 1);
+      }
+    }
+    __syncwarp();
     if (lane < 24) {
-      const u8* plane;
-      int stride, bx, by, size, px, py;
-      if (lane < 16) { plane = yp; stride = pw; bx = lane & 3; by = lane >> 2; size = 16; px = mbx * 16; py = mby * 16; }
-      else { plane = lane < 20 ? up : vp; stride = cwid; bx = lane & 1; by = (lane >> 1) & 1; size = 8; px = mbx * 8; py = mby * 8; }
-      const u8* o = plane + (size_t)py * stride + px;  // MB origin in this plane
+      const u8* o;   // macroblock origin inside its tile
+      int stride, bx, by, size;
+      if (lane < 16) { o = ty + 32 + 16; stride = 32; bx = lane & 3; by = lane >> 2; size = 16; }
+      else { o = (lane < 20 ? tu : tv) + 16 + 8; stride = 16; bx = lane & 1; by = (lane >> 1) & 1; size = 8; }
       // DC value over the whole MB border (analysis.rs:259-291 / :378-419)
       int dcv;
       {
         int st = 0, sl = 0;
         if (has_top) for (int i = 0; i < size; i++) st += o[i - stride];
-        if (has_left) for (int i = 0; i < size; i++) sl += o[(ptrdiff_t)i * stride - 1];
+        if (has_left) for (int i = 0; i < size; i++) sl += o[i * stride - 1];
         const int shift = size == 16 ? 5 : 4;
         if (has_top && has_left) dcv = (st + sl + size) >> shift;
         else if (has_top) dcv = (2 * st + size) >> shift;
@@ -209,11 +238,11 @@ __global__ void __launch_bounds__(AN_WARPS * 32) k_analysis(ChunkParams P) {
 #pragma unroll
         for (int x = 0; x < 4; x++) {
           const int xx = bx * 4 + x, yy = by * 4 + y;
-          const int s = o[(size_t)yy * stride + xx];
+          const int s = o[yy * stride + xx];
           int tm;
-          if (has_left && has_top) tm = clip255((int)o[(ptrdiff_t)yy * stride - 1] + (int)o[xx - stride] - tl);
-          else if (has_left) tm = o[(ptrdiff_t)yy * stride - 1];   // horizontal_pred
-          else if (has_top) tm = o[xx - stride];                    // vertical_pred
+          if (has_left && has_top) tm = clip255((int)o[yy * stride - 1] + (int)o[xx - stride] - tl);
+          else if (has_left) tm = o[yy * stride - 1];   // horizontal_pred
+          else if (has_top) tm = o[xx - stride];         // vertical_pred
           else tm = 129;
           rdc[y * 4 + x] = s - dcv;
           rtm[y * 4 + x] = s - tm;
