@@ -33,13 +33,14 @@ constexpr int SEARCH_WARPS = 4;  // warps per CTA of the free-running wavefront 
 // "no instruction"); warps that share a scheduler now run the same code at the same time.  Measured:
 // pass 2 78 -> 67 ms in spite of the idle time at the barriers.  0 = free-running like pass 1.
 #ifndef ZW_LS_WARPS
-#define ZW_LS_WARPS 10
+#define ZW_LS_WARPS 5
 #endif
 constexpr int LS_WARPS = ZW_LS_WARPS;
 #ifndef ZW_I4_LANES8
 #define ZW_I4_LANES8 3  // I4 candidates with 8 lanes x 2 values per candidate (four per step) instead of 16 lanes x 1 (two per step):
                         // bit 0 = in pass 1, bit 1 = in pass 2.  Measured: pass 1 23.0 -> 20.6 ms; pass 2 needs the registers of
-                        // 10-warp CTAs (2 per SM, 96 registers): 41.2 -> 39.3 ms (with 12-warp CTAs / 80 registers it loses: 42.3)
+                        // 20 warps per SM (96 registers): 41.2 -> 39.3 ms with 10-warp CTAs, 38.8 ms with 5-warp CTAs (with 24 warps /
+                        // 80 registers it loses: 42.3; CTA sizes that spread unevenly over the 4 schedulers lose too: 6 -> 42.8, 11 -> 43.0)
 #endif
 #ifndef ZW_LS_I4SYNC
 #define ZW_LS_I4SYNC 0
@@ -1412,7 +1413,7 @@ __host__ __device__ constexpr int search_min_blocks(int pass) {
 #ifdef ZW_LS_MIN_BLOCKS
   return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
 #else
-  return search_lockstep(pass) ? 2 : ZW_SEARCH_MIN_BLOCKS;  // lock-step CTAs: two per SM
+  return search_lockstep(pass) ? 20 / (LS_WARPS > 0 ? LS_WARPS : 1) : ZW_SEARCH_MIN_BLOCKS;  // lock-step CTAs: 20 warps per SM (96 registers)
 #endif
 #endif
 }
