@@ -53,7 +53,7 @@ class ZwTiming(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "yuv_ms", "analysis_ms", "pass1_ms", "stats_ms", "pass2_ms", "token_ms",
                                          "boolcode_ms", "assemble_ms", "d2h_ms", "device_total_ms", "wall_ms")] + \
                [(n, C.c_uint64) for n in ("kernel_launches", "h2d_bytes", "d2h_bytes", "pixels")] + \
-               [(n, C.c_float) for n in ("chroma1_ms", "chroma2_ms")]
+               [(n, C.c_float) for n in ("chroma1_ms", "chroma2_ms")] + [("symbols", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -510,6 +510,7 @@ static int lane_encode_finish(Lane* c) {
   cudaEventElapsedTime(&ms, c->ev[13], c->ev[10]); T.device_total_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms = ms;
   T.kernel_launches = c->launches;
+  for (u32 i = 0; i < c->n_valid; i++) T.symbols += (u64)c->st[i].hdr_tokens + c->st[i].tok_tokens;
 #ifdef ZW_WAIT_STATS
   {
     unsigned long long w[8];
@@ -603,6 +604,7 @@ static void add_timing(zw_timing& a, const zw_timing& L) {
   a.stats_ms += L.stats_ms; a.pass2_ms += L.pass2_ms; a.token_ms += L.token_ms; a.boolcode_ms += L.boolcode_ms;
   a.assemble_ms += L.assemble_ms; a.d2h_ms += L.d2h_ms; a.chroma1_ms += L.chroma1_ms; a.chroma2_ms += L.chroma2_ms;
   a.kernel_launches += L.kernel_launches; a.h2d_bytes += L.h2d_bytes; a.d2h_bytes += L.d2h_bytes; a.pixels += L.pixels;
+  a.symbols += L.symbols;
 }
 
 extern "C" {

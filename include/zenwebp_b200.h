@@ -33,8 +33,9 @@ enum {
   ZW_ERR_CUDA = 100              /* 100 + cudaError_t                                                      */
 };
 
-/* ColorType (src/encoder/api.rs:83-92).  This round the CUDA path accepts RGB8 and RGBA8
- * (alpha ignored by the VP8 path exactly as vp8.rs:1296 does); L8/La8 return ZW_ERR_INVALID_PARAM. */
+/* ColorType (src/encoder/api.rs:83-92).  All four are accepted: L8/La8 go through convert_image_y
+ * (decoder/yuv.rs:806: Y = the grey sample, U = V = 127); the alpha of La8/Rgba8 is ignored by the
+ * VP8 payload exactly as vp8.rs:1296 does (see zw_encode_webp_batch for the container). */
 enum { ZW_COLOR_L8 = 0, ZW_COLOR_LA8 = 1, ZW_COLOR_RGB8 = 2, ZW_COLOR_RGBA8 = 3 };
 
 typedef struct zw_ctx zw_ctx;
@@ -78,6 +79,7 @@ typedef struct zw_timing {
   uint64_t pixels;
   float chroma1_ms, chroma2_ms; /* pass-1 chroma chain / pass-2 chroma wavefront (pass1_ms and
                                    pass2_ms time the luma wavefront kernels alone)             */
+  uint64_t symbols;             /* boolean-coder input symbols of both partitions, all images    */
 } zw_timing;
 
 /* Create / destroy an encoder context bound to one CUDA device.  One context per (host thread,

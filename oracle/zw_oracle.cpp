@@ -2797,6 +2797,34 @@ size_t zwo_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32
   return total.load();
 }
 
+// Same, keeping the outputs: image i's file (container != 0: RIFF-wrapped) is copied to out + i * out_stride
+// (truncated there if longer; out_lens[i] always holds the full length, 0 on failure).
+size_t zwo_encode_batch_mt_out(const uint8_t* data, size_t n, uint32_t width, uint32_t height, int color, int quality, int method,
+                               int threads, int container, uint8_t* out, size_t out_stride, uint32_t* out_lens) {
+  std::atomic<size_t> next(0), total(0);
+  const size_t per = (size_t)width * height * (size_t)(color + 1);
+  auto work = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= n) break;
+      uint8_t* o = nullptr;
+      size_t len = 0;
+      const int rc = container ? zwo_encode_webp(data + i * per, per, width, height, color, quality, method, &o, &len, nullptr)
+                               : zwo_encode_vp8(data + i * per, per, width, height, color, quality, method, &o, &len, nullptr);
+      if (rc != 0) { if (out_lens) out_lens[i] = 0; continue; }
+      if (out) memcpy(out + i * out_stride, o, len < out_stride ? len : out_stride);
+      if (out_lens) out_lens[i] = (uint32_t)len;
+      total.fetch_add(len);
+      free(o);
+    }
+  };
+  if (threads <= 1) { work(); return total.load(); }
+  std::vector<std::thread> ts;
+  for (int t = 0; t < threads; t++) ts.emplace_back(work);
+  for (auto& t : ts) t.join();
+  return total.load();
+}
+
 zwo_dump* zwo_dump_new(void) { return new zwo_dump(); }
 void zwo_dump_free(zwo_dump* d) { delete d; }
 int zwo_dump_get(const zwo_dump* d, const char* name, const uint8_t** ptr, size_t* len) {

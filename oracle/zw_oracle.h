@@ -56,6 +56,12 @@ void zwo_free(void* p);
 size_t zwo_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32_t height,
                            int quality, int method, int threads);
 
+/* Same for any colour type, keeping the outputs: file i is copied to out + i*out_stride (truncated there if
+ * longer), out_lens[i] = its full length (0 on failure).  container != 0 adds the RIFF wrap. */
+size_t zwo_encode_batch_mt_out(const uint8_t* data, size_t n, uint32_t width, uint32_t height, int color,
+                               int quality, int method, int threads, int container, uint8_t* out,
+                               size_t out_stride, uint32_t* out_lens);
+
 zwo_dump* zwo_dump_new(void);
 void zwo_dump_free(zwo_dump* d);
 /* Returns 1 and sets ptr/len (bytes) if a stage called `name` was recorded, else 0. */

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
+import photo_inputs  # noqa: E402
 from image_webp_b200 import synth  # noqa: E402
 
 CASES = [
@@ -30,11 +31,18 @@ CASES = [
     ("photo768_s0_q75_m6", "photo_like", (768, 512, 0), 75, 6),
     ("photo768_s9_q90_m4", "photo_like", (768, 512, 9), 90, 4),
     ("photo17_s4_q50_m2", "photo_like", (17, 17, 4), 50, 2),
+    # real photographs (tests/golden/photos, the reference's gallery1 PNGs): SURVEY.md 8(d) config 1(i) and friends
+    ("real3_256_104_q75_m4", "crop", ("3", 256, 104), 75, 4),
+    ("real3_256_104_q75_m6", "crop", ("3", 256, 104), 75, 6),
+    ("real4_100_200_q90_m4", "crop", ("4", 100, 200), 90, 4),
+    ("real5_0_0_q50_m0", "crop", ("5", 0, 0), 50, 0),
+    ("real5_200_240_q75_m1", "crop", ("5", 200, 240), 75, 1),
+    ("real4_full_q75_m4", "photo", ("4",), 75, 4),
 ]
 
 
 def build_image(kind, args):
-    return getattr(synth, kind)(*args)
+    return (getattr(synth, kind, None) or getattr(photo_inputs, kind))(*args)
 
 
 def main():
