@@ -2,7 +2,7 @@
 include/zenwebp_b200.h; a drop-in for the WebPEncoder / EncoderParams::lossy(q) + method path of
 imazen/image-webp (`zenwebp` 0.2.0).  Hand-written CUDA for sm_100a, no CPU fallback."""
 from .encoder import (BatchPipeline, ColorType, Context, DeviceError, EncoderParams, EncodingError, InvalidBufferSize,
-                      InvalidDimensions, WebPEncoder, default_context, encode_batch)
+                      InvalidDimensions, MultiContext, PendingBatch, WebPEncoder, default_context, encode_batch)
 
 __all__ = ["BatchPipeline", "ColorType", "Context", "DeviceError", "EncoderParams", "EncodingError", "InvalidBufferSize",
-           "InvalidDimensions", "WebPEncoder", "default_context", "encode_batch"]
+           "InvalidDimensions", "MultiContext", "PendingBatch", "WebPEncoder", "default_context", "encode_batch"]

@@ -59,9 +59,16 @@ class ZwTiming(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ZwBatchView(C.Structure):
+    _fields_ = [("arena", C.c_void_p), ("n", C.c_size_t), ("offsets", C.POINTER(C.c_uint64)), ("lens", C.POINTER(C.c_uint32)),
+                ("status", C.POINTER(C.c_int32))]
+
+
 # Every symbol include/zenwebp_b200.h declares.
 EXPORTS = ["zw_create", "zw_destroy", "zw_last_error", "zw_strerror", "zw_free", "zw_max_output_size",
-           "zw_encode_vp8_batch", "zw_encode_webp_batch", "zw_stage_batch", "zw_encode_resident", "zw_download",
+           "zw_encode_vp8_batch", "zw_encode_webp_batch", "zw_submit", "zw_wait", "zw_release",
+           "zw_multi_create", "zw_multi_destroy", "zw_multi_device_count", "zw_multi_encode",
+           "zw_stage_batch", "zw_encode_resident", "zw_download",
            "zw_dump_stage", "zw_version", "zw_measure_int_peak"]
 
 _lib = None
@@ -89,6 +96,14 @@ def load():
     L.zw_max_output_size.argtypes = [C.c_uint32, C.c_uint32]
     for f in ("zw_encode_vp8_batch", "zw_encode_webp_batch"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.c_int, C.c_int, C.POINTER(ZwOutput), C.POINTER(ZwTiming)]
+    L.zw_submit.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.zw_wait.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ZwBatchView), C.POINTER(ZwTiming)]
+    L.zw_release.argtypes = [C.c_void_p, C.c_int]
+    L.zw_multi_create.restype = C.c_void_p
+    L.zw_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(ZwLimits)]
+    L.zw_multi_destroy.argtypes = [C.c_void_p]
+    L.zw_multi_device_count.argtypes = [C.c_void_p]
+    L.zw_multi_encode.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(ZwOutput), C.POINTER(ZwTiming)]
     L.zw_stage_batch.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t]
     L.zw_encode_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ZwTiming)]
     L.zw_download.argtypes = [C.c_void_p, C.POINTER(ZwOutput), C.c_size_t, C.c_int, C.POINTER(ZwTiming)]

@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
   const u32 nmb = d.mbw * d.mbh;
   const u32 mb = blockIdx.x * TOK_WARPS + warp;
   if (mb >= nmb) return;
+  if (MODE == 1 && P.tot->overflow) return;  // stream arenas too small: the host grows them and re-runs
   const u32 gmb = d.mb_off + mb;
   const int mbx = mb % d.mbw, mby = mb / d.mbw;
   const MbRecord& r = P.rec2[gmb];
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
     }
     if (do_block) {
       WriteSink s;
-      s.p = P.tok_tokens + d.tok_off + P.mb_tok_cnt[gmb] + (incl - cnt);
+      s.p = P.tok_tokens + P.lay[img].tok_off + P.mb_tok_cnt[gmb] + (incl - cnt);
       block_tokens(s, r.levels[lane], I.type, I.first, I.ctx, probs);
     }
     {
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
       }
       if (lane < 18) {
         WriteSink s;
-        s.p = P.hdr_tokens + d.hdr_off + P.mb_hdr_cnt[gmb] + (hincl - c.n);  // frame-header length is folded into the scan
+        s.p = P.hdr_tokens + P.lay[img].hdr_off + P.mb_hdr_cnt[gmb] + (hincl - c.n);  // frame-header length is folded into the scan
         mb_header_slot(s, lane, IS, r, top, left);
       }
     }
@@ -548,12 +549,76 @@ __global__ void __launch_bounds__(256) k_tokscan(ChunkParams P) {
   }
 }
 
+// Chunk-wide placement of the variable-size data (one CTA): exclusive scans over the images of the symbol counts
+// (8-token aligned) and of the partition capacities (7 bits per symbol bound + 16, 16-byte aligned pairs), checked
+// against the arenas the host allocated before it knew the counts.
+__global__ void __launch_bounds__(1024) k_layout(ChunkParams P) {
+  __shared__ u64 s_h[32], s_t[32], s_p[32];
+  __shared__ u64 s_base[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 3) s_base[threadIdx.x] = 0;
+  __syncthreads();
+  for (u32 i0 = 0; i0 < P.n_img; i0 += blockDim.x) {
+    const u32 i = i0 + threadIdx.x;
+    u64 h = 0, t = 0, pb = 0;
+    u32 c0 = 0, c1 = 0;
+    if (i < P.n_img) {
+      const ImageState& IS = P.st[i];
+      h = ((u64)IS.hdr_tokens + 7) & ~7ull;
+      t = ((u64)IS.tok_tokens + 7) & ~7ull;
+      c0 = (u32)(((u64)IS.hdr_tokens * 7) / 8 + 16);
+      c1 = (u32)(((u64)IS.tok_tokens * 7) / 8 + 16);
+      pb = ((u64)c0 + c1 + 15) & ~15ull;
+    }
+    u64 ih = h, it = t, ip = pb;  // inclusive scans inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 a = (u64)shfl_up64_full((i64)ih, o), b = (u64)shfl_up64_full((i64)it, o), c = (u64)shfl_up64_full((i64)ip, o);
+      if (lane >= o) { ih += a; it += b; ip += c; }
+    }
+    if (lane == 31) { s_h[warp] = ih; s_t[warp] = it; s_p[warp] = ip; }
+    __syncthreads();
+    if (warp == 0) {
+      u64 a = s_h[lane], b = s_t[lane], c = s_p[lane];
+      const u64 a0 = a, b0 = b, c0w = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 x = (u64)shfl_up64_full((i64)a, o), y = (u64)shfl_up64_full((i64)b, o), z = (u64)shfl_up64_full((i64)c, o);
+        if (lane >= o) { a += x; b += y; c += z; }
+      }
+      s_h[lane] = a - a0; s_t[lane] = b - b0; s_p[lane] = c - c0w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    if (i < P.n_img) {
+      ImageLayout L;
+      L.hdr_off = s_base[0] + s_h[warp] + ih - h;
+      L.tok_off = s_base[1] + s_t[warp] + it - t;
+      L.part_off = s_base[2] + s_p[warp] + ip - pb;
+      L.out_off = 0;
+      L.p0_cap = c0; L.p1_cap = c1;
+      P.lay[i] = L;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {  // last thread holds the block totals of this step
+      s_base[0] += s_h[warp] + ih; s_base[1] += s_t[warp] + it; s_base[2] += s_p[warp] + ip;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ChunkTotals T;
+    T.hdr_tokens = s_base[0]; T.tok_tokens = s_base[1]; T.part_bytes = s_base[2]; T.out_bytes = 0;
+    T.overflow = (T.hdr_tokens > P.cap_hdr_tokens || T.tok_tokens > P.cap_tok_tokens || T.part_bytes > P.cap_part_bytes) ? 1u : 0u;
+    T.pad = 0;
+    *P.tot = T;
+  }
+}
+
 // Frame-header tokens of every image (tiny, one thread each).
 __global__ void k_frame_header(ChunkParams P) {
   const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
-  if (img >= P.n_img) return;
+  if (img >= P.n_img || P.tot->overflow) return;
   WriteSink s;
-  s.p = P.hdr_tokens + P.img[img].hdr_off;
+  s.p = P.hdr_tokens + P.lay[img].hdr_off;
   frame_header_tokens(s, P, P.st[img], P.probs + (size_t)img * 1056);
 }
 
@@ -572,80 +637,6 @@ __device__ __forceinline__ void bool_carry(u8* out, u32 pos, u32 cap) {
   }
 }
 
-#ifdef ZW_BOOLCODE_SERIAL
-// One WARP per (image, partition) stream: the 32 lanes fetch 32 symbols with one coalesced load and
-// then all run the (strictly serial) range-coder recurrence in lock step on identical state -- no
-// divergence between different streams, symbol fetch latency off the critical path -- while lane 0
-// owns the output bytes.  Streams 0..n_img-1 are the token partitions, n_img..2n_img-1 the first
-// partitions.
-constexpr int BC_WARPS = 4;
-__global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
-  const int lane = threadIdx.x & 31;
-  const u32 sid = blockIdx.x * BC_WARPS + (threadIdx.x >> 5);
-  if (sid >= 2 * P.n_img) return;
-  const bool is_hdr = sid >= P.n_img;
-  const u32 img = is_hdr ? sid - P.n_img : sid;
-  const ImageDesc d = P.img[img];
-  ImageState& IS = P.st[img];
-  const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
-  const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
-  // partition scratch: [first partition | token partition]
-  u8* out = P.part_bytes + d.part_off + (is_hdr ? 0 : d.p0_cap);
-  const u32 cap = is_hdr ? d.p0_cap : d.p1_cap;
-  u32 bottom = 0, range = 255, pos = 0;
-  int bit_num = 24;
-  bool overflow = false;
-  // write_bool (arithmetic.rs:67-95) with the bit-at-a-time renormalisation loop collapsed: the
-  // `s` shifts a symbol needs are applied in at most two steps around the byte boundary.  Bits
-  // reaching bit 31 are carries into the bytes already written (at most one per symbol).
-  u32 mine = lane < n ? tk[lane] : 0;
-  for (u32 i0 = 0; i0 < n; i0 += 32) {
-    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
-    const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
-#pragma unroll 4
-    for (int k = 0; k < cnt; k++) {
-      const u32 t = __shfl_sync(FULL, mine, k);
-      const u32 split = 1 + (((range - 1) * (t & 255)) >> 8);
-      const bool bit = (t >> 8) != 0;
-      bottom += bit ? split : 0u;
-      range = bit ? range - split : split;
-      int s2 = __clz(range) - 24;  // shifts needed to bring range back to >= 128
-      range <<= s2;
-      if (s2 >= bit_num) {  // a byte completes inside this renormalisation (bit_num <= 7 here)
-        if (bottom >> (32 - bit_num)) { if (lane == 0) bool_carry(out, pos, cap); }
-        bottom <<= bit_num;
-        if (lane == 0) { if (pos < cap) out[pos] = (u8)(bottom >> 24); else overflow = true; }
-        pos++;
-        bottom &= 0xffffffu;
-        s2 -= bit_num;
-        bit_num = 8;
-      }
-      const u64 w = (u64)bottom << s2;  // s2 may be 0
-      if ((u32)(w >> 32)) { if (lane == 0) bool_carry(out, pos, cap); }
-      bottom = (u32)w;
-      bit_num -= s2;
-    }
-    mine = nxt;
-  }
-  // flush_and_get_buffer (arithmetic.rs:176-195)
-  if (lane == 0) {
-    int c = bit_num;
-    u32 v = bottom;
-    if (bottom & (1u << (32 - bit_num))) bool_carry(out, pos, cap);
-    v <<= (c & 7);
-    c = (c >> 3) - 1;
-    while (c >= 0) { v <<= 8; c--; }
-    for (c = 3; c >= 0; c--) {
-      if (pos < cap) out[pos] = (u8)(v >> 24); else overflow = true;
-      pos++;
-      v <<= 8;
-    }
-    if (is_hdr) IS.part0_bytes = pos; else IS.part1_bytes = pos;
-    if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
-  }
-}
-
-#else
 // One WARP per (image, partition) stream.  Streams 0..n_img-1 are the token partitions,
 // n_img..2n_img-1 the first partitions.
 //
@@ -677,10 +668,10 @@ __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1;
   const bool chain_warp = (warp & 1) == 0;
   const u32 sid = blockIdx.x * BC_STREAMS + pair;
-  if (sid >= 2 * P.n_img) return;  // both warps of a pair leave together
+  if (sid >= 2 * P.n_img || P.tot->overflow) return;  // both warps of a pair leave together
   const bool is_hdr = sid >= P.n_img;
   const u32 img = is_hdr ? sid - P.n_img : sid;
-  const ImageDesc d = P.img[img];
+  const ImageLayout d = P.lay[img];
   ImageState& IS = P.st[img];
   const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
   const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
@@ -810,15 +801,14 @@ __global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
   }
 }
 
-#endif  // ZW_BOOLCODE_SERIAL
 
 // ---------------------------------------------------------------------------------------------
 // (6) Assembly: frame tag + start code + dimensions + first partition + token partition, packed
 //     back to back in the output arena in image order.  (Only the RIFF wrap stays on the host.)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_outscan(ChunkParams P, u64* out_offsets /*[n_img+1]*/) {
-  // one warp: exclusive scan of the 16-byte-aligned payload sizes, 32 images per step
-  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // one warp: exclusive scan of the 16-byte-aligned file sizes, 32 images per step
+  if (blockIdx.x != 0 || threadIdx.x >= 32 || P.tot->overflow) return;
   const int lane = threadIdx.x;
   u64 acc = 0;
   for (u32 i0 = 0; i0 < P.n_img; i0 += 32) {
@@ -827,8 +817,9 @@ __global__ void k_outscan(ChunkParams P, u64* out_offsets /*[n_img+1]*/) {
     if (i < P.n_img) {
       ImageState& IS = P.st[i];
       IS.vp8_bytes = 10 + IS.part0_bytes + IS.part1_bytes;
+      IS.file_bytes = 20 + IS.vp8_bytes + (IS.vp8_bytes & 1);
       if (IS.part0_bytes >= (1u << 19) && IS.status == 0) IS.status = 5;  // ZW_ERR_PARTITION_TOO_LARGE
-      sz = (IS.vp8_bytes + 15u) & ~15u;
+      sz = (IS.file_bytes + 15u) & ~15u;
     }
     u64 incl = sz;
 #pragma unroll
@@ -836,28 +827,40 @@ __global__ void k_outscan(ChunkParams P, u64* out_offsets /*[n_img+1]*/) {
       const u64 v = (u64)shfl_up64_full((i64)incl, o);
       if (lane >= o) incl += v;
     }
-    if (i < P.n_img) out_offsets[i] = acc + incl - sz;
+    if (i < P.n_img) { out_offsets[i] = acc + incl - sz; P.lay[i].out_off = acc + incl - sz; }
     acc += (u64)shfl64((i64)incl, 31);
   }
-  if (lane == 0) out_offsets[P.n_img] = acc;
+  if (lane == 0) { out_offsets[P.n_img] = acc; P.tot->out_bytes = acc; }
 }
 
+// The finished file of every image: RIFF header (api.rs:1325-1329, write_chunk :1232-1241) + frame tag + start code +
+// dimensions + first partition + token partition + pad byte.  The VP8 payload alone is bytes [20, 20 + vp8_bytes).
 __global__ void __launch_bounds__(256) k_assemble(ChunkParams P, const u64* out_offsets) {
+  if (P.tot->overflow) return;
   const int img = blockIdx.x;
   const ImageDesc d = P.img[img];
+  const ImageLayout L = P.lay[img];
   const ImageState& IS = P.st[img];
   u8* o = P.out + out_offsets[img];
-  const u8* p0 = P.part_bytes + d.part_off;
-  const u8* p1 = p0 + d.p0_cap;
+  const u8* p0 = P.part_bytes + L.part_off;
+  const u8* p1 = p0 + L.p0_cap;
   if (threadIdx.x == 0) {
+    const u32 payload = IS.vp8_bytes;
+    const u32 chunk = payload + (payload & 1) + 8, riff = chunk + 4;
+    o[0] = 'R'; o[1] = 'I'; o[2] = 'F'; o[3] = 'F';
+    o[4] = (u8)riff; o[5] = (u8)(riff >> 8); o[6] = (u8)(riff >> 16); o[7] = (u8)(riff >> 24);
+    o[8] = 'W'; o[9] = 'E'; o[10] = 'B'; o[11] = 'P'; o[12] = 'V'; o[13] = 'P'; o[14] = '8'; o[15] = ' ';
+    o[16] = (u8)payload; o[17] = (u8)(payload >> 8); o[18] = (u8)(payload >> 16); o[19] = (u8)(payload >> 24);
+    if (payload & 1) o[20 + payload] = 0;
+    u8* v = o + 20;
     const u32 tag = (IS.part0_bytes << 5) | (1u << 4);  // show_frame=1, version 0, key frame
-    o[0] = (u8)tag; o[1] = (u8)(tag >> 8); o[2] = (u8)(tag >> 16);
-    o[3] = 0x9d; o[4] = 0x01; o[5] = 0x2a;
+    v[0] = (u8)tag; v[1] = (u8)(tag >> 8); v[2] = (u8)(tag >> 16);
+    v[3] = 0x9d; v[4] = 0x01; v[5] = 0x2a;
     const u32 w = d.width & 0x3fff, h = d.height & 0x3fff;
-    o[6] = (u8)w; o[7] = (u8)(w >> 8); o[8] = (u8)h; o[9] = (u8)(h >> 8);
+    v[6] = (u8)w; v[7] = (u8)(w >> 8); v[8] = (u8)h; v[9] = (u8)(h >> 8);
   }
-  for (u32 i = threadIdx.x; i < IS.part0_bytes; i += blockDim.x) o[10 + i] = p0[i];
-  u8* o1 = o + 10 + IS.part0_bytes;
+  for (u32 i = threadIdx.x; i < IS.part0_bytes; i += blockDim.x) o[30 + i] = p0[i];
+  u8* o1 = o + 30 + IS.part0_bytes;
   for (u32 i = threadIdx.x; i < IS.part1_bytes; i += blockDim.x) o1[i] = p1[i];
 }
 

@@ -1,6 +1,7 @@
 // zw_capi.cu -- host side of the C ABI (include/zenwebp_b200.h): validation, HBM layout of a
-// chunk, kernel sequencing, D2H and host chunk assembly.  Only RIFF/VP8 chunk assembly and the
-// tiny f64 quality->quantiser tables are computed on the host; there is no CPU encode fallback.
+// chunk, kernel sequencing, the pipeline of batches in flight, D2H.  Only the tiny f64
+// quality->quantiser tables are computed on the host (the RIFF wrap is written by k_assemble);
+// there is no CPU encode fallback.
 //
 // Reference (file:line under /root/reference):
 //   quality_to_quant_index      src/encoder/vp8.rs:37-55       (+ fast_math.rs:15-43 cbrt)
@@ -18,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zenwebp_b200.h"
@@ -142,7 +144,7 @@ static TokenTables make_token_tables() {
   return t;
 }
 
-// ---- device buffer that only grows -----------------------------------------------------------
+// ---- device / pinned-host buffers that only grow ----------------------------------------------
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -158,6 +160,21 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
 
 #define CK(expr)                                                         \
   do {                                                                   \
@@ -167,33 +184,44 @@ struct DevBuf {
 
 }  // namespace
 
-// One "lane": a stream with its own chunk buffers.  A context owns several lanes and splits
-// every staged chunk between them so that the low-parallelism kernels of one lane (pass-1 chroma
-// chain, boolean coder) and its host round trip overlap the wavefront kernels / copies of the other.
+// One "lane": a stream with its own chunk buffers, i.e. one batch in flight.  A context owns `depth` lanes;
+// zw_submit hands a batch to a free lane, whose H2D copy then runs under the kernels of the lane submitted
+// before it and whose D2H copy runs under the kernels of the lane submitted after it.  Kernels of different
+// lanes never overlap (measured: concurrent persistent kernels only slow each other down): a lane's first
+// kernel waits for the previous lane's last one.
+enum { LANE_FREE = 0, LANE_STAGED = 1, LANE_IN_FLIGHT = 2, LANE_SIZED = 3, LANE_DONE = 4 };
+enum { EV_H2D0 = 0, EV_H2D1, EV_YUV0, EV_YUV1, EV_AN1, EV_P1, EV_C1, EV_ST0, EV_ST1, EV_C2, EV_P2, EV_TOK, EV_BC, EV_END, EV_START,
+       EV_D2H0, EV_D2H1, EV_SIZES, EV_COUNT };
 struct Lane {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[16], ev2[2];
+  cudaEvent_t ev[EV_COUNT];
+  bool ev_ok = false;
   const SegParams* segtab = nullptr;  // shared constant tables (owned by the context)
   const u8* lut = nullptr;
-  DevBuf d_img, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
+  DevBuf d_img, d_lay, d_tot, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
       d_derr1, d_derr2, d_c1, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
       d_part, d_out, d_outoff;
+  PinBuf h_st, h_outoff, h_tot, h_arena;  // pinned mirrors: ImageState[n], out offsets[n+1], ChunkTotals, the finished files
   std::vector<ImageDesc> img;
-  std::vector<ImageState> st;
   std::vector<RowRef> rows;
-  std::vector<u64> out_off;
   std::vector<int> img_status;  // host-side validation result per image handed to this lane (0 = staged)
   std::vector<int> slot_of;     // image index within the lane -> position among staged (valid) images, or -1
-  u8* h_pinned = nullptr;
-  size_t h_pinned_cap = 0;
+  std::vector<u64> v_off;       // per input image: offset of its file (or payload) in h_arena
+  std::vector<u32> v_len;
+  std::vector<int32_t> v_status;
+  size_t n_in = 0;
   u32 n_valid = 0, n_rows = 0, n_mb = 0, max_pw = 0, max_ph = 0, max_mb = 0;
   u64 layout_key = 0;
-  bool staged = false, encoded = false;
+  u64 cap_h = 0, cap_t = 0, cap_p = 0;  // capacities the phase-B arenas were launched with
+  double tok_per_mb = 3.0 * 256;        // symbol-arena estimate (token partition), raised when a batch overflows it
+  int state = LANE_FREE;
+  int container = 1;
   int quality = -1, method = -1, base_qidx = 0;
   int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0;
   u32 start_slack = 0;  // measured: rows wait 1.1-1.4 % of their time at 1024 images; extra start slack only idles warps
   u64 launches = 0;
+  u32 reruns = 0;
   dim3 tok_grid;
   ChunkParams P;
   zw_timing last;
@@ -205,20 +233,19 @@ struct zw_ctx {
   size_t budget = 0;
   DevBuf d_segtab, d_lut;
   std::vector<Lane*> lanes;
-  std::vector<size_t> lane_begin;  // image ranges of the staged chunk: lane k owns [lane_begin[k], lane_begin[k+1])
-  size_t n_staged = 0;
-  int active_lanes = 0;
-  int resident_lanes = 1;  // lanes used by zw_stage_batch (inputs already resident: nothing to overlap)
-  int batch_lanes = 1;     // lanes used by the host-buffer batch entry points
+  Lane* prev = nullptr;  // lane whose kernels were launched last (the next lane's kernels wait for them)
+  size_t n_staged = 0;   // split API (lane 0)
   bool staged = false, encoded = false;
-  int base_qidx = 0;
+  int dump_lane = -1;    // lane zw_dump_stage reads: the last chunk handed to the device
   zw_timing last;
 };
 
 static void fill_params(Lane* c) {
   ChunkParams& P = c->P;
   memset(&P, 0, sizeof(P));
-  P.img = c->d_img.as<ImageDesc>(); P.st = c->d_st.as<ImageState>(); P.rows = c->d_rows.as<RowRef>();
+  P.img = c->d_img.as<ImageDesc>(); P.lay = c->d_lay.as<ImageLayout>(); P.tot = c->d_tot.as<ChunkTotals>();
+  P.cap_hdr_tokens = c->cap_h; P.cap_tok_tokens = c->cap_t; P.cap_part_bytes = c->cap_p;
+  P.st = c->d_st.as<ImageState>(); P.rows = c->d_rows.as<RowRef>();
   P.segtab = c->segtab; P.segquant_lut = c->lut;
   P.n_img = c->n_valid; P.n_rows = c->n_rows; P.n_mb = c->n_mb;
   P.rgb = c->d_rgb.as<u8>(); P.planes = c->d_planes.as<u8>();
@@ -256,23 +283,22 @@ static size_t image_footprint(u32 w, u32 h, u32 bpp) {
   b += nmb * 384;                              // planes
   b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8 + 8);
   b += mbh * (2112 * 4 + 8 + 8);               // row statistics, progress, row table
-  b += 1056 * 7 + 6528 * 2 + 2048;             // per-image tables
-  b += nmb * 256 * 10 + nmb * 256;             // token streams (estimate: 5 symbols/px) + bitstream
+  b += 1056 * 7 + 6528 * 2 + 2048 + 9700 * 2;  // per-image tables, frame-header symbols
+  b += nmb * 256 * 10 + nmb * 256 * 5;         // token streams (estimate: 5 symbols/px) + partitions + files
   return b;
 }
 
 static void lane_destroy(Lane* c) {
   if (!c) return;
-  DevBuf* all[] = {&c->d_img, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
+  DevBuf* all[] = {&c->d_img, &c->d_lay, &c->d_tot, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
                    &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_c1, &c->d_uvflags, &c->d_progress,
                    &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_htok,
                    &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : all) b->release();
-  if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  for (auto& ev : c->ev) cudaEventDestroy(ev);
-  for (auto& ev : c->ev2) cudaEventDestroy(ev);
+  c->h_st.release(); c->h_outoff.release(); c->h_tot.release(); c->h_arena.release();
+  if (c->ev_ok) for (auto& ev : c->ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
-
   delete c;
 }
 
@@ -282,15 +308,25 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   c->segtab = ctx->d_segtab.as<SegParams>();
   c->lut = ctx->d_lut.as<u8>();
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
-  for (auto& ev : c->ev) cudaEventCreate(&ev);
-  for (auto& ev : c->ev2) cudaEventCreate(&ev);
-  if (c->d_ticket.reserve(64) != cudaSuccess) { lane_destroy(c); return nullptr; }
+  for (int i = 0; i < EV_COUNT; i++) {
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) {
+      for (int k = 0; k < i; k++) cudaEventDestroy(c->ev[k]);
+      cudaStreamDestroy(c->stream);
+      delete c;
+      return nullptr;
+    }
+  }
+  c->ev_ok = true;
+  if (c->d_ticket.reserve(64) != cudaSuccess || c->d_tot.reserve(sizeof(ChunkTotals)) != cudaSuccess ||
+      c->h_tot.reserve(sizeof(ChunkTotals)) != cudaSuccess) { lane_destroy(c); return nullptr; }
   int b1 = 0, b2 = 0, b4 = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared));
-  cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(1)));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, search_warps(1) * 32, search_smem_bytes(search_warps(1)));
-  cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2)));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2)));
+  bool ok = true;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared)) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(1))) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, search_warps(1) * 32, search_smem_bytes(search_warps(1))) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2))) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2))) == cudaSuccess;
+  if (!ok) { lane_destroy(c); return nullptr; }
   if (warps_hint > 0) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
     b1 = std::min(b1, std::max(1, warps_hint / search_warps(1))); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
@@ -302,9 +338,11 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   return c;
 }
 
-// Validate + lay out + start the H2D copies of one lane's images (asynchronous on its stream).
-static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after) {
-  c->staged = false; c->encoded = false;
+// Validate + lay out + start the H2D copies of one lane's images (asynchronous on its stream).  The caller's
+// buffers must stay valid and unchanged until the copy has finished (EV_H2D1).
+static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
+  c->state = LANE_FREE;
+  c->n_in = n;
   c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
   u64 rgb_bytes = 0, plane_bytes = 0, key = 1469598103934665603ull;
   u32 n_mb = 0, n_rows = 0, max_pw = 0, max_ph = 0, max_mb = 0, max_mbh = 0;
@@ -332,9 +370,10 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after)
   c->n_valid = (u32)c->img.size(); c->n_mb = n_mb; c->n_rows = n_rows;
   c->max_pw = max_pw; c->max_ph = max_ph; c->max_mb = max_mb;
   c->last = zw_timing();
-  if (c->n_valid == 0) { c->staged = true; return ZW_OK; }
+  c->reruns = 0;
+  if (c->n_valid == 0) { c->state = LANE_STAGED; return ZW_OK; }
   const u32 ni = c->n_valid;
-  CK(c->d_img.reserve(ni * sizeof(ImageDesc))); CK(c->d_st.reserve(ni * sizeof(ImageState)));
+  CK(c->d_img.reserve(ni * sizeof(ImageDesc))); CK(c->d_lay.reserve(ni * sizeof(ImageLayout))); CK(c->d_st.reserve(ni * sizeof(ImageState)));
   CK(c->d_rows.reserve((size_t)n_rows * sizeof(RowRef))); CK(c->d_rgb.reserve(rgb_bytes + 64)); CK(c->d_planes.reserve(plane_bytes + 64));
   CK(c->d_alpha_hist.reserve((size_t)ni * 1024)); CK(c->d_map256.reserve((size_t)ni * 256));
   CK(c->d_alpha.reserve(n_mb)); CK(c->d_segmap.reserve(n_mb));
@@ -345,6 +384,7 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after)
   CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
   CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
   CK(c->d_outoff.reserve(((size_t)ni + 1) * 8));
+  CK(c->h_st.reserve(ni * sizeof(ImageState))); CK(c->h_outoff.reserve(((size_t)ni + 1) * 8));
   // ticket order: macroblock row y of every image before row y+1 of any image ("many images
   // interleaved"): each image has at most a couple of rows in flight, so rows rarely wait.
   if (key != c->layout_key || c->rows.size() != n_rows) {
@@ -357,42 +397,75 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after)
     c->layout_key = key;
   }
   CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
-  // copies of consecutive lanes go one after the other over the link (sharing it would only delay
-  // the first lane's kernels); the second lane's copy then runs under the first lane's kernels
-  if (copy_after && copy_after->n_valid) CK(cudaStreamWaitEvent(c->stream, copy_after->ev[1], 0));
-  CK(cudaEventRecord(c->ev[0], c->stream));
-  for (size_t i = 0; i < n; i++) {
-    if (c->slot_of[i] < 0) continue;
-    const ImageDesc& d = c->img[c->slot_of[i]];
-    CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + d.rgb_off, imgs[i].data, imgs[i].len, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+  {  // one copy per run of images that are contiguous in host memory (and need no alignment gap on the device)
+    const u8* run_src = nullptr;
+    u64 run_dst = 0, run_len = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (c->slot_of[i] < 0) continue;
+      const ImageDesc& d = c->img[c->slot_of[i]];
+      if (run_len && imgs[i].data == run_src + run_len && d.rgb_off == run_dst + run_len) { run_len += imgs[i].len; continue; }
+      if (run_len) CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + run_dst, run_src, run_len, cudaMemcpyHostToDevice, c->stream));
+      run_src = imgs[i].data; run_dst = d.rgb_off; run_len = imgs[i].len;
+    }
+    if (run_len) CK(cudaMemcpyAsync(c->d_rgb.as<u8>() + run_dst, run_src, run_len, cudaMemcpyHostToDevice, c->stream));
   }
-  CK(cudaEventRecord(c->ev[1], c->stream));
+  CK(cudaEventRecord(c->ev[EV_H2D1], c->stream));
   c->last.h2d_bytes = rgb_bytes;
   for (const ImageDesc& d : c->img) c->last.pixels += (u64)d.width * d.height;
-  c->staged = true;
+  c->state = LANE_STAGED;
   return ZW_OK;
 }
 
-// Phase A: everything up to the symbol counts (asynchronous; ends with the D2H of ImageState).
-static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
-  c->encoded = false;
-  c->launches = 0;
-  if (c->n_valid == 0) return ZW_OK;
+// Phase B: place the streams (k_layout), emit + code + assemble, then start the D2H of the per-image results.
+// Everything is asynchronous; the arenas were sized before the symbol counts were known (see lane_sync_sizes).
+static int lane_launch_b(Lane* c) {
   const u32 ni = c->n_valid;
   cudaStream_t s = c->stream;
-  // Lanes run their kernels strictly one after the other (measured: concurrent persistent kernels
-  // only slow each other down); what overlaps is this lane's H2D copy with the previous lane's
-  // kernels, and the previous lane's D2H with this lane's kernels.
-  if (after && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[10], 0));
-  c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
+  // first-partition symbols have a hard bound (MB header <= 122 symbols, frame header <= 9620); the token partition
+  // is sized by estimate (raised on overflow); a symbol codes to at most 7 bits
+  c->cap_h = (u64)c->n_mb * 128 + (u64)ni * 9700;
+  c->cap_t = std::max(c->cap_t, (u64)((double)c->n_mb * c->tok_per_mb) + (u64)ni * 8);
+  c->cap_p = ((c->cap_h + c->cap_t) * 7) / 8 + (u64)ni * 48;
+  CK(c->d_htok.reserve(c->cap_h * sizeof(Token) + 64)); CK(c->d_ttok.reserve(c->cap_t * sizeof(Token) + 64));
+  CK(c->d_part.reserve(c->cap_p + 64)); CK(c->d_out.reserve(c->cap_p + (u64)ni * 64 + 64));
   fill_params(c);
   ChunkParams& P = c->P;
-  CK(cudaEventRecord(c->ev[13], s));
+  k_layout<<<1, 1024, 0, s>>>(P);
+  k_tokenize<1><<<c->tok_grid, TOK_WARPS * 32, 0, s>>>(P);
+  k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
+  c->launches += 3;
+  CK(cudaEventRecord(c->ev[EV_TOK], s));
+  k_boolcode<<<(2 * ni + BC_STREAMS - 1) / BC_STREAMS, BC_WARPS * 32, 0, s>>>(P);
+  c->launches++;
+  CK(cudaEventRecord(c->ev[EV_BC], s));
+  k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
+  k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
+  c->launches += 2;
+  CK(cudaEventRecord(c->ev[EV_END], s));
+  CK(cudaMemcpyAsync(c->h_st.p, c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->h_outoff.p, c->d_outoff.p, ((size_t)ni + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->h_tot.p, c->d_tot.p, sizeof(ChunkTotals), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(c->ev[EV_SIZES], s));
+  return ZW_OK;
+}
+
+// Every kernel of one batch, asynchronous on the lane's stream (17 launches + 1 for the placement scan).
+static int lane_launch(Lane* c, int quality, int method, Lane* after) {
+  c->launches = 0;
+  c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);
+  if (c->n_valid == 0) { c->state = LANE_IN_FLIGHT; return ZW_OK; }
+  const u32 ni = c->n_valid;
+  cudaStream_t s = c->stream;
+  if (after && after != c && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[EV_END], 0));
+  fill_params(c);
+  ChunkParams& P = c->P;
+  CK(cudaEventRecord(c->ev[EV_START], s));
   CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
   CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
   CK(cudaMemsetAsync(c->d_progress.p, 0, (size_t)c->n_rows * 3 * sizeof(int), s));
   CK(cudaMemsetAsync(c->d_ticket.p, 0, 64, s));
-  CK(cudaEventRecord(c->ev[2], s));  // yuv_ms times k_yuv alone; device_total_ms starts at ev[13]
+  CK(cudaEventRecord(c->ev[EV_YUV0], s));  // yuv_ms times k_yuv alone; device_total_ms starts at EV_START
   {  // (1) RGB -> YUV420
     const int rows_per_cta = YUV_ROWPAIRS * YUV_STEPS * 2;
     dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + rows_per_cta - 1) / rows_per_cta, ni);
@@ -401,7 +474,7 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
     k_yuv<<<grid, block, sm, s>>>(P);
     c->launches++;
   }
-  CK(cudaEventRecord(c->ev[3], s));
+  CK(cudaEventRecord(c->ev[EV_YUV1], s));
   {  // (2) analysis + segments
     bool any_seg = false;
     for (const ImageDesc& d : c->img) any_seg |= d.use_segments != 0;
@@ -413,104 +486,75 @@ static int lane_encode_a(Lane* c, int quality, int method, Lane* after) {
     k_segments<<<ni, 256, 0, s>>>(P);
     c->launches++;
   }
-  CK(cudaEventRecord(c->ev[4], s));
+  CK(cudaEventRecord(c->ev[EV_AN1], s));
   {  // (3) pass 1: luma wavefront, then the per-image chroma chains, then the bookkeeping.  (Running the
      // chains on a side stream UNDER the wavefront was measured: they starve -- 43 ms instead of 8.8 ms,
      // instruction-cache contention with the wavefront's code -- so the kernels stay back to back.)
     const int w1 = search_warps(1);
     const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + w1 - 1) / w1);
     k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
-    CK(cudaEventRecord(c->ev[15], s));
+    CK(cudaEventRecord(c->ev[EV_P1], s));
     const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    CK(cudaEventRecord(c->ev2[0], s));
+    CK(cudaEventRecord(c->ev[EV_C1], s));
     k_finish1<<<ni, 256, 0, s>>>(P);
     c->launches += 3;
   }
-  CK(cudaEventRecord(c->ev[5], s));
+  CK(cudaEventRecord(c->ev[EV_ST0], s));
   {  // (4) token statistics -> probabilities, level costs, skip probability
     k_rowstats<<<(c->n_rows + STAT_WARPS - 1) / STAT_WARPS, STAT_WARPS * 32, 0, s>>>(P);
     k_probs<<<ni, 256, 0, s>>>(P);
     c->launches += 2;
   }
-  CK(cudaEventRecord(c->ev[6], s));
+  CK(cudaEventRecord(c->ev[EV_ST1], s));
   {  // (3') pass 2: chroma wavefront first (independent of luma), then the luma wavefront
     const int g4 = (int)std::min<u64>((u64)c->chroma2_blocks, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    CK(cudaEventRecord(c->ev[14], s));
+    CK(cudaEventRecord(c->ev[EV_C2], s));
     const int w2 = search_warps(2);
     const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);
     k_search<2><<<g2, w2 * 32, search_smem_bytes(w2), s>>>(P);
     c->launches += 2;
   }
-  CK(cudaEventRecord(c->ev[7], s));
-  {  // (5a) count symbols, scan
+  CK(cudaEventRecord(c->ev[EV_P2], s));
+  {  // (5a) count symbols per macroblock, scan per image
     c->tok_grid = dim3((c->max_mb + TOK_WARPS - 1) / TOK_WARPS, ni);
     k_tokenize<0><<<c->tok_grid, TOK_WARPS * 32, 0, s>>>(P);
     k_tokscan<<<ni, 256, 0, s>>>(P);
     c->launches += 2;
-    c->st.resize(ni);
-    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
   }
+  int rc = lane_launch_b(c);
+  if (rc != ZW_OK) return rc;
+  c->state = LANE_IN_FLIGHT;
   return ZW_OK;
 }
 
-// Phase B: wait for the symbol counts, size the streams, emit + code + assemble (asynchronous).
-static int lane_encode_b(Lane* c) {
-  if (c->n_valid == 0) return ZW_OK;
-  const u32 ni = c->n_valid;
-  cudaStream_t s = c->stream;
-  CK(cudaStreamSynchronize(s));
-  u64 hoff = 0, toff = 0, poff = 0;
-  for (u32 i = 0; i < ni; i++) {
-    ImageDesc& d = c->img[i];
-    d.hdr_off = hoff; d.tok_off = toff; d.part_off = poff;
-    d.p0_cap = (u32)(((u64)c->st[i].hdr_tokens * 7) / 8 + 16);
-    d.p1_cap = (u32)(((u64)c->st[i].tok_tokens * 7) / 8 + 16);
-    hoff += ((u64)c->st[i].hdr_tokens + 7) & ~7ull;
-    toff += ((u64)c->st[i].tok_tokens + 7) & ~7ull;
-    poff += ((u64)d.p0_cap + d.p1_cap + 15) & ~15ull;
+// Wait for the per-image results of a launched batch; re-run phase B with larger arenas in the (rare) case the
+// symbol estimate was too small.  Fills the per-stage device times.
+static int lane_sync_sizes(Lane* c) {
+  if (c->n_valid == 0) { c->state = LANE_SIZED; return ZW_OK; }
+  CK(cudaEventSynchronize(c->ev[EV_SIZES]));
+  const ChunkTotals* T = c->h_tot.as<ChunkTotals>();
+  while (T->overflow) {
+    if (c->reruns++ > 2) return g_last_error = ZW_ERR_OUTPUT_TOO_SMALL;
+    c->tok_per_mb = std::max(c->tok_per_mb * 1.25, 1.15 * (double)T->tok_tokens / (double)c->n_mb);
+    c->cap_t = (u64)(1.15 * (double)T->tok_tokens) + 64;
+    int rc = lane_launch_b(c);
+    if (rc != ZW_OK) return rc;
+    CK(cudaEventSynchronize(c->ev[EV_SIZES]));
   }
-  CK(c->d_htok.reserve(hoff * sizeof(Token) + 64)); CK(c->d_ttok.reserve(toff * sizeof(Token) + 64));
-  CK(c->d_part.reserve(poff + 64)); CK(c->d_out.reserve(poff + (u64)ni * 32 + 64));
-  fill_params(c);
-  ChunkParams& P = c->P;
-  CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, s));
-  k_tokenize<1><<<c->tok_grid, TOK_WARPS * 32, 0, s>>>(P);
-  k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
-  c->launches += 2;
-  CK(cudaEventRecord(c->ev[8], s));
-  k_boolcode<<<(2 * ni + BC_STREAMS - 1) / BC_STREAMS, BC_WARPS * 32, 0, s>>>(P);
-  c->launches++;
-  CK(cudaEventRecord(c->ev[9], s));
-  k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
-  k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
-  c->launches += 2;
-  CK(cudaEventRecord(c->ev[10], s));
-  return ZW_OK;
-}
-
-static int lane_encode_finish(Lane* c) {
-  if (c->n_valid == 0) { c->encoded = true; return ZW_OK; }
-  CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
-  zw_timing T = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
-  T.h2d_bytes = c->last.h2d_bytes; T.pixels = c->last.pixels;
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); T.yuv_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); T.analysis_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[4], c->ev[15]); T.pass1_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[15], c->ev2[0]); T.chroma1_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev2[0], c->ev[6]); T.stats_ms = ms;  // k_finish1 + statistics + probabilities
-  cudaEventElapsedTime(&ms, c->ev[6], c->ev[14]); T.chroma2_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[14], c->ev[7]); T.pass2_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); T.token_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); T.boolcode_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); T.assemble_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[13], c->ev[10]); T.device_total_ms = ms;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); T.h2d_ms = ms;
-  T.kernel_launches = c->launches;
-  for (u32 i = 0; i < c->n_valid; i++) T.symbols += (u64)c->st[i].hdr_tokens + c->st[i].tok_tokens;
+  zw_timing Tm = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
+  Tm.h2d_bytes = c->last.h2d_bytes; Tm.pixels = c->last.pixels;
+  auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+  Tm.yuv_ms = el(EV_YUV0, EV_YUV1); Tm.analysis_ms = el(EV_YUV1, EV_AN1); Tm.pass1_ms = el(EV_AN1, EV_P1);
+  Tm.chroma1_ms = el(EV_P1, EV_C1); Tm.stats_ms = el(EV_C1, EV_ST1);  // k_finish1 + statistics + probabilities
+  Tm.chroma2_ms = el(EV_ST1, EV_C2); Tm.pass2_ms = el(EV_C2, EV_P2); Tm.token_ms = el(EV_P2, EV_TOK);
+  Tm.boolcode_ms = el(EV_TOK, EV_BC); Tm.assemble_ms = el(EV_BC, EV_END); Tm.device_total_ms = el(EV_START, EV_END);
+  Tm.h2d_ms = el(EV_H2D0, EV_H2D1);
+  Tm.kernel_launches = c->launches;
+  const ImageState* st = c->h_st.as<ImageState>();
+  for (u32 i = 0; i < c->n_valid; i++) Tm.symbols += (u64)st[i].hdr_tokens + st[i].tok_tokens;
 #ifdef ZW_WAIT_STATS
   {
     unsigned long long w[8];
@@ -519,68 +563,63 @@ static int lane_encode_finish(Lane* c) {
             100.0 * (double)w[4] / (double)(w[6] ? w[6] : 1));
   }
 #endif
-  c->last = T;
-  c->encoded = true;
+  c->last = Tm;
+  c->state = LANE_SIZED;
   return ZW_OK;
 }
 
-static int lane_download(Lane* c, zw_output* outs, size_t n, int container) {
+// One D2H of the finished files into the lane's pinned arena + the per-image view (offset, length, status).
+static int lane_fetch(Lane* c, int container) {
   const u32 ni = c->n_valid;
   cudaStream_t s = c->stream;
+  const ImageState* st = c->h_st.as<ImageState>();
+  const u64* off = c->h_outoff.as<u64>();
   if (ni) {
-    c->st.resize(ni); c->out_off.resize(ni + 1);
-    CK(cudaEventRecord(c->ev[11], s));
-    CK(cudaMemcpyAsync(c->st.data(), c->d_st.p, ni * sizeof(ImageState), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c->out_off.data(), c->d_outoff.p, ((size_t)ni + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const size_t total = (size_t)c->out_off[ni];
-    if (total > c->h_pinned_cap) {
-      if (c->h_pinned) cudaFreeHost(c->h_pinned);
-      c->h_pinned = nullptr; c->h_pinned_cap = 0;
-      CK(cudaMallocHost((void**)&c->h_pinned, total + total / 4 + 4096));
-      c->h_pinned_cap = total + total / 4 + 4096;
-    }
-    CK(cudaMemcpyAsync(c->h_pinned, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(c->ev[12], s));
+    const size_t total = (size_t)off[ni];
+    CK(c->h_arena.reserve(total + 64));
+    CK(cudaEventRecord(c->ev[EV_D2H0], s));
+    CK(cudaMemcpyAsync(c->h_arena.p, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c->ev[EV_D2H1], s));
     CK(cudaStreamSynchronize(s));
     float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]);
+    cudaEventElapsedTime(&ms, c->ev[EV_D2H0], c->ev[EV_D2H1]);
     c->last.d2h_ms = ms;
-    c->last.d2h_bytes = total + ni * sizeof(ImageState) + ((size_t)ni + 1) * 8;
+    c->last.d2h_bytes = total + ni * sizeof(ImageState) + ((size_t)ni + 1) * 8 + sizeof(ChunkTotals);
   }
+  const size_t n = c->n_in;
+  c->v_off.assign(n, 0); c->v_len.assign(n, 0); c->v_status.assign(n, 0);
   for (size_t i = 0; i < n; i++) {
-    zw_output& o = outs[i];
-    o.len = 0;
-    if (c->slot_of[i] < 0) { o.status = c->img_status[i]; continue; }
+    if (c->slot_of[i] < 0) { c->v_status[i] = c->img_status[i]; continue; }
     const u32 k = (u32)c->slot_of[i];
     // lossy + alpha files need VP8X + ALPH (api.rs:1330-1394), which is not built: refuse rather than
     // emit a simple container the reference would not produce
-    if (container && (c->img[k].bpp == 2 || c->img[k].bpp == 4)) { o.status = ZW_ERR_INVALID_PARAM; continue; }
-    const ImageState& st = c->st[k];
-    if (st.status != 0) { o.status = (int)st.status; continue; }
-    const size_t payload = st.vp8_bytes;
-    const size_t need = container ? 20 + payload + (payload & 1) : payload;
+    if (container && (c->img[k].bpp == 2 || c->img[k].bpp == 4)) { c->v_status[i] = ZW_ERR_INVALID_PARAM; continue; }
+    if (st[k].status != 0) { c->v_status[i] = (int)st[k].status; continue; }
+    c->v_off[i] = off[k] + (container ? 0 : 20);
+    c->v_len[i] = container ? st[k].file_bytes : st[k].vp8_bytes;
+  }
+  c->container = container;
+  c->state = LANE_DONE;
+  return ZW_OK;
+}
+
+// Copy a finished lane's files into caller-style output slots (malloc'ed when data == NULL).
+static void lane_emit(const Lane* c, zw_output* outs) {
+  const u8* arena = c->h_arena.as<u8>();
+  for (size_t i = 0; i < c->n_in; i++) {
+    zw_output& o = outs[i];
+    o.len = 0;
+    o.status = c->v_status[i];
+    if (o.status != ZW_OK) continue;
+    const size_t need = c->v_len[i];
     if (o.data == nullptr) {
       o.data = (uint8_t*)malloc(need ? need : 1);
       o.cap = need;
       if (!o.data) { o.status = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; continue; }
     } else if (o.cap < need) { o.status = ZW_ERR_OUTPUT_TOO_SMALL; o.len = need; continue; }
-    uint8_t* w = o.data;
-    if (container) {  // api.rs:1325-1329 + write_chunk :1232-1241
-      const u32 chunk = (u32)(payload + (payload & 1)) + 8;
-      const u32 riff = chunk + 4;
-      memcpy(w, "RIFF", 4); w[4] = (u8)riff; w[5] = (u8)(riff >> 8); w[6] = (u8)(riff >> 16); w[7] = (u8)(riff >> 24);
-      memcpy(w + 8, "WEBP", 4); memcpy(w + 12, "VP8 ", 4);
-      const u32 pl = (u32)payload;
-      w[16] = (u8)pl; w[17] = (u8)(pl >> 8); w[18] = (u8)(pl >> 16); w[19] = (u8)(pl >> 24);
-      w += 20;
-    }
-    memcpy(w, c->h_pinned + c->out_off[k], payload);
-    if (container && (payload & 1)) w[payload] = 0;
+    memcpy(o.data, arena + c->v_off[i], need);
     o.len = need;
-    o.status = ZW_OK;
   }
-  return ZW_OK;
 }
 
 // Integer issue peak (measurement only, SURVEY.md 8(d) "INT peak: measure, don't assume"): eight
@@ -603,13 +642,34 @@ static void add_timing(zw_timing& a, const zw_timing& L) {
   a.h2d_ms += L.h2d_ms; a.yuv_ms += L.yuv_ms; a.analysis_ms += L.analysis_ms; a.pass1_ms += L.pass1_ms;
   a.stats_ms += L.stats_ms; a.pass2_ms += L.pass2_ms; a.token_ms += L.token_ms; a.boolcode_ms += L.boolcode_ms;
   a.assemble_ms += L.assemble_ms; a.d2h_ms += L.d2h_ms; a.chroma1_ms += L.chroma1_ms; a.chroma2_ms += L.chroma2_ms;
+  a.device_total_ms += L.device_total_ms;
   a.kernel_launches += L.kernel_launches; a.h2d_bytes += L.h2d_bytes; a.d2h_bytes += L.d2h_bytes; a.pixels += L.pixels;
   a.symbols += L.symbols;
 }
 
+static int check_params(int quality, int method) {
+  return (quality < 0 || quality > 100 || method < 0) ? ZW_ERR_INVALID_PARAM : ZW_OK;
+}
+
+// Hand one batch (one chunk) to lane `k`: stage + launch everything, asynchronous.
+static int ctx_submit_lane(zw_ctx* c, int k, const zw_image* imgs, size_t n, int quality, int method) {
+  Lane* l = c->lanes[k];
+  int rc = lane_stage(l, imgs, n);
+  if (rc != ZW_OK) return rc;
+  rc = lane_launch(l, quality, std::min(method, 6) /* vp8.rs:1291 */, c->prev);
+  if (rc != ZW_OK) { l->state = LANE_FREE; return rc; }
+  if (l->n_valid) c->prev = l;
+  c->dump_lane = k;
+  return ZW_OK;
+}
+
+struct zw_multi {
+  std::vector<zw_ctx*> ctx;
+};
+
 extern "C" {
 
-const char* zw_version(void) { return "zenwebp_b200 0.1 (CUDA, sm_100a)"; }
+const char* zw_version(void) { return "zenwebp_b200 0.2 (CUDA, sm_100a)"; }
 int zw_last_error(void) { return g_last_error; }
 void zw_free(void* p) { free(p); }
 size_t zw_max_output_size(uint32_t w, uint32_t h) {
@@ -624,7 +684,9 @@ const char* zw_strerror(int code) {
     case ZW_ERR_INVALID_PARAM: return "invalid parameter";
     case ZW_ERR_OUTPUT_TOO_SMALL: return "output buffer too small";
     case ZW_ERR_PARTITION_TOO_LARGE: return "first partition exceeds the 19-bit size field";
-    case ZW_ERR_NOT_STAGED: return "no staged batch";
+    case ZW_ERR_NOT_STAGED: return "no staged batch / no such ticket";
+    case ZW_ERR_BUSY: return "every pipeline slot of the context holds a batch (wait + release one first)";
+    case ZW_ERR_TOO_LARGE: return "batch exceeds the per-chunk device budget (split it, or use zw_encode_*_batch)";
     default: break;
   }
   if (code >= ZW_ERR_CUDA) return cudaGetErrorString((cudaError_t)(code - ZW_ERR_CUDA));
@@ -640,17 +702,15 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
   zw_ctx* c = new zw_ctx();
   c->device = device;
   cudaDeviceProp prop;
-  cudaGetDeviceProperties(&prop, device);
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_last_error = ZW_ERR_CUDA + (int)e; delete c; return nullptr; }
   c->sm_count = prop.multiProcessorCount;
   c->budget = (limits && limits->max_device_bytes) ? limits->max_device_bytes : ((size_t)32 << 30);
   int warps_hint = limits ? limits->persistent_warps_per_sm : 0;
   if (const char* env = getenv("ZW_WARPS_PER_SM")) warps_hint = atoi(env);
-  int n_lanes = limits ? limits->reserved[0] : 0;  // reserved[0]: lanes of the host-buffer batch path (0 = default 2)
-  if (const char* env = getenv("ZW_LANES")) n_lanes = atoi(env);
-  if (n_lanes <= 0) n_lanes = 1;  // measured on B200: extra lanes cost more (tails, per-lane syncs) than the copy overlap returns
-  n_lanes = std::min(n_lanes, 8);
-  c->batch_lanes = n_lanes;
-  if (const char* env = getenv("ZW_RESIDENT_LANES")) c->resident_lanes = std::max(1, std::min(atoi(env), n_lanes));
+  int depth = limits ? limits->reserved[0] : 0;  // reserved[0]: pipeline depth = batches in flight (0 = default 3)
+  if (const char* env = getenv("ZW_LANES")) depth = atoi(env);
+  if (depth <= 0) depth = 3;
+  depth = std::min(depth, 8);
   // constant tables
   std::vector<SegParams> segtab(128);
   for (int i = 0; i < 128; i++) segtab[i] = make_segparams(i);
@@ -658,15 +718,18 @@ zw_ctx* zw_create(int device, const zw_limits* limits) {
   for (int b = 0; b < 128; b++)
     for (int a = -127; a <= 127; a++) lut[b * 255 + (a + 127)] = (u8)compute_segment_quant(b, a, 50);
   const TokenTables tt = make_token_tables();
-  if (c->d_segtab.reserve(segtab.size() * sizeof(SegParams)) != cudaSuccess || c->d_lut.reserve(lut.size()) != cudaSuccess) {
-    g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr;
+  if ((e = c->d_segtab.reserve(segtab.size() * sizeof(SegParams))) != cudaSuccess || (e = c->d_lut.reserve(lut.size())) != cudaSuccess ||
+      (e = cudaMemcpy(c->d_segtab.p, segtab.data(), segtab.size() * sizeof(SegParams), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(c->d_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpyToSymbol(c_tok, &tt, sizeof(tt))) != cudaSuccess) {
+    g_last_error = ZW_ERR_CUDA + (int)e; zw_destroy(c); return nullptr;
   }
-  cudaMemcpy(c->d_segtab.p, segtab.data(), segtab.size() * sizeof(SegParams), cudaMemcpyHostToDevice);
-  cudaMemcpy(c->d_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice);
-  cudaMemcpyToSymbol(c_tok, &tt, sizeof(tt));
-  for (int k = 0; k < n_lanes; k++) {
+  for (int k = 0; k < depth; k++) {
     Lane* l = lane_create(c, warps_hint);
-    if (!l) { g_last_error = ZW_ERR_CUDA + (int)cudaErrorMemoryAllocation; zw_destroy(c); return nullptr; }
+    if (!l) {
+      e = cudaGetLastError();
+      g_last_error = ZW_ERR_CUDA + (int)(e != cudaSuccess ? e : cudaErrorMemoryAllocation); zw_destroy(c); return nullptr;
+    }
     c->lanes.push_back(l);
   }
   e = cudaGetLastError();
@@ -683,72 +746,94 @@ void zw_destroy(zw_ctx* c) {
   delete c;
 }
 
-static int stage_internal(zw_ctx* c, const zw_image* imgs, size_t n, int use_lanes) {
-  if (!c || (!imgs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
-  if (n > 65535 * c->lanes.size()) return g_last_error = ZW_ERR_INVALID_PARAM;  // grid.y / grid.z limit per lane
+// ---- streaming entry points: one context keeps `depth` batches in flight ---------------------------------
+int zw_submit(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, int* ticket) {
+  if (!c || (!imgs && n) || !ticket) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (check_params(quality, method) != ZW_OK) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (n > 65535) return g_last_error = ZW_ERR_TOO_LARGE;  // grid.y limit of the per-image kernels
+  size_t bytes = 0;
+  for (size_t i = 0; i < n; i++)
+    if (validate_image(imgs[i]) == ZW_OK) bytes += image_footprint(imgs[i].width, imgs[i].height, color_bpp(imgs[i].color));
+  if (n > 1 && bytes > c->budget) return g_last_error = ZW_ERR_TOO_LARGE;
   CK(cudaSetDevice(c->device));
-  c->staged = false; c->encoded = false;
-  // split the chunk between the lanes by pixel count (contiguous image ranges)
-  const int L = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(c->lanes.size(), (size_t)use_lanes), n / 2 > 0 ? n / 2 : 1));
-  u64 total_px = 0;
-  for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
-  c->lane_begin.assign(L + 1, n);
-  c->lane_begin[0] = 0;
-  {
-    u64 acc = 0;
-    int k = 1;
-    for (size_t i = 0; i < n && k < L; i++) {
-      acc += (u64)imgs[i].width * imgs[i].height;
-      if (acc * L >= total_px * k) { c->lane_begin[k++] = i + 1; }
-    }
-    for (; k < L; k++) c->lane_begin[k] = n;
-  }
-  c->active_lanes = L;
-  c->n_staged = n;
-  for (int k = 0; k < L; k++) {
-    const size_t b = c->lane_begin[k], e = c->lane_begin[k + 1];
-    if (e - b > 65535) return g_last_error = ZW_ERR_INVALID_PARAM;
-    int rc = lane_stage(c->lanes[k], imgs + b, e - b, k ? c->lanes[k - 1] : nullptr);
-    if (rc != ZW_OK) return g_last_error = rc;
-  }
-  c->staged = true;
+  int k = -1;
+  for (size_t i = 0; i < c->lanes.size(); i++)
+    if (c->lanes[i]->state == LANE_FREE) { k = (int)i; break; }
+  if (k < 0) return g_last_error = ZW_ERR_BUSY;
+  if (k == 0) { c->staged = false; c->encoded = false; }  // lane 0 doubles as the split API's lane
+  int rc = ctx_submit_lane(c, k, imgs, n, quality, method);
+  if (rc != ZW_OK) return g_last_error = rc;
+  *ticket = k;
   return g_last_error = ZW_OK;
 }
 
+int zw_wait(zw_ctx* c, int ticket, int container, zw_batch_view* view, zw_timing* timing) {
+  if (!c || ticket < 0 || ticket >= (int)c->lanes.size()) return g_last_error = ZW_ERR_INVALID_PARAM;
+  Lane* l = c->lanes[ticket];
+  if (l->state != LANE_IN_FLIGHT && l->state != LANE_SIZED && l->state != LANE_DONE) return g_last_error = ZW_ERR_NOT_STAGED;
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if (l->state == LANE_IN_FLIGHT && (rc = lane_sync_sizes(l)) != ZW_OK) return g_last_error = rc;
+  if (l->state != LANE_DONE || l->container != (container != 0)) {
+    if ((rc = lane_fetch(l, container != 0)) != ZW_OK) return g_last_error = rc;
+  }
+  if (view) {
+    view->arena = l->h_arena.as<uint8_t>();
+    view->n = l->n_in;
+    view->offsets = l->v_off.data();
+    view->lens = l->v_len.data();
+    view->status = l->v_status.data();
+  }
+  if (timing) *timing = l->last;
+  return g_last_error = ZW_OK;
+}
+
+int zw_release(zw_ctx* c, int ticket) {
+  if (!c || ticket < 0 || ticket >= (int)c->lanes.size()) return g_last_error = ZW_ERR_INVALID_PARAM;
+  Lane* l = c->lanes[ticket];
+  if (l->state == LANE_IN_FLIGHT) {  // abandon: let the device finish before the buffers are reused
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(l->stream);
+  }
+  l->state = LANE_FREE;
+  return g_last_error = ZW_OK;
+}
+
+// ---- split form on lane 0 (kernel-only timing; inputs stay resident) ---------------------------------------
 int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
-  return stage_internal(c, imgs, n, c ? c->resident_lanes : 1);
+  if (!c || (!imgs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (n > 65535) return g_last_error = ZW_ERR_TOO_LARGE;
+  CK(cudaSetDevice(c->device));
+  c->staged = false; c->encoded = false;
+  Lane* l = c->lanes[0];
+  if (l->state == LANE_IN_FLIGHT) CK(cudaStreamSynchronize(l->stream));
+  int rc = lane_stage(l, imgs, n);
+  if (rc != ZW_OK) return g_last_error = rc;
+  // the caller may reuse or free its buffers as soon as this returns: wait for the copies
+  if (l->n_valid) CK(cudaEventSynchronize(l->ev[EV_H2D1]));
+  float ms = 0;
+  if (l->n_valid && cudaEventElapsedTime(&ms, l->ev[EV_H2D0], l->ev[EV_H2D1]) == cudaSuccess) l->last.h2d_ms = ms;
+  c->n_staged = n;
+  c->staged = true;
+  return g_last_error = ZW_OK;
 }
 
 int zw_encode_resident(zw_ctx* c, int quality, int method, zw_timing* timing) {
   if (!c) return g_last_error = ZW_ERR_INVALID_PARAM;
   if (!c->staged) return g_last_error = ZW_ERR_NOT_STAGED;
-  if (quality < 0 || quality > 100 || method < 0) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (check_params(quality, method) != ZW_OK) return g_last_error = ZW_ERR_INVALID_PARAM;
   CK(cudaSetDevice(c->device));
   c->encoded = false;
-  method = std::min(method, 6);  // vp8.rs:1291
-  c->base_qidx = quality_to_quant_index(quality);
-  const int L = c->active_lanes;
-  int rc;
-  for (int k = 0; k < L; k++) {
-    if ((rc = lane_encode_a(c->lanes[k], quality, method, k ? c->lanes[k - 1] : nullptr)) != ZW_OK) return g_last_error = rc;
-    if ((rc = lane_encode_b(c->lanes[k])) != ZW_OK) return g_last_error = rc;
-  }
-  for (int k = 0; k < L; k++) if ((rc = lane_encode_finish(c->lanes[k])) != ZW_OK) return g_last_error = rc;
-  // device span over all lanes: first "start" event to last "end" event
-  zw_timing T = zw_timing();
-  float span = 0;
-  for (int a = 0; a < L; a++) {
-    if (c->lanes[a]->n_valid == 0) continue;
-    add_timing(T, c->lanes[a]->last);
-    for (int b = 0; b < L; b++) {
-      if (c->lanes[b]->n_valid == 0) continue;
-      float ms = 0;
-      if (cudaEventElapsedTime(&ms, c->lanes[a]->ev[13], c->lanes[b]->ev[10]) == cudaSuccess) span = std::max(span, ms);
-    }
-  }
-  T.device_total_ms = span;
-  c->last = T;
-  if (timing) *timing = T;
+  Lane* l = c->lanes[0];
+  const zw_timing keep = l->last;
+  int rc = lane_launch(l, quality, std::min(method, 6), c->prev);
+  if (rc != ZW_OK) return g_last_error = rc;
+  if (l->n_valid) c->prev = l;
+  c->dump_lane = 0;
+  if ((rc = lane_sync_sizes(l)) != ZW_OK) return g_last_error = rc;
+  l->last.h2d_ms = keep.h2d_ms;
+  c->last = l->last;
+  if (timing) *timing = c->last;
   c->encoded = true;
   return g_last_error = ZW_OK;
 }
@@ -758,43 +843,83 @@ int zw_download(zw_ctx* c, zw_output* outs, size_t n, int container, zw_timing* 
   if (!c->staged || !c->encoded) return g_last_error = ZW_ERR_NOT_STAGED;
   if (n != c->n_staged) return g_last_error = ZW_ERR_INVALID_PARAM;
   CK(cudaSetDevice(c->device));
-  for (int k = 0; k < c->active_lanes; k++) {
-    const size_t b = c->lane_begin[k], e = c->lane_begin[k + 1];
-    int rc = lane_download(c->lanes[k], outs + b, e - b, container);
-    if (rc != ZW_OK) return g_last_error = rc;
-    c->last.d2h_ms += c->lanes[k]->last.d2h_ms;
-    c->last.d2h_bytes += c->lanes[k]->last.d2h_bytes;
-  }
+  Lane* l = c->lanes[0];
+  int rc = lane_fetch(l, container != 0);
+  if (rc != ZW_OK) return g_last_error = rc;
+  lane_emit(l, outs);
+  l->state = LANE_SIZED;  // stays staged + encoded: download / re-encode again at will
+  c->last = l->last;
   if (timing) *timing = c->last;
   return g_last_error = ZW_OK;
 }
 
+// ---- batch entry points: chunked by the device budget, chunks pipelined over the context's lanes ----------
 static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing,
                         int container) {
   if (!c || (!imgs && n) || (!outs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
-  if (quality < 0 || quality > 100 || method < 0) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (check_params(quality, method) != ZW_OK) return g_last_error = ZW_ERR_INVALID_PARAM;
+  CK(cudaSetDevice(c->device));
   const auto t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < n; i++) { outs[i].len = 0; outs[i].status = ZW_ERR_NOT_STAGED; }  // overwritten per chunk; what a failed call leaves behind
+  for (Lane* l : c->lanes) {  // a batch call owns the whole context
+    if (l->state == LANE_IN_FLIGHT) CK(cudaStreamSynchronize(l->stream));
+    l->state = LANE_FREE;
+  }
+  c->staged = false; c->encoded = false;
+  // Chunks: bounded by the device budget, and small enough that a large batch becomes several chunks whose
+  // H2D / D2H copies hide behind each other's kernels (ZW_SPLIT, default 4 chunks when the batch allows it).
+  u64 total_px = 0;
+  for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
+  int split = 4;
+  if (const char* env = getenv("ZW_SPLIT")) split = std::max(1, atoi(env));
+  if (c->lanes.size() < 2) split = 1;
+  const u64 min_chunk_px = 48ull << 20;  // below ~50 Mpx a chunk no longer fills the wavefront kernels
+  const u64 px_target = std::max(min_chunk_px, (total_px + split - 1) / split);
+  struct Pending { int lane; size_t i0, i1; };
+  std::vector<Pending> q;
   zw_timing acc = zw_timing();
+  int rc = ZW_OK;
+  auto drain_one = [&]() -> int {
+    const Pending p = q.front();
+    q.erase(q.begin());
+    Lane* l = c->lanes[p.lane];
+    int r = lane_sync_sizes(l);
+    if (r == ZW_OK) r = lane_fetch(l, container);
+    if (r == ZW_OK) { lane_emit(l, outs + p.i0); add_timing(acc, l->last); }
+    else for (size_t i = p.i0; i < p.i1; i++) outs[i].status = r;
+    l->state = LANE_FREE;
+    return r;
+  };
   size_t i0 = 0;
-  while (i0 < n) {
+  while (i0 < n && rc == ZW_OK) {
     size_t i1 = i0, bytes = 0;
+    u64 px = 0;
     while (i1 < n && (i1 - i0) < 32768) {
-      const size_t f = validate_image(imgs[i1]) == ZW_OK ? image_footprint(imgs[i1].width, imgs[i1].height, color_bpp(imgs[i1].color)) : 0;
-      if (i1 > i0 && bytes + f > c->budget) break;
-      bytes += f; i1++;
+      const bool ok = validate_image(imgs[i1]) == ZW_OK;
+      const size_t f = ok ? image_footprint(imgs[i1].width, imgs[i1].height, color_bpp(imgs[i1].color)) : 0;
+      if (i1 > i0 && (bytes + f > c->budget || px >= px_target)) break;
+      bytes += f; px += ok ? (u64)imgs[i1].width * imgs[i1].height : 0; i1++;
     }
-    // host-buffer path: two lanes so that the second half's H2D copy hides behind the first half's kernels
-    int rc = stage_internal(c, imgs + i0, i1 - i0, (i1 - i0) >= 16 ? c->batch_lanes : 1);
-    if (rc != ZW_OK) return rc;
-    rc = zw_encode_resident(c, quality, method, nullptr);
-    if (rc != ZW_OK) return rc;
-    rc = zw_download(c, outs + i0, i1 - i0, container, nullptr);
-    if (rc != ZW_OK) return rc;
-    add_timing(acc, c->last);
-    acc.device_total_ms += c->last.device_total_ms;
+    int k = -1;
+    for (;;) {
+      for (size_t j = 0; j < c->lanes.size(); j++)
+        if (c->lanes[j]->state == LANE_FREE) { k = (int)j; break; }
+      if (k >= 0 || q.empty()) break;
+      if ((rc = drain_one()) != ZW_OK) break;
+    }
+    if (rc != ZW_OK || k < 0) break;
+    rc = ctx_submit_lane(c, k, imgs + i0, i1 - i0, quality, method);
+    if (rc != ZW_OK) { for (size_t i = i0; i < i1; i++) outs[i].status = rc; break; }
+    q.push_back({k, i0, i1});
     i0 = i1;
   }
+  while (!q.empty()) { const int r = drain_one(); if (rc == ZW_OK) rc = r; }
+  if (rc != ZW_OK) {  // chunks that never ran carry the failing code
+    for (size_t i = i0; i < n; i++) if (outs[i].status == ZW_ERR_NOT_STAGED) outs[i].status = rc;
+    return g_last_error = rc;
+  }
   acc.wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->last = acc;
   if (timing) *timing = acc;
   return g_last_error = ZW_OK;
 }
@@ -804,6 +929,44 @@ int zw_encode_vp8_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
 }
 int zw_encode_webp_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method, zw_output* outs, zw_timing* timing) {
   return encode_batch(c, imgs, n, quality, method, outs, timing, 1);
+}
+
+// ---- one batch over several GPUs: contiguous slices of ceil(n / G) images, one host thread + context per GPU,
+//      no collective; results land in outs in image order --------------------------------------
+zw_multi* zw_multi_create(const int* devices, int n_devices, const zw_limits* limits) {
+  if (!devices || n_devices <= 0) { g_last_error = ZW_ERR_INVALID_PARAM; return nullptr; }
+  zw_multi* m = new zw_multi();
+  for (int i = 0; i < n_devices; i++) {
+    zw_ctx* c = zw_create(devices[i], limits);
+    if (!c) { const int err = g_last_error; zw_multi_destroy(m); g_last_error = err; return nullptr; }
+    m->ctx.push_back(c);
+  }
+  return m;
+}
+void zw_multi_destroy(zw_multi* m) {
+  if (!m) return;
+  for (zw_ctx* c : m->ctx) zw_destroy(c);
+  delete m;
+}
+int zw_multi_device_count(const zw_multi* m) { return m ? (int)m->ctx.size() : 0; }
+int zw_multi_encode(zw_multi* m, const zw_image* imgs, size_t n, int quality, int method, int container, zw_output* outs,
+                    zw_timing* per_device /* [device_count] or NULL */) {
+  if (!m || (!imgs && n) || (!outs && n)) return g_last_error = ZW_ERR_INVALID_PARAM;
+  if (check_params(quality, method) != ZW_OK) return g_last_error = ZW_ERR_INVALID_PARAM;
+  const size_t G = m->ctx.size(), per = (n + G - 1) / G;
+  std::vector<int> rcs(G, ZW_OK);
+  std::vector<std::thread> ts;
+  for (size_t g = 0; g < G; g++) {
+    const size_t b = std::min(n, g * per), e = std::min(n, b + per);
+    if (per_device) per_device[g] = zw_timing();
+    if (e == b) continue;
+    ts.emplace_back([=, &rcs]() {
+      rcs[g] = encode_batch(m->ctx[g], imgs + b, e - b, quality, method, outs + b, per_device ? per_device + g : nullptr, container);
+    });
+  }
+  for (auto& t : ts) t.join();
+  for (size_t g = 0; g < G; g++) if (rcs[g] != ZW_OK) return g_last_error = rcs[g];
+  return g_last_error = ZW_OK;
 }
 
 int zw_measure_int_peak(zw_ctx* c, double* int_instr_per_s) {
@@ -836,13 +999,10 @@ int zw_measure_int_peak(zw_ctx* c, double* int_instr_per_s) {
 
 int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len) {
   if (!ctx || !stage || !len) return g_last_error = ZW_ERR_INVALID_PARAM;
-  if (!ctx->staged || !ctx->encoded || index >= ctx->n_staged) return g_last_error = ZW_ERR_NOT_STAGED;
+  if (ctx->dump_lane < 0) return g_last_error = ZW_ERR_NOT_STAGED;
+  Lane* c = ctx->lanes[ctx->dump_lane];
+  if (index >= c->n_in || c->slot_of[index] < 0 || c->state == LANE_IN_FLIGHT) return g_last_error = ZW_ERR_NOT_STAGED;
   CK(cudaSetDevice(ctx->device));
-  int lk = 0;
-  while (lk + 1 < ctx->active_lanes && index >= ctx->lane_begin[lk + 1]) lk++;
-  Lane* c = ctx->lanes[lk];
-  index -= ctx->lane_begin[lk];
-  if (c->slot_of[index] < 0) return g_last_error = ZW_ERR_NOT_STAGED;
   const u32 k = (u32)c->slot_of[index];
   const ImageDesc& d = c->img[k];
   const size_t nmb = (size_t)d.mbw * d.mbh, ysz = nmb * 256, csz = nmb * 64;
@@ -850,9 +1010,10 @@ int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_
   const void* src = nullptr;
   size_t bytes = 0;
   std::vector<u8> tmp;
-  c->st.resize(c->n_valid);
-  CK(cudaMemcpy(c->st.data(), c->d_st.p, c->n_valid * sizeof(ImageState), cudaMemcpyDeviceToHost));
-  const ImageState& st = c->st[k];
+  ImageState st;
+  ImageLayout lay;
+  CK(cudaMemcpy(&st, c->d_st.as<ImageState>() + k, sizeof(ImageState), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&lay, c->d_lay.as<ImageLayout>() + k, sizeof(ImageLayout), cudaMemcpyDeviceToHost));
   if (s == "YUV_Y") { src = c->d_planes.as<u8>() + d.y_off; bytes = ysz; }
   else if (s == "YUV_U") { src = c->d_planes.as<u8>() + d.y_off + ysz; bytes = csz; }
   else if (s == "YUV_V") { src = c->d_planes.as<u8>() + d.y_off + ysz + csz; bytes = csz; }
@@ -865,15 +1026,13 @@ int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_
   else if (s == "STATS") { src = c->d_stats.as<u8>() + (size_t)k * 1056 * 4; bytes = 1056 * 4; }
   else if (s == "PROBS") { src = c->d_probs.as<u8>() + (size_t)k * 1056; bytes = 1056; }
   else if (s == "LCOST") { src = c->d_lcost.as<u8>() + (size_t)k * 6528 * 2; bytes = 6528 * 2; }
-  else if (s == "PART0") { src = c->d_part.as<u8>() + d.part_off; bytes = st.part0_bytes; }
-  else if (s == "PART1") { src = c->d_part.as<u8>() + d.part_off + d.p0_cap; bytes = st.part1_bytes; }
-  else if (s == "HDR_TOKENS") { src = c->d_htok.as<Token>() + d.hdr_off; bytes = (size_t)st.hdr_tokens * 2; }
-  else if (s == "TOK_TOKENS") { src = c->d_ttok.as<Token>() + d.tok_off; bytes = (size_t)st.tok_tokens * 2; }
-  else if (s == "VP8") {
-    c->out_off.resize(c->n_valid + 1);
-    CK(cudaMemcpy(c->out_off.data(), c->d_outoff.p, ((size_t)c->n_valid + 1) * 8, cudaMemcpyDeviceToHost));
-    src = c->d_out.as<u8>() + c->out_off[k]; bytes = st.vp8_bytes;
-  } else {
+  else if (s == "PART0") { src = c->d_part.as<u8>() + lay.part_off; bytes = st.part0_bytes; }
+  else if (s == "PART1") { src = c->d_part.as<u8>() + lay.part_off + lay.p0_cap; bytes = st.part1_bytes; }
+  else if (s == "HDR_TOKENS") { src = c->d_htok.as<Token>() + lay.hdr_off; bytes = (size_t)st.hdr_tokens * 2; }
+  else if (s == "TOK_TOKENS") { src = c->d_ttok.as<Token>() + lay.tok_off; bytes = (size_t)st.tok_tokens * 2; }
+  else if (s == "VP8") { src = c->d_out.as<u8>() + lay.out_off + 20; bytes = st.vp8_bytes; }
+  else if (s == "WEBP") { src = c->d_out.as<u8>() + lay.out_off; bytes = st.file_bytes; }
+  else {
     // small scalar stages served from the host copy of ImageState
     if (s == "SEG_QIDX") tmp.assign(st.seg_qidx, st.seg_qidx + 4);
     else if (s == "SEG_TREE_PROBS") tmp.assign(st.tree_probs, st.tree_probs + 3);

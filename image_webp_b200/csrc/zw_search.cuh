@@ -4,7 +4,7 @@
 // walks it left to right; rows are handed out through a global ticket counter in an order in
 // which row y-1 of an image always precedes row y, many images interleaved.  Row y may process
 // macroblock x once row y-1 has finished x+1 (left / top / top-right dependency, SURVEY.md
-// Appendix C), which it learns from a per-row progress counter (st.release / ld.acquire).
+// Appendix C), which it learns from a per-row progress counter (release / acquire pattern, see ld_flag).
 // Left-neighbour state (borders, complexities, chroma diffusion errors) never leaves the warp.
 //
 // Pass 1 is split in two kernels because of a reference quirk: in pass 1 the
@@ -88,20 +88,40 @@ struct SearchShared {
   WarpScratch w[SEARCH_WARPS];
 };
 
-// Progress flags.  On sm_100a an acquire load / fence.sc / fence.acq_rel each end in CCTL.IVALL -- an
-// invalidation of the SM's whole L1 -- which, issued per poll and per macroblock by 24 warps, keeps
-// the rate tables out of L1.  None of it is needed here: everything a waiting row reads from its
-// producer goes through ld.global.cg (L2 only: MbBottom, nz_after, derr2), so the consumer polls with
-// a relaxed gpu-scope load (the dependent loads issue after the branch on its value) and the
-// producer orders its data stores with fence.release (MEMBAR, no L1 invalidation) + a relaxed store.
+// Progress flags (row y-1 -> row y of the same image), a release / acquire pattern of the PTX memory model:
+//   producer: every lane stores its part of MbBottom / nz_after / derr2 / uvflags; __syncwarp() (bar.warp.sync orders
+//             the participating lanes' accesses); then LANE 0 ALONE issues fence.release.gpu + st.relaxed.gpu of the
+//             flag, so the fence is cumulative over what the other lanes stored before the barrier.
+//   consumer: lane 0 polls with ld.relaxed.gpu; once the poll succeeds it issues ONE fence.acquire.gpu (not one per
+//             poll), then __syncwarp() / a shuffle releases the other lanes, whose loads are ordered after it.
+// Cost on sm_100a (cuobjdump -sass): fence.release.gpu = MEMBAR.ALL.GPU, fence.acquire.gpu = CCTL.IVALL -- an
+// invalidation of the SM's whole L1, which also drops the rate tables other warps keep there.  -DZW_ACQUIRE_FENCE=0
+// builds the variant without it (round 1's protocol).  That variant relies on three hardware properties instead of
+// the memory model: (1) everything a waiting row reads from its producer is read with ld.global.cg, which never
+// allocates in or hits L1, so no stale L1 line can be observed; (2) the producer's MEMBAR.ALL.GPU makes its data
+// visible in L2 before the flag store is performed; (3) an SM issues a warp's instructions in order and the dependent
+// loads sit behind a branch on the polled value.  tests/test_gpu_soak.py runs both builds against one hash set.
+#ifndef ZW_ACQUIRE_FENCE
+#define ZW_ACQUIRE_FENCE 1
+#endif
 __device__ __forceinline__ int ld_flag(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void fence_release() { asm volatile("fence.release.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire() {
+#if ZW_ACQUIRE_FENCE
+  asm volatile("fence.acquire.gpu;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void st_flag(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// lane 0 of the producer, after the __syncwarp() that follows the warp's data stores
+__device__ __forceinline__ void publish_flag(int* p, int v) {
+  fence_release();
+  st_flag(p, v);
 }
 __device__ __forceinline__ i64 shfl64(i64 v, int src) {
   int lo = __shfl_sync(FULL, (int)(v & 0xffffffff), src);
@@ -1410,11 +1430,7 @@ __host__ __device__ constexpr int search_min_blocks(int pass) {
 #ifdef ZW_LS_MIN_BLOCKS
   return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
 #else
-#ifdef ZW_LS_MIN_BLOCKS
-  return search_lockstep(pass) ? ZW_LS_MIN_BLOCKS : ZW_SEARCH_MIN_BLOCKS;
-#else
   return search_lockstep(pass) ? 20 / (LS_WARPS > 0 ? LS_WARPS : 1) : ZW_SEARCH_MIN_BLOCKS;  // lock-step CTAs: 20 warps per SM (96 registers)
-#endif
 #endif
 }
 // dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
@@ -1507,7 +1523,11 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
       const int need = min(mbx == 0 ? max(2, (int)P.start_slack) : mbx + 2, mbw);
       if (LS) {  // never block inside a lock-step round: look once, sit the round out if not ready
         int ok = 1;
-        if (lane == 0 && seen < need) { seen = ld_flag(&progress[row_off + mby - 1]); ok = seen >= need; }
+        if (lane == 0 && seen < need) {
+          seen = ld_flag(&progress[row_off + mby - 1]);
+          ok = seen >= need;
+          if (ok) fence_acquire();
+        }
         work = __shfl_sync(FULL, ok, 0) != 0;
       } else {
         if (lane == 0 && seen < need) {
@@ -1515,6 +1535,7 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
           const long long w0 = clock64();
 #endif
           while ((seen = ld_flag(&progress[row_off + mby - 1])) < need) __nanosleep(100);
+          fence_acquire();
 #ifdef ZW_WAIT_STATS
           atomicAdd(reinterpret_cast<unsigned long long*>(P.ticket) + 2 + PASS, (unsigned long long)(clock64() - w0));
 #endif
@@ -1587,9 +1608,8 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
     MbBottom* bo = &P.bottom[gmb];
     if (lane < 16) bo->y[lane] = W.yws[16 * 32 + 1 + lane];
     if (PASS == 2 && lane == 0) P.nz_after[gmb] = (u16)out_top;
-    fence_release();
     __syncwarp();
-    if (lane == 0) st_flag(&progress[row_off + mby], mbx + 1);
+    if (lane == 0) publish_flag(&progress[row_off + mby], mbx + 1);
     mbx++;
     if (mbx == mbw) {
       have_row = false;
@@ -1725,6 +1745,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_chr
         const int need = min(mbx == 0 ? max(1, (int)P.start_slack) : mbx + 1, mbw);
         if (lane == 0 && seen < need) {
           while ((seen = ld_flag(&progress[d.row_off + mby - 1])) < need) __nanosleep(100);
+          fence_acquire();
         }
         __syncwarp();
       }
@@ -1753,9 +1774,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, ZW_SEARCH_MIN_BLOCKS) k_chr
       MbBottom* bo = &P.bottom[gmb];
       if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
       if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
-      fence_release();
       __syncwarp();
-      if (lane == 0) st_flag(&progress[d.row_off + mby], mbx + 1);
+      if (lane == 0) publish_flag(&progress[d.row_off + mby], mbx + 1);
     }
   }
 }

@@ -47,11 +47,23 @@ struct ImageDesc {
   u32 use_segments;  // mbw*mbh >= 256 (vp8.rs:2481)
   u64 rgb_off;   // byte offset into the RGB arena (16-byte aligned)
   u64 y_off;     // byte offset of the padded Y plane in the plane arena; U follows, then V
-  // filled in after the token count (second upload of the descriptor table):
+};
+
+// Device-computed placement of one image's variable-size data (k_layout, after the symbol count): the host never
+// waits for the counts in the middle of a batch.
+struct ImageLayout {
   u64 hdr_off;   // offset (in tokens) of the image's first-partition symbol stream
   u64 tok_off;   // offset (in tokens) of the image's token-partition symbol stream
   u64 part_off;  // byte offset of its coded partitions in the partition scratch: [p0 | p1]
-  u32 p0_cap, p1_cap;  // byte capacities of the two coded partitions
+  u64 out_off;   // byte offset of its finished file in the output arena (16-byte aligned; k_outscan)
+  u32 p0_cap, p1_cap;  // byte capacities of the two coded partitions (7 bits per symbol bound)
+};
+
+// Chunk-wide totals of the same scan, checked against the capacities the host allocated up front.
+struct ChunkTotals {
+  u64 hdr_tokens, tok_tokens, part_bytes, out_bytes;
+  u32 overflow;  // a stream arena is too small: the emit / code / assemble kernels do nothing, the host grows and re-runs them
+  u32 pad;
 };
 
 // Device-written per-image state.
@@ -70,7 +82,8 @@ struct ImageState {
   u32 hdr_tokens;    // tokens in the first-partition stream
   u32 tok_tokens;    // tokens in the token-partition stream
   u32 part0_bytes, part1_bytes;
-  u32 vp8_bytes;
+  u32 vp8_bytes;    // frame tag .. end of the token partition (the VP8 payload)
+  u32 file_bytes;   // RIFF header + payload + pad byte (api.rs:1325-1329), assembled on the device
   u32 status;   // 0 or a ZW_ERR_* code raised on the device
 };
 static_assert(sizeof(ImageState) <= 80, "ImageState is copied back per image; keep it small");
@@ -86,6 +99,9 @@ typedef u16 Token;
 // Everything the kernels need, passed by value.
 struct ChunkParams {
   const ImageDesc* img;
+  ImageLayout* lay;       // [n_img] device-computed stream / partition / output placement
+  ChunkTotals* tot;
+  u64 cap_hdr_tokens, cap_tok_tokens, cap_part_bytes;  // capacities of the symbol / partition arenas
   ImageState* st;
   const RowRef* rows;     // ticket -> (image, mb row), ordered so that row y-1 precedes row y
   const SegParams* segtab;  // [128]

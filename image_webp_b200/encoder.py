@@ -12,10 +12,9 @@ header include/zenwebp_b200.hpp) stand where the `zenwebp-b200` wrapper crate wo
 INTEGRATION.md for the -sys crate a maintainer would add.  Only the lossy VP8 path is provided:
 lossless parameters raise NotImplementedError (out of scope).  No CPU fallback.
 """
-import concurrent.futures
 import ctypes as C
 import enum
-import queue
+import threading
 
 import numpy as np
 
@@ -93,13 +92,47 @@ def _raise_for(status, lib):
     raise DeviceError(status, lib.zw_strerror(status).decode())
 
 
+class PendingBatch:
+    """A batch in flight (zw_submit ticket).  `result()` blocks until it is finished and returns
+    (list of .webp / VP8 bytes, timing dict); the pipeline slot is released then."""
+
+    def __init__(self, ctx, ticket, keep, container, raise_errors):
+        self._ctx, self._ticket, self._keep = ctx, ticket, keep
+        self._container, self._raise = container, raise_errors
+        self._res = None
+
+    def result(self):
+        if self._res is None:
+            ctx = self._ctx
+            view = _lib.ZwBatchView()
+            t = _lib.ZwTiming()
+            rc = ctx.lib.zw_wait(ctx.h, self._ticket, 1 if self._container else 0, C.byref(view), C.byref(t))
+            if rc != 0:
+                ctx.lib.zw_release(ctx.h, self._ticket)
+                _raise_for(rc, ctx.lib)
+            outs, first_bad = [], 0
+            for i in range(view.n):
+                st = view.status[i]
+                if st != 0:
+                    first_bad = first_bad or st
+                    outs.append(None)
+                else:
+                    outs.append(C.string_at(view.arena + view.offsets[i], view.lens[i]))
+            ctx.lib.zw_release(ctx.h, self._ticket)
+            self._keep = None
+            self._res = (outs, t.as_dict())
+            if first_bad and self._raise:
+                _raise_for(first_bad, ctx.lib)
+        return self._res
+
+
 class Context:
     """One encoder context per (host thread, GPU) -- wraps zw_create / zw_destroy."""
 
-    def __init__(self, device=0, max_device_bytes=0, persistent_warps_per_sm=0, lanes=0):
+    def __init__(self, device=0, max_device_bytes=0, persistent_warps_per_sm=0, depth=0, lanes=0):
         self.lib = _lib.load()
         res = (C.c_int * 5)()
-        res[0] = lanes  # streams the context pipelines a chunk over (0 = library default)
+        res[0] = depth or lanes  # batches the context keeps in flight (0 = library default)
         lim = _lib.ZwLimits(max_device_bytes, persistent_warps_per_sm, res)
         self.h = self.lib.zw_create(device, C.byref(lim))
         if not self.h:
@@ -136,38 +169,59 @@ class Context:
         return arr, keep
 
     def _collect(self, outs, raise_errors):
-        res = []
+        """Copy every output out of its malloc'ed buffer and free it; raise (if asked) only afterwards."""
+        res, first_bad = [], 0
         for o in outs:
             if o.status != 0:
-                if raise_errors:
-                    _raise_for(o.status, self.lib)
+                first_bad = first_bad or o.status
                 res.append(None)
-                continue
-            res.append(C.string_at(o.data, o.len))
-            self.lib.zw_free(o.data)
+            else:
+                res.append(C.string_at(o.data, o.len))
+            if o.data:
+                self.lib.zw_free(o.data)
+        if first_bad and raise_errors:
+            _raise_for(first_bad, self.lib)
         return res
 
-    # -- public ----------------------------------------------------------------------------
-    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
-        """Batch entry point: list of uint8 arrays [h,w,c] (or (bytes,w,h) tuples) -> list of bytes.
-        Returns (outputs, timing dict)."""
+    @staticmethod
+    def _check(params, color, container):
         if not params.use_lossy:
             raise NotImplementedError("only the lossy VP8 path is implemented on the GPU (SURVEY.md §2)")
         if container and color.has_alpha():
             # the reference wraps lossy + alpha in VP8X with a lossless ALPH chunk (api.rs:1330-1394): not built
             raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f); container=False returns the VP8 payload")
+
+    # -- public ----------------------------------------------------------------------------
+    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+        """Batch entry point: list of uint8 arrays [h,w,c] (or (bytes,w,h) tuples) -> list of bytes.
+        Returns (outputs, timing dict).  (zw_encode_webp_batch / zw_encode_vp8_batch.)"""
+        self._check(params, color, container)
         arr, keep = self._as_images(images, color)
         outs = (_lib.ZwOutput * len(images))()
         t = _lib.ZwTiming()
         fn = self.lib.zw_encode_webp_batch if container else self.lib.zw_encode_vp8_batch
         rc = fn(self.h, arr, len(images), int(params.lossy_quality), int(params.method), outs, C.byref(t))
         if rc != 0:
+            self._collect(outs, False)
             _raise_for(rc, self.lib)
         return self._collect(outs, raise_errors), t.as_dict()
 
+    def submit(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+        """Streaming entry (zw_submit): starts the batch and returns a PendingBatch at once, or None when every
+        pipeline slot of the context is taken (take `.result()` of an earlier batch first).  The batch must fit
+        the device budget in one chunk."""
+        self._check(params, color, container)
+        arr, keep = self._as_images(images, color)
+        ticket = C.c_int(-1)
+        rc = self.lib.zw_submit(self.h, arr, len(images), int(params.lossy_quality), int(params.method), C.byref(ticket))
+        if rc == 7:  # ZW_ERR_BUSY
+            return None
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return PendingBatch(self, ticket.value, (arr, keep), container, raise_errors)
+
     def stage(self, images, color=ColorType.Rgb8):
         arr, keep = self._as_images(images, color)
-        self._keep = keep
         rc = self.lib.zw_stage_batch(self.h, arr, len(images))
         if rc != 0:
             _raise_for(rc, self.lib)
@@ -185,6 +239,7 @@ class Context:
         t = _lib.ZwTiming()
         rc = self.lib.zw_download(self.h, outs, self._n, 1 if container else 0, C.byref(t))
         if rc != 0:
+            self._collect(outs, False)
             _raise_for(rc, self.lib)
         return self._collect(outs, raise_errors), t.as_dict()
 
@@ -209,31 +264,28 @@ class Context:
 
 
 class BatchPipeline:
-    """Streaming batch entry: `depth` contexts on one GPU, each driven by its own host thread, so
-    that the H2D copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of
-    the next (the C ABI is thread-safe across contexts; ctypes drops the GIL during the call).
-    `submit` returns a concurrent.futures.Future of (list of .webp bytes, timing dict); batches are
-    independent, results are bit-identical to `Context.encode_batch`."""
+    """Streaming batch entry on ONE context: `depth` batches in flight through zw_submit / zw_wait, so that the
+    H2D copy of a batch runs under the kernels of the one before it and its D2H copy under the kernels of the one
+    after it -- no extra contexts or host threads.  `submit` returns a PendingBatch (`.result()` -> (list of
+    .webp bytes, timing dict)); when every slot is taken it first completes the oldest batch.  Results are
+    bit-identical to `Context.encode_batch`."""
 
-    def __init__(self, device=0, depth=2, **ctx_kwargs):
+    def __init__(self, device=0, depth=3, **ctx_kwargs):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.depth = depth
-        self._free = queue.Queue()
-        self._ctxs = [Context(device, **ctx_kwargs) for _ in range(depth)]
-        for c in self._ctxs:
-            self._free.put(c)
-        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=depth, thread_name_prefix="zw-pipe")
-
-    def _run(self, images, params, color, container):
-        ctx = self._free.get()
-        try:
-            return ctx.encode_batch(images, params, color, container)
-        finally:
-            self._free.put(ctx)
+        self.ctx = Context(device, depth=depth, **ctx_kwargs)
+        self._inflight = []
 
     def submit(self, images, params, color=ColorType.Rgb8, container=True):
-        return self._pool.submit(self._run, images, params, color, container)
+        while True:
+            p = self.ctx.submit(images, params, color, container)
+            if p is not None:
+                self._inflight.append(p)
+                return p
+            if not self._inflight:
+                raise DeviceError(7, "no free pipeline slot")
+            self._inflight.pop(0).result()  # completes (and caches) the oldest batch, freeing its slot
 
     def encode_batches(self, batches, params, color=ColorType.Rgb8, container=True):
         """Encode an iterable of batches; returns the list of per-batch outputs, in order."""
@@ -241,10 +293,13 @@ class BatchPipeline:
         return [f.result()[0] for f in futs]
 
     def close(self):
-        self._pool.shutdown(wait=True)
-        for c in self._ctxs:
-            c.close()
-        self._ctxs = []
+        for p in self._inflight:
+            try:
+                p.result()
+            except Exception:
+                pass
+        self._inflight = []
+        self.ctx.close()
 
     def __enter__(self):
         return self
@@ -253,13 +308,56 @@ class BatchPipeline:
         self.close()
 
 
+class MultiContext:
+    """One batch over several GPUs of one box (zw_multi_*): contiguous slices of ceil(n / G) images, one host
+    thread + context per GPU inside the library, no collective; results come back in image order."""
+
+    def __init__(self, devices, max_device_bytes=0, depth=0):
+        self.lib = _lib.load()
+        res = (C.c_int * 5)()
+        res[0] = depth
+        lim = _lib.ZwLimits(max_device_bytes, 0, res)
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = self.lib.zw_multi_create(devs, len(devices), C.byref(lim))
+        if not self.h:
+            code = self.lib.zw_last_error()
+            raise DeviceError(code, self.lib.zw_strerror(code).decode() + " (no CPU fallback exists)")
+        self.devices = list(devices)
+
+    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+        Context._check(params, color, container)
+        arr, keep = Context._as_images(images, color)
+        outs = (_lib.ZwOutput * len(images))()
+        tm = (_lib.ZwTiming * len(self.devices))()
+        rc = self.lib.zw_multi_encode(self.h, arr, len(images), int(params.lossy_quality), int(params.method), 1 if container else 0, outs, tm)
+        if rc != 0:
+            Context._collect(self, outs, False)
+            _raise_for(rc, self.lib)
+        return Context._collect(self, outs, raise_errors), [t.as_dict() for t in tm]
+
+    def close(self):
+        if self.h:
+            self.lib.zw_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _default_ctx = {}
+_default_lock = threading.Lock()
 
 
 def default_context(device=0):
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+    """One cached context per (thread, device): a zw_ctx is not thread-safe."""
+    key = (threading.get_ident(), device)
+    with _default_lock:
+        if key not in _default_ctx:
+            _default_ctx[key] = Context(device)
+        return _default_ctx[key]
 
 
 class WebPEncoder:

@@ -1,7 +1,6 @@
 """Image sharding across GPUs: images are independent, so a batch is split into
 contiguous slices of ceil(n/G) images, one slice per GPU, no collective on the data path; the
 finished bitstreams are gathered on the host in image order."""
-import threading
 
 
 def shard_range(n, rank, world):
@@ -25,27 +24,15 @@ def gather_in_order(shards):
     return out
 
 
+_multi = {}
+
+
 def encode_batch_sharded(images, params, devices, color=None, container=True):
-    """One host thread + one context per GPU (contexts are independent)."""
-    from .encoder import ColorType, default_context
+    """The library's multi-GPU entry (zw_multi_encode): one host thread + context per GPU inside the C ABI,
+    contiguous slices of ceil(n / G) images, results in image order."""
+    from .encoder import ColorType, MultiContext
     color = color or ColorType.Rgb8
-    world = len(devices)
-    results = [None] * world
-    errors = [None] * world
-
-    def work(r):
-        try:
-            b, e = shard_range(len(images), r, world)
-            results[r] = default_context(devices[r]).encode_batch(images[b:e], params, color, container)[0] if e > b else []
-        except Exception as ex:  # surfaced to the caller below
-            errors[r] = ex
-
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    for ex in errors:
-        if ex is not None:
-            raise ex
-    return gather_in_order(results)
+    key = tuple(devices)
+    if key not in _multi:
+        _multi[key] = MultiContext(list(devices))
+    return _multi[key].encode_batch(images, params, color, container)[0]

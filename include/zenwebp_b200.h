@@ -29,7 +29,10 @@ enum {
   ZW_ERR_OUTPUT_TOO_SMALL = 4,   /* caller-provided output buffer smaller than the bitstream               */
   ZW_ERR_PARTITION_TOO_LARGE = 5,/* first partition >= 2^19 bytes: the 19-bit size field would overflow
                                     (the reference silently emits a corrupt tag here, vp8.rs:320)         */
-  ZW_ERR_NOT_STAGED = 6,         /* zw_encode_resident / zw_download without a staged batch                */
+  ZW_ERR_NOT_STAGED = 6,         /* zw_encode_resident / zw_download without a staged batch; unknown ticket */
+  ZW_ERR_BUSY = 7,               /* zw_submit: every pipeline slot holds a batch (zw_wait + zw_release one)  */
+  ZW_ERR_TOO_LARGE = 8,          /* zw_submit / zw_stage_batch: batch exceeds max_device_bytes or 65535
+                                    images (zw_encode_*_batch split such batches into chunks themselves)  */
   ZW_ERR_CUDA = 100              /* 100 + cudaError_t                                                      */
 };
 
@@ -43,13 +46,19 @@ typedef struct zw_ctx zw_ctx;
 typedef struct zw_limits {
   size_t max_device_bytes; /* working-set budget per chunk of a batch; 0 = default (32 GiB)     */
   int persistent_warps_per_sm; /* 0 = default; tuning knob of the wavefront kernels            */
-  int reserved[5];         /* reserved[0]: lanes (streams) the host-buffer batch entry points split a
-                              chunk over so H2D/D2H copies hide behind kernels; 0 = default (1).
-                              Others must be 0.                                                  */
+  int reserved[5];         /* reserved[0]: pipeline depth = batches (chunks) one context keeps in flight,
+                              each on its own stream with its own buffers, so that the H2D / D2H
+                              copies of one hide behind the kernels of another; 0 = default (3),
+                              max 8.  Buffers are allocated on first use.  Others must be 0.     */
 } zw_limits;
 
 /* One input image: caller-owned, tightly packed rows (stride = width * bpp), host memory
- * (pinned memory makes the H2D copy asynchronous; pageable memory also works). */
+ * (pinned memory makes the H2D copy asynchronous; pageable memory also works).  Images that are
+ * contiguous in host memory (image i+1 starts where image i ends, lengths multiples of 16) are
+ * copied with one transfer per run.
+ * LIFETIME: the buffers must stay valid and unchanged until the call that received them returns
+ * (zw_encode_*_batch, zw_multi_encode, zw_stage_batch) or, for zw_submit, until zw_wait on its ticket
+ * has returned. */
 typedef struct zw_image {
   const uint8_t* data;
   size_t len;      /* bytes in data; must equal width*height*bpp                                  */
@@ -93,9 +102,12 @@ void zw_free(void* p);
 /* Conservative bound for one output (payload + RIFF header). */
 size_t zw_max_output_size(uint32_t width, uint32_t height);
 
-/* Batch entry: n independent images -> n raw VP8 key-frame payloads, byte-identical to what the
- * reference's encode_frame_lossy appends (vp8.rs:3132).  quality 0..100, method 0..6 (clamped
- * like vp8.rs:1291).  Returns ZW_OK if the call ran; per-image results are in outs[i].status. */
+/* Batch entry: n independent images -> n raw VP8 key-frame payloads, byte-identical to the CPU port
+ * (oracle/) of what the reference's encode_frame_lossy appends (vp8.rs:3132).  quality 0..100,
+ * method 0..6 (larger values clamped like vp8.rs:1291).  The batch is split into chunks (device
+ * budget; ~4 chunks for large batches) that are pipelined over the context's slots, so the copies
+ * of one chunk hide behind the kernels of another.  Returns ZW_OK if the call ran; per-image results
+ * are in outs[i].status (every outs[i] is initialised even when the call fails). */
 int zw_encode_vp8_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
                         zw_output* outs, zw_timing* timing);
 
@@ -108,8 +120,44 @@ int zw_encode_vp8_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality
 int zw_encode_webp_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
                          zw_output* outs, zw_timing* timing);
 
+/* Streaming form: one context keeps up to `depth` batches in flight (zw_limits.reserved[0]).
+ *   zw_submit   validate + start the H2D copy + enqueue every kernel of one batch; returns at once with
+ *               a ticket.  No host synchronisation happens inside a batch: stream offsets are computed on
+ *               the device (k_layout), the symbol arenas are sized by estimate and checked on the device.
+ *               ZW_ERR_BUSY when every slot is taken, ZW_ERR_TOO_LARGE when the batch exceeds the budget.
+ *   zw_wait     block until that batch is finished, fetch all files with ONE D2H copy into a pinned arena
+ *               owned by the slot, and describe them in *view (no per-image allocation, no copy):
+ *               file i = view->arena[view->offsets[i] .. + view->lens[i]), view->status[i] = ZW_* code.
+ *               container != 0: the .webp file (RIFF wrap as api.rs:1325-1329); 0: the raw VP8 payload.
+ *               May be called again (e.g. with the other container flag) until the ticket is released.
+ *   zw_release  give the slot back; the view of that ticket becomes invalid.
+ * Batches submitted to one context run their kernels in submission order; the copies of a batch overlap
+ * the kernels of its neighbours.  Bytes are identical to zw_encode_*_batch. */
+typedef struct zw_batch_view {
+  const uint8_t* arena;    /* pinned host memory owned by the slot, valid until zw_release(ticket)   */
+  size_t n;                /* images of the batch                                                       */
+  const uint64_t* offsets; /* [n] byte offset of file i in arena                                        */
+  const uint32_t* lens;    /* [n] bytes of file i (0 when status[i] != ZW_OK)                           */
+  const int32_t* status;   /* [n] per-image ZW_* code                                                   */
+} zw_batch_view;
+int zw_submit(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method, int* ticket);
+int zw_wait(zw_ctx* ctx, int ticket, int container, zw_batch_view* view, zw_timing* timing);
+int zw_release(zw_ctx* ctx, int ticket);
+
+/* One batch over several GPUs of one box (north_star "sharded by image across the 8
+ * GPUs ... gathered to the host"): contiguous slices of ceil(n / G) images, one host thread + context per
+ * GPU (created once by zw_multi_create), no collective on the data path; outs[] is filled in image order.
+ * per_device (NULL or [device count]) receives each GPU's timing.  container as in zw_wait. */
+typedef struct zw_multi zw_multi;
+zw_multi* zw_multi_create(const int* devices, int n_devices, const zw_limits* limits);
+void zw_multi_destroy(zw_multi* m);
+int zw_multi_device_count(const zw_multi* m);
+int zw_multi_encode(zw_multi* m, const zw_image* imgs, size_t n, int quality, int method, int container,
+                    zw_output* outs, zw_timing* per_device);
+
 /* Split form, for callers that keep inputs resident in HBM (and for kernel-only timing):
- *   zw_stage_batch     validate + H2D copy of one chunk (must fit max_device_bytes)
+ *   zw_stage_batch     validate + H2D copy of one chunk (must fit max_device_bytes); returns when
+ *                      the copy has finished (the caller may reuse its buffers)
  *   zw_encode_resident run every kernel on the staged inputs; bitstreams stay on the device
  *   zw_download        D2H + host chunk assembly into outs (container != 0 adds the RIFF wrap) */
 int zw_stage_batch(zw_ctx* ctx, const zw_image* imgs, size_t n);
@@ -125,11 +173,12 @@ int zw_measure_int_peak(zw_ctx* ctx, double* int_instr_per_s);
 /* Parity/debug: copy a named intermediate stage of image `index` of the last encoded chunk to
  * host memory (names follow SURVEY.md Appendix F: "YUV_Y","YUV_U","YUV_V","ALPHA","ALPHA_HIST",
  * "SEG_MAP","SEG_QIDX","SEG_TREE_PROBS","SEG_UPDATE_MAP","P1MB","STATS","PROBS","SKIP_PROB",
- * "LCOST","P2MB","PART0","PART1","VP8").  *len receives the stage size; if cap is too small
+ * "LCOST","P2MB","PART0","PART1","VP8","WEBP").  For a batch that was split into chunks, `index`
+ * counts inside the LAST chunk.  *len receives the stage size; if cap is too small
  * nothing is copied and ZW_ERR_OUTPUT_TOO_SMALL is returned. */
 int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
 
-/* Library build info, e.g. "zenwebp_b200 0.1 sm_100a". */
+/* Library build info, e.g. "zenwebp_b200 0.2 (CUDA, sm_100a)". */
 const char* zw_version(void);
 
 #ifdef __cplusplus
