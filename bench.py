@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""bench.py -- lossy encode MPix/s (q75 m4, byte-identical) on N B200s, beside the CPU baseline.
+"""bench.py -- lossy encode MPix/s (q75 m4, byte-identical to the CPU port) on N B200s, beside the CPU baseline.
 
 Workload (BASELINE.json configs[1]): a batch of 1024 x 768x512 RGB images, quality 75, method 4,
 synthetic "photo-like" content (image_webp_b200/synth.py).  One step = one encode of the whole
@@ -7,10 +7,17 @@ batch.  Images are independent, so N GPUs each encode their own batch of 1024 (w
 collective on the data path); the metric is Σ pixels of all ranks / max-over-ranks time.
 
   value : kernel-only, inputs already resident in HBM (zw_encode_resident), CUDA-event time
-  e2e   : zw_encode_webp_batch from pinned HOST buffers: H2D + kernels + D2H + host RIFF assembly
+  e2e   : the streaming entry of the C ABI (zw_submit / zw_wait / zw_release on ONE context, via
+          BatchPipeline): pinned HOST RGB in, .webp bytes out; every step's H2D and D2H copies
+          are inside the timed region (they overlap the neighbouring steps' kernels)
+  photo : the same two figures on 1024 DISTINCT 768x512 crops of the reference's own test
+          photographs (tests/golden/photos) -- real photographs carry 2-5x the token symbols of the
+          synthetic generator; EVERY output of that batch is compared with the multi-threaded oracle
+  other_configs : BASELINE.json configs 1, 3, 4, 5 (kernel-only, end to end, parity sample, CPU port)
   --impl reference : the CPU oracle (a C++ restatement of the reference; the Rust reference cannot
                      be built in this image) on all host cores, one image per thread.
-"""
+"byte-identical" everywhere means: identical to the CPU port under oracle/ (the Rust reference cannot
+be run here)."""
 import argparse
 import json
 import os
@@ -26,10 +33,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, QUALITY, METHOD = 768, 512, 75, 4
 WORKLOAD = "batch of %d x 768x512 RGB, q75 method 4"
+METRIC = "lossy encode MPix/s (q75 m4, byte-identical)"
 # algorithmic HBM bytes per pixel of the dominant kernel (pass-2 luma search k_search<2>): read the Y
 # plane (1 B/px) + write the 32-byte header and 17 luma blocks (544 B) of one macroblock record per
 # 256 px (2.25 B/px).  DESIGN.md §Measurement.
-SEARCH_BYTES_PER_PX = 1.0 + 576.0 / 256.0  # luma kernel: Y plane read + header and luma part of the record written
+SEARCH_BYTES_PER_PX = 1.0 + 576.0 / 256.0
+# the reference's own published single-thread figure for this exact metric (768x512 Kodak photo, q75 m4, SIMD Rust
+# build, hardware unstated): /root/reference/CLAUDE.md:14, BASELINE.md section 1
+REF_PUBLISHED_MPIX_S_PER_THREAD = 6.2
+STAGES = ("yuv_ms", "analysis_ms", "pass1_ms", "chroma1_ms", "stats_ms", "chroma2_ms", "pass2_ms", "token_ms", "boolcode_ms", "assemble_ms")
 
 
 def rank_env():
@@ -102,22 +114,41 @@ def native_oracle():
         L = O.lib()
     L.zwo_encode_batch_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
     L.zwo_encode_batch_mt.restype = C.c_size_t
+    L.zwo_encode_batch_mt_out.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]
+    L.zwo_encode_batch_mt_out.restype = C.c_size_t
     return L
 
 
-def cpu_run(imgs, threads, lib):
+def cpu_run(imgs, threads, lib, quality=QUALITY, method=METHOD):
     """Encode imgs ([n,h,w,3] uint8) with the oracle, one image per thread at a time.  Returns seconds."""
     n, h, w, _ = imgs.shape
     t0 = time.perf_counter()
-    lib.zwo_encode_batch_mt(imgs.ctypes.data, n, w, h, QUALITY, METHOD, threads)
+    lib.zwo_encode_batch_mt(imgs.ctypes.data, n, w, h, quality, method, threads)
     return time.perf_counter() - t0
+
+
+def cpu_baseline(sample, lib, cores, what, quality=QUALITY, method=METHOD):
+    import numpy as np
+    sample = np.ascontiguousarray(sample)
+    n, h, w = sample.shape[:3]
+    cpu_run(sample[:min(n, cores)], cores, lib, quality, method)
+    ts = cpu_run(sample, cores, lib, quality, method)
+    k = min(n, 4)
+    t1 = cpu_run(sample[:k], 1, lib, quality, method)
+    return {"value": n * w * h / ts / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
+            "single_thread_mpix_s": k * w * h / t1 / 1e6,
+            "reference_published_single_thread_mpix_s": REF_PUBLISHED_MPIX_S_PER_THREAD,
+            "note": "kind=port: the scalar C++ restatement of the reference (oracle/, -O3 -march=native); the reference's own SIMD Rust "
+                    "build publishes %.1f MPix/s per thread for q75 m4 on a 768x512 photograph (reference CLAUDE.md:14, hardware "
+                    "unstated) and cannot be built here (no Rust toolchain)" % REF_PUBLISHED_MPIX_S_PER_THREAD,
+            "sample": "%d %s, one image per thread on %d threads" % (n, what, cores)}
 
 
 def run_reference(args):
     rank, _, world = rank_env()
     if rank != 0:
         return 0
-    import numpy as np
     from image_webp_b200 import synth
     cores = os.cpu_count() or 1
     lib = native_oracle()
@@ -128,16 +159,151 @@ def run_reference(args):
     times = [cpu_run(imgs, cores, lib) for _ in range(args.steps)]
     tsum = sum(times)
     value = n_sample * W * H * args.steps / tsum / 1e6
-    line = {"metric": "lossy encode MPix/s (q75 m4, byte-identical)", "value": value, "unit": "MPix/s", "n_gpus": args.gpus,
+    line = {"metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD % 1024, "quality": QUALITY, "method": METHOD,
                        "note": "bounded sample of the workload per step; CPU only"},
             "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "port",
+                             "reference_published_single_thread_mpix_s": REF_PUBLISHED_MPIX_S_PER_THREAD,
                              "sample": "%d of the 1024 768x512 images per step, one image per thread on %d threads" % (n_sample, cores)},
             "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def pinned_batch(torch, arr):
+    host = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[...] = arr
+    return host
+
+
+def run_workload(Z, torch, ctx, pipe, imgs, params, steps, warmup, barrier, sampler=None):
+    """Kernel-only (resident) and end-to-end (streaming C ABI) legs of one workload.  Returns a dict of raw sums."""
+    ctx.stage(imgs)
+    for _ in range(warmup):
+        ctx.encode_resident(params)
+    barrier()
+    if sampler:
+        sampler.start()
+    stage_ms = {k: 0.0 for k in STAGES}
+    dev_ms, launches, symbols = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t = ctx.encode_resident(params)
+        dev_ms += t["device_total_ms"]
+        launches += t["kernel_launches"]
+        symbols = t["symbols"]
+        for k in STAGES:
+            stage_ms[k] += t[k]
+    barrier()
+    wall_kernel_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    outs_resident, _ = ctx.download()
+    # end to end: (a) the streaming entry, `depth` batches in flight on one context
+    for f in [pipe.submit(imgs, params) for _ in range(pipe.depth)]:
+        f.result()
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    outs = None
+    futs = []
+    for _ in range(steps):
+        futs.append(pipe.submit(imgs, params))
+    for f in futs:
+        outs, t = f.result()
+        h2d += t["h2d_bytes"]; d2h += t["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # (b) one blocking call per step (zw_encode_webp_batch: chunks pipelined inside the call)
+    pipe.ctx.encode_batch(imgs, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, steps // 2)):
+        outs_b, tb = pipe.ctx.encode_batch(imgs, params)
+    barrier()
+    e2e_call_s = (time.perf_counter() - t0) / max(1, steps // 2) * steps
+    return {"dev_s": dev_ms / 1e3, "wall_kernel_s": wall_kernel_s, "e2e_s": e2e_s, "e2e_call_s": e2e_call_s, "stage_ms": stage_ms,
+            "launches": launches, "symbols": symbols, "h2d": h2d, "d2h": d2h, "clocks": clocks,
+            "outs": outs, "outs_resident": outs_resident, "outs_call": outs_b, "h2d_ms": t["h2d_ms"], "d2h_ms": t["d2h_ms"]}
+
+
+def other_configs(Z, torch, ctx, pipe, lib, cores, world):
+    """BASELINE.json configs 1, 3, 4, 5 on one GPU (kernel-only + end to end + parity sample + CPU port)."""
+    import numpy as np
+    import oracle_lib as O
+    import photo_inputs as PI
+    from image_webp_b200 import synth
+    res = {}
+
+    def run(name, imgs, q, m, check, cpu_sample, reps=3):
+        p = Z.EncoderParams.lossy(q)
+        p.method = m
+        px = sum(i.shape[0] * i.shape[1] for i in imgs)
+        ctx.stage(imgs)
+        ctx.encode_resident(p)
+        ts = [ctx.encode_resident(p) for _ in range(reps)]
+        dev = min(t["device_total_ms"] for t in ts)
+        tb = ts[-1]
+        pipe.ctx.encode_batch(imgs, p)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            outs, _ = pipe.ctx.encode_batch(imgs, p)
+        e2e = (time.perf_counter() - t0) / reps
+        ok = 0
+        for i in check:
+            rc, ref, _ = O.encode(imgs[i], q, m)
+            ok += int(rc == 0 and outs[i] == ref)
+        r = {"pixels": px, "kernel_only_ms": dev, "kernel_only_mpix_s": px / dev / 1e3, "e2e_ms": 1e3 * e2e, "e2e_mpix_s": px / e2e / 1e6,
+             "stage_ms": {k: tb[k] for k in STAGES}, "symbols_per_px": tb["symbols"] / px,
+             "parity": {"checked": len(check), "identical": ok}}
+        if cpu_sample is not None:
+            cb = cpu_baseline(cpu_sample, lib, cores, "images of this config", q, m)
+            r["cpu_port"] = {k: cb[k] for k in ("value", "cores", "single_thread_mpix_s", "sample")}
+        res[name] = r
+        assert ok == len(check), "%s: GPU output differs from the oracle" % name
+
+    c1 = PI.survey_crop()
+    run("config1_photo: 1 x 768x512 photograph crop (gallery1/3.png @256,104) q75 m4", [c1], 75, 4, [0], np.stack([c1] * 4), reps=5)
+    s1 = synth.photo_like(768, 512, 0)
+    run("config1_synthetic: 1 x 768x512 G(0) q75 m4", [s1], 75, 4, [0], np.stack([s1] * 4), reps=5)
+    big = synth.photo_like(4096, 4096, 3, freq_scale=4.0)
+    run("config3: 1 x 4096x4096 q90 m4", [big], 90, 4, [0], big[None], reps=2)
+    del big
+    base = [synth.photo_like(1920, 1080, 100 + i) for i in range(8)]
+    run("config4: 256 x 1920x1080 q75 m6", [base[i % 8] for i in range(256)], 75, 6, [0, 255], np.stack(base[:max(2, min(8, cores // 2))]), reps=2)
+    tb_ = [synth.photo_like(256, 256, 200 + i) for i in range(64)]
+    run("config5_shard: 8192 x 256x256 q50 m0 (the 1/8 shard one GPU owns)", [tb_[i % 64] for i in range(8192)], 50, 0, [0, 63, 8191],
+        np.stack(tb_), reps=2)
+    return res
+
+
+def config5_multi(Z, torch, n_dev):
+    """Config 5 through the library's own multi-GPU entry (zw_multi_encode) in ONE process: 8192 thumbnails per GPU
+    (65 536 at 8 GPUs), sharded by image, gathered in image order."""
+    import numpy as np
+    import oracle_lib as O
+    from image_webp_b200 import synth
+    n = 8192 * n_dev
+    block = pinned_batch(torch, np.stack([synth.photo_like(256, 256, 200 + i) for i in range(64)]))
+    imgs = [block.numpy()[i % 64] for i in range(n)]
+    p = Z.EncoderParams.lossy(50)
+    p.method = 0
+    mc = Z.MultiContext(list(range(n_dev)))
+    try:
+        mc.encode_batch(imgs, p)
+        t0 = time.perf_counter()
+        outs, tm = mc.encode_batch(imgs, p)
+        dt = time.perf_counter() - t0
+    finally:
+        mc.close()
+    ok = sum(int(outs[i] == O.encode(imgs[i], 50, 0)[1]) for i in (0, 63, n // 2 + 5, n - 1))
+    assert ok == 4 and all(o is not None for o in outs)
+    px = n * 256 * 256
+    return {"api": "zw_multi_encode (one process, one host thread + context per GPU, no collective)", "n_gpus": n_dev, "images": n,
+            "e2e_ms": 1e3 * dt, "e2e_mpix_s": px / dt / 1e6, "per_gpu_kernel_ms": [t["device_total_ms"] for t in tm],
+            "parity": {"checked": 4, "identical": ok}}
 
 
 def main():
@@ -147,9 +313,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU (default: the BASELINE config)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end leg (BatchPipeline depth)")
-    ap.add_argument("--check", type=int, default=8, help="images per step byte-compared with the oracle after timing")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-photo", action="store_true", help="skip the photo workload")
+    ap.add_argument("--no-other", action="store_true", help="skip other_configs")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end leg (pipeline slots of the context)")
+    ap.add_argument("--check", type=int, default=16, help="synthetic images per step byte-compared with the oracle after timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -170,16 +338,12 @@ def main():
     import image_webp_b200 as Z
     from image_webp_b200 import synth
     n = args.batch
-    # distinct content per rank; pinned host staging (the e2e leg copies from here every step)
-    host = torch.empty((n, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    base = synth.batch_photo_like(n, W, H, seed0=1000 * rank)
-    host.numpy()[...] = base
-    del base
-    imgs = [host.numpy()[i] for i in range(n)]
     params = Z.EncoderParams.lossy(QUALITY)
     params.method = METHOD
-    ctx = Z.Context(dev)
+    ctx = Z.Context(dev)                      # kernel-only leg (split API, lane 0)
+    pipe = Z.BatchPipeline(dev, depth=args.depth)  # end-to-end leg: ONE context, `depth` batches in flight
     pix = n * W * H
+    cores = os.cpu_count() or 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -187,120 +351,96 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- kernel-only: inputs resident in HBM -------------------------------------------------
-    ctx.stage(imgs)
-    for _ in range(args.warmup):
-        ctx.encode_resident(params)
-    sampler = ClockSampler(dev)
-    barrier()
-    sampler.start()
-    stage_ms = {}
-    dev_ms = 0.0
-    launches = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        t = ctx.encode_resident(params)
-        dev_ms += t["device_total_ms"]
-        launches += t["kernel_launches"]
-        for k in ("yuv_ms", "analysis_ms", "pass1_ms", "chroma1_ms", "stats_ms", "chroma2_ms", "pass2_ms", "token_ms", "boolcode_ms", "assemble_ms"):
-            stage_ms[k] = stage_ms.get(k, 0.0) + t[k]
-    barrier()
-    wall_kernel_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-    outs_resident, _ = ctx.download()
-
-    # ---- end to end: host buffers in, .webp bytes out ------------------------------------------
-    # (a) one call at a time through Context.encode_batch (zw_encode_webp_batch)
-    for _ in range(2):
-        ctx.encode_batch(imgs, params)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        outs, t = ctx.encode_batch(imgs, params)
-    barrier()
-    e2e_serial_s = time.perf_counter() - t0
-    # (b) the streaming entry point (BatchPipeline, args.depth contexts / host threads): every step still
-    #     copies its inputs H2D and its .webp bytes D2H, but under the kernels of the neighbouring step
-    pipe = Z.BatchPipeline(dev, depth=args.depth)
-    for f in [pipe.submit(imgs, params) for _ in range(args.depth)]:
-        f.result()
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    futs = [pipe.submit(imgs, params) for _ in range(args.steps)]
-    for f in futs:
-        outs, t = f.result()
-        h2d += t["h2d_bytes"]; d2h += t["d2h_bytes"]
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    pipe.close()
-
+    # ---- synthetic workload (the BASELINE config): distinct content per rank, pinned host staging ------------
+    host = pinned_batch(torch, synth.batch_photo_like(n, W, H, seed0=1000 * rank))
+    imgs = [host.numpy()[i] for i in range(n)]
+    R = run_workload(Z, torch, ctx, pipe, imgs, params, args.steps, args.warmup, barrier, ClockSampler(dev))
     int_peak = ctx.measure_int_peak()  # thread-level integer instructions / s (microbenchmark, outside the timed regions)
 
-    # ---- parity spot check (after the timed regions) -----------------------------------------
     parity = None
     if rank == 0 and args.check > 0:
         import oracle_lib as O
-        ok = 0
         idx = list(range(0, n, max(1, n // args.check)))[:args.check]
-        for i in idx:
-            rc, ref, _ = O.encode(imgs[i], QUALITY, METHOD)
-            ok += int(rc == 0 and outs[i] == ref and outs_resident[i] == ref)
-        parity = {"checked": len(idx), "identical": ok}
+        ref = O.encode_batch_mt(host.numpy()[idx], QUALITY, METHOD)
+        ok = sum(int(R["outs"][i] == r and R["outs_resident"][i] == r and R["outs_call"][i] == r) for i, r in zip(idx, ref))
+        parity = {"checked": len(idx), "identical": ok, "against": "CPU port (oracle/), three GPU entry points each"}
         assert ok == len(idx), "GPU output differs from the oracle"
+    bytes_per_px = sum(len(o) for o in R["outs"]) / pix
 
-    # ---- reduce over ranks: max time ------------------------------------------------------------
-    times = torch.tensor([dev_ms / 1e3, e2e_s, wall_kernel_s, e2e_serial_s], dtype=torch.float64, device="cuda")
+    # ---- photo workload: 1024 distinct crops of real photographs, every output checked ---------------------------
+    P = None
+    photo_host = None
+    if not args.no_photo:
+        import photo_inputs as PI
+        photo_host = torch.empty((n, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        PI.batch(n, W, H, out=photo_host.numpy(), first=(n * rank) % 1024)
+        pimgs = [photo_host.numpy()[i] for i in range(n)]
+        P = run_workload(Z, torch, ctx, pipe, pimgs, params, args.steps, args.warmup, barrier)
+
+    # ---- reduce over ranks: max time -------------------------------------------------------------------------
+    tl = [R["dev_s"], R["e2e_s"], R["wall_kernel_s"], R["e2e_call_s"]] + ([P["dev_s"], P["e2e_s"], P["e2e_call_s"]] if P else [0, 0, 0])
+    times = torch.tensor(tl, dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s, wall_kernel_s, e2e_serial_s = [float(x) for x in times.tolist()]
+    dev_s, e2e_s, wall_kernel_s, e2e_call_s, p_dev_s, p_e2e_s, p_call_s = [float(x) for x in times.tolist()]
     total_pix = pix * world * args.steps
     value = total_pix / dev_s / 1e6
     e2e_value = total_pix / e2e_s / 1e6
 
     if rank == 0:
         peaks, how = measured_peaks()
-        dom = max(("pass1_ms", "pass2_ms", "boolcode_ms", "token_ms", "stats_ms", "yuv_ms", "analysis_ms"), key=lambda k: stage_ms[k])
-        dom_s = stage_ms["pass2_ms"] / args.steps / 1e3   # k_search<2> alone (CUDA events around that launch)
-        achieved = pix * SEARCH_BYTES_PER_PX / dom_s / 1e9
+        stage_ms = R["stage_ms"]
+        dom = max(STAGES, key=lambda k: stage_ms[k])
+        p2_s = stage_ms["pass2_ms"] / args.steps / 1e3   # k_search<2> alone (CUDA events around that launch)
+        p1_s = stage_ms["pass1_ms"] / args.steps / 1e3
         yuv_s = stage_ms["yuv_ms"] / args.steps / 1e3
-        traffic = traffic_yuv = None
-        try:  # DRAM bytes per pixel from the committed ncu --set full capture (profiles/r1_traffic.json)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
-            for kname, v in tj.items():
-                if "k_search<2>" in kname or "k_search<(int)2>" in kname:
-                    traffic = v["dram_bytes_per_pixel"] * pix
-                if "k_yuv" in kname:
-                    traffic_yuv = v["dram_bytes_per_pixel"] * pix
+        prof = {}
+        try:  # figures of the committed ncu --set full capture of this round (tools/ncu_summary.py)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         except Exception:
-            pass
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            except Exception:
+                prof = {}
+
+        def prof_of(sub):
+            for kname, v in prof.get("kernels", {}).items():
+                if sub in kname:
+                    return v
+            return {}
+        ps2, pyuv = prof_of("k_search<(int)2>") or prof_of("k_search<2>"), prof_of("k_yuv")
+        traffic = ps2.get("dram_bytes_per_pixel", 0) * pix or None
+        traffic_yuv = pyuv.get("dram_bytes_per_pixel", 0) * pix or None
         line = {
-            "metric": "lossy encode MPix/s (q75 m4, byte-identical)", "value": value, "unit": "MPix/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": WORKLOAD % n, "images_per_gpu": n, "quality": QUALITY, "method": METHOD,
-                       "l2": "inputs (%.2f GB per step) larger than L2" % (n * W * H * 3 / 1e9), "timing": "cuda events on the library stream, max over ranks"},
-            "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "BatchPipeline(depth=%d).submit -> zw_encode_webp_batch, pinned host RGB in, .webp bytes out" % args.depth,
-                    "one_call_at_a_time": {"value": total_pix / e2e_serial_s / 1e6, "ms_per_step": 1e3 * e2e_serial_s / args.steps,
-                                           "api": "Context.encode_batch -> zw_encode_webp_batch"}},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_search<2> (pass-2 mode search + transform)", "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                         "peak_source": how, "ms_per_launch": 1e3 * dom_s,
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md and profiles/ for the ALU pipe figures"},
-            "roofline_yuv": {"bound": "hbm", "kernel": "k_yuv", "achieved": pix * 4.5 / yuv_s / 1e9, "peak": peaks["hbm_gbs"],
-                             "unit": "GB/s", "frac": pix * 4.5 / yuv_s / 1e9 / peaks["hbm_gbs"], "ms_per_launch": 1e3 * yuv_s, "traffic": traffic_yuv},
+                       "l2": "inputs (%.2f GB per step) larger than L2" % (n * W * H * 3 / 1e9), "timing": "cuda events on the library stream, max over ranks",
+                       "byte_identical_to": "the CPU port of the reference (oracle/); the Rust reference itself cannot be run here"},
+            "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": R["h2d"] // args.steps, "d2h_bytes_per_step": R["d2h"] // args.steps,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "frac_of_kernel_only": e2e_value / value,
+                    "api": "zw_submit / zw_wait / zw_release on one context, %d batches in flight (BatchPipeline): pinned host RGB in, .webp bytes out" % args.depth,
+                    "h2d_gb_s": R["h2d"] / args.steps / max(R["h2d_ms"], 1e-6) / 1e6,
+                    "one_call_at_a_time": {"value": total_pix / e2e_call_s / 1e6, "ms_per_step": 1e3 * e2e_call_s / args.steps,
+                                           "api": "zw_encode_webp_batch, one blocking call per step (chunks pipelined inside the call)"}},
+            "gpu_launches": R["launches"] + (P["launches"] if P else 0),
+            "clocks": R["clocks"],
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "dominant_stage": dom,
+            "symbols_per_px": R["symbols"] / pix, "bytes_per_px": bytes_per_px,
             "kernel_wall_ms_per_step": 1e3 * wall_kernel_s / args.steps,
             "parity": parity,
         }
-        # Integer roofline of the mode search (north_star: "ALU/IMAD pipe utilisation against the sm_100a integer issue
-        # peak"): algorithmic int-ops = primitive invocations counted by the instrumented oracle on sample images of this
-        # workload x fixed per-primitive costs (tests/oracle_lib.py OP_COST), per pass and plane.
+        # Rooflines.  The dominant kernel (k_search<2>, the pass-2 luma mode search) is bound by the integer issue rate,
+        # not by HBM: `roofline` is its integer figure -- algorithmic int-ops = primitive invocations counted by the
+        # instrumented oracle on sample images of this workload x fixed per-primitive costs (tests/oracle_lib.py OP_COST,
+        # SURVEY.md 8(d)) against the integer issue peak measured in this run (zw_measure_int_peak).  The HBM view the
+        # contract defines is kept beside it as roofline_hbm; roofline_yuv is the one HBM-bound stage.
+        hbm = {"bound": "hbm", "kernel": "k_search<2> (pass-2 mode search + transform)", "achieved": pix * SEARCH_BYTES_PER_PX / p2_s / 1e9,
+               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pix * SEARCH_BYTES_PER_PX / p2_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+               "traffic_source": "profiles/ (committed ncu --set full capture, per launch)", "peak_source": how, "ms_per_launch": 1e3 * p2_s,
+               "note": "this kernel is integer-issue bound: see `roofline`"}
         try:
             import oracle_lib as O
             ops = {}
@@ -309,34 +449,71 @@ def main():
                 _, o = O.count_ops(imgs[i * (n // n_s)], QUALITY, METHOD)
                 for k, v in o.items():
                     ops[k] = ops.get(k, 0.0) + v / (n_s * W * H)
-            p2_s = stage_ms["pass2_ms"] / args.steps / 1e3
-            p1_s = stage_ms["pass1_ms"] / args.steps / 1e3
             all_s = dev_s / args.steps
-            line["roofline_int"] = {
-                "bound": "int-issue", "unit": "Tint-op/s", "peak": int_peak / 1e12, "peak_source": "zw_measure_int_peak (IMAD + LOP3/IADD3 chains, this run)",
+            line["roofline"] = {
+                "bound": "int-issue", "kernel": "k_search<2> (pass-2 luma mode search + final transform + trellis)", "unit": "Tint-op/s",
+                "achieved": ops["pass2_luma"] * pix / p2_s / 1e12, "peak": int_peak / 1e12, "frac": ops["pass2_luma"] * pix / p2_s / int_peak,
+                "traffic": traffic, "ms_per_launch": 1e3 * p2_s,
+                "peak_source": "zw_measure_int_peak in this run (IMAD + LOP3/IADD3 chains at full occupancy); MEASURED_PEAKS.json has no integer peak",
                 "ops_per_px": ops,
-                "kernel": "k_search<2> (pass-2 luma)", "achieved": ops["pass2_luma"] * pix / p2_s / 1e12,
-                "frac": ops["pass2_luma"] * pix / p2_s / int_peak,
-                "pass1_luma": {"achieved": ops["pass1_luma"] * pix / p1_s / 1e12, "frac": ops["pass1_luma"] * pix / p1_s / int_peak},
+                "ncu": {k: ps2.get(k) for k in ("alu_pipe_pct", "fma_pipe_pct", "issue_slots_busy_pct", "warp_instructions", "threads_per_instruction") if k in ps2},
+                "pass1_luma": {"kernel": "k_search<1>", "achieved": ops["pass1_luma"] * pix / p1_s / 1e12, "frac": ops["pass1_luma"] * pix / p1_s / int_peak,
+                               "ms_per_launch": 1e3 * p1_s},
                 "whole_step": {"achieved": sum(ops.values()) * pix / all_s / 1e12, "frac": sum(ops.values()) * pix / all_s / int_peak},
-                "note": "1 algorithmic op counted as 1 instruction slot; sample = %d images of the batch" % n_s}
-        except Exception as e:  # the figure is informative; never fail the bench on it
-            line["roofline_int"] = {"error": str(e)}
+                "note": "1 algorithmic op counted as 1 thread-instruction slot; ops counted by the oracle on %d images of the batch" % n_s}
+        except Exception as e:  # never fail the bench on the informative figure
+            line["roofline"] = dict(hbm, error="int-op count failed: %s" % e)
+        line["roofline_hbm"] = hbm
+        line["roofline_yuv"] = {"bound": "hbm", "kernel": "k_yuv", "achieved": pix * 4.5 / yuv_s / 1e9, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": pix * 4.5 / yuv_s / 1e9 / peaks["hbm_gbs"], "ms_per_launch": 1e3 * yuv_s, "traffic": traffic_yuv}
+        lib = None
         if not args.no_cpu and world == 1:
             lib = native_oracle()
-            cores = os.cpu_count() or 1
             ns = max(cores * 32, 256)  # ~5-10 s of all-core CPU work
-            sample = host.numpy()[:ns]
-            cpu_run(sample[:cores], cores, lib)
-            ts = cpu_run(sample, cores, lib)
-            t1 = cpu_run(sample[:4], 1, lib)
-            line["cpu_baseline"] = {"value": ns * W * H / ts / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
-                                    "single_thread_mpix_s": 4 * W * H / t1 / 1e6,
-                                    "sample": "%d of the %d images, one image per thread on %d threads (oracle -O3 -march=native)" % (ns, n, cores)}
+            line["cpu_baseline"] = cpu_baseline(host.numpy()[:ns], lib, cores, "of the %d synthetic images (oracle -O3 -march=native)" % n)
+        if P:
+            p_total = pix * world * args.steps
+            photo = {"workload": "%d distinct 768x512 crops of the reference's test photographs (tests/golden/photos), q75 m4" % n,
+                     "value": p_total / p_dev_s / 1e6, "ms_per_step": 1e3 * p_dev_s / args.steps,
+                     "e2e": {"value": p_total / p_e2e_s / 1e6, "ms_per_step": 1e3 * p_e2e_s / args.steps, "h2d_bytes_per_step": P["h2d"] // args.steps,
+                             "d2h_bytes_per_step": P["d2h"] // args.steps, "frac_of_kernel_only": (p_total / p_e2e_s) / (p_total / p_dev_s),
+                             "one_call_at_a_time": {"value": p_total / p_call_s / 1e6, "ms_per_step": 1e3 * p_call_s / args.steps}},
+                     "stage_ms": {k: v / args.steps for k, v in P["stage_ms"].items()},
+                     "symbols_per_px": P["symbols"] / pix, "bytes_per_px": sum(len(o) for o in P["outs"]) / pix}
+            be = sum(P["stage_ms"][k] for k in ("token_ms", "boolcode_ms", "assemble_ms")) + 0.0
+            photo["back_end_share"] = be / sum(P["stage_ms"].values())
+            # EVERY image of the batch against the multi-threaded oracle (after the timed regions)
+            import oracle_lib as O
+            t0 = time.perf_counter()
+            ref = O.encode_batch_mt(photo_host.numpy(), QUALITY, METHOD, threads=cores, L=lib)
+            dt = time.perf_counter() - t0
+            bad = [i for i in range(n) if not (P["outs"][i] == ref[i] and P["outs_resident"][i] == ref[i] and P["outs_call"][i] == ref[i])]
+            photo["parity"] = {"checked": n, "identical": n - len(bad), "against": "CPU port (oracle/), every image, three GPU entry points each"}
+            photo["cpu_baseline"] = {"value": n * W * H / dt / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
+                                     "sample": "all %d photo crops, one image per thread on %d threads (incl. copying the files out)" % (n, cores)}
+            line["photo"] = photo
+            assert not bad, "photo workload: images %s differ from the oracle" % bad[:8]
+        if not args.no_other and world == 1:
+            try:
+                line["other_configs"] = other_configs(Z, torch, ctx, pipe, lib or native_oracle(), cores, world)
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["other_configs"] = {"error": str(e)}
+        if not args.no_other:
+            try:
+                nd = torch.cuda.device_count() if world == 1 else world
+                nd = min(nd, args.gpus) if args.gpus > 0 else nd
+                line["config5_multi"] = config5_multi(Z, torch, max(1, nd))
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["config5_multi"] = {"error": str(e)}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    pipe.close()
     ctx.close()
     return 0
 

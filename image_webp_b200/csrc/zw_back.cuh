@@ -9,10 +9,11 @@
 //   encode_compressed_frame_header vp8.rs:332-372 (+ :393-496) (frame_header_tokens)
 //   write_macroblock_header vp8.rs:498-560                     (mb_header_tokens)
 //   encode_residual_data / encode_coefficients vp8.rs:650-958  (block_tokens)
-//   ArithmeticEncoder       src/encoder/arithmetic.rs:7-196    (k_boolcode)
+//   ArithmeticEncoder       src/encoder/arithmetic.rs:7-196    (k_bc_*)
 //   write_uncompressed_frame_header / write_partitions vp8.rs:315-330, :374-391 (k_assemble)
 #ifndef ZW_BACK_CUH
 #define ZW_BACK_CUH
+#include "zw_boolcoder.cuh"
 #include "zw_search.cuh"
 
 namespace zw {
@@ -550,65 +551,80 @@ __global__ void __launch_bounds__(256) k_tokscan(ChunkParams P) {
 }
 
 // Chunk-wide placement of the variable-size data (one CTA): exclusive scans over the images of the symbol counts
-// (8-token aligned) and of the partition capacities (7 bits per symbol bound + 16, 16-byte aligned pairs), checked
-// against the arenas the host allocated before it knew the counts.
+// (8-token aligned), of the partition capacities (7 bits per symbol bound + 16, 16-byte aligned pairs) and of the
+// boolean-coder segment counts, checked against the arenas the host allocated before it knew the counts.
 __global__ void __launch_bounds__(1024) k_layout(ChunkParams P) {
-  __shared__ u64 s_h[32], s_t[32], s_p[32];
-  __shared__ u64 s_base[3];
+  constexpr int NQ = 5;  // scanned quantities: hdr tokens, tok tokens, partition bytes, tok segments, hdr segments
+  __shared__ u64 s_w[NQ][32];
+  __shared__ u64 s_base[NQ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < 3) s_base[threadIdx.x] = 0;
+  if (threadIdx.x < NQ) s_base[threadIdx.x] = 0;
   __syncthreads();
   for (u32 i0 = 0; i0 < P.n_img; i0 += blockDim.x) {
     const u32 i = i0 + threadIdx.x;
-    u64 h = 0, t = 0, pb = 0;
+    u64 v[NQ] = {0, 0, 0, 0, 0}, inc[NQ];
     u32 c0 = 0, c1 = 0;
     if (i < P.n_img) {
       const ImageState& IS = P.st[i];
-      h = ((u64)IS.hdr_tokens + 7) & ~7ull;
-      t = ((u64)IS.tok_tokens + 7) & ~7ull;
+      v[0] = ((u64)IS.hdr_tokens + 7) & ~7ull;
+      v[1] = ((u64)IS.tok_tokens + 7) & ~7ull;
       c0 = (u32)(((u64)IS.hdr_tokens * 7) / 8 + 16);
       c1 = (u32)(((u64)IS.tok_tokens * 7) / 8 + 16);
-      pb = ((u64)c0 + c1 + 15) & ~15ull;
+      v[2] = ((u64)c0 + c1 + 15) & ~15ull;
+      v[3] = bc_segments(IS.tok_tokens);
+      v[4] = bc_segments(IS.hdr_tokens);
     }
-    u64 ih = h, it = t, ip = pb;  // inclusive scans inside the warp
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u64 a = (u64)shfl_up64_full((i64)ih, o), b = (u64)shfl_up64_full((i64)it, o), c = (u64)shfl_up64_full((i64)ip, o);
-      if (lane >= o) { ih += a; it += b; ip += c; }
-    }
-    if (lane == 31) { s_h[warp] = ih; s_t[warp] = it; s_p[warp] = ip; }
-    __syncthreads();
-    if (warp == 0) {
-      u64 a = s_h[lane], b = s_t[lane], c = s_p[lane];
-      const u64 a0 = a, b0 = b, c0w = c;
+    for (int q = 0; q < NQ; q++) {  // inclusive scans inside the warp
+      u64 x = v[q];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const u64 x = (u64)shfl_up64_full((i64)a, o), y = (u64)shfl_up64_full((i64)b, o), z = (u64)shfl_up64_full((i64)c, o);
-        if (lane >= o) { a += x; b += y; c += z; }
+        const u64 y = (u64)shfl_up64_full((i64)x, o);
+        if (lane >= o) x += y;
       }
-      s_h[lane] = a - a0; s_t[lane] = b - b0; s_p[lane] = c - c0w;  // exclusive warp offsets
+      inc[q] = x;
+      if (lane == 31) s_w[q][warp] = x;
     }
     __syncthreads();
+    if (warp < NQ) {  // warp q scans the 32 warp totals of quantity q (exclusive)
+      const u64 w0 = s_w[warp][lane];
+      u64 x = w0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 y = (u64)shfl_up64_full((i64)x, o);
+        if (lane >= o) x += y;
+      }
+      s_w[warp][lane] = x - w0;
+    }
+    __syncthreads();
+    u64 ex[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) ex[q] = s_base[q] + s_w[q][warp] + inc[q] - v[q];
     if (i < P.n_img) {
       ImageLayout L;
-      L.hdr_off = s_base[0] + s_h[warp] + ih - h;
-      L.tok_off = s_base[1] + s_t[warp] + it - t;
-      L.part_off = s_base[2] + s_p[warp] + ip - pb;
+      L.hdr_off = ex[0]; L.tok_off = ex[1]; L.part_off = ex[2];
       L.out_off = 0;
       L.p0_cap = c0; L.p1_cap = c1;
       P.lay[i] = L;
+      P.seg_off[i] = (u32)ex[3];            // token-partition streams first ...
+      P.seg_off[P.n_img + i] = (u32)ex[4];  // ... first partitions after them (offset added below)
     }
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) {  // last thread holds the block totals of this step
-      s_base[0] += s_h[warp] + ih; s_base[1] += s_t[warp] + it; s_base[2] += s_p[warp] + ip;
+    if (threadIdx.x == blockDim.x - 1) {  // the last thread holds the totals of this step
+#pragma unroll
+      for (int q = 0; q < NQ; q++) s_base[q] = ex[q] + v[q];
     }
     __syncthreads();
   }
+  const u32 tseg = (u32)s_base[3], hseg = (u32)s_base[4];
+  for (u32 i = threadIdx.x; i < P.n_img; i += blockDim.x) P.seg_off[P.n_img + i] += tseg;
   if (threadIdx.x == 0) {
+    P.seg_off[2 * P.n_img] = tseg + hseg;
     ChunkTotals T;
     T.hdr_tokens = s_base[0]; T.tok_tokens = s_base[1]; T.part_bytes = s_base[2]; T.out_bytes = 0;
-    T.overflow = (T.hdr_tokens > P.cap_hdr_tokens || T.tok_tokens > P.cap_tok_tokens || T.part_bytes > P.cap_part_bytes) ? 1u : 0u;
-    T.pad = 0;
+    T.overflow = (T.hdr_tokens > P.cap_hdr_tokens || T.tok_tokens > P.cap_tok_tokens || T.part_bytes > P.cap_part_bytes ||
+                  (u64)tseg + hseg > P.cap_segments) ? 1u : 0u;
+    T.segments = tseg + hseg;
     *P.tot = T;
   }
 }
@@ -623,184 +639,207 @@ __global__ void k_frame_header(ChunkParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// (5b) Boolean entropy coder: one lane per (image, partition) stream.
-//      Streams 0..n_img-1 are the token partitions, n_img..2n_img-1 the first partitions, so the
-//      lanes of a warp carry streams of similar length.
-// ---------------------------------------------------------------------------------------------
-// add_one_to_output (arithmetic.rs:47-60): ripple a carry through trailing 0xFF bytes.
-__device__ __forceinline__ void bool_carry(u8* out, u32 pos, u32 cap) {
-  u32 j = pos < cap ? pos : cap;
-  while (j > 0) {
-    j--;
-    if (out[j] < 255) { out[j]++; break; }
-    out[j] = 0;
-  }
-}
-
-// One WARP per (image, partition) stream.  Streams 0..n_img-1 are the token partitions,
-// n_img..2n_img-1 the first partitions.
+// (5b) Boolean entropy coder (ArithmeticEncoder, arithmetic.rs:7-196), segment-parallel and exact.
 //
-// The coder is split into its strictly serial part and a parallel part.  write_bool
-// (arithmetic.rs:67-95) does, per symbol, `bottom += bit ? split : 0; bottom <<= s` with
-// split = 1 + (((range - 1) * prob) >> 8) and s = the renormalisation shift of the new range:
-//   * (range, split, s) depend only on the previous range and the symbol -- a short dependent
-//     chain (multiply, shift, select, count-leading-zeros, shift) that all lanes run in lock step
-//     over the 32 symbols the warp fetched with one coalesced load;
-//   * `bottom` with its carries is a long binary number: symbol k contributes its 8-bit `split`
-//     with the most significant bit at stream bit P_k = s_0 + .. + s_(k-1) (byte 0 = stream bits
-//     0..7: the initial bit_num = 24 aligns the first addend with the first byte).  Lane k adds its
-//     symbol's contribution into a shared-memory window of 16-bit cells, the cells are carry-
-//     normalised with a ballot-based carry look-ahead, completed cells are flushed as bytes and the
-//     window slides.  A carry out of the window ripples into bytes already written exactly like
-//     add_one_to_output (arithmetic.rs:47-60).
-// The flush (arithmetic.rs:176-195) emits the pending bits and pads to pos + 4 bytes, where
-// pos = 0 if T < 24 else 1 + (T - 24) / 8 for T total shifts: the first pos + 4 bytes of the number.
-// Two warps per stream, software-pipelined over the groups of 32 symbols: the CHAIN warp runs the range
-// recurrence of group g + 1 (parking the range every symbol starts from in a double-buffered shared
-// slot) while the SUM warp does the parallel part of group g; one named barrier per group and pair.
-constexpr int BC_STREAMS = 2;            // streams per CTA
-constexpr int BC_WARPS = 2 * BC_STREAMS;  // warp 2s: chain, warp 2s + 1: sum
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-__global__ void __launch_bounds__(BC_WARPS * 32) k_boolcode(ChunkParams P) {
-  __shared__ u32 s_cells[BC_STREAMS][32];
-  __shared__ u32 s_range[BC_STREAMS][2][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1;
-  const bool chain_warp = (warp & 1) == 0;
-  const u32 sid = blockIdx.x * BC_STREAMS + pair;
-  if (sid >= 2 * P.n_img || P.tot->overflow) return;  // both warps of a pair leave together
-  const bool is_hdr = sid >= P.n_img;
-  const u32 img = is_hdr ? sid - P.n_img : sid;
-  const ImageLayout d = P.lay[img];
-  ImageState& IS = P.st[img];
-  const Token* tk = is_hdr ? P.hdr_tokens + d.hdr_off : P.tok_tokens + d.tok_off;
-  const u32 n = is_hdr ? IS.hdr_tokens : IS.tok_tokens;
-  const u32 groups = (n + 31) / 32;
-  if (chain_warp) {
-    // ---- serial part: the range recurrence; lane 0 parks range - 1 of every symbol ----
-    u32 rm1 = 254;  // range - 1, uniform across the warp (the recurrence is shortest in this form)
-    u32 mine = lane < n ? tk[lane] : 0;
-    for (u32 g = 0; g <= groups; g++) {
-      if (g < groups) {
-        const u32 i0 = g * 32;
-        const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;  // prefetch the next 32 symbols
-        const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
-        const u32 mine24 = ((mine & 255u) << 24) | (mine >> 8);  // prob in the top byte, bit in bit 0
-        u32* rsave = s_range[pair][g & 1];
-        if (cnt == 32) {
+// write_bool is a serial recurrence per stream, but its two halves separate:
+//   * the RANGE after a symbol depends only on the range before it and the symbol; renormalised it takes one of
+//     128 values (range - 1 in [127, 254]);
+//   * `bottom` with its carries is a sum: symbol k adds its 8-bit split at stream bit P_k = s_0 + .. + s_(k-1)
+//     (s = renormalisation shifts).  Sums can be formed piecewise and added up afterwards.
+// So a stream is cut into segments of BC_SEG symbols and every segment is coded by ONE LANE with the
+// reference's own serial algorithm, all segments of all streams of the batch in parallel, once each segment knows
+// the range it starts with and its start bit:
+//   k_bc_cands   which range states can a segment possibly start in?  All 128 states are run through the BC_WARM
+//                symbols before the segment start; the state map is many-to-one, so a handful (1..6) survive.
+//   k_bc_trans   per segment and surviving start state: end state and total shift of the segment (one lane each).
+//   k_bc_resolve per stream: walk the segments, picking the transition of the state actually reached -> start state
+//                and start bit of every segment.  (The true state at the warm-up start is one of the 128, so the
+//                true segment start state is always among the candidates: no speculation, no fallback.)
+//   k_bc_code    one lane per segment: the reference's write_bool from (state, bottom = 0, bit position), bytes
+//                written straight to their final place; what is still pending in `bottom` at the segment end
+//                (the tail) and carries that leave the segment's own bytes are recorded.
+//   k_bc_fix     per stream: add every tail to the bytes that follow it, ripple the recorded carries
+//                (add_one_to_output, arithmetic.rs:47-60), set the partition sizes.
+// Round 1 ran one warp PAIR per stream with all 32 lanes of the chain warp on the same recurrence: 47 ms for the
+// 1024-photo batch (2.4 symbols per pixel), bound by the per-symbol latency of ~1000 concurrent chains.
+// ---------------------------------------------------------------------------------------------
+struct BcStream {
+  const Token* tk;
+  u32 n;     // symbols
+  u8* out;   // coded partition
+  u32 cap;
+  u32 img;
+  bool is_hdr;
+};
+__device__ __forceinline__ BcStream bc_stream(const ChunkParams& P, u32 sid) {
+  BcStream S;
+  S.is_hdr = sid >= P.n_img;
+  S.img = S.is_hdr ? sid - P.n_img : sid;
+  const ImageLayout L = P.lay[S.img];
+  const ImageState& IS = P.st[S.img];
+  S.tk = S.is_hdr ? P.hdr_tokens + L.hdr_off : P.tok_tokens + L.tok_off;
+  S.n = S.is_hdr ? IS.hdr_tokens : IS.tok_tokens;
+  S.out = P.part_bytes + L.part_off + (S.is_hdr ? 0 : L.p0_cap);  // partition scratch: [first | token]
+  S.cap = S.is_hdr ? L.p0_cap : L.p1_cap;
+  return S;
+}
+// global segment index -> (stream, segment within the stream)
+__device__ __forceinline__ void bc_locate(const ChunkParams& P, u32 g, u32& sid, u32& j) {
+  u32 lo = 0, hi = 2 * P.n_img;  // seg_off[lo] <= g < seg_off[hi]
+  while (hi - lo > 1) {
+    const u32 mid = (lo + hi) >> 1;
+    if (P.seg_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  sid = lo;
+  j = g - P.seg_off[lo];
+}
+constexpr int BC_CAND_FIRST = 64;  // symbols all 128 states are run through before the survivors move into one warp
+__global__ void __launch_bounds__(128) k_bc_cands(ChunkParams P) {
+  if (P.tot->overflow) return;
+  __shared__ u32 s_map[4];
+  const u32 total = P.seg_off[2 * P.n_img];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (u32 g = blockIdx.x; g < total; g += gridDim.x) {
+    u32 sid, j;
+    bc_locate(P, g, sid, j);
+    if (j == 0) {  // a stream starts with range 255
+      if (tid < 4) P.seg[g].cand[tid] = tid == 3 ? 0x80000000u : 0u;
+      continue;
+    }
+    const BcStream S = bc_stream(P, sid);
+    const Token* tk = S.tk + (size_t)j * BC_SEG - BC_WARM;  // 16-byte aligned: stream starts and BC_SEG, BC_WARM are multiples of 8 tokens
+    u32 st = 127u + (u32)tid, add, sh;
+    auto run = [&](u32 from, u32 to) {
+      for (u32 i = from; i < to; i += 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));  // the same address in every lane: one broadcast
 #pragma unroll
-          for (int k = 0; k < 32; k++) {
-            const u32 t = __shfl_sync(FULL, mine24, k);
-            if (lane == 0) rsave[k] = rm1;
-            const u32 x = __umulhi(rm1, t & 0xff000000u);  // ((range - 1) * prob) >> 8 = split - 1
-            const u32 r2 = (t & 1) ? rm1 - x : x + 1;
-            const u32 r2m1 = (t & 1) ? rm1 - x - 1 : x;
-            rm1 = __funnelshift_l(0xffffffffu, r2m1, __clz(r2) - 24);  // (r2 << s) - 1
-          }
-        } else {
-#pragma unroll 1
-          for (int k = 0; k < cnt; k++) {
-            const u32 t = __shfl_sync(FULL, mine24, k);
-            if (lane == 0) rsave[k] = rm1;
-            const u32 x = __umulhi(rm1, t & 0xff000000u);
-            const u32 r2 = (t & 1) ? rm1 - x : x + 1;
-            const u32 r2m1 = (t & 1) ? rm1 - x - 1 : x;
-            rm1 = __funnelshift_l(0xffffffffu, r2m1, __clz(r2) - 24);
-          }
-        }
-        mine = nxt;
+        for (int e = 0; e < 8; e++) st = bc_step(st, bc_sym8(q.x, q.y, q.z, q.w, e), add, sh);
       }
-      pair_barrier(1 + pair);  // barrier g: slot g & 1 is complete and slot (g + 1) & 1 has been consumed
+    };
+    run(0, BC_CAND_FIRST);
+    if (tid < 4) s_map[tid] = 0;
+    __syncthreads();
+    atomicOr(&s_map[(st - 127u) >> 5], 1u << ((st - 127u) & 31u));
+    __syncthreads();
+    const u32 m0 = s_map[0], m1 = s_map[1], m2 = s_map[2], m3 = s_map[3];
+    const u32 k = (u32)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
+    const bool narrow = k <= 32;  // the survivors fit one warp (always, on real streams): three warps retire
+    if (narrow) {
+      if (warp == 0) {
+        st = 127u + bc_nth_bit(m0, m1, m2, m3, (u32)tid < k ? (u32)tid : 0u);
+        run(BC_CAND_FIRST, BC_WARM);
+      }
+    } else {
+      run(BC_CAND_FIRST, BC_WARM);
     }
-    return;
-  }
-  // ---- SUM warp: the parallel part, one group behind the chain ----
-  u8* out = P.part_bytes + d.part_off + (is_hdr ? 0 : d.p0_cap);  // partition scratch: [first | token]
-  const u32 cap = is_hdr ? d.p0_cap : d.p1_cap;
-  u32* cells = s_cells[pair];
-  cells[lane] = 0;
-  __syncwarp();
-  u32 T = 0;        // total renormalisation shifts so far == stream bit of the next addend's MSB
-  u32 base = 0;     // stream bit of cell 0 (multiple of 16); base / 8 bytes are already written
-  bool overflow = false;
-  u32 mine = lane < n ? tk[lane] : 0;
-  for (u32 g = 0; g <= groups; g++) {
-    pair_barrier(1 + pair);  // barrier g: slot g & 1 is complete; the chain now fills slot (g + 1) & 1
-    if (g == groups) break;  // the chain's last barrier
-    const u32 i0 = g * 32;
-    const u32 nxt = (i0 + 32 + lane < n) ? tk[i0 + 32 + lane] : 0;
-    const int cnt = (int)(n - i0 < 32 ? n - i0 : 32);
-    const u32* rsave = s_range[pair][g & 1];
-    // lane k redoes symbol k from its parked range
-    u32 add = 0, sh = 0;
-    if (lane < cnt) {
-      const u32 r1 = rsave[lane];  // range - 1 this symbol starts from
-      const u32 x = (r1 * (mine & 255)) >> 8;
-      const bool bit = (mine >> 8) != 0;
-      const u32 r2 = bit ? r1 - x : x + 1;
-      add = bit ? x + 1 : 0;
-      sh = (u32)(__clz(r2) - 24);
-    }
-    u32 incl = sh;  // inclusive prefix sum of the shifts
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const u32 v = __shfl_up_sync(FULL, incl, dlt);
-      if (lane >= dlt) incl += v;
-    }
-    const u32 total = __shfl_sync(FULL, incl, 31);
-    if (add) {
-      const u32 o = T + incl - sh - base;  // window offset of the addend's MSB
-      const u32 c = o >> 4, b = o & 15;
-      const u32 f = add << (24 - b);       // two-cell field: cell c in the high half, c + 1 in the low half
-      atomicAdd(&cells[c], f >> 16);
-      if (f & 0xffffu) atomicAdd(&cells[c + 1], f & 0xffffu);
-    }
-    T += total;
-    __syncwarp();
-    // ---- carry normalisation: cell c keeps 16 bits, the excess moves to cell c - 1 ----
-    const u32 v = cells[lane];
-    const u32 from_next = __shfl_down_sync(FULL, v >> 16, 1);
-    const u32 v1 = (v & 0xffffu) + (lane < 31 ? from_next : 0u);  // <= 0xffff + 31
-    // look-ahead on the reversed cell order (bit i <-> cell 31 - i) so that carries move up
-    const u32 G = __brev(__ballot_sync(FULL, v1 > 0xffffu)), Pm = __brev(__ballot_sync(FULL, v1 == 0xffffu));
-    const u64 sum = (u64)Pm + ((u64)G << 1);
-    const u32 cin = ((u32)sum ^ Pm);  // carry into reversed position i
-    const u32 my_cin = (cin >> (31 - lane)) & 1;
-    const u32 fin = (v1 + my_cin) & 0xffffu;
-    // carry out of cell 0 (reversed position 31): generated there or propagated through it
-    u32 carry0 = (__shfl_sync(FULL, v, 0) >> 16) + (u32)((sum >> 32) & 1);
-    if (lane == 0) {
-      for (; carry0 > 0; carry0--) bool_carry(out, base >> 3, cap);
-    }
-    // ---- flush the cells no later symbol can reach (only carries can, through bool_carry) ----
-    const u32 nf = (T - base) >> 4;
-    if ((u32)lane < nf) {
-      const u32 bp = (base >> 3) + 2 * lane;
-      if (bp + 1 < cap) { out[bp] = (u8)(fin >> 8); out[bp + 1] = (u8)fin; } else overflow = true;
-    }
-    const u32 moved = __shfl_sync(FULL, fin, (lane + nf) & 31);
-    __syncwarp();
-    cells[lane] = (lane + nf < 32) ? moved : 0u;
-    base += 16 * nf;
-    __syncwarp();
-    mine = nxt;
-  }
-  // flush_and_get_buffer (arithmetic.rs:176-195): the first pos + 4 bytes of the number
-  const u32 pos = T < 24 ? 0u : 1u + (T - 24) / 8;
-  const u32 total_bytes = pos + 4;
-  {
-    const u32 fin = cells[lane];  // already normalised
-    const u32 bp = (base >> 3) + 2 * lane;
-    if (bp < total_bytes) { if (bp < cap) out[bp] = (u8)(fin >> 8); else overflow = true; }
-    if (bp + 1 < total_bytes) { if (bp + 1 < cap) out[bp + 1] = (u8)fin; else overflow = true; }
-  }
-  overflow = __any_sync(FULL, overflow);
-  if (lane == 0) {
-    if (is_hdr) IS.part0_bytes = total_bytes; else IS.part1_bytes = total_bytes;
-    if (overflow) IS.status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
+    __syncthreads();
+    if (tid < 4) s_map[tid] = 0;
+    __syncthreads();
+    if (!narrow || warp == 0) atomicOr(&s_map[(st - 127u) >> 5], 1u << ((st - 127u) & 31u));
+    __syncthreads();
+    if (tid < 4) P.seg[g].cand[tid] = s_map[tid];
+    __syncthreads();
   }
 }
 
+// Four lanes per segment: lane q of a group takes the candidate start states of rank q, q + 4, ...
+__global__ void __launch_bounds__(128) k_bc_trans(ChunkParams P) {
+  if (P.tot->overflow) return;
+  const u32 total = P.seg_off[2 * P.n_img];
+  const u32 gl = threadIdx.x & 3u;
+  const u32 stride = (gridDim.x * blockDim.x) >> 2;
+  for (u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < total; g += stride) {
+    u32 sid, j;
+    bc_locate(P, g, sid, j);
+    const BcStream S = bc_stream(P, sid);
+    const u32 first = j * BC_SEG;
+    const u32 n = S.n > first ? min(BC_SEG, S.n - first) : 0u;
+    const Token* tk = S.tk + first;
+    const u32 m0 = P.seg[g].cand[0], m1 = P.seg[g].cand[1], m2 = P.seg[g].cand[2], m3 = P.seg[g].cand[3];
+    const u32 k = (u32)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
+    for (u32 c = gl; c < k; c += 4) {
+      u32 st = 127u + bc_nth_bit(m0, m1, m2, m3, c), T = 0, add, sh;
+      u32 i = 0;
+      for (; i + 8 <= n; i += 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
+#pragma unroll
+        for (int e = 0; e < 8; e++) { st = bc_step(st, bc_sym8(q.x, q.y, q.z, q.w, e), add, sh); T += sh; }
+      }
+      for (; i < n; i++) { st = bc_step(st, tk[i], add, sh); T += sh; }
+      P.seg_trans[(size_t)g * 128 + c] = st | (T << 8);
+    }
+  }
+}
+
+// One thread per stream: the state and the bit position every segment starts with.
+__global__ void __launch_bounds__(128) k_bc_resolve(ChunkParams P) {
+  if (P.tot->overflow) return;
+  const u32 sid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sid >= 2 * P.n_img) return;
+  const u32 g0 = P.seg_off[sid], g1 = P.seg_off[sid + 1];
+  u32 st = 254;
+  u64 bits = 0;
+  for (u32 g = g0; g < g1; g++) {
+    BcSegment& sg = P.seg[g];
+    const u32 e = P.seg_trans[(size_t)g * 128 + bc_rank(sg.cand[0], sg.cand[1], sg.cand[2], sg.cand[3], st - 127u)];
+    sg.state = (u8)st;
+    sg.start_bit = bits;
+    st = e & 255u;
+    bits += e >> 8;
+  }
+}
+
+// One LANE per segment: write_bool (arithmetic.rs:67-95) with the bit-at-a-time renormalisation loop collapsed into at
+// most two steps around the byte boundary, starting from bottom = 0.
+__global__ void __launch_bounds__(128) k_bc_code(ChunkParams P) {
+  if (P.tot->overflow) return;
+  const u32 total = P.seg_off[2 * P.n_img];
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+    u32 sid, j;
+    bc_locate(P, g, sid, j);
+    const BcStream S = bc_stream(P, sid);
+    const bool last = g + 1 == P.seg_off[sid + 1];
+    const u32 first = j * BC_SEG;
+    const u32 n = S.n > first ? min(BC_SEG, S.n - first) : 0u;
+    const Token* tk = S.tk + first;
+    BcSegment& sg = P.seg[g];
+    BcCoder cd;
+    cd.begin(sg.state, sg.start_bit, S.out, S.cap);
+    u32 i = 0;
+    for (; i + 8 <= n; i += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
+#pragma unroll
+      for (int e = 0; e < 8; e++) cd.put(bc_sym8(q.x, q.y, q.z, q.w, e));
+    }
+    for (; i < n; i++) cd.put(tk[i]);
+    if (!last) {
+      sg.tail = cd.tail();
+    } else {
+      const u32 bytes = cd.flush();
+      sg.tail = 0;
+      ImageState& IS = P.st[S.img];
+      if (S.is_hdr) IS.part0_bytes = bytes; else IS.part1_bytes = bytes;
+    }
+    const u32 carries = cd.carries;
+    const bool overflow = cd.overflow;
+    sg.carries = carries;
+    if (overflow) P.st[S.img].status = 4;  // ZW_ERR_OUTPUT_TOO_SMALL (cannot happen with the 7-bits-per-symbol bound)
+  }
+}
+
+// One thread per stream: add the tail of every segment to the bytes that follow it and ripple the carries.
+__global__ void __launch_bounds__(128) k_bc_fix(ChunkParams P) {
+  if (P.tot->overflow) return;
+  const u32 sid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sid >= 2 * P.n_img) return;
+  const BcStream S = bc_stream(P, sid);
+  if (P.st[S.img].status == 4) return;
+  const u32 g0 = P.seg_off[sid], g1 = P.seg_off[sid + 1];
+  for (u32 g = g0 + 1; g < g1; g++) {
+    bc_fix_boundary(S.out, P.seg[g].start_bit, P.seg[g - 1].tail, P.seg[g].carries);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // (6) Assembly: frame tag + start code + dimensions + first partition + token partition, packed

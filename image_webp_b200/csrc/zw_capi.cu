@@ -201,7 +201,7 @@ struct Lane {
   const u8* lut = nullptr;
   DevBuf d_img, d_lay, d_tot, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
       d_derr1, d_derr2, d_c1, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
-      d_part, d_out, d_outoff;
+      d_part, d_out, d_outoff, d_segoff, d_seg, d_segtrans;
   PinBuf h_st, h_outoff, h_tot, h_arena;  // pinned mirrors: ImageState[n], out offsets[n+1], ChunkTotals, the finished files
   std::vector<ImageDesc> img;
   std::vector<RowRef> rows;
@@ -213,12 +213,12 @@ struct Lane {
   size_t n_in = 0;
   u32 n_valid = 0, n_rows = 0, n_mb = 0, max_pw = 0, max_ph = 0, max_mb = 0;
   u64 layout_key = 0;
-  u64 cap_h = 0, cap_t = 0, cap_p = 0;  // capacities the phase-B arenas were launched with
+  u64 cap_h = 0, cap_t = 0, cap_p = 0, cap_seg = 0;  // capacities the phase-B arenas were launched with
   double tok_per_mb = 3.0 * 256;        // symbol-arena estimate (token partition), raised when a batch overflows it
   int state = LANE_FREE;
   int container = 1;
   int quality = -1, method = -1, base_qidx = 0;
-  int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0;
+  int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0, sm_count = 0;
   u32 start_slack = 0;  // measured: rows wait 1.1-1.4 % of their time at 1024 images; extra start slack only idles warps
   u64 launches = 0;
   u32 reruns = 0;
@@ -244,7 +244,8 @@ static void fill_params(Lane* c) {
   ChunkParams& P = c->P;
   memset(&P, 0, sizeof(P));
   P.img = c->d_img.as<ImageDesc>(); P.lay = c->d_lay.as<ImageLayout>(); P.tot = c->d_tot.as<ChunkTotals>();
-  P.cap_hdr_tokens = c->cap_h; P.cap_tok_tokens = c->cap_t; P.cap_part_bytes = c->cap_p;
+  P.cap_hdr_tokens = c->cap_h; P.cap_tok_tokens = c->cap_t; P.cap_part_bytes = c->cap_p; P.cap_segments = c->cap_seg;
+  P.seg_off = c->d_segoff.as<u32>(); P.seg = c->d_seg.as<BcSegment>(); P.seg_trans = c->d_segtrans.as<u32>();
   P.st = c->d_st.as<ImageState>(); P.rows = c->d_rows.as<RowRef>();
   P.segtab = c->segtab; P.segquant_lut = c->lut;
   P.n_img = c->n_valid; P.n_rows = c->n_rows; P.n_mb = c->n_mb;
@@ -293,7 +294,7 @@ static void lane_destroy(Lane* c) {
   DevBuf* all[] = {&c->d_img, &c->d_lay, &c->d_tot, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
                    &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_c1, &c->d_uvflags, &c->d_progress,
                    &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_htok,
-                   &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff};
+                   &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff, &c->d_segoff, &c->d_seg, &c->d_segtrans};
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : all) b->release();
   c->h_st.release(); c->h_outoff.release(); c->h_tot.release(); c->h_arena.release();
@@ -332,6 +333,7 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
     b1 = std::min(b1, std::max(1, warps_hint / search_warps(1))); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
   }
   if (const char* env = getenv("ZW_START_SLACK")) c->start_slack = (u32)std::max(0, atoi(env));
+  c->sm_count = ctx->sm_count;
   c->chroma2_blocks = std::max(1, b4) * ctx->sm_count;
   c->search_blocks1 = std::max(1, b1) * ctx->sm_count;
   c->search_blocks2 = std::max(1, b2) * ctx->sm_count;
@@ -429,6 +431,8 @@ static int lane_launch_b(Lane* c) {
   c->cap_p = ((c->cap_h + c->cap_t) * 7) / 8 + (u64)ni * 48;
   CK(c->d_htok.reserve(c->cap_h * sizeof(Token) + 64)); CK(c->d_ttok.reserve(c->cap_t * sizeof(Token) + 64));
   CK(c->d_part.reserve(c->cap_p + 64)); CK(c->d_out.reserve(c->cap_p + (u64)ni * 64 + 64));
+  c->cap_seg = (c->cap_h + c->cap_t) / BC_SEG + 2ull * ni + 8;
+  CK(c->d_segoff.reserve((2ull * ni + 1) * 4)); CK(c->d_seg.reserve(c->cap_seg * sizeof(BcSegment))); CK(c->d_segtrans.reserve(c->cap_seg * 128 * 4));
   fill_params(c);
   ChunkParams& P = c->P;
   k_layout<<<1, 1024, 0, s>>>(P);
@@ -436,8 +440,15 @@ static int lane_launch_b(Lane* c) {
   k_frame_header<<<(ni + 63) / 64, 64, 0, s>>>(P);
   c->launches += 3;
   CK(cudaEventRecord(c->ev[EV_TOK], s));
-  k_boolcode<<<(2 * ni + BC_STREAMS - 1) / BC_STREAMS, BC_WARPS * 32, 0, s>>>(P);
-  c->launches++;
+  {  // boolean coder: candidate start states -> transitions -> resolve -> code (one lane per segment) -> fix up
+    const u64 wide = (u64)c->sm_count * 16;
+    k_bc_cands<<<(unsigned)std::min<u64>(c->cap_seg, wide), 128, 0, s>>>(P);
+    k_bc_trans<<<(unsigned)std::min<u64>((c->cap_seg * 4 + 127) / 128, wide), 128, 0, s>>>(P);
+    k_bc_resolve<<<(2 * ni + 127) / 128, 128, 0, s>>>(P);
+    k_bc_code<<<(unsigned)std::min<u64>((c->cap_seg + 63) / 64, wide * 2), 64, 0, s>>>(P);
+    k_bc_fix<<<(2 * ni + 127) / 128, 128, 0, s>>>(P);
+    c->launches += 5;
+  }
   CK(cudaEventRecord(c->ev[EV_BC], s));
   k_outscan<<<1, 32, 0, s>>>(P, c->d_outoff.as<u64>());
   k_assemble<<<ni, 256, 0, s>>>(P, c->d_outoff.as<u64>());
@@ -450,7 +461,7 @@ static int lane_launch_b(Lane* c) {
   return ZW_OK;
 }
 
-// Every kernel of one batch, asynchronous on the lane's stream (17 launches + 1 for the placement scan).
+// Every kernel of one batch, asynchronous on the lane's stream (22 launches).
 static int lane_launch(Lane* c, int quality, int method, Lane* after) {
   c->launches = 0;
   c->quality = quality; c->method = method; c->base_qidx = quality_to_quant_index(quality);

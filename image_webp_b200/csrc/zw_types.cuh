@@ -63,7 +63,17 @@ struct ImageLayout {
 struct ChunkTotals {
   u64 hdr_tokens, tok_tokens, part_bytes, out_bytes;
   u32 overflow;  // a stream arena is too small: the emit / code / assemble kernels do nothing, the host grows and re-runs them
-  u32 pad;
+  u32 segments;  // boolean-coder segments of all streams
+};
+
+// One boolean-coder segment (k_bc_*): what the passes hand to each other.
+struct BcSegment {
+  u32 cand[4];   // bitmap of the range states (range - 128 = bit index) the segment can possibly start in
+  u64 start_bit; // total renormalisation shifts before the segment (absolute stream bit of its first addend)
+  u64 tail;      // bottom << bit_num when the segment ends: still to be added to the bytes that follow
+  u32 carries;   // carries that left the segment's own bytes towards earlier bytes
+  u8 state;      // range - 1 the segment really starts with
+  u8 pad[3];
 };
 
 // Device-written per-image state.
@@ -102,6 +112,10 @@ struct ChunkParams {
   ImageLayout* lay;       // [n_img] device-computed stream / partition / output placement
   ChunkTotals* tot;
   u64 cap_hdr_tokens, cap_tok_tokens, cap_part_bytes;  // capacities of the symbol / partition arenas
+  u64 cap_segments;       // capacity of the boolean-coder segment arrays
+  u32* seg_off;           // [2 n_img + 1] first segment of every stream (token partitions, then first partitions)
+  BcSegment* seg;         // [cap_segments]
+  u32* seg_trans;         // [cap_segments][128] per candidate start state (by rank in cand): end state | total shift << 8
   ImageState* st;
   const RowRef* rows;     // ticket -> (image, mb row), ordered so that row y-1 precedes row y
   const SegParams* segtab;  // [128]

@@ -3,6 +3,8 @@
 // suite can compare them with the oracle on random inputs without a GPU.  Not part of the
 // product; the shipped library only runs these functions inside CUDA kernels.
 #include <cstring>
+#include <vector>
+#include "../../image_webp_b200/csrc/zw_boolcoder.cuh"
 #include "../../image_webp_b200/csrc/zw_cost.cuh"
 using namespace zw;
 static const u16 kPredTab[8][16] = ZW_PRED_TABLE_INIT;
@@ -31,5 +33,64 @@ int hc_trellis(i32* coeffs, i32* out, const u16* q, const u32* iq, const u32* bi
 }
 void hc_token_events(const i16* zz, int t, int first, int ctx, u32* stats /*1056 packed like ProbaStats (no halving)*/) {
   token_events(zz, t, first, ctx, [&](int slot, int bit) { stats[slot] += 0x10000u + (u32)bit; });
+}
+// The five steps of the segment-parallel boolean coder (k_bc_cands / k_bc_trans / k_bc_resolve / k_bc_code / k_bc_fix in
+// zw_back.cuh), run serially with the SAME lane-local functions the kernels call; `seg` / `warm` stand for BC_SEG / BC_WARM
+// so that small streams cross many segment boundaries.  Returns the stream length; stats[0] = segments, [1] = largest
+// candidate set, [2] = carries that crossed a segment start, [3] = candidate sets summed.
+size_t hc_boolcode_segmented(const u16* tk, size_t n, u32 seg, u32 warm, u8* out, u32 cap, u32* stats) {
+  const u32 J = n == 0 ? 1u : (u32)((n + seg - 1) / seg);
+  struct Seg { u32 cand[4]; u64 start_bit, tail; u32 carries; u8 state; };
+  std::vector<Seg> S(J);
+  std::vector<std::vector<u32>> trans(J);
+  u32 maxk = 0, sumk = 0, crossed = 0;
+  for (u32 j = 0; j < J; j++) {  // k_bc_cands
+    Seg& sg = S[j];
+    sg.cand[0] = sg.cand[1] = sg.cand[2] = sg.cand[3] = 0;
+    if (j == 0) { sg.cand[3] = 0x80000000u; continue; }
+    const u16* w = tk + (size_t)j * seg - warm;
+    for (u32 s0 = 127; s0 < 255; s0++) {
+      u32 st = s0, add, sh;
+      for (u32 i = 0; i < warm; i++) st = bc_step(st, w[i], add, sh);
+      sg.cand[(st - 127) >> 5] |= 1u << ((st - 127) & 31);
+    }
+  }
+  for (u32 j = 0; j < J; j++) {  // k_bc_trans
+    const Seg& sg = S[j];
+    const u32 k = bc_popc(sg.cand[0]) + bc_popc(sg.cand[1]) + bc_popc(sg.cand[2]) + bc_popc(sg.cand[3]);
+    maxk = k > maxk ? k : maxk; sumk += k;
+    const size_t first = (size_t)j * seg;
+    const u32 cnt = n > first ? (u32)((n - first) < seg ? (n - first) : seg) : 0u;
+    for (u32 c = 0; c < k; c++) {
+      u32 st = 127u + bc_nth_bit(sg.cand[0], sg.cand[1], sg.cand[2], sg.cand[3], c), T = 0, add, sh;
+      for (u32 i = 0; i < cnt; i++) { st = bc_step(st, tk[first + i], add, sh); T += sh; }
+      trans[j].push_back(st | (T << 8));
+    }
+  }
+  {  // k_bc_resolve
+    u32 st = 254;
+    u64 bits = 0;
+    for (u32 j = 0; j < J; j++) {
+      const u32 e = trans[j][bc_rank(S[j].cand[0], S[j].cand[1], S[j].cand[2], S[j].cand[3], st - 127u)];
+      S[j].state = (u8)st; S[j].start_bit = bits;
+      st = e & 255u; bits += e >> 8;
+    }
+  }
+  size_t bytes = 0;
+  for (u32 jj = 0; jj < J; jj++) {  // k_bc_code, in an order that is NOT the stream order
+    const u32 j = (jj % 2 == 0) ? (J - 1 - jj / 2) : (jj / 2);
+    const size_t first = (size_t)j * seg;
+    const u32 cnt = n > first ? (u32)((n - first) < seg ? (n - first) : seg) : 0u;
+    BcCoder cd;
+    cd.begin(S[j].state, S[j].start_bit, out, cap);
+    for (u32 i = 0; i < cnt; i++) cd.put(tk[first + i]);
+    if (j + 1 < J) S[j].tail = cd.tail(); else { bytes = cd.flush(); S[j].tail = 0; }
+    S[j].carries = cd.carries;
+    crossed += cd.carries;
+    if (cd.overflow) return (size_t)-1;
+  }
+  for (u32 j = 1; j < J; j++) bc_fix_boundary(out, S[j].start_bit, S[j - 1].tail, S[j].carries);  // k_bc_fix
+  if (stats) { stats[0] = J; stats[1] = maxk; stats[2] = crossed; stats[3] = sumk; }
+  return bytes;
 }
 }

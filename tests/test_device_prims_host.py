@@ -16,7 +16,7 @@ SO = os.path.join(ROOT, "tests", "hostcheck", "_build", "libzw_hostcheck.so")
 
 
 def _build():
-    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc")]
+    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc", "zw_boolcoder.cuh")]
     if (not os.path.exists(SO)) or any(os.path.getmtime(SO) < os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO])
@@ -169,3 +169,50 @@ def test_token_events_match_oracle_record_coeffs():
         z = lv.astype(np.int16)
         H.hc_token_events(z.ctypes.data_as(C.c_void_p), t, first, ctx, got.ctypes.data_as(C.c_void_p))
         assert (np.array(list(ref), np.uint32) == got).all()
+
+
+def _ref_bool_encode(tok):
+    bits = (tok >> 8).astype(np.uint8)
+    probs = (tok & 255).astype(np.uint8)
+    out = np.zeros(tok.size + 16, np.uint8)
+    n = L.zwo_bool_encode(bits.ctypes.data_as(C.c_void_p), probs.ctypes.data_as(C.c_void_p), C.c_size_t(tok.size), out.ctypes.data_as(C.c_void_p))
+    return out[:n].tobytes()
+
+
+def _seg_bool_encode(tok, seg, warm):
+    H.hc_boolcode_segmented.restype = C.c_size_t
+    H.hc_boolcode_segmented.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    tok = np.ascontiguousarray(tok, np.uint16)
+    out = np.full(tok.size + 64, 0xEE, np.uint8)
+    stats = np.zeros(4, np.uint32)
+    n = H.hc_boolcode_segmented(tok.ctypes.data, tok.size, seg, warm, out.ctypes.data, out.size, stats.ctypes.data)
+    assert n != 2 ** 64 - 1
+    return out[:n].tobytes(), stats
+
+
+def test_segment_parallel_boolcoder_equals_the_serial_coder():
+    """The five-step segment-parallel scheme the GPU runs (same lane-local code, zw_boolcoder.cuh) reproduces the
+    reference's serial ArithmeticEncoder byte for byte: real token streams, adversarial streams (carry chains across
+    segment starts, literal runs that keep all range states apart, empty / one-symbol streams), many segment sizes."""
+    rng = np.random.default_rng(7)
+    import photo_inputs as PI
+    streams = []
+    _, _, d = O.encode(PI.crop("3", 300, 200, 256, 192), 75, 4, want_dump=True)
+    streams += [d["TOK_TOKENS"], d["HDR_TOKENS"]]
+    _, _, d = O.encode(PI.crop("5", 100, 100, 128, 128), 100, 4, want_dump=True)
+    streams += [d["TOK_TOKENS"]]
+    n = 40000
+    streams.append(((rng.integers(0, 2, n) << 8) | rng.integers(1, 256, n)).astype(np.uint16))        # uniform random
+    streams.append(((np.ones(n, np.int64) << 8) | rng.integers(1, 4, n)).astype(np.uint16))           # improbable ones: long 0xFF / carry chains
+    streams.append(((rng.integers(0, 2, n) << 8) | 128).astype(np.uint16))                            # literals: states stay apart
+    streams.append(((rng.random(n) < 0.02).astype(np.int64) << 8 | 250).astype(np.uint16))            # nearly no shifts per symbol
+    streams.append(((rng.random(n) < 0.98).astype(np.int64) << 8 | 5).astype(np.uint16))
+    streams += [np.zeros(0, np.uint16), np.array([0x0180], np.uint16), np.array([0x0080] * 23, np.uint16)]
+    worst = 0
+    for tok in streams:
+        ref = _ref_bool_encode(np.ascontiguousarray(tok, np.uint16))
+        for seg, warm in ((8192, 1024), (512, 64), (64, 16), (8, 8), (16, 0)):
+            got, st = _seg_bool_encode(tok, seg, warm)
+            assert got == ref, "stream of %d symbols, seg %d warm %d: differs (%d vs %d bytes)" % (tok.size, seg, warm, len(got), len(ref))
+            worst = max(worst, int(st[1]))
+    assert worst >= 16  # the literal stream really keeps many candidate states alive: the general path is exercised
