@@ -7,12 +7,8 @@
 #ifndef ZENWEBP_B200_HPP
 #define ZENWEBP_B200_HPP
 #include <cstdint>
-#include <future>
-#include <memory>
-#include <mutex>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "zenwebp_b200.h"
@@ -62,11 +58,11 @@ class Context {
       in[i] = zw_image{imgs[i].data, imgs[i].len, imgs[i].width, imgs[i].height, (uint32_t)imgs[i].color, 0};
       out[i] = zw_output{nullptr, 0, 0, 0, 0};
     }
-    raise_for(zw_encode_webp_batch(h_, in.data(), in.size(), p.lossy_quality, p.method, out.data(), t));
+    const int rc = zw_encode_webp_batch(h_, in.data(), in.size(), p.lossy_quality, p.method, out.data(), t);
     std::vector<std::vector<uint8_t>> res(imgs.size());
-    int first_err = 0;
+    int first_err = rc;
     for (size_t i = 0; i < imgs.size(); i++) {
-      if (out[i].status == ZW_OK) res[i].assign(out[i].data, out[i].data + out[i].len);
+      if (out[i].status == ZW_OK && out[i].data) res[i].assign(out[i].data, out[i].data + out[i].len);
       else if (!first_err) first_err = out[i].status;
       zw_free(out[i].data);
     }
@@ -78,31 +74,92 @@ class Context {
   zw_ctx* h_;
 };
 
-// Streaming batch entry: `depth` contexts on one GPU, one host thread per in-flight batch, so that the
-// H2D copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of the next.
-// Contexts are independent (the C ABI is thread-safe across contexts); results equal encode_batch's.
-// The caller keeps at most `depth` futures outstanding and must keep the image memory alive until get().
+// Streaming batch entry on ONE context (zw_submit / zw_wait / zw_release): up to `depth` batches in flight, the
+// H2D copy of a batch running under the kernels of the one before it and its D2H copy under the kernels of the one
+// after it.  `submit` returns a ticket object; `get()` blocks until that batch is finished and returns its files.
+// The caller must keep the image memory alive until get() returns.  Results equal encode_batch's.
 class BatchPipeline {
  public:
-  explicit BatchPipeline(int device = 0, int depth = 2) {
-    for (int i = 0; i < depth; i++) free_.push_back(std::unique_ptr<Context>(new Context(device)));
-  }
-  std::future<std::vector<std::vector<uint8_t>>> submit(std::vector<Context::ImageRef> imgs, EncoderParams p) {
-    return std::async(std::launch::async, [this, imgs, p]() {
-      std::unique_ptr<Context> c;
-      for (;;) {  // take a free context (at most `depth` batches run at once)
-        std::unique_lock<std::mutex> l(m_);
-        if (!free_.empty()) { c = std::move(free_.back()); free_.pop_back(); break; }
-        l.unlock();
-        std::this_thread::yield();
+  class Pending {
+   public:
+    Pending(Pending&& o) noexcept : ctx_(o.ctx_), ticket_(o.ticket_) { o.ticket_ = -1; }
+    Pending(const Pending&) = delete;
+    ~Pending() { if (ticket_ >= 0) zw_release(ctx_, ticket_); }
+    std::vector<std::vector<uint8_t>> get(zw_timing* t = nullptr) {
+      if (ticket_ < 0) throw std::logic_error("batch already collected");
+      zw_batch_view v;
+      const int rc = zw_wait(ctx_, ticket_, 1, &v, t);
+      if (rc != ZW_OK) { zw_release(ctx_, ticket_); ticket_ = -1; raise_for(rc); }
+      std::vector<std::vector<uint8_t>> res(v.n);
+      int first_err = 0;
+      for (size_t i = 0; i < v.n; i++) {
+        if (v.status[i] == ZW_OK) res[i].assign(v.arena + v.offsets[i], v.arena + v.offsets[i] + v.lens[i]);
+        else if (!first_err) first_err = v.status[i];
       }
-      struct Return { BatchPipeline* p; std::unique_ptr<Context>& c; ~Return() { std::lock_guard<std::mutex> l(p->m_); p->free_.push_back(std::move(c)); } } ret{this, c};
-      return c->encode_batch(imgs, p);
-    });
+      zw_release(ctx_, ticket_);
+      ticket_ = -1;
+      raise_for(first_err);
+      return res;
+    }
+   private:
+    friend class BatchPipeline;
+    Pending(zw_ctx* c, int t) : ctx_(c), ticket_(t) {}
+    zw_ctx* ctx_;
+    int ticket_;
+  };
+  explicit BatchPipeline(int device = 0, int depth = 3) {
+    zw_limits lim{};
+    lim.reserved[0] = depth;
+    h_ = zw_create(device, &lim);
+    if (!h_) throw EncodingError(zw_last_error());
+  }
+  ~BatchPipeline() { zw_destroy(h_); }
+  BatchPipeline(const BatchPipeline&) = delete;
+  BatchPipeline& operator=(const BatchPipeline&) = delete;
+  // Throws EncodingError(ZW_ERR_BUSY) when `depth` batches are outstanding: get() one first.
+  Pending submit(const std::vector<Context::ImageRef>& imgs, const EncoderParams& p) {
+    if (!p.use_lossy) throw std::logic_error("only the lossy VP8 path is implemented on the GPU");
+    std::vector<zw_image> in(imgs.size());
+    for (size_t i = 0; i < imgs.size(); i++)
+      in[i] = zw_image{imgs[i].data, imgs[i].len, imgs[i].width, imgs[i].height, (uint32_t)imgs[i].color, 0};
+    int ticket = -1;
+    raise_for(zw_submit(h_, in.data(), in.size(), p.lossy_quality, p.method, &ticket));
+    return Pending(h_, ticket);
   }
  private:
-  std::mutex m_;
-  std::vector<std::unique_ptr<Context>> free_;
+  zw_ctx* h_;
+};
+
+// One batch over several GPUs of one box (zw_multi_*): sharded by image, gathered in image order.
+class MultiContext {
+ public:
+  explicit MultiContext(const std::vector<int>& devices) : h_(zw_multi_create(devices.data(), (int)devices.size(), nullptr)) {
+    if (!h_) throw EncodingError(zw_last_error());
+  }
+  ~MultiContext() { zw_multi_destroy(h_); }
+  MultiContext(const MultiContext&) = delete;
+  MultiContext& operator=(const MultiContext&) = delete;
+  std::vector<std::vector<uint8_t>> encode_batch(const std::vector<Context::ImageRef>& imgs, const EncoderParams& p) {
+    if (!p.use_lossy) throw std::logic_error("only the lossy VP8 path is implemented on the GPU");
+    std::vector<zw_image> in(imgs.size());
+    std::vector<zw_output> out(imgs.size());
+    for (size_t i = 0; i < imgs.size(); i++) {
+      in[i] = zw_image{imgs[i].data, imgs[i].len, imgs[i].width, imgs[i].height, (uint32_t)imgs[i].color, 0};
+      out[i] = zw_output{nullptr, 0, 0, 0, 0};
+    }
+    const int rc = zw_multi_encode(h_, in.data(), in.size(), p.lossy_quality, p.method, 1, out.data(), nullptr);
+    std::vector<std::vector<uint8_t>> res(imgs.size());
+    int first_err = rc;
+    for (size_t i = 0; i < imgs.size(); i++) {
+      if (out[i].status == ZW_OK && out[i].data) res[i].assign(out[i].data, out[i].data + out[i].len);
+      else if (!first_err) first_err = out[i].status;
+      zw_free(out[i].data);
+    }
+    raise_for(first_err);
+    return res;
+  }
+ private:
+  zw_multi* h_;
 };
 
 // WebPEncoder::new(&mut Vec<u8>) / set_params / encode: appends the .webp bytes to `writer`.

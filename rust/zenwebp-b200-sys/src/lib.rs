@@ -21,8 +21,20 @@ pub struct zw_timing {
     pub token_ms: f32, pub boolcode_ms: f32, pub assemble_ms: f32, pub d2h_ms: f32, pub device_total_ms: f32, pub wall_ms: f32,
     pub kernel_launches: u64, pub h2d_bytes: u64, pub d2h_bytes: u64, pub pixels: u64,
     pub chroma1_ms: f32, pub chroma2_ms: f32,
+    pub symbols: u64,
 }
 
+/// What `zw_wait` hands back: the files of one batch inside the slot's pinned arena (valid until `zw_release`).
+#[repr(C)]
+pub struct zw_batch_view { pub arena: *const u8, pub n: usize, pub offsets: *const u64, pub lens: *const u32, pub status: *const i32 }
+
+#[repr(C)]
+pub struct zw_multi { _private: [u8; 0] }
+
+pub const ZW_ERR_BUSY: c_int = 7;
+pub const ZW_ERR_TOO_LARGE: c_int = 8;
+pub const ZW_COLOR_L8: u32 = 0;
+pub const ZW_COLOR_LA8: u32 = 1;
 pub const ZW_COLOR_RGB8: u32 = 2;
 pub const ZW_COLOR_RGBA8: u32 = 3;
 
@@ -37,6 +49,14 @@ extern "C" {
                                outs: *mut zw_output, timing: *mut zw_timing) -> c_int;
     pub fn zw_encode_webp_batch(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize, quality: c_int, method: c_int,
                                 outs: *mut zw_output, timing: *mut zw_timing) -> c_int;
+    pub fn zw_submit(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize, quality: c_int, method: c_int, ticket: *mut c_int) -> c_int;
+    pub fn zw_wait(ctx: *mut zw_ctx, ticket: c_int, container: c_int, view: *mut zw_batch_view, timing: *mut zw_timing) -> c_int;
+    pub fn zw_release(ctx: *mut zw_ctx, ticket: c_int) -> c_int;
+    pub fn zw_multi_create(devices: *const c_int, n_devices: c_int, limits: *const zw_limits) -> *mut zw_multi;
+    pub fn zw_multi_destroy(m: *mut zw_multi);
+    pub fn zw_multi_device_count(m: *const zw_multi) -> c_int;
+    pub fn zw_multi_encode(m: *mut zw_multi, imgs: *const zw_image, n: usize, quality: c_int, method: c_int, container: c_int,
+                           outs: *mut zw_output, per_device: *mut zw_timing) -> c_int;
     pub fn zw_stage_batch(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize) -> c_int;
     pub fn zw_encode_resident(ctx: *mut zw_ctx, quality: c_int, method: c_int, timing: *mut zw_timing) -> c_int;
     pub fn zw_download(ctx: *mut zw_ctx, outs: *mut zw_output, n: usize, container: c_int, timing: *mut zw_timing) -> c_int;

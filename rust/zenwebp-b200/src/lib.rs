@@ -5,7 +5,8 @@
 use zenwebp_b200_sys as sys;
 
 #[derive(Copy, Clone, Debug, PartialEq, Eq)]
-pub enum ColorType { L8, La8, Rgb8, Rgba8 }
+#[repr(u32)]
+pub enum ColorType { L8 = 0, La8 = 1, Rgb8 = 2, Rgba8 = 3 }
 
 #[derive(Debug, thiserror::Error)]
 #[non_exhaustive]
@@ -14,6 +15,9 @@ pub enum EncodingError {
     InvalidDimensions,
     #[error("Invalid buffer size: {0}")]
     InvalidBufferSize(String),
+    /// Lossless (VP8L) parameters, or an alpha colour type in the simple container (needs VP8X + ALPH): not built.
+    #[error("unsupported by the GPU path: {0}")]
+    Unsupported(&'static str),
     #[error("device error {0}")]
     Device(i32),
 }
@@ -42,6 +46,9 @@ impl Context {
     }
     /// Batch entry point: one `.webp` per image, byte-identical to `WebPEncoder::encode` of the reference.
     pub fn encode_batch(&mut self, imgs: &[ImageRef<'_>], p: &EncoderParams) -> Vec<Result<Vec<u8>, EncodingError>> {
+        if !p.use_lossy {  // the reference would emit VP8L here: never silently substitute a lossy file
+            return imgs.iter().map(|_| Err(EncodingError::Unsupported("lossless (VP8L) encoding"))).collect();
+        }
         let cimgs: Vec<sys::zw_image> = imgs.iter().map(|i| sys::zw_image {
             data: i.data.as_ptr(), len: i.data.len(), width: i.width, height: i.height,
             color: match i.color { ColorType::Rgb8 => sys::ZW_COLOR_RGB8, ColorType::Rgba8 => sys::ZW_COLOR_RGBA8, ColorType::L8 => 0, ColorType::La8 => 1 },
@@ -54,23 +61,34 @@ impl Context {
                 0 => Ok(unsafe { core::slice::from_raw_parts(o.data, o.len) }.to_vec()),
                 1 => Err(EncodingError::InvalidDimensions),
                 2 => Err(EncodingError::InvalidBufferSize("width/height doesn't match data length".into())),
+                3 => Err(EncodingError::Unsupported("lossy + alpha needs the VP8X/ALPH container, or a bad parameter")),
                 c => Err(EncodingError::Device(c)),
             };
-            unsafe { sys::zw_free(o.data as *mut _) };
+            if !o.data.is_null() { unsafe { sys::zw_free(o.data as *mut _) }; }
             r
         }).collect()
     }
 }
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::zw_destroy(self.h) } } }
 
+thread_local! {
+    /// One cached context per (thread, device 0): building a context allocates streams, events and tables, which a
+    /// drop-in single-image caller must not pay per image.
+    static DEFAULT_CTX: std::cell::RefCell<Option<Context>> = const { std::cell::RefCell::new(None) };
+}
+
 /// Same shape as the reference: `WebPEncoder::new(&mut out); set_params(..); encode(data, w, h, color)`.
-pub struct WebPEncoder<'a> { writer: &'a mut Vec<u8>, params: EncoderParams, ctx: Context }
+pub struct WebPEncoder<'a> { writer: &'a mut Vec<u8>, params: EncoderParams }
 impl<'a> WebPEncoder<'a> {
-    pub fn new(w: &'a mut Vec<u8>) -> Self { Self { writer: w, params: EncoderParams::default(), ctx: Context::new(0).expect("no CUDA device (there is no CPU fallback)") } }
+    pub fn new(w: &'a mut Vec<u8>) -> Self { Self { writer: w, params: EncoderParams::default() } }
     pub fn set_params(&mut self, params: EncoderParams) { self.params = params; }
-    pub fn encode(mut self, data: &[u8], width: u32, height: u32, color: ColorType) -> Result<(), EncodingError> {
+    pub fn encode(self, data: &[u8], width: u32, height: u32, color: ColorType) -> Result<(), EncodingError> {
         if width > 65535 || height > 65535 { return Err(EncodingError::InvalidDimensions); }
-        let out = self.ctx.encode_batch(&[ImageRef { data, width, height, color }], &self.params).pop().unwrap()?;
+        let out = DEFAULT_CTX.with(|c| -> Result<Vec<u8>, EncodingError> {
+            let mut c = c.borrow_mut();
+            if c.is_none() { *c = Some(Context::new(0)?); }  // no CUDA device -> Device(code): there is no CPU fallback
+            c.as_mut().unwrap().encode_batch(&[ImageRef { data, width, height, color }], &self.params).pop().unwrap()
+        })?;
         self.writer.extend_from_slice(&out);
         Ok(())
     }
@@ -80,24 +98,45 @@ impl<'a> WebPEncoder<'a> {
 // thread-safe across contexts; one context must not be used from two threads at once).
 unsafe impl Send for Context {}
 
-/// Streaming batch entry: `depth` contexts on one GPU, one worker thread each, so that the H2D
-/// copy, the D2H copy and the host RIFF assembly of one batch run under the kernels of the next
-/// (same design as `BatchPipeline` in the Python / C++ mirrors).  `encode_batches` returns the
-/// per-batch results in order.
-pub struct BatchPipeline { ctxs: Vec<Context> }
+/// Streaming batch entry on ONE context (`zw_submit` / `zw_wait` / `zw_release`): up to `depth` batches in flight,
+/// the copies of one hidden behind the kernels of its neighbours.  `encode_batches` returns the per-batch results in order.
+pub struct BatchPipeline { ctx: Context, depth: usize }
 impl BatchPipeline {
     pub fn new(device: i32, depth: usize) -> Result<Self, EncodingError> {
-        Ok(Self { ctxs: (0..depth.max(1)).map(|_| Context::new(device)).collect::<Result<_, _>>()? })
+        let lim = sys::zw_limits { max_device_bytes: 0, persistent_warps_per_sm: 0, reserved: [depth.clamp(1, 8) as i32, 0, 0, 0, 0] };
+        let h = unsafe { sys::zw_create(device, &lim) };
+        if h.is_null() { return Err(EncodingError::Device(unsafe { sys::zw_last_error() })); }
+        Ok(Self { ctx: Context { h }, depth: depth.clamp(1, 8) })
+    }
+    fn collect(&mut self, ticket: i32) -> Vec<Result<Vec<u8>, EncodingError>> {
+        let mut v = sys::zw_batch_view { arena: core::ptr::null(), n: 0, offsets: core::ptr::null(), lens: core::ptr::null(), status: core::ptr::null() };
+        let rc = unsafe { sys::zw_wait(self.ctx.h, ticket, 1, &mut v, core::ptr::null_mut()) };
+        let res = if rc != 0 { Vec::new() } else {
+            (0..v.n).map(|i| unsafe {
+                match *v.status.add(i) {
+                    0 => Ok(core::slice::from_raw_parts(v.arena.add(*v.offsets.add(i) as usize), *v.lens.add(i) as usize).to_vec()),
+                    1 => Err(EncodingError::InvalidDimensions),
+                    2 => Err(EncodingError::InvalidBufferSize("width/height doesn't match data length".into())),
+                    c => Err(EncodingError::Device(c)),
+                }
+            }).collect()
+        };
+        unsafe { sys::zw_release(self.ctx.h, ticket) };
+        res
     }
     pub fn encode_batches(&mut self, batches: &[Vec<ImageRef<'_>>], p: &EncoderParams) -> Vec<Vec<Result<Vec<u8>, EncodingError>>> {
-        let depth = self.ctxs.len();
-        let mut out: Vec<Option<Vec<Result<Vec<u8>, EncodingError>>>> = (0..batches.len()).map(|_| None).collect();
-        std::thread::scope(|s| {
-            let handles: Vec<_> = self.ctxs.iter_mut().enumerate().map(|(k, ctx)| {
-                s.spawn(move || (k..batches.len()).step_by(depth).map(|i| (i, ctx.encode_batch(&batches[i], p))).collect::<Vec<_>>())
-            }).collect();
-            for h in handles { for (i, r) in h.join().unwrap() { out[i] = Some(r); } }
-        });
-        out.into_iter().map(|o| o.unwrap()).collect()
+        let mut out = Vec::with_capacity(batches.len());
+        let mut inflight: std::collections::VecDeque<(i32, Vec<sys::zw_image>)> = Default::default();
+        for b in batches {
+            if inflight.len() == self.depth { let (t, _keep) = inflight.pop_front().unwrap(); out.push(self.collect(t)); }
+            let cimgs: Vec<sys::zw_image> = b.iter().map(|i| sys::zw_image { data: i.data.as_ptr(), len: i.data.len(), width: i.width, height: i.height,
+                color: i.color as u32, reserved: 0 }).collect();
+            let mut ticket = -1;
+            let rc = unsafe { sys::zw_submit(self.ctx.h, cimgs.as_ptr(), cimgs.len(), p.lossy_quality as i32, p.method as i32, &mut ticket) };
+            if rc != 0 { out.push(b.iter().map(|_| Err(EncodingError::Device(rc))).collect()); continue; }
+            inflight.push_back((ticket, cimgs));
+        }
+        while let Some((t, _keep)) = inflight.pop_front() { out.push(self.collect(t)); }
+        out
     }
 }
