@@ -264,18 +264,22 @@ def other_configs(Z, torch, ctx, pipe, lib, cores, world):
         res[name] = r
         assert ok == len(check), "%s: GPU output differs from the oracle" % name
 
-    c1 = PI.survey_crop()
-    run("config1_photo: 1 x 768x512 photograph crop (gallery1/3.png @256,104) q75 m4", [c1], 75, 4, [0], np.stack([c1] * 4), reps=5)
-    s1 = synth.photo_like(768, 512, 0)
-    run("config1_synthetic: 1 x 768x512 G(0) q75 m4", [s1], 75, 4, [0], np.stack([s1] * 4), reps=5)
-    big = synth.photo_like(4096, 4096, 3, freq_scale=4.0)
-    run("config3: 1 x 4096x4096 q90 m4", [big], 90, 4, [0], big[None], reps=2)
+    def pinned(arrs):  # inputs of the end-to-end legs live in pinned host memory, like the main workload's
+        return pinned_batch(torch, np.stack(arrs)).numpy()
+
+    c1 = pinned([PI.survey_crop()])
+    run("config1_photo: 1 x 768x512 photograph crop (gallery1/3.png @256,104) q75 m4", [c1[0]], 75, 4, [0], np.stack([c1[0]] * 4), reps=5)
+    s1 = pinned([synth.photo_like(768, 512, 0)])
+    run("config1_synthetic: 1 x 768x512 G(0) q75 m4", [s1[0]], 75, 4, [0], np.stack([s1[0]] * 4), reps=5)
+    big = pinned([synth.photo_like(4096, 4096, 3, freq_scale=4.0)])
+    run("config3: 1 x 4096x4096 q90 m4", [big[0]], 90, 4, [0], big, reps=2)
     del big
-    base = [synth.photo_like(1920, 1080, 100 + i) for i in range(8)]
-    run("config4: 256 x 1920x1080 q75 m6", [base[i % 8] for i in range(256)], 75, 6, [0, 255], np.stack(base[:max(2, min(8, cores // 2))]), reps=2)
-    tb_ = [synth.photo_like(256, 256, 200 + i) for i in range(64)]
-    run("config5_shard: 8192 x 256x256 q50 m0 (the 1/8 shard one GPU owns)", [tb_[i % 64] for i in range(8192)], 50, 0, [0, 63, 8191],
-        np.stack(tb_), reps=2)
+    base = pinned([synth.photo_like(1920, 1080, 100 + i) for i in range(8)])
+    run("config4: 256 x 1920x1080 q75 m6 (8 distinct images, 32 times each)", [base[i % 8] for i in range(256)], 75, 6, [0, 255],
+        base[:max(2, min(8, cores // 2))], reps=2)
+    tb_ = pinned([synth.photo_like(256, 256, 200 + i) for i in range(64)])
+    run("config5_shard: 8192 x 256x256 q50 m0 (the 1/8 shard one GPU owns; 64 distinct images)", [tb_[i % 64] for i in range(8192)], 50, 0,
+        [0, 63, 8191], tb_, reps=2)
     return res
 
 

@@ -234,6 +234,7 @@ struct zw_ctx {
   DevBuf d_segtab, d_lut;
   std::vector<Lane*> lanes;
   Lane* prev = nullptr;  // lane whose kernels were launched last (the next lane's kernels wait for them)
+  Lane* prev_copy = nullptr;  // lane whose H2D copy was enqueued last
   size_t n_staged = 0;   // split API (lane 0)
   bool staged = false, encoded = false;
   int dump_lane = -1;    // lane zw_dump_stage reads: the last chunk handed to the device
@@ -342,7 +343,7 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
 
 // Validate + lay out + start the H2D copies of one lane's images (asynchronous on its stream).  The caller's
 // buffers must stay valid and unchanged until the copy has finished (EV_H2D1).
-static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
+static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after = nullptr) {
   c->state = LANE_FREE;
   c->n_in = n;
   c->img.clear(); c->img_status.assign(n, 0); c->slot_of.assign(n, -1);
@@ -399,6 +400,9 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n) {
     c->layout_key = key;
   }
   CK(cudaMemcpyAsync(c->d_img.p, c->img.data(), ni * sizeof(ImageDesc), cudaMemcpyHostToDevice, c->stream));
+  // copies of different lanes go over the link one after the other: sharing it would only delay the batch submitted
+  // first (its kernels could not start) without finishing the later one any sooner
+  if (copy_after && copy_after != c && copy_after->n_valid) CK(cudaStreamWaitEvent(c->stream, copy_after->ev[EV_H2D1], 0));
   CK(cudaEventRecord(c->ev[EV_H2D0], c->stream));
   {  // one copy per run of images that are contiguous in host memory (and need no alignment gap on the device)
     const u8* run_src = nullptr;
@@ -665,8 +669,9 @@ static int check_params(int quality, int method) {
 // Hand one batch (one chunk) to lane `k`: stage + launch everything, asynchronous.
 static int ctx_submit_lane(zw_ctx* c, int k, const zw_image* imgs, size_t n, int quality, int method) {
   Lane* l = c->lanes[k];
-  int rc = lane_stage(l, imgs, n);
+  int rc = lane_stage(l, imgs, n, c->prev_copy);
   if (rc != ZW_OK) return rc;
+  if (l->n_valid) c->prev_copy = l;
   rc = lane_launch(l, quality, std::min(method, 6) /* vp8.rs:1291 */, c->prev);
   if (rc != ZW_OK) { l->state = LANE_FREE; return rc; }
   if (l->n_valid) c->prev = l;
@@ -818,8 +823,9 @@ int zw_stage_batch(zw_ctx* c, const zw_image* imgs, size_t n) {
   c->staged = false; c->encoded = false;
   Lane* l = c->lanes[0];
   if (l->state == LANE_IN_FLIGHT) CK(cudaStreamSynchronize(l->stream));
-  int rc = lane_stage(l, imgs, n);
+  int rc = lane_stage(l, imgs, n, c->prev_copy);
   if (rc != ZW_OK) return g_last_error = rc;
+  if (l->n_valid) c->prev_copy = l;
   // the caller may reuse or free its buffers as soon as this returns: wait for the copies
   if (l->n_valid) CK(cudaEventSynchronize(l->ev[EV_H2D1]));
   float ms = 0;
@@ -877,15 +883,21 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
     l->state = LANE_FREE;
   }
   c->staged = false; c->encoded = false;
-  // Chunks: bounded by the device budget, and small enough that a large batch becomes several chunks whose
-  // H2D / D2H copies hide behind each other's kernels (ZW_SPLIT, default 4 chunks when the batch allows it).
+  // Chunks: bounded by the device budget.  A large batch is cut into THREE chunks of growing size (1 : 3 : 9):
+  // only the first, small chunk's H2D copy is exposed, every later copy runs under the kernels of the chunk before
+  // it (the link moves pixels ~3.7x faster than the kernels consume them), and most images still go through the
+  // kernels in one large chunk (equal chunks cost ~10-20 % in wavefront ramps and tails, measured).
+  // ZW_SPLIT=n forces n equal chunks (1 = no split).
   u64 total_px = 0;
   for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
-  int split = 4;
-  if (const char* env = getenv("ZW_SPLIT")) split = std::max(1, atoi(env));
+  int split = 0;
+  if (const char* env = getenv("ZW_SPLIT")) split = std::max(0, atoi(env));
   if (c->lanes.size() < 2) split = 1;
-  const u64 min_chunk_px = 48ull << 20;  // below ~50 Mpx a chunk no longer fills the wavefront kernels
-  const u64 px_target = std::max(min_chunk_px, (total_px + split - 1) / split);
+  std::vector<u64> px_targets;  // pixel budget of chunk 0, 1, ...; the last entry repeats
+  if (split >= 1) px_targets.push_back((total_px + split - 1) / split);
+  else if (total_px >= (96ull << 20)) { px_targets = {total_px / 13, 3 * total_px / 13, total_px}; }
+  else if (total_px >= (24ull << 20)) { px_targets = {total_px / 4, total_px}; }
+  else px_targets.push_back(total_px + 1);
   struct Pending { int lane; size_t i0, i1; };
   std::vector<Pending> q;
   zw_timing acc = zw_timing();
@@ -901,10 +913,12 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
     l->state = LANE_FREE;
     return r;
   };
-  size_t i0 = 0;
+  size_t i0 = 0, chunk_no = 0;
   while (i0 < n && rc == ZW_OK) {
     size_t i1 = i0, bytes = 0;
     u64 px = 0;
+    const u64 px_target = px_targets[std::min(chunk_no, px_targets.size() - 1)];
+    chunk_no++;
     while (i1 < n && (i1 - i0) < 32768) {
       const bool ok = validate_image(imgs[i1]) == ZW_OK;
       const size_t f = ok ? image_footprint(imgs[i1].width, imgs[i1].height, color_bpp(imgs[i1].color)) : 0;
