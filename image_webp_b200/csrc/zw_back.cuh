@@ -14,7 +14,7 @@
 #ifndef ZW_BACK_CUH
 #define ZW_BACK_CUH
 #include "zw_boolcoder.cuh"
-#include "zw_search.cuh"
+#include "zw_searchq.cuh"
 
 namespace zw {
 

@@ -87,38 +87,6 @@ static int compute_filter_level(int quant_index) {  // sharpness 0, filter_stren
   const u32 f = base * level0 / 256;
   return f < 2 ? 0 : (f > 63 ? 63 : (int)f);
 }
-static Matrix make_matrix(u32 q_dc, u32 q_ac, int type) {
-  static const u32 B[3][2] = {{96, 110}, {96, 108}, {110, 115}};
-  Matrix m;
-  m.q[0] = (u16)q_dc; m.q[1] = (u16)q_ac;
-  for (int i = 0; i < 2; i++) {
-    m.iq[i] = (u32)((1ull << 17) / (u64)m.q[i]);
-    m.bias[i] = ((B[type][i] << 17) + 128) >> 8;
-  }
-  return m;
-}
-static SegParams make_segparams(int idx) {
-  SegParams s;
-  memset(&s, 0, sizeof(s));
-  const u32 ydc = (u32)host::kDcQuant[idx], yac = (u32)host::kAcQuant[idx];
-  const u32 y2dc = ydc * 2, y2ac = std::max<u32>((u32)((int)yac * 155 / 100), 8);
-  const u32 uvdc = ydc, uvac = yac;  // note: not clamped to 132 (Q18)
-  s.y1 = make_matrix(ydc, yac, 0);
-  s.y2 = make_matrix(y2dc, y2ac, 1);
-  s.uv = make_matrix(uvdc, uvac, 2);
-  for (int i = 0; i < 16; i++) s.sharpen[i] = (u16)(((u32)host::kFreqSharpening[i] * (u32)s.y1.q[i > 0]) >> 11);
-  const u32 q_i4 = (ydc + 15 * yac + 8) >> 4, q_i16 = (y2dc + 15 * y2ac + 8) >> 4, q_uv = (uvdc + 15 * uvac + 8) >> 4;
-  s.lambda_trellis_i4 = std::max<u32>((7 * q_i4 * q_i4) >> 3, 1);
-  s.lambda_trellis_i16 = std::max<u32>((q_i16 * q_i16) >> 2, 1);
-  s.lambda_i4 = std::max<u32>((3 * q_i4 * q_i4) >> 7, 1);
-  s.lambda_i16 = std::max<u32>(3 * q_i16 * q_i16, 1);
-  s.lambda_uv = std::max<u32>((3 * q_uv * q_uv) >> 6, 1);
-  s.lambda_mode = std::max<u32>((q_i4 * q_i4) >> 7, 1);
-  s.tlambda = (50u * q_i4) >> 5;
-  s.uv_dc_zthresh = ((1u << 17) - 1 - s.uv.bias[0]) / s.uv.iq[0];
-  return s;
-}
-
 // ---- token trees (RFC 6386 / src/common/types.rs:191-205, :332, :700-703) --------------------
 static const i8 T_SEG[6] = {2, 4, 0, -1, -2, -3};
 static const i8 T_YMODE[8] = {-4, 2, 4, 6, 0, -1, -2, -3};
@@ -219,6 +187,8 @@ struct Lane {
   int container = 1;
   int quality = -1, method = -1, base_qidx = 0;
   int search_blocks1 = 0, search_blocks2 = 0, chroma2_blocks = 0, sm_count = 0;
+  int quad_blocks1 = 0, quad_blocks2 = 0;  // persistent grids of the quad (four lanes per row) luma kernels
+  int quad_mode = -1;                      // -1 auto (by row count), 0 never, 1 always (ZW_QUAD)
   u32 start_slack = 0;  // measured: rows wait 1.1-1.4 % of their time at 1024 images; extra start slack only idles warps
   u64 launches = 0;
   u32 reruns = 0;
@@ -328,7 +298,16 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, search_warps(1) * 32, search_smem_bytes(search_warps(1))) == cudaSuccess;
   ok &= cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2))) == cudaSuccess;
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2))) == cudaSuccess;
+  int bq1 = 0, bq2 = 0;
+  ok &= cudaFuncSetAttribute(k_searchq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes()) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq1, k_searchq<1>, SQ_WARPS * 32, searchq_smem_bytes()) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_searchq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes()) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq2, k_searchq<2>, SQ_WARPS * 32, searchq_smem_bytes()) == cudaSuccess;
   if (!ok) { lane_destroy(c); return nullptr; }
+  if (warps_hint > 0) { bq1 = std::min(bq1, std::max(1, warps_hint / SQ_WARPS)); bq2 = std::min(bq2, std::max(1, warps_hint / SQ_WARPS)); }
+  c->quad_blocks1 = std::max(1, bq1) * ctx->sm_count;
+  c->quad_blocks2 = std::max(1, bq2) * ctx->sm_count;
+  if (const char* env = getenv("ZW_QUAD")) c->quad_mode = atoi(env);
   if (warps_hint > 0) {
     const int cap = std::max(1, warps_hint / SEARCH_WARPS);
     b1 = std::min(b1, std::max(1, warps_hint / search_warps(1))); b2 = std::min(b2, std::max(1, warps_hint / search_warps(2))); b4 = std::min(b4, cap);
@@ -475,6 +454,7 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
   if (after && after != c && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[EV_END], 0));
   fill_params(c);
   ChunkParams& P = c->P;
+  bool use_quads = false;
   CK(cudaEventRecord(c->ev[EV_START], s));
   CK(cudaMemsetAsync(c->d_st.p, 0, ni * sizeof(ImageState), s));
   CK(cudaMemsetAsync(c->d_alpha_hist.p, 0, (size_t)ni * 1024, s));
@@ -505,9 +485,21 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
   {  // (3) pass 1: luma wavefront, then the per-image chroma chains, then the bookkeeping.  (Running the
      // chains on a side stream UNDER the wavefront was measured: they starve -- 43 ms instead of 8.8 ms,
      // instruction-cache contention with the wavefront's code -- so the kernels stay back to back.)
-    const int w1 = search_warps(1);
-    const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + w1 - 1) / w1);
-    k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
+    // Batches with an I4 search: four lanes per macroblock row (k_searchq), eight rows per warp -- the I4 candidates run
+    // lane-private (measured on 1024 x 768x512: pass 1 20.7 -> 17.5 ms at method 4, 31.9 -> 24.1 ms at method 6).  One warp
+    // per row (k_search) stays for: too few rows to fill the GPU with quads (single images); methods 0 / 1 (no I4: the
+    // warp kernel's lane-private I16 layout is already dense, 7.2 vs 8.3 ms); pass 2 with trellis (a macroblock offers at
+    // most two independent trellis blocks, so half a quad idles: 39 vs 54 ms).  ZW_QUAD=0 / 1 / 2 forces never / both / pass 1.
+    const bool quad_fill = c->n_rows >= (u32)(c->sm_count * SQ_QUADS * 2);
+    use_quads = c->quad_mode < 0 ? (quad_fill && P.i4_modes > 0) : c->quad_mode != 0;
+    if (use_quads) {
+      const int g1 = (int)std::min<u64>((u64)c->quad_blocks1, ((u64)c->n_rows + SQ_QUADS - 1) / SQ_QUADS);
+      k_searchq<1><<<g1, SQ_WARPS * 32, searchq_smem_bytes(), s>>>(P);
+    } else {
+      const int w1 = search_warps(1);
+      const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + w1 - 1) / w1);
+      k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
+    }
     CK(cudaEventRecord(c->ev[EV_P1], s));
     const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
@@ -526,9 +518,14 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     const int g4 = (int)std::min<u64>((u64)c->chroma2_blocks, ((u64)c->n_rows + SEARCH_WARPS - 1) / SEARCH_WARPS);
     k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     CK(cudaEventRecord(c->ev[EV_C2], s));
-    const int w2 = search_warps(2);
-    const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);
-    k_search<2><<<g2, w2 * 32, search_smem_bytes(w2), s>>>(P);
+    if (c->quad_mode < 0 ? (use_quads && !P.do_trellis) : c->quad_mode == 1) {
+      const int g2 = (int)std::min<u64>((u64)c->quad_blocks2, ((u64)c->n_rows + SQ_QUADS - 1) / SQ_QUADS);
+      k_searchq<2><<<g2, SQ_WARPS * 32, searchq_smem_bytes(), s>>>(P);
+    } else {
+      const int w2 = search_warps(2);
+      const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);
+      k_search<2><<<g2, w2 * 32, search_smem_bytes(w2), s>>>(P);
+    }
     c->launches += 2;
   }
   CK(cudaEventRecord(c->ev[EV_P2], s));

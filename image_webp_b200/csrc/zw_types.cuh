@@ -1,6 +1,8 @@
 // zw_types.cuh -- device-side data layout of one staged chunk of images (see DESIGN.md "HBM layout").
 #ifndef ZW_TYPES_CUH
 #define ZW_TYPES_CUH
+#include <string.h>
+
 #include "zw_cost.cuh"
 
 namespace zw {
@@ -14,6 +16,42 @@ struct SegParams {
   u32 lambda_trellis_i4, lambda_trellis_i16, tlambda;
   u32 uv_dc_zthresh;  // ((1<<17)-1-bias)/iq of the chroma DC entry (error diffusion, vp8.rs:600)
 };
+
+// Segment::init_matrices (src/common/types.rs:806-853) + VP8Matrix::new (src/encoder/cost.rs:401-447) for one quantiser
+// index, on the host (zw_create builds all 128; tests/hostcheck builds the ones it needs).
+inline u32 zw_umax(u32 a, u32 b) { return a > b ? a : b; }
+inline u32 zw_umin(u32 a, u32 b) { return a < b ? a : b; }
+inline Matrix make_matrix(u32 q_dc, u32 q_ac, int type) {
+  static const u32 B[3][2] = {{96, 110}, {96, 108}, {110, 115}};
+  Matrix m;
+  m.q[0] = (u16)q_dc; m.q[1] = (u16)q_ac;
+  for (int i = 0; i < 2; i++) {
+    m.iq[i] = (u32)((1ull << 17) / (u64)m.q[i]);
+    m.bias[i] = ((B[type][i] << 17) + 128) >> 8;
+  }
+  return m;
+}
+inline SegParams make_segparams(int idx) {
+  SegParams s;
+  memset(&s, 0, sizeof(s));
+  const u32 ydc = (u32)host::kDcQuant[idx], yac = (u32)host::kAcQuant[idx];
+  const u32 y2dc = ydc * 2, y2ac = zw_umax((u32)((int)yac * 155 / 100), 8);
+  const u32 uvdc = ydc, uvac = yac;  // note: not clamped to 132 (Q18)
+  s.y1 = make_matrix(ydc, yac, 0);
+  s.y2 = make_matrix(y2dc, y2ac, 1);
+  s.uv = make_matrix(uvdc, uvac, 2);
+  for (int i = 0; i < 16; i++) s.sharpen[i] = (u16)(((u32)host::kFreqSharpening[i] * (u32)s.y1.q[i > 0]) >> 11);
+  const u32 q_i4 = (ydc + 15 * yac + 8) >> 4, q_i16 = (y2dc + 15 * y2ac + 8) >> 4, q_uv = (uvdc + 15 * uvac + 8) >> 4;
+  s.lambda_trellis_i4 = zw_umax((7 * q_i4 * q_i4) >> 3, 1);
+  s.lambda_trellis_i16 = zw_umax((q_i16 * q_i16) >> 2, 1);
+  s.lambda_i4 = zw_umax((3 * q_i4 * q_i4) >> 7, 1);
+  s.lambda_i16 = zw_umax(3 * q_i16 * q_i16, 1);
+  s.lambda_uv = zw_umax((3 * q_uv * q_uv) >> 6, 1);
+  s.lambda_mode = zw_umax((q_i4 * q_i4) >> 7, 1);
+  s.tlambda = (50u * q_i4) >> 5;
+  s.uv_dc_zthresh = ((1u << 17) - 1 - s.uv.bias[0]) / s.uv.iq[0];
+  return s;
+}
 
 // Per-macroblock record: the interface between the search passes, the statistics kernel and
 // the tokeniser, and the P1MB / P2MB parity dump (832-byte POD, the layout tests/ compare against their CPU checker).

@@ -6,10 +6,14 @@
 #include <vector>
 #include "../../image_webp_b200/csrc/zw_boolcoder.cuh"
 #include "../../image_webp_b200/csrc/zw_cost.cuh"
+#include "../../image_webp_b200/csrc/zw_quad.cuh"
 using namespace zw;
 static const u16 kPredTab[8][16] = ZW_PRED_TABLE_INIT;
 static const u16 kDTaps[32] = ZW_DTAPS_INIT;
 static const u8 kPredIdx[10][16] = ZW_PRED_IDX_INIT;
+struct HostExec {
+  template <class F> void run(F&& f) { for (int q = 0; q < zw::QG; q++) f(q); }
+};
 extern "C" {
 void hc_fdct(i32* b) { fdct4x4(b); }
 void hc_idct(i32* b) { idct4x4(b); }
@@ -30,6 +34,11 @@ int hc_trellis(i32* coeffs, i32* out, const u16* q, const u32* iq, const u32* bi
                const u8* probs, const u16* lcost, int ctype, int ctx0) {
   CostCtx cc; cc.probs = probs; cc.level_cost = lcost;
   return trellis_quantize(coeffs, out, mk(q, iq, bias), sharpen, lambda, first, cc, ctype, ctx0) ? 1 : 0;
+}
+int hc_trellis_rolled(i32* coeffs, i32* out, const u16* q, const u32* iq, const u32* bias, const u16* sharpen, u32 lambda, int first,
+                      const u8* probs, const u16* lcost, int ctype, int ctx0) {
+  CostCtx cc; cc.probs = probs; cc.level_cost = lcost;
+  return q_trellis(coeffs, out, mk(q, iq, bias), sharpen, lambda, first, cc, ctype, ctx0) ? 1 : 0;
 }
 void hc_token_events(const i16* zz, int t, int first, int ctx, u32* stats /*1056 packed like ProbaStats (no halving)*/) {
   token_events(zz, t, first, ctx, [&](int slot, int bit) { stats[slot] += 0x10000u + (u32)bit; });
@@ -92,5 +101,77 @@ size_t hc_boolcode_segmented(const u16* tk, size_t n, u32 seg, u32 warm, u8* out
   for (u32 j = 1; j < J; j++) bc_fix_boundary(out, S[j].start_bit, S[j - 1].tail, S[j].carries);  // k_bc_fix
   if (stats) { stats[0] = J; stats[1] = maxk; stats[2] = crossed; stats[3] = sumk; }
   return bytes;
+}
+// The quad (four lanes per macroblock row) luma path of zw_quad.cuh, run over a whole image on the CPU: the lanes of a quad
+// are called one after the other at every sync point.  y: padded luma plane (stride 16 * mbw); segmap / seg_qidx: the image's
+// segments (segmap == NULL: all base_qidx); pass 1: default probabilities, zero level costs, no trellis; pass 2: the
+// image's probabilities / level costs and, for method >= 4, trellis.  uvnz: pass-2 chroma has_coeffs bits per macroblock.
+// out: one MbRecord per macroblock with the luma-owned fields filled (ymode, bmodes, levels[0..16]; pass 2 also skip,
+// top_nz, left_nz).
+void hc_quad_luma_image(const u8* y, int mbw, int mbh, int pass, int method, int base_qidx, const u8* segmap, const u8* seg_qidx,
+                        const u8* probs, const u16* lcost, const u8* uvnz, MbRecord* out) {
+  static u8 pidx[10][16];
+  static bool init = false;
+  if (!init) {
+    memcpy(pidx, kPredIdx, sizeof(pidx));
+    for (int i = 0; i < 16; i++) pidx[1][i] = (u8)(32 + i);  // TM pixels live in dtab[32 + n]
+    init = true;
+  }
+  QuadConst K; K.pidx = pidx; K.dtaps = kDTaps;
+  std::vector<MbBottom> bottom((size_t)mbw * mbh);
+  std::vector<u16> nz_after((size_t)mbw * mbh);
+  const int pw = mbw * 16;
+  HostExec X;
+  for (int mby = 0; mby < mbh; mby++) {
+    QuadScratch S;
+    memset(&S, 0, sizeof(S));
+    u32 left_nz = 0;
+    for (int mbx = 0; mbx < mbw; mbx++) {
+      const int mb = mby * mbw + mbx;
+      const SegParams SP = make_segparams(segmap ? seg_qidx[segmap[mb]] : base_qidx);
+      // load_luma_mb (zw_search.cuh): source, top / top-right / left borders
+      for (int r = 0; r < 16; r++) memcpy(&S.src_y[r * 16], y + (size_t)(mby * 16 + r) * pw + mbx * 16, 16);
+      if (mby == 0) { for (int k = 0; k < 32; k++) S.yws[k] = 127; }
+      else {
+        const MbBottom* bt = &bottom[mb - mbw];
+        for (int k = 0; k < 16; k++) S.yws[1 + k] = bt->y[k];
+        for (int k = 16; k < 20; k++) S.yws[1 + k] = (mbx == mbw - 1) ? bt->y[15] : (bt + 1)->y[k - 16];
+      }
+      for (int k = 0; k < 16; k++) S.yws[(1 + k) * 32] = (mbx == 0) ? 129 : S.left_y[1 + k];
+      S.yws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : S.left_y[0]);
+      for (int k = 0; k < 12; k++) { const int r = 4 * (1 + k / 4), c = 17 + (k & 3); S.yws[r * 32 + c] = S.yws[c]; }
+      memset(S.lv, 0, sizeof(S.lv));
+      QuadMbIn in;
+      in.SP = &SP;
+      in.cc.probs = pass == 1 ? host::kCoeffProbs : probs;
+      in.cc.level_cost = pass == 1 ? nullptr : lcost;
+      in.i4_modes = method <= 1 ? 0 : (method <= 3 ? 3 : (method == 4 ? 4 : 10));
+      in.i4_always = method >= 5;
+      in.trellis = pass == 2 && method >= 4;
+      in.mbx = mbx; in.mby = mby;
+      in.in_top_nz = (pass == 2 && mby > 0) ? nz_after[mb - mbw] : 0;
+      in.in_left_nz = left_nz;
+      const QuadLumaOut L = quad_luma_mb<QG>(X, S, K, in);
+      MbRecord& r = out[mb];
+      memset(&r, 0, sizeof(r));
+      r.ymode = L.use_i4 ? 4 : (u8)L.mode16;
+      if (L.use_i4) memcpy(r.bmodes, S.bmodes, 16);
+      r.segment = segmap ? segmap[mb] : 0;
+      bool skip = false;
+      u32 out_top = 0, out_left = 0;
+      if (pass == 2) {
+        skip = !(L.simple_nz || uvnz[mb] != 0);
+        q_complexity_after(L.use_i4, skip, L.y2nz, L.ynz, uvnz[mb], in.in_top_nz, left_nz, out_top, out_left);
+        r.skip = skip; r.top_nz = (u16)in.in_top_nz; r.left_nz = (u16)left_nz;
+        nz_after[mb] = (u16)out_top;
+      } else {
+        r.top_nz = (u16)L.ynz; r.left_nz = (u16)((L.y2nz ? 1 : 0) | (L.simple_nz ? 2 : 0));  // parked for k_finish1
+      }
+      if (!skip) memcpy(r.levels, S.lv, sizeof(S.lv));
+      left_nz = out_left;
+      for (int k = 0; k < 17; k++) S.left_y[k] = S.yws[k * 32 + 16];
+      for (int k = 0; k < 16; k++) bottom[mb].y[k] = S.yws[16 * 32 + 1 + k];
+    }
+  }
 }
 }

@@ -16,7 +16,7 @@ SO = os.path.join(ROOT, "tests", "hostcheck", "_build", "libzw_hostcheck.so")
 
 
 def _build():
-    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc", "zw_boolcoder.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc", "zw_boolcoder.cuh", "zw_quad.cuh", "zw_types.cuh")]
     if (not os.path.exists(SO)) or any(os.path.getmtime(SO) < os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO])
@@ -154,6 +154,11 @@ def test_trellis_matches_oracle():
         rb = H.hc_trellis(b.ctypes.data_as(i32p), ob.ctypes.data_as(i32p), q2, iq2, b2, sh, lamb, first, p.ctypes.data_as(C.c_void_p),
                           lc.ctypes.data_as(C.c_void_p), ctype, ctx0)
         assert ra == rb and (oa == ob).all() and (a == b).all(), (trial, co, oa, ob)
+        # the rolled form the quad kernels call (zw_quad.cuh q_trellis)
+        c3 = co.copy(); o3 = np.zeros(16, np.int32)
+        rc3 = H.hc_trellis_rolled(c3.ctypes.data_as(i32p), o3.ctypes.data_as(i32p), q2, iq2, b2, sh, lamb, first, p.ctypes.data_as(C.c_void_p),
+                                  lc.ctypes.data_as(C.c_void_p), ctype, ctx0)
+        assert rc3 == ra and (o3 == oa).all() and (c3 == a).all(), ("rolled", trial, co, oa, o3)
 
 
 def test_token_events_match_oracle_record_coeffs():
@@ -216,3 +221,55 @@ def test_segment_parallel_boolcoder_equals_the_serial_coder():
             assert got == ref, "stream of %d symbols, seg %d warm %d: differs (%d vs %d bytes)" % (tok.size, seg, warm, len(got), len(ref))
             worst = max(worst, int(st[1]))
     assert worst >= 16  # the literal stream really keeps many candidate states alive: the general path is exercised
+
+
+def _quad_luma(img, q, m, dump, pas):
+    """Run zw_quad.cuh's four-lanes-per-macroblock luma path over the image on the CPU (same source the kernel compiles)."""
+    h, w = img.shape[:2]
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    y = np.ascontiguousarray(dump["YUV_Y"])
+    assert y.size == mbw * mbh * 256
+    segmap = np.ascontiguousarray(dump["SEG_MAP"]) if "SEG_MAP" in dump and dump["SEG_ENABLED"][0] else None
+    segq = np.ascontiguousarray(dump["SEG_QIDX"]) if "SEG_QIDX" in dump else np.zeros(4, np.uint8)
+    probs = np.ascontiguousarray(dump["PROBS"])
+    lcost = np.ascontiguousarray(dump["LCOST"])
+    p2 = dump["P2MB"]
+    uvnz = np.zeros(mbw * mbh, np.uint8)
+    nzb = (p2["levels"][:, 17:25, :] != 0).any(axis=2)
+    for b in range(8):
+        uvnz |= (nzb[:, b].astype(np.uint8) << b)
+    out = np.zeros(mbw * mbh, O.MB_DTYPE)
+    H.hc_quad_luma_image(y.ctypes.data_as(C.c_void_p), mbw, mbh, pas, m, int(dump["BASE_QIDX"][0]),
+                         segmap.ctypes.data_as(C.c_void_p) if segmap is not None else None, segq.ctypes.data_as(C.c_void_p),
+                         probs.ctypes.data_as(C.c_void_p), lcost.ctypes.data_as(C.c_void_p), uvnz.ctypes.data_as(C.c_void_p),
+                         out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+@pytest.mark.parametrize("name,q,m", [("synth", 75, 4), ("photo", 75, 4), ("photo", 50, 6), ("synth", 90, 2), ("photo", 75, 0), ("small", 75, 5),
+                                      ("photo", 20, 3)])
+def test_quad_luma_path_matches_oracle_records(name, q, m):
+    """zw_quad.cuh (lane-private 4x4 work, four lanes per macroblock row) against the oracle's P1MB / P2MB: modes, sub-block
+    modes, every coded luma level, and in pass 2 the skip flags and complexity contexts."""
+    import photo_inputs as PI
+    from image_webp_b200 import synth
+    img = {"synth": lambda: synth.photo_like(320, 272, 21), "photo": lambda: PI.crop("3", 400, 200, 320, 272),
+           "small": lambda: synth.photo_like(99, 87, 2)}[name]()
+    rc, _, dump = O.encode(img, q, m, want_dump=True)
+    assert rc == 0
+    for pas, key in ((1, "P1MB"), (2, "P2MB")):
+        got = _quad_luma(img, q, m, dump, pas)
+        ref = dump[key]
+        assert (got["ymode"] == ref["ymode"]).all(), "pass %d ymode: %s" % (pas, np.nonzero(got["ymode"] != ref["ymode"])[0][:8])
+        assert (got["bmodes"] == ref["bmodes"]).all(), "pass %d bmodes differ at MB %s" % (pas, np.nonzero((got["bmodes"] != ref["bmodes"]).any(axis=1))[0][:8])
+        if pas == 2:
+            for f in ("skip", "top_nz", "left_nz"):
+                assert (got[f] == ref[f]).all(), "pass 2 %s differs at MB %s" % (f, np.nonzero(got[f] != ref[f])[0][:8])
+            lv_ref = ref["levels"][:, :17, :]
+        else:
+            # pass-1 records of skipped macroblocks are zeroed later (k_finish1); compare the unskipped ones
+            keep = ref["skip"] == 0
+            got, ref = got[keep], ref[keep]
+            lv_ref = ref["levels"][:, :17, :]
+        bad = np.nonzero((got["levels"][:, :17, :] != lv_ref).any(axis=(1, 2)))[0]
+        assert bad.size == 0, "pass %d: luma levels differ at %d MBs, first %s" % (pas, bad.size, bad[:8])
