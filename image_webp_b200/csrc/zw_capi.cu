@@ -769,11 +769,14 @@ int zw_submit(zw_ctx* c, const zw_image* imgs, size_t n, int quality, int method
     if (validate_image(imgs[i]) == ZW_OK) bytes += image_footprint(imgs[i].width, imgs[i].height, color_bpp(imgs[i].color));
   if (n > 1 && bytes > c->budget) return g_last_error = ZW_ERR_TOO_LARGE;
   CK(cudaSetDevice(c->device));
+  if (c->staged) {  // lane 0 doubles as the split API's lane: a batch left staged there is dropped, not a taken slot
+    c->lanes[0]->state = LANE_FREE;
+    c->staged = false; c->encoded = false;
+  }
   int k = -1;
   for (size_t i = 0; i < c->lanes.size(); i++)
     if (c->lanes[i]->state == LANE_FREE) { k = (int)i; break; }
   if (k < 0) return g_last_error = ZW_ERR_BUSY;
-  if (k == 0) { c->staged = false; c->encoded = false; }  // lane 0 doubles as the split API's lane
   int rc = ctx_submit_lane(c, k, imgs, n, quality, method);
   if (rc != ZW_OK) return g_last_error = rc;
   *ticket = k;
