@@ -2731,6 +2731,8 @@ static void write_chunk(std::vector<u8>& w, const char* name, const std::vector<
   if (data.size() % 2 == 1) w.push_back(0);
 }
 
+#include "zw_dec_oracle.inc"
+
 }  // namespace
 
 // =============================================================================================
@@ -2767,6 +2769,60 @@ int zwo_encode_webp(const uint8_t* data, size_t data_len, uint32_t width, uint32
   memcpy(*out, w.data(), w.size());
   *out_len = w.size();
   return 0;
+}
+
+
+// ---- decoder (zw_dec_oracle.inc): test infrastructure for the on-device decoder / verifier ----
+// Decodes a VP8 key frame (bare, or inside RIFF/WEBP).  Any output pointer may be NULL.  *rgb: width*height*3
+// (fancy != 0: bilinear chroma upsampling like WebPDecoder::read_image's default, else nearest); *planes: Y | U | V of
+// the padded frame (16*mbw x 16*mbh, 8*mbw x 8*mbh twice) after the loop filter, *planes_unfiltered the same before it;
+// *mbinfo: 24 bytes per macroblock {luma_mode, chroma_mode, segment, coeffs_skipped, non_zero_dct, 0,0,0, bpred[16]};
+// hdr[16]: width, height, mbw, mbh, filter_type, filter_level, sharpness, num_partitions, segments_enabled, update_map,
+// lf_adj, has_skip_prob, prob_skip_false, version, pixel_type, first-partition bytes consumed (approx.)
+int zwo_decode(const uint8_t* data, size_t len, int fancy, uint8_t** rgb, uint8_t** planes, uint8_t** planes_unfiltered,
+               uint8_t** mbinfo, uint32_t hdr[16]) {
+  if (rgb) *rgb = nullptr;
+  if (planes) *planes = nullptr;
+  if (planes_unfiltered) *planes_unfiltered = nullptr;
+  if (mbinfo) *mbinfo = nullptr;
+  const u8* vp8 = nullptr;
+  size_t vlen = 0;
+  int rc = dy_find_vp8(data, len, &vp8, &vlen);
+  if (rc != ZWD_OK) return rc;
+  Vp8DecoderO d;
+  d.data = vp8; d.len = vlen;
+  d.keep_unfiltered = planes_unfiltered != nullptr;
+  rc = d.decode_frame();
+  if (hdr) {
+    const uint32_t h[16] = {d.width, d.height, d.mbwidth, d.mbheight, d.filter_type, d.filter_level, d.sharpness_level, (uint32_t)d.num_partitions,
+                            d.segments_enabled, d.segments_update_map, d.lf_adj, d.has_skip_prob, d.prob_skip_false, d.version, d.pixel_type, 0};
+    memcpy(hdr, h, sizeof(h));
+  }
+  if (rc != ZWD_OK) return rc;
+  const size_t ysz = d.ybuf.size(), csz = d.ubuf.size();
+  if (rgb) {
+    *rgb = (uint8_t*)malloc((size_t)d.width * d.height * 3 + 1);
+    dy_fill_rgb(*rgb, d, fancy != 0);
+  }
+  if (planes) {
+    *planes = (uint8_t*)malloc(ysz + 2 * csz);
+    memcpy(*planes, d.ybuf.data(), ysz); memcpy(*planes + ysz, d.ubuf.data(), csz); memcpy(*planes + ysz + csz, d.vbuf.data(), csz);
+  }
+  if (planes_unfiltered) {
+    *planes_unfiltered = (uint8_t*)malloc(ysz + 2 * csz);
+    memcpy(*planes_unfiltered, d.ybuf0.data(), ysz); memcpy(*planes_unfiltered + ysz, d.ubuf0.data(), csz); memcpy(*planes_unfiltered + ysz + csz, d.vbuf0.data(), csz);
+  }
+  if (mbinfo) {
+    const size_t nmb = d.macroblocks.size();
+    *mbinfo = (uint8_t*)calloc(nmb ? nmb : 1, 24);
+    for (size_t i = 0; i < nmb; i++) {
+      const DecMacroBlock& m = d.macroblocks[i];
+      uint8_t* o = *mbinfo + i * 24;
+      o[0] = m.luma_mode; o[1] = m.chroma_mode; o[2] = m.segmentid; o[3] = m.coeffs_skipped; o[4] = m.non_zero_dct;
+      memcpy(o + 8, m.bpred, 16);
+    }
+  }
+  return ZWD_OK;
 }
 
 void zwo_free(void* p) { free(p); }

@@ -51,6 +51,10 @@ int zwo_encode_webp(const uint8_t* data, size_t data_len, uint32_t width, uint32
                     zwo_dump* dump);
 void zwo_free(void* p);
 
+/* VP8 key-frame decoder restated from src/decoder/ (zw_dec_oracle.inc): checker of the on-device decoder. */
+int zwo_decode(const uint8_t* data, size_t len, int fancy, uint8_t** rgb, uint8_t** planes, uint8_t** planes_unfiltered,
+               uint8_t** mbinfo, uint32_t hdr[16]);
+
 /* Encode n same-sized images with `threads` host threads (one image per thread at a time);
  * returns total output bytes. Used by bench.py's CPU baseline. outs/out_lens may be NULL. */
 size_t zwo_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32_t height,

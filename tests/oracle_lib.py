@@ -96,6 +96,39 @@ def encode(img, quality, method, color="Rgb8", container=True, want_dump=False):
     return rc, data, dump
 
 
+DEC_MB_DTYPE = np.dtype([("luma_mode", "u1"), ("chroma_mode", "u1"), ("segment", "u1"), ("skipped", "u1"), ("non_zero_dct", "u1"),
+                         ("pad", "u1", (3,)), ("bpred", "u1", (16,))])
+DEC_HDR = ["width", "height", "mbw", "mbh", "filter_type", "filter_level", "sharpness", "num_partitions", "segments_enabled",
+           "update_map", "lf_adj", "has_skip_prob", "prob_skip_false", "version", "pixel_type", "reserved"]
+
+
+def decode(data: bytes, fancy=True, want=("rgb",)):
+    """Decode a VP8 key frame (bare or RIFF/WEBP) with the decoder oracle.  Returns (status, dict) with the keys asked
+    for in `want` out of rgb [h,w,3], planes / planes_unfiltered (dict y,u,v of the padded frame), mbinfo, plus hdr."""
+    L = lib()
+    u8p = C.POINTER(C.c_uint8)
+    L.zwo_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(u8p), C.POINTER(u8p), C.POINTER(u8p), C.POINTER(u8p), C.POINTER(C.c_uint32)]
+    ptr = {k: u8p() for k in ("rgb", "planes", "planes_unfiltered", "mbinfo")}
+    hdr = (C.c_uint32 * 16)()
+    rc = L.zwo_decode(data, len(data), 1 if fancy else 0, *[C.byref(ptr[k]) if k in want else None for k in ("rgb", "planes", "planes_unfiltered", "mbinfo")], hdr)
+    out = {"hdr": dict(zip(DEC_HDR, list(hdr)))}
+    if rc != 0:
+        return rc, out
+    w, h, mbw, mbh = hdr[0], hdr[1], hdr[2], hdr[3]
+    ysz, csz = mbw * mbh * 256, mbw * mbh * 64
+    for k in want:
+        if k == "rgb":
+            out[k] = np.frombuffer(C.string_at(ptr[k], w * h * 3), np.uint8).reshape(h, w, 3).copy()
+        elif k in ("planes", "planes_unfiltered"):
+            raw = np.frombuffer(C.string_at(ptr[k], ysz + 2 * csz), np.uint8)
+            out[k] = {"y": raw[:ysz].reshape(mbh * 16, mbw * 16).copy(), "u": raw[ysz:ysz + csz].reshape(mbh * 8, mbw * 8).copy(),
+                      "v": raw[ysz + csz:].reshape(mbh * 8, mbw * 8).copy()}
+        elif k == "mbinfo":
+            out[k] = np.frombuffer(C.string_at(ptr[k], mbw * mbh * 24), DEC_MB_DTYPE).reshape(mbh, mbw).copy()
+        L.zwo_free(ptr[k])
+    return rc, out
+
+
 def encode_batch_mt(imgs, quality, method, threads=None, color="Rgb8", container=True, L=None):
     """imgs: uint8 array [n,h,w,c] of same-sized images -> list of n files (bytes), encoded with `threads` host threads."""
     L = L or lib()
