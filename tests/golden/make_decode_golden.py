@@ -19,5 +19,12 @@ for i in range(1, 6):
         e[key] = {"sha256": hashlib.sha256(im.tobytes()).hexdigest(), "width": im.shape[1], "height": im.shape[0],
                   "sum": int(im.astype(np.uint64).sum())}
     out["gallery1/%d" % i] = e
+# lossy + alpha files (VP8X: ALPH + 'VP8 ', NORMAL loop filter, level up to 63) and a 1x1 regression file: colour channels only
+for name in ["gallery2/%d_webp_a" % i for i in range(1, 6)] + ["regression/dark"]:
+    shutil.copyfile("%s/images/%s.webp" % (REF, name), os.path.join(HERE, "decode", name.replace("/", "_") + ".webp"))
+    im = np.asarray(Image.open("%s/reference/%s.png" % (REF, name)).convert("RGBA"))[:, :, :3]
+    im = np.ascontiguousarray(im)
+    out[name] = {"fancy": {"sha256": hashlib.sha256(im.tobytes()).hexdigest(), "width": im.shape[1], "height": im.shape[0],
+                           "sum": int(im.astype(np.uint64).sum())}}
 json.dump(out, open(os.path.join(HERE, "decode_golden.json"), "w"), indent=1, sort_keys=True)
 print(json.dumps(out, indent=1))

@@ -36,6 +36,18 @@ def test_reference_decode_fixtures(i, mode):
     assert hashlib.sha256(out["rgb"].tobytes()).hexdigest() == g["sha256"]
 
 
+@pytest.mark.parametrize("name", ["gallery2/%d_webp_a" % i for i in range(1, 6)] + ["regression/dark"])
+def test_reference_decode_fixtures_normal_filter(name):
+    """tests/decode.rs:193,195-198: lossy + alpha files (VP8X, NORMAL loop filter, level 3..63) and a 1x1 image; colour
+    channels of the reference PNGs (alpha is a VP8L plane, not part of this path)."""
+    data = open(os.path.join(HERE, "golden", "decode", name.replace("/", "_") + ".webp"), "rb").read()
+    rc, out = O.decode(data, want=("rgb",))
+    g = GOLD[name]["fancy"]
+    assert rc == 0 and out["hdr"]["filter_type"] == 0
+    assert out["rgb"].shape == (g["height"], g["width"], 3)
+    assert hashlib.sha256(out["rgb"].tobytes()).hexdigest() == g["sha256"]
+
+
 def test_photo_fixture_pixels():
     """gallery1/3.png is committed in full (tests/golden/photos): compare pixels, not just the hash."""
     rc, out = O.decode(_file(3), want=("rgb",))
