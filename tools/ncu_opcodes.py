@@ -10,7 +10,13 @@ import sys
 
 rep, out_md = sys.argv[1], sys.argv[2]
 want = sys.argv[3:]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".gz"):
+    import gzip
+    txt = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    txt = open(rep).read()
+else:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 
 CLASSES = [

@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
 """Summarise an ncu --set full report into profiles/<name>_summary.md and profiles/<name>_traffic.json.
-usage: python tools/ncu_summary.py gpurun_out/prof_r1_final.ncu-rep r1 <pixels per launch>"""
+usage: python tools/ncu_summary.py <ncu-rep | raw-page csv> r1 <pixels per launch>"""
 import csv, json, subprocess, sys, collections
 
 rep, name, pixels = sys.argv[1], sys.argv[2], float(sys.argv[3])
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):  # the raw page exported on the GPU box (ncu -i X.ncu-rep --page raw --csv)
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
