@@ -4,5 +4,7 @@ imazen/image-webp (`zenwebp` 0.2.0).  Hand-written CUDA for sm_100a, no CPU fall
 from .encoder import (BatchPipeline, ColorType, Context, DeviceError, EncoderParams, EncodingError, InvalidBufferSize,
                       InvalidDimensions, MultiContext, PendingBatch, WebPEncoder, default_context, encode_batch)
 
-__all__ = ["BatchPipeline", "ColorType", "Context", "DeviceError", "EncoderParams", "EncodingError", "InvalidBufferSize",
+from .decoder import DecodingError, UpsamplingMethod, WebPDecoder, decode_batch, decode_rgb, verify_pending
+
+__all__ = ["DecodingError", "UpsamplingMethod", "WebPDecoder", "decode_batch", "decode_rgb", "verify_pending", "BatchPipeline", "ColorType", "Context", "DeviceError", "EncoderParams", "EncodingError", "InvalidBufferSize",
            "InvalidDimensions", "MultiContext", "PendingBatch", "WebPEncoder", "default_context", "encode_batch"]

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libzenwebp_b200.so")
-SOURCES = ["zw_capi.cu", "zw_back.cuh", "zw_search.cuh", "zw_front.cuh", "zw_types.cuh", "zw_cost.cuh", "zw_prims.cuh", "zw_tables.inc"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc")))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
 
@@ -64,12 +64,26 @@ class ZwBatchView(C.Structure):
                 ("status", C.POINTER(C.c_int32))]
 
 
+class ZwBlob(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
+
+
+class ZwDecodeInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32), ("filter_type", C.c_uint32),
+                ("filter_level", C.c_uint32), ("sharpness", C.c_uint32), ("num_partitions", C.c_uint32),
+                ("segments_enabled", C.c_uint32), ("sse_rgb", C.c_uint64), ("psnr_rgb", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # Every symbol include/zenwebp_b200.h declares.
 EXPORTS = ["zw_create", "zw_destroy", "zw_last_error", "zw_strerror", "zw_free", "zw_max_output_size",
            "zw_encode_vp8_batch", "zw_encode_webp_batch", "zw_submit", "zw_wait", "zw_release",
            "zw_multi_create", "zw_multi_destroy", "zw_multi_device_count", "zw_multi_encode",
            "zw_stage_batch", "zw_encode_resident", "zw_download",
-           "zw_dump_stage", "zw_version", "zw_measure_int_peak"]
+           "zw_dump_stage", "zw_version", "zw_measure_int_peak",
+           "zw_decode_batch", "zw_verify", "zw_decode_dump_stage"]
 
 _lib = None
 
@@ -109,5 +123,9 @@ def load():
     L.zw_download.argtypes = [C.c_void_p, C.POINTER(ZwOutput), C.c_size_t, C.c_int, C.POINTER(ZwTiming)]
     L.zw_dump_stage.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.zw_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.zw_decode_batch.argtypes = [C.c_void_p, C.POINTER(ZwBlob), C.c_size_t, C.c_int, C.POINTER(ZwOutput), C.POINTER(ZwImage),
+                                  C.POINTER(ZwDecodeInfo), C.POINTER(C.c_float)]
+    L.zw_verify.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ZwDecodeInfo), C.POINTER(C.c_float)]
+    L.zw_decode_dump_stage.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,7 @@
 
 #include "../../include/zenwebp_b200.h"
 #include "zw_back.cuh"
+#include "zw_dec.cuh"
 #include "zw_front.cuh"
 
 using namespace zw;
@@ -197,6 +199,23 @@ struct Lane {
   zw_timing last;
 };
 
+// Buffers of the decoder / verifier entry points (zw_dec_host.inc); allocated on first use.
+struct DecCtx {
+  DevBuf d_img, d_st, d_bytes, d_planes, d_mbinfo, d_topnz, d_topmodes, d_rgb, d_src;
+  PinBuf h_st;
+  cudaEvent_t ev[3];
+  bool ev_ok = false;
+  u32 last_n = 0;
+  std::vector<DecImage> last_img;
+  void release() {
+    DevBuf* all[] = {&d_img, &d_st, &d_bytes, &d_planes, &d_mbinfo, &d_topnz, &d_topmodes, &d_rgb, &d_src};
+    for (DevBuf* b : all) b->release();
+    h_st.release();
+    if (ev_ok) for (auto& e : ev) cudaEventDestroy(e);
+    ev_ok = false;
+  }
+};
+
 struct zw_ctx {
   int device = 0;
   int sm_count = 0;
@@ -209,6 +228,7 @@ struct zw_ctx {
   bool staged = false, encoded = false;
   int dump_lane = -1;    // lane zw_dump_stage reads: the last chunk handed to the device
   zw_timing last;
+  DecCtx dec;
 };
 
 static void fill_params(Lane* c) {
@@ -231,6 +251,7 @@ static void fill_params(Lane* c) {
   P.hdr_tokens = c->d_htok.as<Token>(); P.tok_tokens = c->d_ttok.as<Token>();
   P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
   P.method = (u32)c->method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = c->method >= 4;
+  if (getenv("ZW_EXP_NOTRELLIS")) P.do_trellis = 0;  // timing experiment only: output is no longer the reference's
   P.i4_modes = c->method <= 1 ? 0u : (c->method <= 3 ? 3u : (c->method == 4 ? 4u : 10u));
   P.i4_always = c->method >= 5;
   P.filter_level = (u8)compute_filter_level(c->base_qidx);
@@ -755,6 +776,7 @@ void zw_destroy(zw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (Lane* l : c->lanes) lane_destroy(l);
+  c->dec.release();
   c->d_segtab.release(); c->d_lut.release();
   delete c;
 }
@@ -1081,3 +1103,5 @@ int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_
 }
 
 }  // extern "C"
+
+#include "zw_dec_host.inc"

@@ -98,6 +98,7 @@ class PendingBatch:
 
     def __init__(self, ctx, ticket, keep, container, raise_errors):
         self._ctx, self._ticket, self._keep = ctx, ticket, keep
+        self._n = len(keep[0])
         self._container, self._raise = container, raise_errors
         self._res = None
 

@@ -5,6 +5,7 @@
  *     reference: src/encoder/api.rs:1291-1329 (caller, RIFF wrap), src/encoder/vp8.rs:3132-3153 (seam)
  * The reference has no FFI of its own (it is #![forbid(unsafe_code)] Rust); these entry points are
  * what a `zenwebp-b200-sys` crate binds (see INTEGRATION.md for the Rust / ctypes stubs).
+ * Next to it: an on-device VP8 key-frame DECODER used as the batch verifier (zw_decode_batch / zw_verify below).
  *
  * Everything device-side is hand-written CUDA for sm_100a.  There is NO CPU fallback: every
  * call fails with ZW_ERR_CUDA (>= 100) when no CUDA device / driver is usable.
@@ -177,6 +178,53 @@ int zw_measure_int_peak(zw_ctx* ctx, double* int_instr_per_s);
  * counts inside the LAST chunk.  *len receives the stage size; if cap is too small
  * nothing is copied and ZW_ERR_OUTPUT_TOO_SMALL is returned. */
 int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
+
+/* ---- On-device VP8 key-frame decoder, used as the batch verifier --------------------------
+ * Reference: Vp8Decoder::decode_frame (src/decoder/vp8.rs:1526) + the loop filter (loop_filter.rs) + the
+ * YUV->RGB conversion WebPDecoder::read_image applies (src/decoder/yuv.rs:82 bilinear "fancy" upsampling, the
+ * default, and :402 UpsamplingMethod::Simple).  Decoded pixels are identical to the CPU port of that decoder
+ * (oracle/zw_dec_oracle.inc), which is pinned pixel-exact by the reference's own decode fixtures.
+ * Key frames only (every WebP still image); any number of token partitions, both loop filters, segments. */
+enum {
+  ZW_DEC_OK = 0,
+  ZW_DEC_BITSTREAM = 1,   /* DecodingError::BitStreamError: a partition ended early                          */
+  ZW_DEC_UNSUPPORTED = 2, /* not a key frame (DecodingError::UnsupportedFeature)                             */
+  ZW_DEC_MAGIC = 3,       /* start code != 9d 01 2a (DecodingError::Vp8MagicInvalid)                          */
+  ZW_DEC_COLORSPACE = 4,  /* DecodingError::ColorSpaceInvalid                                                */
+  ZW_DEC_TRUNCATED = 5,   /* file shorter than its headers / first partition say                            */
+  ZW_DEC_CONTAINER = 6,   /* RIFF/WEBP without a 'VP8 ' chunk (lossless VP8L files are not this path)        */
+  ZW_DEC_DIMENSIONS = 7   /* zero-sized frame, or the source handed in for verification has another size    */
+};
+typedef struct zw_blob {
+  const uint8_t* data; /* a .webp file (RIFF container, simple or VP8X) or a bare VP8 frame; host memory */
+  size_t len;
+} zw_blob;
+typedef struct zw_decode_info {
+  int32_t status; /* ZW_DEC_* */
+  uint32_t width, height;
+  uint32_t filter_type, filter_level, sharpness, num_partitions, segments_enabled; /* frame header fields */
+  uint64_t sse_rgb; /* verification: sum over width*height*3 samples of (decoded - source)^2       */
+  double psnr_rgb;  /* verification: 10 log10(255^2 * 3wh / sse_rgb); 99.0 for identical pixels   */
+} zw_decode_info;
+
+/* Decode n files on the GPU (one warp per image for the serial bitstream + reconstruction + loop filter, then a
+ * data-parallel colour conversion).  upsampling: 1 = bilinear (the reference's default), 0 = nearest.
+ *   rgb_outs  NULL, or n slots that receive width*height*3 RGB bytes (allocated with malloc when data == NULL)
+ *   sources   NULL, or n source images: every decoded image is scored against sources[i] on the device
+ *             (sse_rgb / psnr_rgb; grey sources compare each channel with the grey value, alpha is ignored)
+ *   infos     n results;  device_ms NULL or [2]: frame kernel, colour kernel (CUDA events) */
+int zw_decode_batch(zw_ctx* ctx, const zw_blob* files, size_t n, int upsampling, zw_output* rgb_outs,
+                    const zw_image* sources, zw_decode_info* infos, float* device_ms);
+
+/* Verify a batch where it lies: decode the files zw_submit left in device memory and score them against the
+ * batch's source pixels, which are still resident there as well -- only the per-image results cross the link.
+ * Call between zw_submit (any time: it waits for the batch's kernels) and zw_release of that ticket; infos has
+ * one entry per image of the batch. */
+int zw_verify(zw_ctx* ctx, int ticket, int upsampling, zw_decode_info* infos, float* device_ms);
+
+/* Parity/debug: a stage of image `index` of the last decoded chunk: "DEC_PLANES" (filtered Y | U | V of the
+ * padded frame), "DEC_MBINFO" (4 words per macroblock: flags, sub-block modes), "DEC_STATE". */
+int zw_decode_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
 
 /* Library build info, e.g. "zenwebp_b200 0.2 (CUDA, sm_100a)". */
 const char* zw_version(void);

@@ -7,12 +7,16 @@
 #include "../../image_webp_b200/csrc/zw_boolcoder.cuh"
 #include "../../image_webp_b200/csrc/zw_cost.cuh"
 #include "../../image_webp_b200/csrc/zw_quad.cuh"
+#include "../../image_webp_b200/csrc/zw_dec.cuh"
 using namespace zw;
 static const u16 kPredTab[8][16] = ZW_PRED_TABLE_INIT;
 static const u16 kDTaps[32] = ZW_DTAPS_INIT;
 static const u8 kPredIdx[10][16] = ZW_PRED_IDX_INIT;
 struct HostExec {
   template <class F> void run(F&& f) { for (int q = 0; q < zw::QG; q++) f(q); }
+};
+struct HostExec32 {
+  template <class F> void run(F&& f) { for (int l = 0; l < 32; l++) f(l); }
 };
 extern "C" {
 void hc_fdct(i32* b) { fdct4x4(b); }
@@ -173,5 +177,39 @@ void hc_quad_luma_image(const u8* y, int mbw, int mbh, int pass, int method, int
       for (int k = 0; k < 16; k++) bottom[mb].y[k] = S.yws[16 * 32 + 1 + k];
     }
   }
+}
+
+// The on-device decoder (zw_dec.cuh), the SAME source the kernels run, lane by lane on the host: one VP8 frame ->
+// filtered planes (Y | U | V padded), macroblock info words, RGB (fancy or simple) and the squared error against `src`.
+// Returns the decoder status.
+int hc_decode(const u8* data, size_t len, u32 width, u32 height, int fancy, u8* planes, u32* mbinfo, u8* rgb, const u8* src, u32 src_bpp,
+              u32* st_out /*[12]*/, u64* sse) {
+  DecImage D;
+  memset(&D, 0, sizeof(D));
+  D.data_off = 0; D.data_len = (u32)len; D.width = width; D.height = height; D.mbw = (width + 15) / 16; D.mbh = (height + 15) / 16;
+  D.src_bpp = src_bpp;
+  std::vector<u16> topnz(D.mbw);
+  std::vector<u32> topmodes(D.mbw);
+  DecState st;
+  memset(&st, 0, sizeof(st));
+  DecParams P;
+  memset(&P, 0, sizeof(P));
+  P.img = &D; P.st = &st; P.n_img = 1; P.fancy = fancy; P.bytes = data; P.planes = planes; P.mbinfo = mbinfo;
+  P.topnz = topnz.data(); P.topmodes = topmodes.data(); P.rgb = rgb; P.src = src;
+  static DecShared S;
+  HostExec32 X;
+  dec_frame(X, S, P, D, st, kPredTab);
+  u64 t = 0;
+  if (st.status == 0)
+    for (u32 row = 0; row < height; row++)
+      for (u32 xx = 0; xx < width; xx++) {
+        u32 px[3];
+        dec_rgb_pixel(planes, D, fancy, row, xx, px);
+        if (rgb) for (int k = 0; k < 3; k++) rgb[((size_t)row * width + xx) * 3 + k] = (u8)px[k];
+        if (src && src_bpp) t += dec_pixel_sse(src + ((size_t)row * width + xx) * src_bpp, src_bpp, px);
+      }
+  if (sse) *sse = t;
+  if (st_out) memcpy(st_out, &st, 12 * sizeof(u32));
+  return (int)st.status;
 }
 }

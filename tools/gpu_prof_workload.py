@@ -19,4 +19,8 @@ ctx.stage(imgs)
 p = Z.EncoderParams.lossy(75); p.method = 4
 for _ in range(reps):
     t = ctx.encode_resident(p)
+if os.environ.get("ZW_HASH"):
+    import hashlib
+    outs, _ = ctx.download()
+    print("hash", hashlib.sha256(b"".join(hashlib.sha256(o).digest() for o in outs)).hexdigest()[:16])
 print("%s n=%d: total %.1f ms pass1 %.1f pass2 %.1f launches %d" % (kind, n, t["device_total_ms"], t["pass1_ms"], t["pass2_ms"], t["kernel_launches"]))
