@@ -201,14 +201,14 @@ struct Lane {
 
 // Buffers of the decoder / verifier entry points (zw_dec_host.inc); allocated on first use.
 struct DecCtx {
-  DevBuf d_img, d_st, d_bytes, d_planes, d_mbinfo, d_topnz, d_topmodes, d_rgb, d_src;
+  DevBuf d_img, d_st, d_bytes, d_planes, d_mbinfo, d_topnz, d_topmodes, d_rgb, d_src, d_rec, d_rows, d_progress;
   PinBuf h_st;
-  cudaEvent_t ev[3];
+  cudaEvent_t ev[5];
   bool ev_ok = false;
   u32 last_n = 0;
   std::vector<DecImage> last_img;
   void release() {
-    DevBuf* all[] = {&d_img, &d_st, &d_bytes, &d_planes, &d_mbinfo, &d_topnz, &d_topmodes, &d_rgb, &d_src};
+    DevBuf* all[] = {&d_img, &d_st, &d_bytes, &d_planes, &d_mbinfo, &d_topnz, &d_topmodes, &d_rgb, &d_src, &d_rec, &d_rows, &d_progress};
     for (DevBuf* b : all) b->release();
     h_st.release();
     if (ev_ok) for (auto& e : ev) cudaEventDestroy(e);

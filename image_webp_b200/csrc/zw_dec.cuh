@@ -6,25 +6,36 @@
 //   frame header           src/decoder/vp8.rs:553-679 (+ :387, :421, :452, :506, :520)   (dec_parse_header)
 //   macroblock header      src/decoder/vp8.rs:681-734                         (dec_parse_mb)
 //   coefficients           src/decoder/vp8.rs:872-1058, residual data :1060-1170        (dec_read_coeffs, dec_parse_mb)
-//   prediction + residue   src/decoder/vp8.rs:736-870; src/common/prediction.rs          (dec_reconstruct_mb)
+//   prediction + residue   src/decoder/vp8.rs:736-870; src/common/prediction.rs          (dec_recon_mb)
 //   loop filter            src/decoder/vp8.rs:1172-1348, :1470-1524; src/decoder/loop_filter.rs      (dec_filter_mb)
 //   YUV -> RGB             src/decoder/yuv.rs:36-78, :82-399 (bilinear), :402-530 (nearest)          (k_dec_rgb)
 //
-// Mapping.  The two bitstream partitions of an image are strictly serial (every symbol's interval depends on the one
-// before), so ONE WARP owns ONE IMAGE: lane 0 parses a macroblock (header from the first partition, coefficients from
-// the token partition of its row) into shared memory, then the 32 lanes reconstruct it -- 16 luma + 8 chroma 4x4 blocks,
-// one block per lane (inverse transforms, whole-block predictors, the sub-block wavefront x + 2y for B_PRED) -- and
-// store it to the plane arena.  A second sweep of the same warp runs the loop filter in macroblock raster order, one
-// lane per pixel row / column of an edge (16 luma + 8 + 8 chroma lanes).  The batch supplies the parallelism: 1024
-// images = 1024 warps.  A separate data-parallel kernel does the chroma upsampling, the colour conversion and the
-// squared error against the source pixels.
+// Four kernels:
+//   k_dec_parse   the two bitstream partitions of an image are strictly serial (every symbol's interval depends on the
+//                 one before), so ONE WARP owns ONE IMAGE and lane 0 walks the bitstream; the warp only helps to move
+//                 each macroblock's record (modes + 25 x 16 coded levels, zig-zag -- the layout the encoder's passes
+//                 use, MbRecord) to HBM.  Latency bound by construction; the batch supplies the parallelism.
+//   k_dec_rows<0> dequantisation, inverse transforms, prediction: a wavefront over macroblock ROWS (one warp per row,
+//                 16 luma + 8 chroma 4x4 blocks on 24 lanes, rows of all images interleaved, row y waits for row y-1 to
+//                 be one macroblock ahead -- the same ticket / progress-flag scheme as the encoder's k_search).
+//   k_dec_rows<1> the loop filter, same wavefront (a macroblock's edges reach into its left, top and top-right
+//                 neighbours), one lane per pixel row / column of an edge (16 luma + 8 + 8 chroma lanes); it runs after
+//                 the whole frame is reconstructed because prediction reads UNFILTERED neighbours.
+//   k_dec_rgb     chroma upsampling + colour conversion + squared error against the source, one thread per pixel.
 //
-// The per-image work is written against an executor X (X::run(f) = "every lane calls f(lane), then the warp
+// The per-macroblock work is written against an executor X (X::run(f) = "every lane calls f(lane), then the warp
 // synchronises") and compiles for the host too: tests/hostcheck runs the same source lane by lane on the CPU and
 // compares planes, modes and RGB with the decoder oracle before the code reaches a GPU.
 #ifndef ZW_DEC_CUH
 #define ZW_DEC_CUH
 #include "zw_types.cuh"
+
+#if !defined(__CUDACC__)  // host build (tests/hostcheck): the two CUDA vector types the record copies use
+struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v = {x, y}; return v; }
+#endif
 
 namespace zw {
 
@@ -36,44 +47,53 @@ struct DecImage {
   u64 data_off;     // the VP8 frame (container already stripped) in the byte arena
   u32 data_len;
   u32 width, height, mbw, mbh;  // as the host read them from the frame header (or knows them from the source)
-  u32 mb_off;       // first macroblock in mbinfo
-  u32 col_off;      // first macroblock column in the top-context scratch
+  u32 mb_off;       // first macroblock in the record / mbinfo arrays
+  u32 row_off;      // first macroblock row in the progress arrays
   u32 src_bpp;      // verify: bytes per source pixel (1 L8, 2 La8, 3 Rgb8, 4 Rgba8), 0 = no source
   u64 plane_off;    // padded Y | U | V planes in the plane arena
   u64 rgb_off;      // decoded RGB (width * height * 3) in the RGB arena
   u64 src_off;      // verify: source pixels in the source arena
 };
 
-// Device-written per-image result.
+// Device-written per-image result + what the frame header leaves for the later kernels.
 struct DecState {
   u32 status;
   u32 filter_type, filter_level, sharpness, num_partitions, segments_enabled, update_map, lf_adj, has_skip_prob, prob_skip_false,
       version, pixel_type;
   u64 sse_rgb;      // sum over the width x height x 3 colour samples of (decoded - source)^2
+  i16 quant[4][6];  // per segment: ydc, yac, y2dc, y2ac, uvdc, uvac (vp8.rs:452-504)
+  i8 seg_lf[4];     // per segment loop-filter level (absolute or delta)
+  u8 seg_delta, pad[3];
+  i32 ref_delta0, mode_delta0;
 };
 
 struct DecParams {
   const DecImage* img;
   DecState* st;
-  u32 n_img;
+  u32 n_img, n_rows;
   int fancy;            // 1: bilinear chroma upsampling (the reference's default), 0: nearest
   const u8* bytes;      // file arena
   const u64* file_off;  // optional (verify after encode): device-side offsets of the files in `bytes` ...
   const ImageState* enc_st;  // ... and their sizes; data_off / data_len are then taken from here (+ 20-byte RIFF wrap)
+  const RowRef* rows;   // ticket -> (image, macroblock row): row y of every image before row y + 1 of any
+  MbRecord* rec;        // [n_mb] parsed macroblocks: modes, coded levels (zig-zag; [0] Y2, [1..16] Y, [17..24] U V),
+                        //        top_nz | left_nz << 16 = the 24 "block has coefficients past its first position" bits
   u8* planes;
   u32* mbinfo;          // [n_mb][4]: flags (luma_mode | chroma_mode << 3 | segment << 5 | skipped << 7 | non_zero_dct << 8), bpred nibbles x2, 0
-  u16* topnz;           // [columns] complexity left behind by the row above (bit 0 y2, 1..4 y, 5..6 u, 7..8 v)
-  u32* topmodes;        // [columns] its bottom four sub-block modes
+  int* progress;        // [2][n_rows] macroblocks completed per row: reconstruction, loop filter
+  u32* ticket;          // [2]
   u8* rgb;              // may be null (verify only)
   const u8* src;        // may be null (decode only)
 };
 
-// ---- boolean decoder: libwebp's VP8GetBitAlt with 56-bit refills, range - 1 stored (bit_reader.rs:29-147) ----
+// ---- boolean decoder: libwebp's VP8GetBitAlt (bit_reader.rs:29-147), range - 1 stored.  The reference refills 56
+// bits at a time on 64-bit hosts and 24 on 32-bit ones (BITS, :15-25); the decoded bits and the point at which `eof`
+// is raised depend only on how many bits have been consumed, so the 24-bit form is used here: all state is 32-bit. ----
 struct DecReader {
-  u64 value, pos, end;
-  u32 range;
+  u64 pos, end;
+  u32 value, range;
   i32 bits;
-  u32 eof, pad;
+  u32 eof;
 };
 ZW_HD int dec_clz(u32 v) {
 #if defined(__CUDA_ARCH__)
@@ -83,16 +103,14 @@ ZW_HD int dec_clz(u32 v) {
 #endif
 }
 ZW_HD void rd_load(DecReader& r, const u8* bytes) {  // load_new_bytes :75 / load_final_bytes :59
-  if (r.end - r.pos >= 7) {
-    u64 in = 0;
-#pragma unroll
-    for (int i = 0; i < 7; i++) in = (in << 8) | (u64)bytes[r.pos + i];
-    r.value = in | (r.value << 56);
-    r.bits += 56;
-    r.pos += 7;
+  if (r.end - r.pos >= 3) {
+    const u32 in = ((u32)bytes[r.pos] << 16) | ((u32)bytes[r.pos + 1] << 8) | (u32)bytes[r.pos + 2];
+    r.value = in | (r.value << 24);
+    r.bits += 24;
+    r.pos += 3;
   } else if (r.pos < r.end) {
     r.bits += 8;
-    r.value = (u64)bytes[r.pos] | (r.value << 8);
+    r.value = (u32)bytes[r.pos] | (r.value << 8);
     r.pos++;
   } else if (!r.eof) {
     r.value <<= 8;
@@ -101,7 +119,7 @@ ZW_HD void rd_load(DecReader& r, const u8* bytes) {  // load_new_bytes :75 / loa
   } else r.bits = 0;
 }
 ZW_HD void rd_init(DecReader& r, const u8* bytes, u64 off, u64 len) {
-  r.value = 0; r.range = 255 - 1; r.bits = -8; r.pos = off; r.end = off + len; r.eof = 0; r.pad = 0;
+  r.value = 0; r.range = 255 - 1; r.bits = -8; r.pos = off; r.end = off + len; r.eof = 0;
   rd_load(r, bytes);
 }
 ZW_HD int rd_bit(DecReader& r, const u8* bytes, u32 prob) {  // get_bit :120
@@ -109,9 +127,9 @@ ZW_HD int rd_bit(DecReader& r, const u8* bytes, u32 prob) {  // get_bit :120
   if (r.bits < 0) rd_load(r, bytes);
   const int p = r.bits;
   const u32 split = (range * prob) >> 8;
-  const u32 v = (u32)(r.value >> p);
+  const u32 v = r.value >> p;
   const int bit = v > split;
-  if (bit) { range -= split; r.value -= ((u64)split + 1) << p; }
+  if (bit) { range -= split; r.value -= (split + 1) << p; }
   else range = split + 1;
   const int shift = 7 ^ (31 ^ dec_clz(range));
   range <<= shift;
@@ -139,27 +157,19 @@ ZW_HD int rd_tree(DecReader& r, const u8* bytes, const i8* tree, const u8* probs
   }
 }
 
-// What the lanes of the warp that owns an image share (one per warp in shared memory; a plain struct on the host).
-struct DecShared {
-  u8 probs[4][8][3][11];  // token probabilities of the frame (types.rs:338, updated :387)
+constexpr int DEC_CTX_COLS = 256;  // macroblock columns whose top contexts live in shared memory (4096 px); wider: global
+
+// What the parsing warp of an image keeps (one per warp in shared memory; a plain struct on the host).
+struct DecParseShared {
+  u8 ppos[4][17][3][11];  // token probabilities by coefficient POSITION (populate_probs_by_position, vp8.rs:405)
+  u8 probs[4][8][3][11];  // ... by band, as the header updates them (types.rs:338, :387)
   DecReader rd[9];        // [0] first partition, [1 + p] token partition p
-  i32 coef[24][16];       // dequantised coefficients, then residuals: 0..15 Y, 16..19 U, 20..23 V (natural order)
-  i32 y2[16];
-  u8 nflag[24];           // block has coefficients past its first position (full inverse DCT)
-  u8 yws[17 * 32];        // bordered work buffers (prediction.rs LUMA_STRIDE / CHROMA_STRIDE = 32)
-  u8 uws[9 * 32];
-  u8 vws[9 * 32];
-  i16 quant[4][6];        // per segment: ydc, yac, y2dc, y2ac, uvdc, uvac (:452-504)
-  i8 seg_quant[4], seg_lf[4];
-  u8 seg_delta;           // segment values are deltas
+  alignas(16) MbRecord rec;  // the macroblock in flight
+  u32 topmodes[DEC_CTX_COLS];  // bottom four sub-block modes of the row above
+  u16 topnz[DEC_CTX_COLS];     // complexity it left behind (bit 0 y2, 1..4 y, 5..6 u, 7..8 v)
   u8 seg_probs[3];
-  i32 ref_delta0, mode_delta0;
-  u32 width, height, mbw, mbh;
-  u8 segments_enabled, update_map, filter_type, filter_level, sharpness, lf_adj, has_skip_prob, prob_skip_false, num_partitions;
-  // the macroblock in flight
-  u8 bpred[16];
+  u8 segments_enabled, update_map, has_skip_prob, prob_skip_false, num_partitions;
   u8 left_bpred[4];
-  u8 luma_mode, chroma_mode, segment, skipped, nzdct;
   u32 left_nz;
   u32 status;
 };
@@ -170,8 +180,8 @@ struct DecShared {
 #define ZW_DT_BMODE {0, 2, -1, 4, -2, 6, 8, 12, -3, 10, -5, -6, -4, 14, -7, 16, -8, -9}
 #define ZW_DT_UV {0, 2, -1, 4, -2, -3}
 
-// read_frame_header (vp8.rs:553-679), lane 0.  Leaves the readers, probabilities, quantisers and filter settings in S.
-ZW_HD int dec_parse_header(DecShared& S, const u8* bytes, u64 off, u64 len, const DecImage& D, DecState& st) {
+// read_frame_header (vp8.rs:553-679), lane 0.  Leaves the readers and probabilities in S, quantisers and filter settings in st.
+ZW_HD int dec_parse_header(DecParseShared& S, const u8* bytes, u64 off, u64 len, const DecImage& D, DecState& st) {
   if (len < 3) return ZWD_TRUNCATED;
   const u32 tag = (u32)bytes[off] | ((u32)bytes[off + 1] << 8) | ((u32)bytes[off + 2] << 16);
   if (tag & 1) return ZWD_UNSUPPORTED;
@@ -182,7 +192,6 @@ ZW_HD int dec_parse_header(DecShared& S, const u8* bytes, u64 off, u64 len, cons
   if (len < 10) return ZWD_TRUNCATED;
   const u32 w = ((u32)bytes[off + 6] | ((u32)bytes[off + 7] << 8)) & 0x3FFF, h = ((u32)bytes[off + 8] | ((u32)bytes[off + 9] << 8)) & 0x3FFF;
   if (w != D.width || h != D.height) return ZWD_DIMENSIONS;  // the arenas were laid out for D's dimensions
-  S.width = w; S.height = h; S.mbw = (w + 15) / 16; S.mbh = (h + 15) / 16;
   u64 rpos = 10;
   if (len - rpos < first_size || first_size == 0) return ZWD_TRUNCATED;
   DecReader b;
@@ -192,29 +201,30 @@ ZW_HD int dec_parse_header(DecShared& S, const u8* bytes, u64 off, u64 len, cons
   st.pixel_type = rd_literal(b, bytes, 1);
   if (color_space != 0) return ZWD_COLORSPACE;
   S.segments_enabled = (u8)rd_bit(b, bytes, 128);
-  S.update_map = 0; S.seg_delta = 0;
-  for (int i = 0; i < 4; i++) { S.seg_quant[i] = 0; S.seg_lf[i] = 0; }
+  S.update_map = 0; st.seg_delta = 0;
+  i8 seg_quant[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) st.seg_lf[i] = 0;
   for (int i = 0; i < 3; i++) S.seg_probs[i] = 255;
   if (S.segments_enabled) {  // read_segment_updates :520
     S.update_map = (u8)rd_bit(b, bytes, 128);
     if (rd_bit(b, bytes, 128)) {
-      S.seg_delta = (u8)!rd_bit(b, bytes, 128);
-      for (int i = 0; i < 4; i++) S.seg_quant[i] = (i8)rd_optional_signed(b, bytes, 7);
-      for (int i = 0; i < 4; i++) S.seg_lf[i] = (i8)rd_optional_signed(b, bytes, 6);
+      st.seg_delta = (u8)!rd_bit(b, bytes, 128);
+      for (int i = 0; i < 4; i++) seg_quant[i] = (i8)rd_optional_signed(b, bytes, 7);
+      for (int i = 0; i < 4; i++) st.seg_lf[i] = (i8)rd_optional_signed(b, bytes, 6);
     }
     if (S.update_map)
       for (int i = 0; i < 3; i++) S.seg_probs[i] = rd_bit(b, bytes, 128) ? (u8)rd_literal(b, bytes, 8) : (u8)255;
     if (b.eof) return ZWD_BITSTREAM;
   }
-  S.filter_type = (u8)rd_bit(b, bytes, 128);
-  S.filter_level = (u8)rd_literal(b, bytes, 6);
-  S.sharpness = (u8)rd_literal(b, bytes, 3);
-  S.lf_adj = (u8)rd_bit(b, bytes, 128);
-  S.ref_delta0 = 0; S.mode_delta0 = 0;
-  if (S.lf_adj) {  // read_loop_filter_adjustments :506 (only ref_delta[0] / mode_delta[0] matter for key frames)
+  st.filter_type = (u32)rd_bit(b, bytes, 128);
+  st.filter_level = rd_literal(b, bytes, 6);
+  st.sharpness = rd_literal(b, bytes, 3);
+  st.lf_adj = (u32)rd_bit(b, bytes, 128);
+  st.ref_delta0 = 0; st.mode_delta0 = 0;
+  if (st.lf_adj) {  // read_loop_filter_adjustments :506 (only ref_delta[0] / mode_delta[0] matter for key frames)
     if (rd_bit(b, bytes, 128)) {
-      for (int i = 0; i < 4; i++) { const i32 v = rd_optional_signed(b, bytes, 6); if (i == 0) S.ref_delta0 = v; }
-      for (int i = 0; i < 4; i++) { const i32 v = rd_optional_signed(b, bytes, 6); if (i == 0) S.mode_delta0 = v; }
+      for (int i = 0; i < 4; i++) { const i32 v = rd_optional_signed(b, bytes, 6); if (i == 0) st.ref_delta0 = v; }
+      for (int i = 0; i < 4; i++) { const i32 v = rd_optional_signed(b, bytes, 6); if (i == 0) st.mode_delta0 = v; }
     }
     if (b.eof) return ZWD_BITSTREAM;
   }
@@ -243,16 +253,16 @@ ZW_HD int dec_parse_header(DecShared& S, const u8* bytes, u64 off, u64 len, cons
     const i32 uvdc_d = rd_optional_signed(b, bytes, 4), uvac_d = rd_optional_signed(b, bytes, 4);
     const int n = S.segments_enabled ? 4 : 1;
     for (int i = 0; i < n; i++) {
-      const i32 base = S.segments_enabled ? (S.seg_delta ? (i32)S.seg_quant[i] + yac_abs : (i32)S.seg_quant[i]) : yac_abs;
+      const i32 base = S.segments_enabled ? (st.seg_delta ? (i32)seg_quant[i] + yac_abs : (i32)seg_quant[i]) : yac_abs;
       i32 v;
-      S.quant[i][0] = ZW_TAB(kDcQuant)[imin(imax(base + ydc_d, 0), 127)];
-      S.quant[i][1] = ZW_TAB(kAcQuant)[imin(imax(base, 0), 127)];
-      S.quant[i][2] = (i16)(ZW_TAB(kDcQuant)[imin(imax(base + y2dc_d, 0), 127)] * 2);
+      st.quant[i][0] = ZW_TAB(kDcQuant)[imin(imax(base + ydc_d, 0), 127)];
+      st.quant[i][1] = ZW_TAB(kAcQuant)[imin(imax(base, 0), 127)];
+      st.quant[i][2] = (i16)(ZW_TAB(kDcQuant)[imin(imax(base + y2dc_d, 0), 127)] * 2);
       v = (i32)ZW_TAB(kAcQuant)[imin(imax(base + y2ac_d, 0), 127)] * 155 / 100;
-      S.quant[i][3] = (i16)(v < 8 ? 8 : v);
+      st.quant[i][3] = (i16)(v < 8 ? 8 : v);
       v = ZW_TAB(kDcQuant)[imin(imax(base + uvdc_d, 0), 127)];
-      S.quant[i][4] = (i16)(v > 132 ? 132 : v);
-      S.quant[i][5] = ZW_TAB(kAcQuant)[imin(imax(base + uvac_d, 0), 127)];
+      st.quant[i][4] = (i16)(v > 132 ? 132 : v);
+      st.quant[i][5] = ZW_TAB(kAcQuant)[imin(imax(base + uvac_d, 0), 127)];
     }
     if (b.eof) return ZWD_BITSTREAM;
   }
@@ -265,22 +275,23 @@ ZW_HD int dec_parse_header(DecShared& S, const u8* bytes, u64 off, u64 len, cons
   S.prob_skip_false = S.has_skip_prob ? (u8)rd_literal(b, bytes, 8) : (u8)0;
   if (b.eof) return ZWD_BITSTREAM;
   S.rd[0] = b;
-  st.filter_type = S.filter_type; st.filter_level = S.filter_level; st.sharpness = S.sharpness; st.num_partitions = S.num_partitions;
-  st.segments_enabled = S.segments_enabled; st.update_map = S.update_map; st.lf_adj = S.lf_adj; st.has_skip_prob = S.has_skip_prob;
-  st.prob_skip_false = S.prob_skip_false;
+  st.num_partitions = S.num_partitions; st.segments_enabled = S.segments_enabled; st.update_map = S.update_map;
+  st.has_skip_prob = S.has_skip_prob; st.prob_skip_false = S.prob_skip_false;
   return ZWD_OK;
 }
 
-// read_coefficients (vp8.rs:872-1058).  Returns 1 / 0 (coefficients past `first` or not), -1 on a bitstream error.
-ZW_HD int dec_read_coeffs(DecReader& r, const u8* bytes, const u8 (*probs)[3][11], int first, int ctx, i32 dcq, i32 acq, i32* block) {
+// read_coefficients (vp8.rs:872-1058) without the dequantisation and the zig-zag: level of position n -> zz[n] (the
+// reconstruction lanes undo both in parallel).  probs = the plane's [17][3][11] position table.  Returns 1 / 0
+// (coefficients past `first` or not), -1 on a bitstream error.
+ZW_HD int dec_read_coeffs(DecReader& r, const u8* bytes, const u8 (*probs)[3][11], int first, int ctx, i16* zz) {
   int n = first;
-  const u8* prob = probs[ZW_TAB(kCoeffBands)[n]][ctx];
+  const u8* prob = probs[n][ctx];
   while (n < 16) {
     if (!rd_bit(r, bytes, prob[0])) break;
     while (!rd_bit(r, bytes, prob[1])) {
       n++;
       if (n >= 16) return r.eof ? -1 : 1;
-      prob = probs[ZW_TAB(kCoeffBands)[n]][0];
+      prob = probs[n][0];
     }
     i32 v;
     int next_ctx;
@@ -307,68 +318,64 @@ ZW_HD int dec_read_coeffs(DecReader& r, const u8* bytes, const u8 (*probs)[3][11
       next_ctx = 2;
     }
     if (rd_bit(r, bytes, 128)) v = -v;
-    const int zz = ZW_TAB(kZigzag)[n];
-    block[zz] = v * (zz > 0 ? acq : dcq);
+    zz[n] = (i16)v;
     n++;
-    if (n < 16) prob = probs[ZW_TAB(kCoeffBands)[n]][next_ctx];
+    prob = probs[n][next_ctx];  // the table has 17 positions: no bounds test (populate_probs_by_position)
   }
   if (r.eof) return -1;
   return n > first;
 }
 
 // One macroblock: read_macroblock_header (:681) + read_residual_data (:1060) or the skip bookkeeping (:1546-1556).
-// Lane 0.  S.coef / S.y2 / S.nflag are zero on entry.
-ZW_HD int dec_parse_mb(DecShared& S, const u8* bytes, const DecParams& P, const DecImage& D, int mbx, int part) {
+// Lane 0.  S.rec is zero on entry.  tnz / topm: the column's top contexts (in and out).
+ZW_HD int dec_parse_mb(DecParseShared& S, const u8* bytes, int part, u32& tnz_io, u32& topm_io) {
   const i8 T_SEG[6] = ZW_DT_SEG, T_YMODE[8] = ZW_DT_YMODE, T_BMODE[18] = ZW_DT_BMODE, T_UV[6] = ZW_DT_UV;
+  MbRecord& R = S.rec;
   DecReader b = S.rd[0];
-  u32 topm = P.topmodes[D.col_off + mbx];
-  S.segment = (S.segments_enabled && S.update_map) ? (u8)rd_tree(b, bytes, T_SEG, S.seg_probs) : (u8)0;
-  S.skipped = S.has_skip_prob ? (u8)rd_bit(b, bytes, S.prob_skip_false) : (u8)0;
-  S.luma_mode = (u8)rd_tree(b, bytes, T_YMODE, ZW_TAB(kKfYmodeProbs));
-  if (S.luma_mode == 4) {
+  u32 topm = topm_io;
+  R.segment = (S.segments_enabled && S.update_map) ? (u8)rd_tree(b, bytes, T_SEG, S.seg_probs) : (u8)0;
+  R.skip = S.has_skip_prob ? (u8)rd_bit(b, bytes, S.prob_skip_false) : (u8)0;
+  R.ymode = (u8)rd_tree(b, bytes, T_YMODE, ZW_TAB(kKfYmodeProbs));
+  if (R.ymode == 4) {
     for (int y = 0; y < 4; y++)
       for (int x = 0; x < 4; x++) {
         const int t = (topm >> (8 * x)) & 255, l = S.left_bpred[y];
         const u8 bm = (u8)rd_tree(b, bytes, T_BMODE, &ZW_TAB(kKfBmodeProbs)[(t * 10 + l) * 9]);
-        S.bpred[x + y * 4] = bm;
+        R.bmodes[x + y * 4] = bm;
         topm = (topm & ~(255u << (8 * x))) | ((u32)bm << (8 * x));
         S.left_bpred[y] = bm;
       }
   } else {
-    const u8 m = S.luma_mode == 0 ? 0 : (S.luma_mode == 1 ? 2 : (S.luma_mode == 2 ? 3 : 1));  // into_intra: DC, VE, HE, TM
-    for (int i = 0; i < 12; i++) S.bpred[i] = 0;
-    for (int i = 0; i < 4; i++) { S.bpred[12 + i] = m; S.left_bpred[i] = m; }
+    const u8 m = R.ymode == 0 ? 0 : (R.ymode == 1 ? 2 : (R.ymode == 2 ? 3 : 1));  // into_intra: DC, VE, HE, TM
+    for (int i = 0; i < 4; i++) { R.bmodes[12 + i] = m; S.left_bpred[i] = m; }
     topm = m * 0x01010101u;
   }
-  S.chroma_mode = (u8)rd_tree(b, bytes, T_UV, ZW_TAB(kKfUvModeProbs));
-  P.topmodes[D.col_off + mbx] = topm;
+  R.uvmode = (u8)rd_tree(b, bytes, T_UV, ZW_TAB(kKfUvModeProbs));
+  topm_io = topm;
   S.rd[0] = b;
   if (b.eof) return ZWD_BITSTREAM;
-  u32 tnz = P.topnz[D.col_off + mbx], lnz = S.left_nz;
-  S.nzdct = 0;
-  if (S.skipped) {
-    if (S.luma_mode != 4) { tnz &= ~1u; lnz &= ~1u; }
+  u32 tnz = tnz_io, lnz = S.left_nz, nflag = 0;
+  if (R.skip) {
+    if (R.ymode != 4) { tnz &= ~1u; lnz &= ~1u; }
     tnz &= 1u; lnz &= 1u;
   } else {
     DecReader r = S.rd[1 + part];
-    const i16* q = S.quant[S.segment];
-    int plane = S.luma_mode == 4 ? 3 : 1;  // Plane::YCoeff0 / Y2 (types.rs:48-57: YCoeff1 0, Y2 1, Chroma 2, YCoeff0 3)
+    int plane = R.ymode == 4 ? 3 : 1;  // Plane::YCoeff0 / Y2 (types.rs:48-57: YCoeff1 0, Y2 1, Chroma 2, YCoeff0 3)
     if (plane == 1) {
       const int ctx = (int)(tnz & 1) + (int)(lnz & 1);
-      const int n = dec_read_coeffs(r, bytes, S.probs[1], 0, ctx, q[2], q[3], S.y2);
+      const int n = dec_read_coeffs(r, bytes, S.ppos[1], 0, ctx, R.levels[0]);
       if (n < 0) return ZWD_BITSTREAM;
       tnz = (tnz & ~1u) | (u32)n; lnz = (lnz & ~1u) | (u32)n;
       plane = 0;
-      S.nflag[0] |= 0x80;  // "Y2 present": the lanes run the inverse WHT
     }
     const int first = plane == 0 ? 1 : 0;
     for (int y = 0; y < 4; y++) {
       u32 l = (lnz >> (1 + y)) & 1;
       for (int x = 0; x < 4; x++) {
         const int ctx = (int)((tnz >> (1 + x)) & 1) + (int)l;
-        const int n = dec_read_coeffs(r, bytes, S.probs[plane], first, ctx, q[0], q[1], S.coef[x + y * 4]);
+        const int n = dec_read_coeffs(r, bytes, S.ppos[plane], first, ctx, R.levels[1 + x + y * 4]);
         if (n < 0) return ZWD_BITSTREAM;
-        S.nflag[x + y * 4] |= (u8)n;
+        nflag |= (u32)n << (x + y * 4);
         l = (u32)n;
         tnz = (tnz & ~(2u << x)) | ((u32)n << (1 + x));
       }
@@ -381,9 +388,9 @@ ZW_HD int dec_parse_mb(DecShared& S, const u8* bytes, const DecParams& P, const 
         for (int x = 0; x < 2; x++) {
           const int i = x + y * 2 + 16 + 4 * pl;
           const int ctx = (int)((tnz >> (j + x)) & 1) + (int)l;
-          const int n = dec_read_coeffs(r, bytes, S.probs[2], 0, ctx, q[4], q[5], S.coef[i]);
+          const int n = dec_read_coeffs(r, bytes, S.ppos[2], 0, ctx, R.levels[1 + i]);
           if (n < 0) return ZWD_BITSTREAM;
-          S.nflag[i] |= (u8)n;
+          nflag |= (u32)n << i;
           l = (u32)n;
           tnz = (tnz & ~(1u << (j + x))) | ((u32)n << (j + x));
         }
@@ -392,9 +399,70 @@ ZW_HD int dec_parse_mb(DecShared& S, const u8* bytes, const DecParams& P, const 
     }
     S.rd[1 + part] = r;
   }
-  P.topnz[D.col_off + mbx] = (u16)tnz;
+  R.top_nz = (u16)(nflag & 0xffffu); R.left_nz = (u16)(nflag >> 16);
+  tnz_io = tnz;
   S.left_nz = lnz;
   return ZWD_OK;
+}
+
+// The whole bitstream of one image -> P.rec (decode_frame_'s loop, vp8.rs:1531-1576, without the pixels).
+// `topnz_g` / `topmodes_g`: global scratch for images wider than DEC_CTX_COLS macroblocks (else unused).
+template <class X>
+ZW_HD void dec_parse_frame(X& x, DecParseShared& S, const DecParams& P, const DecImage& D, u64 off, u64 len, DecState& st,
+                           u16* topnz_g, u32* topmodes_g) {
+  const u8* bytes = P.bytes;
+  const bool wide = D.mbw > (u32)DEC_CTX_COLS;
+  u16* topnz = wide ? topnz_g : S.topnz;
+  u32* topmodes = wide ? topmodes_g : S.topmodes;
+  x.run([&](int lane) {
+    for (int i = lane; i < 1056; i += 32) (&S.probs[0][0][0][0])[i] = ZW_TAB(kCoeffProbs)[i];
+    for (int i = lane; i < (int)D.mbw; i += 32) { topnz[i] = 0; topmodes[i] = 0; }
+    for (int i = lane; i < (int)(sizeof(MbRecord) / 4); i += 32) reinterpret_cast<u32*>(&S.rec)[i] = 0;
+    if (lane == 0) S.status = ZWD_OK;
+  });
+  x.run([&](int lane) {
+    if (lane != 0) return;
+    DecState s0 = st;
+    s0.status = 0; s0.sse_rgb = 0;
+    const int rc = dec_parse_header(S, bytes, off, len, D, s0);
+    s0.status = (u32)rc;
+    S.status = (u32)rc;
+    st = s0;
+  });
+  if (S.status != ZWD_OK) return;
+  x.run([&](int lane) {  // populate_probs_by_position (vp8.rs:405): position 16 is the look-ahead sentinel (band 7)
+    for (int i = lane; i < 4 * 17 * 3; i += 32) {
+      const int pl = i / 51, pos = (i / 3) % 17, ctx = i % 3;
+      const int band = pos < 16 ? ZW_TAB(kCoeffBands)[pos] : 7;
+      for (int t = 0; t < 11; t++) S.ppos[pl][pos][ctx][t] = S.probs[pl][band][ctx][t];
+    }
+  });
+  const int mbw = (int)D.mbw, mbh = (int)D.mbh;
+  for (int mby = 0; mby < mbh && S.status == ZWD_OK; mby++) {
+    const int part = mby % (int)S.num_partitions;
+    x.run([&](int lane) {
+      if (lane == 0) { S.left_nz = 0; for (int i = 0; i < 4; i++) S.left_bpred[i] = 0; }
+    });
+    for (int mbx = 0; mbx < mbw; mbx++) {
+      x.run([&](int lane) {
+        if (lane != 0) return;
+        u32 tnz = topnz[mbx], topm = topmodes[mbx];
+        const int rc = dec_parse_mb(S, bytes, part, tnz, topm);
+        topnz[mbx] = (u16)tnz; topmodes[mbx] = topm;
+        if (rc != ZWD_OK) S.status = (u32)rc;
+      });
+      if (S.status != ZWD_OK) break;
+      x.run([&](int lane) {  // the record goes to HBM in 16-byte pieces; the shared copy is cleared for the next one
+        uint4* dst = reinterpret_cast<uint4*>(&P.rec[(size_t)D.mb_off + (size_t)mby * mbw + mbx]);
+        uint4* srcp = reinterpret_cast<uint4*>(&S.rec);
+        for (int i = lane; i < (int)(sizeof(MbRecord) / 16); i += 32) {
+          dst[i] = srcp[i];
+          srcp[i] = make_uint4(0, 0, 0, 0);
+        }
+      });
+    }
+  }
+  if (S.status != ZWD_OK) x.run([&](int lane) { if (lane == 0) st.status = S.status; });
 }
 
 // inverse DCT with the reference's 64-bit products (transform.rs:35-79): a hostile stream can carry coefficients the
@@ -445,11 +513,88 @@ ZW_HD void dec_pred_whole(const u8* ws, int size, int mode, bool has_top, bool h
   }
 }
 
-// Reconstruction of the parsed macroblock into S.yws / S.uws / S.vws (intra_predict_luma :736, intra_predict_chroma :809,
-// the inverse transforms of read_residual_data :1078-1166).  `tab` = ZW_PRED_TABLE_INIT.
+// What the reconstructing warp of a macroblock row keeps.
+struct DecReconShared {
+  i32 coef[24][16];  // residuals of the 24 blocks (natural order): 0..15 Y, 16..19 U, 20..23 V
+  i32 y2[16];
+  u8 yws[17 * 32];   // bordered work buffers (prediction.rs LUMA_STRIDE / CHROMA_STRIDE = 32)
+  u8 uws[9 * 32];
+  u8 vws[9 * 32];
+  u8 bpred[16];
+  u32 nzdct;
+};
+
+ZW_HD int dec_zigzag(int n) { return (int)((0xFEB7ADC963258410ull >> (4 * n)) & 15); }  // kZigzag as nibbles
+
+// One macroblock from its record to pixels (read_residual_data's transforms :1078-1166, intra_predict_luma :736,
+// intra_predict_chroma :809): planes and the mbinfo words are written; left / top borders are read from the planes
+// (unfiltered: the filter kernel runs after the whole frame is reconstructed).  `tab` = ZW_PRED_TABLE_INIT.
 template <class X>
-ZW_HD void dec_reconstruct_mb(X& x, DecShared& S, int mbx, int mby, const u16 (*tab)[16]) {
-  if (S.nflag[0] & 0x80) {
+ZW_HD void dec_recon_mb(X& x, DecReconShared& S, const DecParams& P, const DecImage& D, const DecState& st, int mbx, int mby,
+                        const u16 (*tab)[16]) {
+  const int mbw = (int)D.mbw, mbh = (int)D.mbh;
+  const size_t ypitch = (size_t)mbw * 16, cpitch = (size_t)mbw * 8;
+  u8* yp = P.planes + D.plane_off;
+  u8* up = yp + ypitch * mbh * 16;
+  u8* vp = up + cpitch * mbh * 8;
+  const size_t mb = (size_t)D.mb_off + (size_t)mby * mbw + mbx;
+  const MbRecord* R = &P.rec[mb];
+  const u32 hdr = *reinterpret_cast<const u32*>(R);  // ymode | uvmode << 8 | segment << 16 | skip << 24
+  const int luma_mode = hdr & 255, chroma_mode = (hdr >> 8) & 255, segment = (hdr >> 16) & 3;
+  const bool skipped = (hdr >> 24) != 0, bpred = luma_mode == 4;
+  const u32 nflag = (u32)R->top_nz | ((u32)R->left_nz << 16);
+  const bool has_y2 = !bpred && !skipped;
+  x.run([&](int lane) {
+    // borders of the work buffers (create_border_luma / create_border_chroma, prediction.rs:15-126)
+    if (lane < 21) {  // luma row 0: corner, 16 above, 4 above-right
+      u8 v;
+      if (mby == 0) v = 127;
+      else if (lane == 0) v = mbx == 0 ? (u8)129 : yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 - 1];
+      else if (lane <= 16 || mbx < mbw - 1) v = yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 + lane - 1];
+      else v = yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 + 15];
+      S.yws[lane] = v;
+      if (lane >= 17) { S.yws[4 * 32 + lane] = v; S.yws[8 * 32 + lane] = v; S.yws[12 * 32 + lane] = v; }
+    }
+    if (lane < 16) S.yws[(1 + lane) * 32] = mbx == 0 ? (u8)129 : yp[(size_t)(mby * 16 + lane) * ypitch + mbx * 16 - 1];
+    if (lane < 18) {  // chroma row 0 of U (lanes 0..8) and V (9..17)
+      const int k = lane % 9;
+      u8* ws = lane < 9 ? S.uws : S.vws;
+      const u8* cp = lane < 9 ? up : vp;
+      u8 v;
+      if (mby == 0) v = 127;
+      else if (k == 0) v = mbx == 0 ? (u8)129 : cp[(size_t)(mby * 8 - 1) * cpitch + mbx * 8 - 1];
+      else v = cp[(size_t)(mby * 8 - 1) * cpitch + mbx * 8 + k - 1];
+      ws[k] = v;
+    }
+    if (lane >= 16) {  // chroma column 0: U rows on lanes 16..23, V rows on 24..31
+      const int r = lane & 7;
+      u8* ws = lane < 24 ? S.uws : S.vws;
+      const u8* cp = lane < 24 ? up : vp;
+      ws[(1 + r) * 32] = mbx == 0 ? (u8)129 : cp[(size_t)(mby * 8 + r) * cpitch + mbx * 8 - 1];
+    }
+    if (lane == 0) S.nzdct = 0;
+    if (lane < 16) S.bpred[lane] = R->bmodes[lane];
+    // dequantisation + de-zig-zag of the block this lane owns; lane 24: Y2
+    if (lane < 24 || (lane == 24 && has_y2)) {
+      const i16* q = st.quant[segment];
+      const int blk = lane == 24 ? 0 : 1 + lane;
+      const i32 dcq = lane == 24 ? q[2] : (lane < 16 ? q[0] : q[4]), acq = lane == 24 ? q[3] : (lane < 16 ? q[1] : q[5]);
+      i32* dst = lane == 24 ? S.y2 : S.coef[lane];
+      if (skipped) {
+#pragma unroll
+        for (int n = 0; n < 16; n++) dst[n] = 0;
+      } else {
+        const uint4 a = reinterpret_cast<const uint4*>(R->levels[blk])[0], b4 = reinterpret_cast<const uint4*>(R->levels[blk])[1];
+        const u32 w[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int n = 0; n < 16; n++) {
+          const i32 lv = (i32)(i16)(w[n >> 1] >> (16 * (n & 1)));
+          dst[dec_zigzag(n)] = lv * (n == 0 ? dcq : acq);
+        }
+      }
+    }
+  });
+  if (has_y2) {
     x.run([&](int lane) {  // inverse WHT of Y2 -> the DCs of the 16 luma blocks (:1084-1088)
       if (lane != 0) return;
       i32 y2[16];
@@ -460,14 +605,13 @@ ZW_HD void dec_reconstruct_mb(X& x, DecShared& S, int mbx, int mby, const u16 (*
       for (int k = 0; k < 16; k++) S.coef[k][0] = y2[k];
     });
   }
-  const bool bpred = S.luma_mode == 4;
   x.run([&](int lane) {  // residuals of the 24 blocks; whole-block prediction + residue for chroma and non-B luma
     if (lane >= 24) return;
     i32 c[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) c[k] = S.coef[lane][k];
-    const bool n = (S.nflag[lane] & 1) != 0;
-    if (c[0] != 0 || n) {
+    const bool n = ((nflag >> lane) & 1) != 0;
+    if (!skipped && (c[0] != 0 || n)) {
       S.nzdct = 1;
       if (n) dec_idct4x4(c);
       else {
@@ -485,13 +629,11 @@ ZW_HD void dec_reconstruct_mb(X& x, DecShared& S, int mbx, int mby, const u16 (*
     const int bi = lane < 16 ? lane : (lane - 16) & 3;
     const int bx = lane < 16 ? bi & 3 : bi & 1, by = lane < 16 ? bi >> 2 : bi >> 1;
     i32 pr[16];
-    dec_pred_whole(ws, lane < 16 ? 16 : 8, lane < 16 ? S.luma_mode : S.chroma_mode, mby != 0, mbx != 0, bx, by, pr);
+    dec_pred_whole(ws, lane < 16 ? 16 : 8, lane < 16 ? luma_mode : chroma_mode, mby != 0, mbx != 0, bx, by, pr);
 #pragma unroll
     for (int k = 0; k < 16; k++) S.coef[lane][k] = clip255(pr[k] + c[k]);  // add_residue (prediction.rs:138); stored below
   });
-  // (the whole-block predictors read row 0 / column 0 of the buffers only: writing the interior needs its own step so
-  // that no lane overwrites what another lane's DC sum still reads -- column 0 and row 0 are never written)
-  x.run([&](int lane) {
+  x.run([&](int lane) {  // (the whole-block predictors only read row 0 / column 0, which are never written)
     if (lane >= 24 || (lane < 16 && bpred)) return;
     u8* ws = lane < 16 ? S.yws : (lane < 20 ? S.uws : S.vws);
     const int bi = lane < 16 ? lane : (lane - 16) & 3;
@@ -520,12 +662,37 @@ ZW_HD void dec_reconstruct_mb(X& x, DecShared& S, int mbx, int mby, const u16 (*
       });
     }
   }
+  x.run([&](int lane) {  // store the macroblock; leave its modes for the filter kernel and the parity dump
+    if (lane < 16) {
+      u8* dst = yp + (size_t)(mby * 16 + lane) * ypitch + mbx * 16;
+      const u8* srcp = &S.yws[(1 + lane) * 32 + 1];
+      u32 w[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] = (u32)srcp[4 * k] | ((u32)srcp[4 * k + 1] << 8) | ((u32)srcp[4 * k + 2] << 16) | ((u32)srcp[4 * k + 3] << 24);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      const int r = lane & 7;
+      u8* dst = (lane < 24 ? up : vp) + (size_t)(mby * 8 + r) * cpitch + mbx * 8;
+      const u8* srcp = (lane < 24 ? S.uws : S.vws) + (1 + r) * 32 + 1;
+      u32 w[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) w[k] = (u32)srcp[4 * k] | ((u32)srcp[4 * k + 1] << 8) | ((u32)srcp[4 * k + 2] << 16) | ((u32)srcp[4 * k + 3] << 24);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+    }
+    if (lane == 0) {
+      u32* mi = P.mbinfo + mb * 4;
+      u32 lo = 0, hi = 0;
+      for (int i = 0; i < 8; i++) { lo |= (u32)S.bpred[i] << (4 * i); hi |= (u32)S.bpred[8 + i] << (4 * i); }
+      mi[0] = (u32)luma_mode | ((u32)chroma_mode << 3) | ((u32)segment << 5) | ((u32)skipped << 7) | (S.nzdct << 8);
+      mi[1] = lo; mi[2] = hi; mi[3] = 0;
+    }
+  });
 }
 
 // calculate_filter_parameters (vp8.rs:1470-1524)
-ZW_HD void dec_filter_params(const DecShared& S, u32 flags, int& fl, int& il, int& hev) {
+ZW_HD void dec_filter_params(const DecState& S, u32 flags, int& fl, int& il, int& hev) {
   const int seg = (flags >> 5) & 3, luma_mode = flags & 7;
-  i32 level = S.filter_level;
+  i32 level = (i32)S.filter_level;
   if (level == 0) { fl = il = hev = 0; return; }
   if (S.segments_enabled) level = S.seg_delta ? level + S.seg_lf[seg] : (i32)S.seg_lf[seg];
   level = imin(imax(level, 0), 63);
@@ -535,199 +702,109 @@ ZW_HD void dec_filter_params(const DecShared& S, u32 flags, int& fl, int& il, in
   }
   fl = imin(imax(level, 0), 63);
   int interior = fl;
-  if (S.sharpness > 0) {
-    interior >>= S.sharpness > 4 ? 2 : 1;
-    if (interior > 9 - S.sharpness) interior = 9 - S.sharpness;
+  const int sharp = (int)S.sharpness;
+  if (sharp > 0) {
+    interior >>= sharp > 4 ? 2 : 1;
+    if (interior > 9 - sharp) interior = 9 - sharp;
   }
   if (interior == 0) interior = 1;
   il = interior;
   hev = fl >= 40 ? 2 : (fl >= 15 ? 1 : 0);
 }
 
-// ---- src/decoder/loop_filter.rs: one position of an edge; px = first pixel after the edge, s = distance of the taps ----
+// ---- src/decoder/loop_filter.rs: one position of an edge.  t[0..7] = p3 p2 p1 p0 q0 q1 q2 q3, filtered in registers;
+//      returns a bit mask of the taps that changed ----
 ZW_HD i32 lf_c(i32 v) { return imin(imax(v, -128), 127); }
-ZW_HD i32 lf_u2s(u8 v) { return (i32)v - 128; }
-ZW_HD u8 lf_s2u(i32 v) { return (u8)(lf_c(v) + 128); }
-ZW_HD i32 lf_common_adjust(bool outer, u8* px, ptrdiff_t s) {  // :24
-  const i32 p1 = lf_u2s(px[-2 * s]), p0 = lf_u2s(px[-s]), q0 = lf_u2s(px[0]), q1 = lf_u2s(px[s]);
+ZW_HD i32 lf_u2s(i32 v) { return v - 128; }
+ZW_HD i32 lf_s2u(i32 v) { return lf_c(v) + 128; }
+ZW_HD i32 lf_common_adjust(bool outer, i32* t) {  // :24
+  const i32 p1 = lf_u2s(t[2]), p0 = lf_u2s(t[3]), q0 = lf_u2s(t[4]), q1 = lf_u2s(t[5]);
   const i32 a0 = lf_c((outer ? lf_c(p1 - q1) : 0) + 3 * (q0 - p0));
   const i32 b = lf_c(a0 + 3) >> 3, a = lf_c(a0 + 4) >> 3;
-  px[0] = lf_s2u(q0 - a);
-  px[-s] = lf_s2u(p0 + b);
+  t[4] = lf_s2u(q0 - a);
+  t[3] = lf_s2u(p0 + b);
   return a;
 }
-ZW_HD bool lf_simple_threshold(i32 limit, const u8* px, ptrdiff_t s) {  // :70
-  return iabs((i32)px[-s] - (i32)px[0]) * 2 + iabs((i32)px[-2 * s] - (i32)px[s]) / 2 <= limit;
+ZW_HD bool lf_simple_threshold(i32 limit, const i32* t) {  // :70
+  return iabs(t[3] - t[4]) * 2 + iabs(t[2] - t[5]) / 2 <= limit;
 }
-ZW_HD bool lf_should_filter(i32 interior, i32 edge, const u8* px, ptrdiff_t s) {  // :90
-  return lf_simple_threshold(edge, px, s) && iabs((i32)px[-4 * s] - (i32)px[-3 * s]) <= interior && iabs((i32)px[-3 * s] - (i32)px[-2 * s]) <= interior &&
-         iabs((i32)px[-2 * s] - (i32)px[-s]) <= interior && iabs((i32)px[3 * s] - (i32)px[2 * s]) <= interior &&
-         iabs((i32)px[2 * s] - (i32)px[s]) <= interior && iabs((i32)px[s] - (i32)px[0]) <= interior;
+ZW_HD bool lf_should_filter(i32 interior, i32 edge, const i32* t) {  // :90
+  return lf_simple_threshold(edge, t) && iabs(t[0] - t[1]) <= interior && iabs(t[1] - t[2]) <= interior && iabs(t[2] - t[3]) <= interior &&
+         iabs(t[7] - t[6]) <= interior && iabs(t[6] - t[5]) <= interior && iabs(t[5] - t[4]) <= interior;
 }
-ZW_HD bool lf_hev(i32 thr, const u8* px, ptrdiff_t s) {  // :120
-  return iabs((i32)px[-2 * s] - (i32)px[-s]) > thr || iabs((i32)px[s] - (i32)px[0]) > thr;
-}
+ZW_HD bool lf_hev(i32 thr, const i32* t) { return iabs(t[2] - t[3]) > thr || iabs(t[5] - t[4]) > thr; }  // :120
 // kind 0: simple_segment (:132), 1: macroblock_filter (:190), 2: subblock_filter (:150)
-ZW_HD void lf_apply(int kind, int hev_t, int interior, int edge, u8* px, ptrdiff_t s) {
+ZW_HD u32 lf_apply(int kind, int hev_t, int interior, int edge, i32* t) {
   if (kind == 0) {
-    if (lf_simple_threshold(edge, px, s)) lf_common_adjust(true, px, s);
-    return;
+    if (!lf_simple_threshold(edge, t)) return 0;
+    lf_common_adjust(true, t);
+    return 0x18;
   }
-  if (!lf_should_filter(interior, edge, px, s)) return;
-  const bool hv = lf_hev(hev_t, px, s);
+  if (!lf_should_filter(interior, edge, t)) return 0;
+  const bool hv = lf_hev(hev_t, t);
   if (kind == 2) {
-    const i32 a = (lf_common_adjust(hv, px, s) + 1) >> 1;
-    if (!hv) {
-      px[s] = lf_s2u(lf_u2s(px[s]) - a);
-      px[-2 * s] = lf_s2u(lf_u2s(px[-2 * s]) + a);
-    }
-    return;
+    const i32 a = (lf_common_adjust(hv, t) + 1) >> 1;
+    if (hv) return 0x18;
+    t[5] = lf_s2u(lf_u2s(t[5]) - a);
+    t[2] = lf_s2u(lf_u2s(t[2]) + a);
+    return 0x3c;
   }
-  if (hv) { lf_common_adjust(true, px, s); return; }
-  const i32 p2 = lf_u2s(px[-3 * s]), p1 = lf_u2s(px[-2 * s]), p0 = lf_u2s(px[-s]), q0 = lf_u2s(px[0]), q1 = lf_u2s(px[s]), q2 = lf_u2s(px[2 * s]);
+  if (hv) { lf_common_adjust(true, t); return 0x18; }
+  const i32 p2 = lf_u2s(t[1]), p1 = lf_u2s(t[2]), p0 = lf_u2s(t[3]), q0 = lf_u2s(t[4]), q1 = lf_u2s(t[5]), q2 = lf_u2s(t[6]);
   const i32 w = lf_c(lf_c(p1 - q1) + 3 * (q0 - p0));
   i32 a = lf_c((27 * w + 63) >> 7);
-  px[0] = lf_s2u(q0 - a); px[-s] = lf_s2u(p0 + a);
+  t[4] = lf_s2u(q0 - a); t[3] = lf_s2u(p0 + a);
   a = lf_c((18 * w + 63) >> 7);
-  px[s] = lf_s2u(q1 - a); px[-2 * s] = lf_s2u(p1 + a);
+  t[5] = lf_s2u(q1 - a); t[2] = lf_s2u(p1 + a);
   a = lf_c((9 * w + 63) >> 7);
-  px[2 * s] = lf_s2u(q2 - a); px[-3 * s] = lf_s2u(p2 + a);
+  t[6] = lf_s2u(q2 - a); t[1] = lf_s2u(p2 + a);
+  return 0x7e;
+}
+// one position: load the eight taps around px (distance s), filter, store what changed
+ZW_HD void lf_position(int kind, int hev_t, int interior, int edge, u8* px, ptrdiff_t s) {
+  i32 t[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) t[k] = px[(k - 4) * s];
+  const u32 m = lf_apply(kind, hev_t, interior, edge, t);
+#pragma unroll
+  for (int k = 1; k < 7; k++)
+    if ((m >> k) & 1) px[(k - 4) * s] = (u8)t[k];
 }
 
 // filter_row_in_cache (vp8.rs:1172-1348) for one macroblock, in place on the frame: lanes 0..15 = the 16 luma rows /
 // columns of an edge, 16..23 / 24..31 = the 8 chroma rows / columns of U / V (normal filter only).
 template <class X>
-ZW_HD void dec_filter_mb(X& x, const DecShared& S, u8* yp, u8* up, u8* vp, int mbx, int mby, u32 flags) {
+ZW_HD void dec_filter_mb(X& x, const DecState& S, const DecImage& D, u8* planes, int mbx, int mby, u32 flags) {
   int fl, il, hev;
   dec_filter_params(S, flags, fl, il, hev);
   if (fl == 0) return;
   const int mbedge = (fl + 2) * 2 + il, sub = fl * 2 + il;
   const bool do_sub = (flags & 7) == 4 || (!((flags >> 7) & 1) && ((flags >> 8) & 1));
   const bool simple = S.filter_type != 0;
-  const ptrdiff_t ys = (ptrdiff_t)S.mbw * 16, cs = (ptrdiff_t)S.mbw * 8;
+  const ptrdiff_t ys = (ptrdiff_t)D.mbw * 16, cs = (ptrdiff_t)D.mbw * 8;
+  u8* yp = planes + D.plane_off;
+  u8* up = yp + ys * D.mbh * 16;
+  u8* vp = up + cs * D.mbh * 8;
   u8* Y = yp + (ptrdiff_t)mby * 16 * ys + mbx * 16;
   u8* U = up + (ptrdiff_t)mby * 8 * cs + mbx * 8;
   u8* V = vp + (ptrdiff_t)mby * 8 * cs + mbx * 8;
-  // one step = one luma edge (+ the chroma edge that the reference filters right after it)
+  // one step = one luma edge (+ the chroma edge of the same kind: the planes are independent)
   auto vertical_edge = [&](int xoff, int kind, int limit, bool chroma) {  // lanes = rows
     x.run([&](int lane) {
-      if (lane < 16) lf_apply(simple ? 0 : kind, hev, il, limit, Y + lane * ys + xoff, 1);
-      else if (chroma && !simple) lf_apply(kind, hev, il, limit, (lane < 24 ? U : V) + (lane & 7) * cs + xoff / 2, 1);
+      if (lane < 16) lf_position(simple ? 0 : kind, hev, il, limit, Y + lane * ys + xoff, 1);
+      else if (chroma && !simple) lf_position(kind, hev, il, limit, (lane < 24 ? U : V) + (lane & 7) * cs + xoff / 2, 1);
     });
   };
   auto horizontal_edge = [&](int yoff, int kind, int limit, bool chroma) {  // lanes = columns
     x.run([&](int lane) {
-      if (lane < 16) lf_apply(simple ? 0 : kind, hev, il, limit, Y + yoff * ys + lane, ys);
-      else if (chroma && !simple) lf_apply(kind, hev, il, limit, (lane < 24 ? U : V) + (yoff / 2) * cs + (lane & 7), cs);
+      if (lane < 16) lf_position(simple ? 0 : kind, hev, il, limit, Y + yoff * ys + lane, ys);
+      else if (chroma && !simple) lf_position(kind, hev, il, limit, (lane < 24 ? U : V) + (yoff / 2) * cs + (lane & 7), cs);
     });
   };
   if (mbx > 0) vertical_edge(0, 1, mbedge, true);
   if (do_sub) { vertical_edge(4, 2, sub, false); vertical_edge(8, 2, sub, true); vertical_edge(12, 2, sub, false); }
   if (mby > 0) horizontal_edge(0, 1, mbedge, true);
   if (do_sub) { horizontal_edge(4, 2, sub, false); horizontal_edge(8, 2, sub, true); horizontal_edge(12, 2, sub, false); }
-}
-
-// The whole frame of one image: header, macroblocks (parse on lane 0, reconstruction on all lanes), loop filter.
-template <class X>
-ZW_HD void dec_frame(X& x, DecShared& S, const DecParams& P, const DecImage& D, DecState& st, const u16 (*tab)[16]) {
-  const u8* bytes = P.bytes;
-  u64 off = D.data_off, len = D.data_len;
-  x.run([&](int lane) {
-    for (int i = lane; i < 1056; i += 32) (&S.probs[0][0][0][0])[i] = ZW_TAB(kCoeffProbs)[i];
-    for (int i = lane; i < (int)D.mbw; i += 32) { P.topnz[D.col_off + i] = 0; P.topmodes[D.col_off + i] = 0; }
-    if (lane == 0) S.status = ZWD_OK;
-  });
-  x.run([&](int lane) {
-    if (lane != 0) return;
-    DecState s0;
-    s0 = st;
-    s0.status = 0; s0.sse_rgb = 0;
-    const int rc = dec_parse_header(S, bytes, off, len, D, s0);
-    s0.status = (u32)rc;
-    S.status = (u32)rc;
-    st = s0;
-  });
-  if (S.status != ZWD_OK) return;
-  const int mbw = (int)S.mbw, mbh = (int)S.mbh;
-  const size_t ypitch = (size_t)mbw * 16, cpitch = (size_t)mbw * 8;
-  u8* yp = P.planes + D.plane_off;
-  u8* up = yp + ypitch * mbh * 16;
-  u8* vp = up + cpitch * mbh * 8;
-  for (int mby = 0; mby < mbh && S.status == ZWD_OK; mby++) {
-    const int part = mby % (int)S.num_partitions;
-    x.run([&](int lane) {
-      if (lane == 0) { S.left_nz = 0; for (int i = 0; i < 4; i++) S.left_bpred[i] = 0; }
-    });
-    for (int mbx = 0; mbx < mbw; mbx++) {
-      x.run([&](int lane) {  // clear the coefficient buffers; borders of the work buffers (create_border_luma / _chroma)
-        for (int i = lane; i < 24 * 16; i += 32) (&S.coef[0][0])[i] = 0;
-        if (lane < 16) S.y2[lane] = 0;
-        if (lane < 24) S.nflag[lane] = 0;
-        if (lane < 21) {  // luma row 0: corner, 16 above, 4 above-right
-          u8 v;
-          if (mby == 0) v = 127;
-          else if (lane == 0) v = mbx == 0 ? (u8)129 : yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 - 1];
-          else if (lane <= 16 || mbx < mbw - 1) v = yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 + lane - 1];
-          else v = yp[(size_t)(mby * 16 - 1) * ypitch + mbx * 16 + 15];
-          S.yws[lane] = v;
-          if (lane >= 17) { S.yws[4 * 32 + lane] = v; S.yws[8 * 32 + lane] = v; S.yws[12 * 32 + lane] = v; }
-        }
-        if (lane < 16) S.yws[(1 + lane) * 32] = mbx == 0 ? (u8)129 : yp[(size_t)(mby * 16 + lane) * ypitch + mbx * 16 - 1];
-        if (lane < 18) {  // chroma row 0 of U (lanes 0..8) and V (9..17)
-          const int k = lane % 9;
-          u8* ws = lane < 9 ? S.uws : S.vws;
-          const u8* cp = lane < 9 ? up : vp;
-          u8 v;
-          if (mby == 0) v = 127;
-          else if (k == 0) v = mbx == 0 ? (u8)129 : cp[(size_t)(mby * 8 - 1) * cpitch + mbx * 8 - 1];
-          else v = cp[(size_t)(mby * 8 - 1) * cpitch + mbx * 8 + k - 1];
-          ws[k] = v;
-        }
-        if (lane >= 16) {  // chroma column 0: U rows on lanes 16..23, V rows on 24..31
-          const int r = lane & 7;
-          u8* ws = lane < 24 ? S.uws : S.vws;
-          const u8* cp = lane < 24 ? up : vp;
-          ws[(1 + r) * 32] = mbx == 0 ? (u8)129 : cp[(size_t)(mby * 8 + r) * cpitch + mbx * 8 - 1];
-        }
-      });
-      x.run([&](int lane) {
-        if (lane != 0) return;
-        const int rc = dec_parse_mb(S, bytes, P, D, mbx, part);
-        if (rc != ZWD_OK) S.status = (u32)rc;
-      });
-      if (S.status != ZWD_OK) break;
-      dec_reconstruct_mb(x, S, mbx, mby, tab);
-      x.run([&](int lane) {  // store the macroblock; leave its modes for the filter sweep and the parity dump
-        if (lane < 16) {
-          u8* dst = yp + (size_t)(mby * 16 + lane) * ypitch + mbx * 16;
-          const u8* srcp = &S.yws[(1 + lane) * 32 + 1];
-#pragma unroll
-          for (int k = 0; k < 16; k++) dst[k] = srcp[k];
-        } else {
-          const int r = lane & 7;
-          u8* dst = (lane < 24 ? up : vp) + (size_t)(mby * 8 + r) * cpitch + mbx * 8;
-          const u8* srcp = (lane < 24 ? S.uws : S.vws) + (1 + r) * 32 + 1;
-#pragma unroll
-          for (int k = 0; k < 8; k++) dst[k] = srcp[k];
-        }
-        if (lane == 0) {
-          u32* mi = P.mbinfo + ((size_t)D.mb_off + (size_t)mby * mbw + mbx) * 4;
-          u32 lo = 0, hi = 0;
-          for (int i = 0; i < 8; i++) { lo |= (u32)S.bpred[i] << (4 * i); hi |= (u32)S.bpred[8 + i] << (4 * i); }
-          mi[0] = (u32)S.luma_mode | ((u32)S.chroma_mode << 3) | ((u32)S.segment << 5) | ((u32)S.skipped << 7) | ((u32)S.nzdct << 8);
-          mi[1] = lo; mi[2] = hi; mi[3] = 0;
-        }
-      });
-    }
-  }
-  if (S.status != ZWD_OK) {
-    x.run([&](int lane) { if (lane == 0) st.status = S.status; });
-    return;
-  }
-  if (S.filter_level == 0) return;
-  for (int mby = 0; mby < mbh; mby++)
-    for (int mbx = 0; mbx < mbw; mbx++)
-      dec_filter_mb(x, S, yp, up, vp, mbx, mby, P.mbinfo[((size_t)D.mb_off + (size_t)mby * mbw + mbx) * 4]);
 }
 
 // One output pixel: chroma upsampling + colour conversion.  fill_rgb_buffer_fancy (yuv.rs:82-157, rows :264-383,
@@ -765,7 +842,13 @@ ZW_HD u32 dec_pixel_sse(const u8* s, u32 bpp, const u32* rgb) {
   return (u32)(dr * dr + dg * dg + db * db);
 }
 
+}  // namespace zw
+
 #if defined(__CUDACC__)
+#include "zw_search.cuh"  // progress-flag helpers (ld_flag / fence_acquire / publish_flag)
+
+namespace zw {
+
 __device__ const u16 d_dec_pred_tab[8][16] = ZW_PRED_TABLE_INIT;
 
 struct DecWarpExec {
@@ -778,26 +861,73 @@ struct DecWarpExec {
   }
 };
 
-constexpr int DEC_WARPS = 4;
+constexpr int DEC_PARSE_WARPS = 2;  // warps (= images) per CTA of the parse kernel: spread the serial walks over all SMs
+constexpr int DEC_ROW_WARPS = 8;    // warps (= macroblock rows in flight) per CTA of the wavefront kernels
 
-// One warp per image: everything up to the filtered planes.
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_dec_frame(DecParams P) {
-  __shared__ DecShared SH[DEC_WARPS];
-  __shared__ u16 s_tab[8][16];
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s_tab[0][0])[i] = (&d_dec_pred_tab[0][0])[i];
-  __syncthreads();
-  const u32 img = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+// One warp per image: the bitstream walk.  topnz_g / topmodes_g: [n_img][1024] scratch for very wide images, or null.
+__global__ void __launch_bounds__(DEC_PARSE_WARPS * 32) k_dec_parse(DecParams P, u16* topnz_g, u32* topmodes_g) {
+  __shared__ DecParseShared SH[DEC_PARSE_WARPS];
+  const u32 img = blockIdx.x * DEC_PARSE_WARPS + (threadIdx.x >> 5);
   if (img >= P.n_img) return;
-  DecImage D = P.img[img];
+  const DecImage D = P.img[img];
+  u64 off = D.data_off, len = D.data_len;
   if (P.file_off) {  // verify after encode: the files sit in the encoder's output arena, placed by the device
     const ImageState es = P.enc_st[img];
     if (es.status != 0) { if ((threadIdx.x & 31) == 0) P.st[img].status = ZWD_CONTAINER; return; }
-    D.data_off = P.file_off[img] + 20;
-    D.data_len = es.vp8_bytes;
+    off = P.file_off[img] + 20;
+    len = es.vp8_bytes;
   }
+  if (D.mbw > (u32)DEC_CTX_COLS && topnz_g == nullptr) { if ((threadIdx.x & 31) == 0) P.st[img].status = ZWD_DIMENSIONS; return; }
   DecWarpExec X;
   X.lane = threadIdx.x & 31;
-  dec_frame(X, SH[threadIdx.x >> 5], P, D, P.st[img], s_tab);
+  dec_parse_frame(X, SH[threadIdx.x >> 5], P, D, off, len, P.st[img], topnz_g ? topnz_g + (size_t)img * 1024 : nullptr,
+                  topmodes_g ? topmodes_g + (size_t)img * 1024 : nullptr);
+}
+
+// Wavefront over macroblock rows: PHASE 0 reconstruction, PHASE 1 loop filter.  A warp takes rows by ticket (row y - 1 of
+// an image always has a lower ticket than row y, so a waiting warp waits for a running one); macroblock x of row y
+// needs x + 1 of row y - 1 (top-right neighbour; the last macroblock needs only its top neighbour).
+template <int PHASE>
+__global__ void __launch_bounds__(DEC_ROW_WARPS * 32) k_dec_rows(DecParams P) {
+  __shared__ DecReconShared SH[PHASE == 0 ? DEC_ROW_WARPS : 1];
+  __shared__ u16 s_tab[8][16];
+  if (PHASE == 0) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s_tab[0][0])[i] = (&d_dec_pred_tab[0][0])[i];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  DecWarpExec X;
+  X.lane = lane;
+  int* progress = P.progress + PHASE * P.n_rows;
+  for (;;) {
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(&P.ticket[PHASE], 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= P.n_rows) return;
+    const RowRef rr = P.rows[t];
+    const DecImage D = P.img[rr.img];
+    const DecState& st = P.st[rr.img];
+    const int mby = (int)rr.mby, mbw = (int)D.mbw;
+    const bool live = st.status == 0 && (PHASE == 0 || st.filter_level != 0);
+    int seen = 0;
+    for (int mbx = 0; mbx < mbw && live; mbx++) {
+      if (mby > 0) {
+        const int need = min(mbx + 2, mbw);
+        if (seen < need) {
+          if (lane == 0) {
+            while ((seen = ld_flag(&progress[D.row_off + mby - 1])) < need) __nanosleep(64);
+            fence_acquire();
+          }
+          seen = __shfl_sync(0xffffffffu, seen, 0);
+        }
+      }
+      if constexpr (PHASE == 0) dec_recon_mb(X, SH[threadIdx.x >> 5], P, D, st, mbx, mby, s_tab);
+      else dec_filter_mb(X, st, D, P.planes, mbx, mby, P.mbinfo[((size_t)D.mb_off + (size_t)mby * mbw + mbx) * 4]);
+      __syncwarp();
+      if (lane == 0) publish_flag(&progress[D.row_off + mby], mbx + 1);
+    }
+    if (!live && lane == 0) publish_flag(&progress[D.row_off + mby], mbw);  // nothing to do: do not hold the row below
+  }
 }
 
 // Chroma upsampling + colour conversion (+ squared error against the source): one thread per pixel.
@@ -828,7 +958,7 @@ __global__ void __launch_bounds__(256) k_dec_rgb(DecParams P) {
     }
   }
 }
-#endif  // __CUDACC__
 
 }  // namespace zw
+#endif  // __CUDACC__
 #endif

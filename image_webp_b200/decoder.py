@@ -40,7 +40,7 @@ def _info_dict(i):
 def decode_batch(files, upsampling=UpsamplingMethod.Bilinear, sources=None, color=ColorType.Rgb8, want_rgb=True, ctx=None,
                  raise_errors=True):
     """Decode a list of .webp files / bare VP8 frames (bytes) on the GPU.  Returns (list of uint8 arrays [h, w, 3] or
-    None, list of info dicts, (frame_ms, colour_ms)).  With `sources` (arrays [h, w, c] matching `color`) every image is
+    None, list of info dicts, (parse_ms, reconstruct_ms, filter_ms, colour_ms)).  With `sources` (arrays [h, w, c] matching `color`) every image is
     also scored against its source on the device: info['sse_rgb'], info['psnr_rgb']."""
     ctx = ctx or default_context()
     n = len(files)
@@ -56,7 +56,7 @@ def decode_batch(files, upsampling=UpsamplingMethod.Bilinear, sources=None, colo
         src_arr, keep2 = ctx._as_images(sources, color)
         keep.append(keep2)
     infos = (_lib.ZwDecodeInfo * n)()
-    ms = (C.c_float * 2)()
+    ms = (C.c_float * 4)()
     rc = ctx.lib.zw_decode_batch(ctx.h, blobs, n, upsampling.value, outs, src_arr, infos, ms)
     res = []
     if want_rgb:
@@ -77,21 +77,21 @@ def decode_batch(files, upsampling=UpsamplingMethod.Bilinear, sources=None, colo
         for d in info:
             if d["status"] != 0:
                 raise DecodingError(d["status"])
-    return res, info, (ms[0], ms[1])
+    return res, info, tuple(ms)
 
 
 def verify_pending(pending, upsampling=UpsamplingMethod.Bilinear):
     """Decode the files of a submitted batch (encoder.PendingBatch, before .result() releases it) where they lie in
     device memory and score them against the batch's source pixels, which are still resident there too (zw_verify).
-    Returns (list of info dicts, (frame_ms, colour_ms))."""
+    Returns (list of info dicts, (parse_ms, reconstruct_ms, filter_ms, colour_ms))."""
     ctx = pending._ctx
     n = pending._n
     infos = (_lib.ZwDecodeInfo * n)()
-    ms = (C.c_float * 2)()
+    ms = (C.c_float * 4)()
     rc = ctx.lib.zw_verify(ctx.h, pending._ticket, upsampling.value, infos, ms)
     if rc != 0:
         raise DeviceError(rc, ctx.lib.zw_strerror(rc).decode())
-    return [_info_dict(infos[i]) for i in range(n)], (ms[0], ms[1])
+    return [_info_dict(infos[i]) for i in range(n)], tuple(ms)
 
 
 def _scan(data):

@@ -207,12 +207,12 @@ typedef struct zw_decode_info {
   double psnr_rgb;  /* verification: 10 log10(255^2 * 3wh / sse_rgb); 99.0 for identical pixels   */
 } zw_decode_info;
 
-/* Decode n files on the GPU (one warp per image for the serial bitstream + reconstruction + loop filter, then a
- * data-parallel colour conversion).  upsampling: 1 = bilinear (the reference's default), 0 = nearest.
+/* Decode n files on the GPU: the serial bitstream walk (one warp per image), then reconstruction and loop filter
+ * as wavefronts over macroblock rows, then a data-parallel colour conversion.  upsampling: 1 = bilinear (the reference's default), 0 = nearest.
  *   rgb_outs  NULL, or n slots that receive width*height*3 RGB bytes (allocated with malloc when data == NULL)
  *   sources   NULL, or n source images: every decoded image is scored against sources[i] on the device
  *             (sse_rgb / psnr_rgb; grey sources compare each channel with the grey value, alpha is ignored)
- *   infos     n results;  device_ms NULL or [2]: frame kernel, colour kernel (CUDA events) */
+ *   infos     n results;  device_ms NULL or [4]: parse, reconstruct, filter, colour kernels (CUDA events) */
 int zw_decode_batch(zw_ctx* ctx, const zw_blob* files, size_t n, int upsampling, zw_output* rgb_outs,
                     const zw_image* sources, zw_decode_info* infos, float* device_ms);
 

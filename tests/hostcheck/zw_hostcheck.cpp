@@ -188,17 +188,26 @@ int hc_decode(const u8* data, size_t len, u32 width, u32 height, int fancy, u8* 
   memset(&D, 0, sizeof(D));
   D.data_off = 0; D.data_len = (u32)len; D.width = width; D.height = height; D.mbw = (width + 15) / 16; D.mbh = (height + 15) / 16;
   D.src_bpp = src_bpp;
-  std::vector<u16> topnz(D.mbw);
-  std::vector<u32> topmodes(D.mbw);
+  std::vector<u16> topnz(1024);
+  std::vector<u32> topmodes(1024);
+  std::vector<uint4> recbuf(((size_t)D.mbw * D.mbh * sizeof(MbRecord)) / 16 + 1);
   DecState st;
   memset(&st, 0, sizeof(st));
   DecParams P;
   memset(&P, 0, sizeof(P));
   P.img = &D; P.st = &st; P.n_img = 1; P.fancy = fancy; P.bytes = data; P.planes = planes; P.mbinfo = mbinfo;
-  P.topnz = topnz.data(); P.topmodes = topmodes.data(); P.rgb = rgb; P.src = src;
-  static DecShared S;
+  P.rec = reinterpret_cast<MbRecord*>(recbuf.data()); P.rgb = rgb; P.src = src;
+  static DecParseShared SP;
+  static DecReconShared SR;
   HostExec32 X;
-  dec_frame(X, S, P, D, st, kPredTab);
+  dec_parse_frame(X, SP, P, D, 0, len, st, topnz.data(), topmodes.data());
+  if (st.status == 0) {
+    for (u32 y = 0; y < D.mbh; y++)
+      for (u32 xm = 0; xm < D.mbw; xm++) dec_recon_mb(X, SR, P, D, st, (int)xm, (int)y, kPredTab);
+    if (st.filter_level != 0)
+      for (u32 y = 0; y < D.mbh; y++)
+        for (u32 xm = 0; xm < D.mbw; xm++) dec_filter_mb(X, st, D, planes, (int)xm, (int)y, mbinfo[((size_t)y * D.mbw + xm) * 4]);
+  }
   u64 t = 0;
   if (st.status == 0)
     for (u32 row = 0; row < height; row++)

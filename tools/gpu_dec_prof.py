@@ -11,4 +11,4 @@ p = Z.EncoderParams.lossy(75); p.method = 4
 pend = ctx.submit(list(PI.batch(n)), p)
 info, ms = Z.verify_pending(pend)
 pend.result()
-print("verify n=%d: frame %.2f ms colour %.2f ms" % (n, ms[0], ms[1]))
+print("verify n=%d: parse %.2f reconstruct %.2f filter %.2f colour %.2f ms" % ((n,) + tuple(ms)))

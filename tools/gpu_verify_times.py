@@ -19,5 +19,5 @@ for name, imgs in (("synthetic", list(synth.batch_photo_like(n, 768, 512, 0))), 
     ps = np.array([i["psnr_rgb"] for i in info])
     bad = sum(1 for i in info if i["status"] != 0)
     px = n * 768 * 512
-    print("%s: encode %.1f ms | verify: frame kernel %.2f ms, colour kernel %.2f ms -> %.0f MPix/s decoded; psnr min %.2f mean %.2f; %d bad; %.2f symbols/px" % (
-        name, t["device_total_ms"], ms[0], ms[1], px / (ms[0] + ms[1]) / 1e3, ps.min(), ps.mean(), bad, t["symbols"] / px), flush=True)
+    print("%s: encode %.1f ms | verify: parse %.2f ms, reconstruct %.2f ms, filter %.2f ms, colour %.2f ms -> %.0f MPix/s decoded; psnr min %.2f mean %.2f; %d bad; %.2f symbols/px" % (
+        name, t["device_total_ms"], ms[0], ms[1], ms[2], ms[3], px / sum(ms) / 1e3, ps.min(), ps.mean(), bad, t["symbols"] / px), flush=True)
