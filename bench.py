@@ -206,13 +206,14 @@ def run_workload(Z, torch, ctx, pipe, imgs, params, steps, warmup, barrier, samp
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    e2e_dev_ms = 0.0
     outs = None
     futs = []
     for _ in range(steps):
         futs.append(pipe.submit(imgs, params))
     for f in futs:
         outs, t = f.result()
-        h2d += t["h2d_bytes"]; d2h += t["d2h_bytes"]
+        h2d += t["h2d_bytes"]; d2h += t["d2h_bytes"]; e2e_dev_ms += t["device_total_ms"]
     barrier()
     e2e_s = time.perf_counter() - t0
     # (b) one blocking call per step (zw_encode_webp_batch: chunks pipelined inside the call)
@@ -224,8 +225,42 @@ def run_workload(Z, torch, ctx, pipe, imgs, params, steps, warmup, barrier, samp
     barrier()
     e2e_call_s = (time.perf_counter() - t0) / max(1, steps // 2) * steps
     return {"dev_s": dev_ms / 1e3, "wall_kernel_s": wall_kernel_s, "e2e_s": e2e_s, "e2e_call_s": e2e_call_s, "stage_ms": stage_ms,
-            "launches": launches, "symbols": symbols, "h2d": h2d, "d2h": d2h, "clocks": clocks,
+            "launches": launches, "symbols": symbols, "h2d": h2d, "d2h": d2h, "clocks": clocks, "e2e_dev_ms": e2e_dev_ms,
             "outs": outs, "outs_resident": outs_resident, "outs_call": outs_b, "h2d_ms": t["h2d_ms"], "d2h_ms": t["d2h_ms"]}
+
+
+def verify_leg(Z, ctx, workloads, params, check=4):
+    """The on-device VP8 decoder as batch verifier (zw_verify): every file of a freshly encoded batch is decoded where it
+    lies in device memory and scored against the source pixels resident there; `check` images per workload are also decoded
+    by the decoder oracle (CPU restatement of the reference's decoder) and must give the same squared error."""
+    import numpy as np
+    import oracle_lib as O
+    res = {"api": "zw_submit -> zw_verify(ticket) -> zw_wait: parse (one warp per image), reconstruct + loop filter (row wavefronts), "
+                  "colour conversion + squared error; nothing but the per-image results crosses the link",
+           "decoder_pinned_by": "the reference's pixel-exact decode fixtures (tests/decode.rs gallery1, gallery1_nofancy, gallery2 *_webp_a) via "
+                                "the decoder oracle; GPU == oracle at every stage (tests/test_gpu_decoder.py)"}
+    for name, imgs in workloads:
+        n = len(imgs)
+        px = sum(i.shape[0] * i.shape[1] for i in imgs)
+        best = None
+        for _ in range(3):
+            pend = ctx.submit(imgs, params)
+            info, ms = Z.verify_pending(pend)
+            outs, t = pend.result()
+            if best is None or sum(ms) < sum(best):
+                best = ms
+        ps = np.array([i["psnr_rgb"] for i in info])
+        ok = sum(1 for i in info if i["status"] == 0)
+        same = 0
+        idx = list(range(0, n, max(1, n // check)))[:check]
+        for i in idx:
+            rc, o = O.decode(outs[i], True, ("rgb",))
+            same += int(rc == 0 and info[i]["sse_rgb"] == int(((o["rgb"].astype(np.int64) - imgs[i].astype(np.int64)) ** 2).sum()))
+        res[name] = {"images": n, "decode_mpix_s": px / sum(best) / 1e3, "ms": {"parse": best[0], "reconstruct": best[1], "filter": best[2], "colour": best[3]},
+                     "encode_ms": t["device_total_ms"], "decoded_ok": ok, "psnr_rgb_min": float(ps.min()), "psnr_rgb_mean": float(ps.mean()),
+                     "sse_equal_to_oracle_decode": {"checked": len(idx), "identical": same}}
+        assert ok == n and same == len(idx), "verification leg: device decoder disagrees with the oracle"
+    return res
 
 
 def other_configs(Z, torch, ctx, pipe, lib, cores, world):
@@ -320,6 +355,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-photo", action="store_true", help="skip the photo workload")
     ap.add_argument("--no-other", action="store_true", help="skip other_configs")
+    ap.add_argument("--no-verify", action="store_true", help="skip the on-device decode / verification leg")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end leg (pipeline slots of the context)")
     ap.add_argument("--check", type=int, default=16, help="synthetic images per step byte-compared with the oracle after timing")
     args = ap.parse_args()
@@ -424,6 +460,7 @@ def main():
                        "byte_identical_to": "the CPU port of the reference (oracle/); the Rust reference itself cannot be run here"},
             "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": R["h2d"] // args.steps, "d2h_bytes_per_step": R["d2h"] // args.steps,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "frac_of_kernel_only": e2e_value / value,
+                    "kernel_ms_per_step_while_streaming": R["e2e_dev_ms"] / args.steps,
                     "api": "zw_submit / zw_wait / zw_release on one context, %d batches in flight (BatchPipeline): pinned host RGB in, .webp bytes out" % args.depth,
                     "h2d_gb_s": R["h2d"] / args.steps / max(R["h2d_ms"], 1e-6) / 1e6,
                     "one_call_at_a_time": {"value": total_pix / e2e_call_s / 1e6, "ms_per_step": 1e3 * e2e_call_s / args.steps,
@@ -497,6 +534,14 @@ def main():
                                      "sample": "all %d photo crops, one image per thread on %d threads (incl. copying the files out)" % (n, cores)}
             line["photo"] = photo
             assert not bad, "photo workload: images %s differ from the oracle" % bad[:8]
+        if not args.no_verify:
+            try:
+                wl = [("synthetic", imgs)] + ([("photo", pimgs)] if P else [])
+                line["verify"] = verify_leg(Z, ctx, wl, params)
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["verify"] = {"error": str(e)}
         if not args.no_other and world == 1:
             try:
                 line["other_configs"] = other_configs(Z, torch, ctx, pipe, lib or native_oracle(), cores, world)
