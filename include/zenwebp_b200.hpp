@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "zenwebp_b200.h"
@@ -66,6 +67,31 @@ class Context {
       else if (!first_err) first_err = out[i].status;
       zw_free(out[i].data);
     }
+    raise_for(first_err);
+    return res;
+  }
+  // Decoder mirror (WebPDecoder::read_image for lossy still images, src/decoder/api.rs:636): n files -> n RGB images
+  // (width * height * 3, bilinear chroma upsampling unless `simple_upsampling`); the first failing file throws.
+  struct Decoded { std::vector<uint8_t> rgb; uint32_t width = 0, height = 0; double psnr_rgb = 0.0; };
+  std::vector<Decoded> decode_batch(const std::vector<std::pair<const uint8_t*, size_t>>& files, bool simple_upsampling = false,
+                                    const std::vector<ImageRef>* sources = nullptr) {
+    std::vector<zw_blob> in(files.size());
+    std::vector<zw_output> out(files.size(), zw_output{nullptr, 0, 0, 0, 0});
+    std::vector<zw_decode_info> info(files.size());
+    std::vector<zw_image> src;
+    for (size_t i = 0; i < files.size(); i++) in[i] = zw_blob{files[i].first, files[i].second};
+    if (sources) for (const ImageRef& r : *sources) src.push_back(zw_image{r.data, r.len, r.width, r.height, (uint32_t)r.color, 0});
+    const int rc = zw_decode_batch(h_, in.data(), in.size(), simple_upsampling ? 0 : 1, out.data(), sources ? src.data() : nullptr, info.data(), nullptr);
+    std::vector<Decoded> res(files.size());
+    int first_err = rc;
+    for (size_t i = 0; i < files.size(); i++) {
+      if (info[i].status == ZW_DEC_OK && out[i].status == ZW_OK && out[i].data) {
+        res[i].rgb.assign(out[i].data, out[i].data + out[i].len);
+        res[i].width = info[i].width; res[i].height = info[i].height; res[i].psnr_rgb = info[i].psnr_rgb;
+      } else if (!first_err) first_err = info[i].status ? 1000 + info[i].status : out[i].status;
+      zw_free(out[i].data);
+    }
+    if (first_err >= 1000) throw std::runtime_error("zenwebp_b200: decoding error " + std::to_string(first_err - 1000));
     raise_for(first_err);
     return res;
   }

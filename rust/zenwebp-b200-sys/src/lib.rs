@@ -30,6 +30,15 @@ pub struct zw_batch_view { pub arena: *const u8, pub n: usize, pub offsets: *con
 
 #[repr(C)]
 pub struct zw_multi { _private: [u8; 0] }
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct zw_blob { pub data: *const u8, pub len: usize }
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct zw_decode_info {
+    pub status: i32, pub width: u32, pub height: u32, pub filter_type: u32, pub filter_level: u32, pub sharpness: u32,
+    pub num_partitions: u32, pub segments_enabled: u32, pub sse_rgb: u64, pub psnr_rgb: f64,
+}
 
 pub const ZW_ERR_BUSY: c_int = 7;
 pub const ZW_ERR_TOO_LARGE: c_int = 8;
@@ -63,4 +72,8 @@ extern "C" {
     pub fn zw_dump_stage(ctx: *mut zw_ctx, index: usize, stage: *const c_char, dst: *mut c_void, cap: usize, len: *mut usize) -> c_int;
     pub fn zw_version() -> *const c_char;
     pub fn zw_measure_int_peak(ctx: *mut zw_ctx, int_instr_per_s: *mut f64) -> c_int;
+    pub fn zw_decode_batch(ctx: *mut zw_ctx, files: *const zw_blob, n: usize, upsampling: c_int, rgb_outs: *mut zw_output,
+                           sources: *const zw_image, infos: *mut zw_decode_info, device_ms: *mut f32) -> c_int;
+    pub fn zw_verify(ctx: *mut zw_ctx, ticket: c_int, upsampling: c_int, infos: *mut zw_decode_info, device_ms: *mut f32) -> c_int;
+    pub fn zw_decode_dump_stage(ctx: *mut zw_ctx, index: usize, stage: *const c_char, dst: *mut c_void, cap: usize, len: *mut usize) -> c_int;
 }

@@ -55,6 +55,14 @@ int main(int argc, char** argv) {
     write_file(prefix + ".multi.webp", mc.encode_batch({ref, ref, ref}, p)[2]);
     try { ctx.encode_batch({Z::Context::ImageRef{rgb.data(), rgb.size() - 1, w, h, Z::ColorType::Rgb8}}, p); return 6; }
     catch (const Z::InvalidBufferSize&) {}
+    {  // decoder mirror: decode what was just encoded, scored against the source; the pixels go to <prefix>.decoded.rgb
+      const std::vector<uint8_t> file = ctx.encode_batch({ref}, p)[0];
+      const std::vector<Z::Context::ImageRef> srcs = {ref};
+      auto dec = ctx.decode_batch({{file.data(), file.size()}}, false, &srcs);
+      if (dec.size() != 1 || dec[0].width != w || dec[0].height != h || dec[0].rgb.size() != (size_t)w * h * 3 || dec[0].psnr_rgb < 20.0) return 7;
+      write_file(prefix + ".decoded.rgb", dec[0].rgb);
+      try { ctx.decode_batch({{file.data(), 5}}); return 8; } catch (const std::runtime_error&) {}
+    }
     printf("encode ok\n");
     return 0;
   }
