@@ -2732,6 +2732,7 @@ static void write_chunk(std::vector<u8>& w, const char* name, const std::vector<
 }
 
 #include "zw_dec_oracle.inc"
+#include "zw_lossless_oracle.inc"
 
 }  // namespace
 
@@ -2823,6 +2824,35 @@ int zwo_decode(const uint8_t* data, size_t len, int fancy, uint8_t** rgb, uint8_
     }
   }
   return ZWD_OK;
+}
+
+// ---- lossless VP8L encoder + full container (zw_lossless_oracle.inc) ----
+static int ll_finish(int rc, std::vector<u8>& w, uint8_t** out, size_t* out_len) {
+  if (rc != 0) { *out = nullptr; *out_len = 0; return rc; }
+  *out = (uint8_t*)malloc(w.size() ? w.size() : 1);
+  memcpy(*out, w.data(), w.size());
+  *out_len = w.size();
+  return 0;
+}
+int zwo_encode_lossless(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, int use_predictor,
+                        int implicit_dimensions, uint8_t** out, size_t* out_len) {
+  std::vector<u8> w;
+  return ll_finish(ll::encode_frame_lossless(w, data, data_len, width, height, color, use_predictor != 0, implicit_dimensions != 0), w, out, out_len);
+}
+int zwo_encode_alpha_lossless(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, uint8_t** out,
+                              size_t* out_len) {
+  std::vector<u8> w;
+  return ll_finish(ll::encode_alpha_lossless(w, data, data_len, width, height, color), w, out, out_len);
+}
+int zwo_webp_encode(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, int use_predictor,
+                    int use_lossy, int quality, int method, const uint8_t* icc, size_t icc_len, const uint8_t* exif,
+                    size_t exif_len, const uint8_t* xmp, size_t xmp_len, uint8_t** out, size_t* out_len) {
+  std::vector<u8> w;
+  const ll::Meta m = {icc, icc_len, exif, exif_len, xmp, xmp_len};
+  return ll_finish(ll::webp_encode(w, data, data_len, width, height, color, use_predictor != 0, use_lossy != 0, quality, method, m), w, out, out_len);
+}
+int zwo_build_huffman(const uint32_t* frequencies, size_t n, int length_limit, uint8_t* lengths, uint16_t* codes) {
+  return ll::build_huffman_tree(frequencies, n, lengths, codes, (u8)length_limit) ? 1 : 0;
 }
 
 void zwo_free(void* p) { free(p); }

@@ -122,6 +122,21 @@ uint16_t zwo_fixed_cost_i4(int top, int left, int mode);
 uint16_t zwo_entropy_cost(int p);
 uint16_t zwo_level_fixed_cost(int level);
 
+/* ---- VP8L lossless encoder and the complete WebPEncoder::encode container logic (zw_lossless_oracle.inc) ----
+ * encode_frame_lossless (src/encoder/api.rs:945-1167): the raw VP8L stream.  color as above; returns 0 OK,
+ * 1 InvalidDimensions (w or h == 0 or > 16384), 2 InvalidBufferSize (assert_eq! panic in the reference). */
+int zwo_encode_lossless(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, int use_predictor,
+                        int implicit_dimensions, uint8_t** out, size_t* out_len);
+/* encode_alpha_lossless (api.rs:1175-1222): the payload of an ALPH chunk (La8 / Rgba8 input). */
+int zwo_encode_alpha_lossless(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, uint8_t** out,
+                              size_t* out_len);
+/* WebPEncoder::encode (api.rs:1291-1394): lossy or lossless frame, simple or VP8X container, ICCP / ALPH / EXIF / XMP. */
+int zwo_webp_encode(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, int use_predictor,
+                    int use_lossy, int quality, int method, const uint8_t* icc, size_t icc_len, const uint8_t* exif,
+                    size_t exif_len, const uint8_t* xmp, size_t xmp_len, uint8_t** out, size_t* out_len);
+/* build_huffman_tree (api.rs:163-287); returns 0 when at most one symbol is used. */
+int zwo_build_huffman(const uint32_t* frequencies, size_t n, int length_limit, uint8_t* lengths, uint16_t* codes);
+
 /* Primitive-invocation counters of the calling thread (measurement: SURVEY.md 8(d) algorithmic
    int-ops).  Order: fdct, idct, wht, iwht, ttransform, quantised coefficients, sse pixels,
    residual-cost coefficients visited, trellis positions, I4 predictor sets, add_residue blocks,

@@ -181,3 +181,66 @@ def count_ops(img, quality, method):
     counts = {s: {OP_NAMES[i]: int(buf[k * n + i]) for i in range(n)} for k, s in enumerate(OP_SETS)}
     ops = {s: sum(counts[s][OP_NAMES[i]] * OP_COST[i] for i in range(n)) for s in OP_SETS}
     return counts, ops
+
+
+# ---- VP8L lossless encoder + full container (oracle/zw_lossless_oracle.inc) ----
+def _take(L, rc, out, n):
+    if rc != 0:
+        return rc, b""
+    data = C.string_at(out, n.value)
+    L.zwo_free(out)
+    return 0, data
+
+
+def encode_lossless(img, color="Rgb8", use_predictor=True, implicit_dimensions=False):
+    """encode_frame_lossless: the raw VP8L stream of `img` (uint8 [h,w,c] or [h,w])."""
+    L = lib()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[0], img.shape[1]
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    L.zwo_encode_lossless.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    rc = L.zwo_encode_lossless(img.ctypes.data, img.nbytes, w, h, COLOR[color], int(use_predictor), int(implicit_dimensions),
+                               C.byref(out), C.byref(n))
+    return _take(L, rc, out, n)
+
+
+def encode_alpha_lossless(img, color="Rgba8"):
+    L = lib()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[0], img.shape[1]
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    L.zwo_encode_alpha_lossless.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
+                                            C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    rc = L.zwo_encode_alpha_lossless(img.ctypes.data, img.nbytes, w, h, COLOR[color], C.byref(out), C.byref(n))
+    return _take(L, rc, out, n)
+
+
+def webp_encode(img, color="Rgb8", use_predictor=True, use_lossy=False, quality=95, method=4, icc=b"", exif=b"", xmp=b"",
+                raw=None, w=None, h=None):
+    """WebPEncoder::encode: the complete .webp file (simple or VP8X container).  raw/w/h override img for bad-size tests."""
+    L = lib()
+    if raw is None:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[0], img.shape[1]
+        raw = img.tobytes()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    L.zwo_webp_encode.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                  C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    rc = L.zwo_webp_encode(raw, len(raw), w, h, COLOR[color], int(use_predictor), int(use_lossy), int(quality), int(method),
+                           icc, len(icc), exif, len(exif), xmp, len(xmp), C.byref(out), C.byref(n))
+    return _take(L, rc, out, n)
+
+
+def build_huffman(freqs, limit):
+    L = lib()
+    f = np.ascontiguousarray(freqs, dtype=np.uint32)
+    lengths = np.zeros(len(f), np.uint8)
+    codes = np.zeros(len(f), np.uint16)
+    L.zwo_build_huffman.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    ok = L.zwo_build_huffman(f.ctypes.data, len(f), int(limit), lengths.ctypes.data, codes.ctypes.data)
+    return bool(ok), lengths, codes
