@@ -77,13 +77,23 @@ class ZwDecodeInfo(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ZwParams(C.Structure):
+    _fields_ = [("use_predictor_transform", C.c_int), ("use_lossy", C.c_int), ("lossy_quality", C.c_int), ("method", C.c_int)]
+
+
+class ZwMetadata(C.Structure):
+    _fields_ = [("icc_profile", C.c_char_p), ("icc_len", C.c_size_t), ("exif", C.c_char_p), ("exif_len", C.c_size_t),
+                ("xmp", C.c_char_p), ("xmp_len", C.c_size_t)]
+
+
 # Every symbol include/zenwebp_b200.h declares.
 EXPORTS = ["zw_create", "zw_destroy", "zw_last_error", "zw_strerror", "zw_free", "zw_max_output_size",
            "zw_encode_vp8_batch", "zw_encode_webp_batch", "zw_submit", "zw_wait", "zw_release",
            "zw_multi_create", "zw_multi_destroy", "zw_multi_device_count", "zw_multi_encode",
            "zw_stage_batch", "zw_encode_resident", "zw_download",
            "zw_dump_stage", "zw_version", "zw_measure_int_peak",
-           "zw_decode_batch", "zw_verify", "zw_decode_dump_stage"]
+           "zw_decode_batch", "zw_verify", "zw_decode_dump_stage",
+           "zw_encode_lossless_batch", "zw_encode_alpha_batch", "zw_params_default", "zw_encode_batch", "zw_lossless_dump_stage"]
 
 _lib = None
 
@@ -127,5 +137,11 @@ def load():
                                   C.POINTER(ZwDecodeInfo), C.POINTER(C.c_float)]
     L.zw_verify.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ZwDecodeInfo), C.POINTER(C.c_float)]
     L.zw_decode_dump_stage.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zw_encode_lossless_batch.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.c_int, C.c_int, C.POINTER(ZwOutput), C.POINTER(ZwTiming)]
+    L.zw_encode_alpha_batch.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.POINTER(ZwOutput), C.POINTER(ZwTiming)]
+    L.zw_params_default.restype = ZwParams
+    L.zw_encode_batch.argtypes = [C.c_void_p, C.POINTER(ZwImage), C.c_size_t, C.POINTER(ZwParams), C.POINTER(ZwMetadata), C.POINTER(ZwOutput),
+                                  C.POINTER(ZwTiming)]
+    L.zw_lossless_dump_stage.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L

@@ -27,6 +27,7 @@
 #include "zw_back.cuh"
 #include "zw_dec.cuh"
 #include "zw_front.cuh"
+#include "zw_lossless.cuh"
 
 using namespace zw;
 
@@ -216,6 +217,23 @@ struct DecCtx {
   }
 };
 
+// Buffers of the lossless (VP8L) entry points (zw_lossless_host.inc); allocated on first use.
+struct LlCtx {
+  DevBuf d_img, d_st, d_src, d_res, d_desc, d_tile_last, d_tile_carry, d_tile_bits, d_tile_bitoff, d_hist, d_codes, d_hdr, d_out, d_outoff;
+  PinBuf h_st, h_arena, h_outoff;
+  cudaEvent_t ev[9];
+  bool ev_ok = false;
+  u32 last_n = 0;
+  void release() {
+    DevBuf* all[] = {&d_img, &d_st, &d_src, &d_res, &d_desc, &d_tile_last, &d_tile_carry, &d_tile_bits, &d_tile_bitoff, &d_hist, &d_codes, &d_hdr,
+                     &d_out, &d_outoff};
+    for (DevBuf* b : all) b->release();
+    h_st.release(); h_arena.release(); h_outoff.release();
+    if (ev_ok) for (auto& e : ev) cudaEventDestroy(e);
+    ev_ok = false;
+  }
+};
+
 struct zw_ctx {
   int device = 0;
   int sm_count = 0;
@@ -229,6 +247,7 @@ struct zw_ctx {
   int dump_lane = -1;    // lane zw_dump_stage reads: the last chunk handed to the device
   zw_timing last;
   DecCtx dec;
+  LlCtx ll;
 };
 
 static void fill_params(Lane* c) {
@@ -777,6 +796,7 @@ void zw_destroy(zw_ctx* c) {
   cudaSetDevice(c->device);
   for (Lane* l : c->lanes) lane_destroy(l);
   c->dec.release();
+  c->ll.release();
   c->d_segtab.release(); c->d_lut.release();
   delete c;
 }
@@ -1105,3 +1125,4 @@ int zw_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_
 }  // extern "C"
 
 #include "zw_dec_host.inc"
+#include "zw_lossless_host.inc"

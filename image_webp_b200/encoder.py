@@ -1,16 +1,19 @@
-"""Host-side mirror of the reference's encoder API for the lossy path, on top of the C ABI.
+"""Host-side mirror of the reference's encoder API, on top of the C ABI.
 
 Mirrors (names, argument meaning, error behaviour) of imazen/image-webp `zenwebp` 0.2.0:
   ColorType        src/encoder/api.rs:83-92
   EncodingError    src/encoder/api.rs:35-48
+  Preset           src/encoder/api.rs:54-76
   EncoderParams    src/encoder/api.rs:419-459   (+ additive .method(m) builder)
-  WebPEncoder      src/encoder/api.rs:1244-1398 (new / set_params / encode)
-plus the batch entry point north_star asks for (`encode_batch`).
+  EncoderConfig    src/encoder/api.rs:488-672   (builder; the knobs the reference stores but never reads are stored too)
+  Encoder          src/encoder/api.rs:703-914   (new_rgba / new_rgb / new_l8 / new_la8 ... encode / encode_into / encode_to_writer)
+  WebPEncoder      src/encoder/api.rs:1244-1398 (new / set_params / set_icc_profile / set_exif_metadata / set_xmp_metadata / encode)
+plus the batch entry point north_star asks for (`encode_batch`).  Lossy (VP8) and lossless (VP8L) frames, the simple and
+the extended (VP8X + ICCP + ALPH + EXIF + XMP) container: everything WebPEncoder::encode writes.
 
 The reference is Rust; no Rust toolchain exists in the build image, so this module (and the C++
 header include/zenwebp_b200.hpp) stand where the `zenwebp-b200` wrapper crate would: see
-INTEGRATION.md for the -sys crate a maintainer would add.  Only the lossy VP8 path is provided:
-lossless parameters raise NotImplementedError (out of scope).  No CPU fallback.
+INTEGRATION.md for the -sys crate a maintainer would add.  No CPU fallback.
 """
 import ctypes as C
 import enum
@@ -32,6 +35,16 @@ class ColorType(enum.Enum):
 
     def has_alpha(self):
         return self in (ColorType.La8, ColorType.Rgba8)
+
+
+class Preset(enum.Enum):
+    """api.rs:54-76.  Stored by the builder; like the reference, the encoder does not read it."""
+    Default = 0
+    Picture = 1
+    Photo = 2
+    Drawing = 3
+    Icon = 4
+    Text = 5
 
 
 class EncodingError(Exception):
@@ -186,26 +199,75 @@ class Context:
 
     @staticmethod
     def _check(params, color, container):
+        """The streaming / multi-GPU entries carry the lossy path with the simple container only."""
         if not params.use_lossy:
-            raise NotImplementedError("only the lossy VP8 path is implemented on the GPU (SURVEY.md §2)")
+            raise NotImplementedError("streaming entry: lossy only (Context.encode_batch handles lossless)")
         if container and color.has_alpha():
-            # the reference wraps lossy + alpha in VP8X with a lossless ALPH chunk (api.rs:1330-1394): not built
-            raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f); container=False returns the VP8 payload")
+            raise NotImplementedError("streaming entry: lossy+alpha needs VP8X + ALPH (Context.encode_batch builds it)")
+
+    @staticmethod
+    def _as_metadata(metadata, n):
+        """metadata: None, one dict(icc=, exif=, xmp=) for every image, or a list of n dicts / None."""
+        if metadata is None:
+            return None, None
+        items = [metadata] * n if isinstance(metadata, dict) else list(metadata)
+        if len(items) != n:
+            raise ValueError("metadata: one entry per image")
+        arr = (_lib.ZwMetadata * n)()
+        keep = []
+        for i, m in enumerate(items):
+            m = m or {}
+            icc, exif, xmp = bytes(m.get("icc", b"")), bytes(m.get("exif", b"")), bytes(m.get("xmp", b""))
+            keep.append((icc, exif, xmp))
+            arr[i] = _lib.ZwMetadata(icc or None, len(icc), exif or None, len(exif), xmp or None, len(xmp))
+        return arr, keep
 
     # -- public ----------------------------------------------------------------------------
-    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+    def encode_batch(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True, metadata=None):
         """Batch entry point: list of uint8 arrays [h,w,c] (or (bytes,w,h) tuples) -> list of bytes.
-        Returns (outputs, timing dict).  (zw_encode_webp_batch / zw_encode_vp8_batch.)"""
-        self._check(params, color, container)
+        Returns (outputs, timing dict).  container=True: complete .webp files exactly as WebPEncoder::encode writes them
+        (zw_encode_batch: lossy or lossless, simple or extended container, optional metadata per image);
+        container=False: the raw frame (VP8 payload, zw_encode_vp8_batch, or VP8L stream, zw_encode_lossless_batch)."""
         arr, keep = self._as_images(images, color)
-        outs = (_lib.ZwOutput * len(images))()
+        n = len(images)
+        outs = (_lib.ZwOutput * n)()
         t = _lib.ZwTiming()
-        fn = self.lib.zw_encode_webp_batch if container else self.lib.zw_encode_vp8_batch
-        rc = fn(self.h, arr, len(images), int(params.lossy_quality), int(params.method), outs, C.byref(t))
+        if container:
+            zp = _lib.ZwParams(1 if params.use_predictor_transform else 0, 1 if params.use_lossy else 0, int(params.lossy_quality), int(params.method))
+            marr, mkeep = self._as_metadata(metadata, n)
+            rc = self.lib.zw_encode_batch(self.h, arr, n, C.byref(zp), marr, outs, C.byref(t))
+        elif metadata is not None:
+            raise ValueError("metadata needs a container")
+        elif params.use_lossy:
+            rc = self.lib.zw_encode_vp8_batch(self.h, arr, n, int(params.lossy_quality), int(params.method), outs, C.byref(t))
+        else:
+            rc = self.lib.zw_encode_lossless_batch(self.h, arr, n, 1 if params.use_predictor_transform else 0, 0, outs, C.byref(t))
         if rc != 0:
             self._collect(outs, False)
             _raise_for(rc, self.lib)
         return self._collect(outs, raise_errors), t.as_dict()
+
+    def encode_alpha_batch(self, images, color=ColorType.Rgba8, raise_errors=True):
+        """ALPH chunk payloads (encode_alpha_lossless, api.rs:1175) of La8 / Rgba8 images."""
+        arr, keep = self._as_images(images, color)
+        outs = (_lib.ZwOutput * len(images))()
+        t = _lib.ZwTiming()
+        rc = self.lib.zw_encode_alpha_batch(self.h, arr, len(images), outs, C.byref(t))
+        if rc != 0:
+            self._collect(outs, False)
+            _raise_for(rc, self.lib)
+        return self._collect(outs, raise_errors), t.as_dict()
+
+    def lossless_dump_stage(self, index, name, dtype=np.uint8):
+        n = C.c_size_t(0)
+        rc = self.lib.zw_lossless_dump_stage(self.h, index, name.encode(), None, 0, C.byref(n))
+        if rc not in (0, 4):
+            _raise_for(rc, self.lib)
+        buf = np.zeros(max(1, n.value), np.uint8)
+        rc = self.lib.zw_lossless_dump_stage(self.h, index, name.encode(), buf.ctypes.data, buf.size, C.byref(n))
+        if rc != 0:
+            _raise_for(rc, self.lib)
+        return buf[:n.value].view(dtype)
 
     def submit(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
         """Streaming entry (zw_submit): starts the batch and returns a PendingBatch at once, or None when every
@@ -368,20 +430,196 @@ class WebPEncoder:
         self.writer = writer
         self.params = EncoderParams()
         self.device = device
+        self.icc_profile = b""
+        self.exif_metadata = b""
+        self.xmp_metadata = b""
+
+    def set_icc_profile(self, icc_profile):
+        self.icc_profile = bytes(icc_profile)
+
+    def set_exif_metadata(self, exif_metadata):
+        self.exif_metadata = bytes(exif_metadata)
+
+    def set_xmp_metadata(self, xmp_metadata):
+        self.xmp_metadata = bytes(xmp_metadata)
 
     def set_params(self, params):
         self.params = params
 
     def encode(self, data, width, height, color):
-        if not self.params.use_lossy:
-            raise NotImplementedError("lossless VP8L encoding is out of scope of the GPU path (SURVEY.md §2)")
-        if color.has_alpha():
-            raise NotImplementedError("lossy+alpha needs the VP8X/ALPH container (SURVEY.md §8f)")
-        if width > 65535 or height > 65535:
-            raise InvalidDimensions()
         ctx = default_context(self.device)
-        outs, _ = ctx.encode_batch([(bytes(data), width, height)], self.params, color)
+        meta = None
+        if self.icc_profile or self.exif_metadata or self.xmp_metadata:
+            meta = {"icc": self.icc_profile, "exif": self.exif_metadata, "xmp": self.xmp_metadata}
+        outs, _ = ctx.encode_batch([(bytes(data), width, height)], self.params, color, metadata=meta)
         self.writer += outs[0]
+
+
+def _validate_buffer_size(size, width, height, bpp):  # api.rs:917-934: only "too small" is an error here
+    expected = width * height * bpp
+    if size < expected:
+        raise InvalidBufferSize("buffer too small: got %d, expected %d" % (size, expected))
+
+
+class EncoderConfig:
+    """api.rs:488-672: dimension-independent, reusable configuration (builder).  Default: lossy, quality 75, method 4."""
+
+    def __init__(self):
+        self._quality = 75.0
+        self._preset = Preset.Default
+        self._lossless = False
+        self._method = 4
+        self._near_lossless = 100
+        self._alpha_quality = 100
+        self._exact = False
+        self._target_size = 0
+        self._use_sharp_yuv = False
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    @classmethod
+    def new_lossless(cls):
+        c = cls()
+        c._lossless = True
+        return c
+
+    @classmethod
+    def with_preset(cls, preset, quality):
+        c = cls()
+        c._preset, c._quality = preset, float(quality)  # not clamped here (api.rs:537-543)
+        return c
+
+    def quality(self, quality):
+        self._quality = min(max(float(quality), 0.0), 100.0)
+        return self
+
+    def preset(self, preset):
+        self._preset = preset
+        return self
+
+    def lossless(self, lossless):
+        self._lossless = bool(lossless)
+        return self
+
+    def method(self, method):
+        self._method = min(int(method), 6)
+        return self
+
+    def near_lossless(self, value):
+        self._near_lossless = min(int(value), 100)
+        return self
+
+    def alpha_quality(self, quality):
+        self._alpha_quality = min(int(quality), 100)
+        return self
+
+    def exact(self, exact):
+        self._exact = bool(exact)
+        return self
+
+    def target_size(self, size):
+        self._target_size = int(size)
+        return self
+
+    def sharp_yuv(self, enable):
+        self._use_sharp_yuv = bool(enable)
+        return self
+
+    def get_quality(self):
+        return self._quality
+
+    def get_preset(self):
+        return self._preset
+
+    def is_lossless(self):
+        return self._lossless
+
+    def get_method(self):
+        return self._method
+
+    def to_params(self):
+        """api.rs:633-640: predictor on, quality rounded like fast_math::roundf ((x + 0.5) as i32, then `as u8` saturates)."""
+        q = min(max(int(np.float32(self._quality) + np.float32(0.5)), 0), 255)
+        return EncoderParams(True, not self._lossless, q, self._method)
+
+    def _encode(self, data, width, height, color, device=0, metadata=None):
+        data = bytes(data)
+        _validate_buffer_size(len(data), width, height, color.bytes_per_pixel())
+        out = bytearray()
+        enc = WebPEncoder(out, device)
+        enc.set_params(self.to_params())
+        if metadata:
+            enc.set_icc_profile(metadata.get("icc", b""))
+            enc.set_exif_metadata(metadata.get("exif", b""))
+            enc.set_xmp_metadata(metadata.get("xmp", b""))
+        enc.encode(data, width, height, color)
+        return bytes(out)
+
+    def encode_rgba(self, data, width, height, device=0):
+        return self._encode(data, width, height, ColorType.Rgba8, device)
+
+    def encode_rgb(self, data, width, height, device=0):
+        return self._encode(data, width, height, ColorType.Rgb8, device)
+
+
+class Encoder:
+    """api.rs:703-914: `Encoder.new_rgba(data, w, h).quality(85).encode()`."""
+
+    def __init__(self, data, width, height, color, device=0):
+        self._data, self._width, self._height, self._color = data, width, height, color
+        self._config = EncoderConfig()
+        self._meta = {}
+        self._device = device
+
+    @classmethod
+    def new_rgba(cls, data, width, height, device=0):
+        return cls(data, width, height, ColorType.Rgba8, device)
+
+    @classmethod
+    def new_rgb(cls, data, width, height, device=0):
+        return cls(data, width, height, ColorType.Rgb8, device)
+
+    @classmethod
+    def new_l8(cls, data, width, height, device=0):
+        return cls(data, width, height, ColorType.L8, device)
+
+    @classmethod
+    def new_la8(cls, data, width, height, device=0):
+        return cls(data, width, height, ColorType.La8, device)
+
+    def config(self, config):
+        self._config = config
+        return self
+
+    def icc_profile(self, profile):
+        self._meta["icc"] = bytes(profile)
+        return self
+
+    def exif_metadata(self, data):
+        self._meta["exif"] = bytes(data)
+        return self
+
+    def xmp_metadata(self, data):
+        self._meta["xmp"] = bytes(data)
+        return self
+
+    def encode(self):
+        return self._config._encode(self._data, self._width, self._height, self._color, self._device, self._meta)
+
+    def encode_into(self, output):
+        output += self.encode()
+
+    def encode_to_writer(self, writer):
+        writer.write(self.encode())
+
+
+for _name in ("quality", "preset", "lossless", "method", "near_lossless", "alpha_quality", "exact", "target_size", "sharp_yuv"):
+    def _fwd(self, value, _n=_name):
+        getattr(self._config, _n)(value)
+        return self
+    setattr(Encoder, _name, _fwd)
 
 
 def encode_batch(images, params, color=ColorType.Rgb8, device=0):

@@ -226,6 +226,45 @@ int zw_verify(zw_ctx* ctx, int ticket, int upsampling, zw_decode_info* infos, fl
  * padded frame), "DEC_MBINFO" (4 words per macroblock: flags, sub-block modes), "DEC_STATE". */
 int zw_decode_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
 
+/* ---- Lossless (VP8L) encoder and the complete WebPEncoder::encode (SURVEY.md 8(f)1 + 8(f)4) --------------------------
+ * Reference: encode_frame_lossless (src/encoder/api.rs:945-1167: subtract-green and "top" predictor transforms, one
+ * Huffman code per channel, run-length back references), encode_alpha_lossless (:1175-1222) and the container logic of
+ * WebPEncoder::encode (:1291-1394).  Bytes are identical to the CPU port (oracle/zw_lossless_oracle.inc), whose files
+ * libwebp decodes back to exactly the input pixels (the reference's own acceptance test, api.rs:1447-1511).
+ * Dimensions 1..16384 (api.rs:968); status codes as above.  These calls own the context while they run (batches in
+ * flight from zw_submit are waited for).  zw_timing fields used: h2d_ms, yuv_ms (transforms + run heads), analysis_ms
+ * (tokens + histograms), stats_ms (Huffman codes), token_ms (bit counts + scan), assemble_ms (bit packing), d2h_ms. */
+
+/* n raw VP8L streams (container == 0) or .webp files in the simple container (container != 0). */
+int zw_encode_lossless_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int use_predictor_transform, int container,
+                             zw_output* outs, zw_timing* timing);
+/* n ALPH chunk payloads: the alpha channel of ZW_COLOR_LA8 / ZW_COLOR_RGBA8 images (encode_alpha_lossless). */
+int zw_encode_alpha_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, zw_output* outs, zw_timing* timing);
+
+/* EncoderParams (api.rs:425-443); zw_params_default() = EncoderParams::default(): lossless, predictor on, q95, m4. */
+typedef struct zw_params {
+  int use_predictor_transform;
+  int use_lossy;
+  int lossy_quality; /* 0..100 */
+  int method;        /* 0..6 (larger values are clamped) */
+} zw_params;
+/* WebPEncoder::set_icc_profile / set_exif_metadata / set_xmp_metadata (api.rs:1267-1279); empty = absent. */
+typedef struct zw_metadata {
+  const uint8_t* icc_profile; size_t icc_len;
+  const uint8_t* exif;        size_t exif_len;
+  const uint8_t* xmp;         size_t xmp_len;
+} zw_metadata;
+zw_params zw_params_default(void);
+/* WebPEncoder::encode for a batch: lossy ("VP8 ") or lossless ("VP8L") frame; simple container, or the extended one
+ * (VP8X + ICCP + ALPH + frame + EXIF + XMP) when an image has metadata or is lossy with an alpha colour type.
+ * meta: NULL or n entries.  outs[i] receives the complete .webp file. */
+int zw_encode_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, const zw_params* params, const zw_metadata* meta,
+                    zw_output* outs, zw_timing* timing);
+/* Parity/debug: a stage of image `index` of the last lossless chunk: "LL_RESIDUAL" (u32 per pixel: R-G, G, B-G, A after
+ * the transforms), "LL_TOKENS" (u16 per pixel: bit 0 literal, bits 1.. run length carried), "LL_HIST" ([4][280] u32: red,
+ * green + lengths, blue, alpha), "LL_CODES" ([4][280] u32: length << 16 | code), "LL_HEADER", "LL_STATE". */
+int zw_lossless_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst, size_t cap, size_t* len);
+
 /* Library build info, e.g. "zenwebp_b200 0.2 (CUDA, sm_100a)". */
 const char* zw_version(void);
 

@@ -8,6 +8,7 @@
 #include "../../image_webp_b200/csrc/zw_cost.cuh"
 #include "../../image_webp_b200/csrc/zw_quad.cuh"
 #include "../../image_webp_b200/csrc/zw_dec.cuh"
+#include "../../image_webp_b200/csrc/zw_lossless.cuh"
 using namespace zw;
 static const u16 kPredTab[8][16] = ZW_PRED_TABLE_INIT;
 static const u16 kDTaps[32] = ZW_DTAPS_INIT;
@@ -220,5 +221,74 @@ int hc_decode(const u8* data, size_t len, u32 width, u32 height, int fancy, u8* 
   if (sse) *sse = t;
   if (st_out) memcpy(st_out, &st, 12 * sizeof(u32));
   return (int)st.status;
+}
+
+// ---- lossless (zw_lossless.cuh): the per-pixel functions, the Huffman construction and the header writer the kernels call,
+// driven serially.  The tile scans, the shared-memory bit packing and the output layout are the kernels' own and are only
+// checked on a GPU.  Returns the stream length in bytes; hist_out [4][280], codes_out [4][280] (length << 16 | code).
+size_t hc_lossless(const u8* src, u32 width, u32 height, u32 bpp, u32 color, u32 flags, u8* out, size_t cap, u32* hist_out, u32* codes_out,
+                   u32* res_out, u16* desc_out) {
+  const u32 npx = width * height;
+  std::vector<u32> res(npx);
+  std::vector<u16> desc(npx);
+  for (u32 i = 0; i < npx; i++) res[i] = ll_residual(src, i, i % width, i / width, width, bpp, color, flags);
+  u32 head = 0;
+  std::vector<u32> hist(4 * 280, 0);
+  for (u32 i = 0; i < npx; i++) {
+    if (i == 0 || res[i] != res[i - 1]) head = i;
+    const u32 d = ll_token_desc(i, head, i + 1 == npx || res[i + 1] != res[i]);
+    desc[i] = (u16)d;
+    if (d & 1) {
+      hist[280 + ((res[i] >> 8) & 255)]++;
+      if (ll_is_color(color)) { hist[res[i] & 255]++; hist[560 + ((res[i] >> 16) & 255)]++; }
+      if (ll_is_alpha(color)) hist[840 + (res[i] >> 24)]++;
+    }
+    if (d >> 1) { u32 sym, eb, ev; ll_run_symbol(d >> 1, sym, eb, ev); hist[280 + sym]++; }
+  }
+  std::vector<u32> words(cap / 4 + 16, 0);
+  LlBits w; w.w = words.data(); w.pos = 0;
+  ll_write_prefix(w, width, height, color, flags);
+  static LlHuffScratch S;
+  u8 lengths[4][280]; u16 codes[4][280];
+  memset(lengths, 0, sizeof(lengths)); memset(codes, 0, sizeof(codes));
+  const int order[4] = {1, 0, 2, 3};
+  for (int k = 0; k < 4; k++) {
+    const int c = order[k];
+    const bool built = c == 1 || (ll_is_color(color) && (c == 0 || c == 2)) || (ll_is_alpha(color) && c == 3);
+    if (built) ll_write_huffman_tree(w, &hist[c * 280], c == 1 ? 280 : 256, lengths[c], codes[c], S);
+    else if (c == 3) ll_write_single_entry_tree(w, (flags & LL_FLAG_PREDICTOR) ? 0u : 255u);
+    else ll_write_single_entry_tree(w, 0);
+  }
+  ll_write_single_entry_tree(w, 1);
+  std::vector<u32> tab(4 * 280);
+  for (int c = 0; c < 4; c++) for (int k = 0; k < 280; k++) tab[c * 280 + k] = ((u32)lengths[c][k] << 16) | codes[c][k];
+  auto table = [&](u32 ch, u32 sym) { return tab[ch * 280 + sym]; };
+  u64 total = w.pos;
+  for (u32 i = 0; i < npx; i++) total += ll_pixel_bits(res[i], desc[i], color, table);
+  if ((total + 7) / 8 > cap) return (size_t)((total + 7) / 8);
+  for (u32 i = 0; i < npx; i++) {
+    const u32 px = res[i], d = desc[i];
+    if (d & 1) {
+      u32 e = table(1, (px >> 8) & 255); w.put(e & 0xFFFF, e >> 16);
+      if (ll_is_color(color)) { e = table(0, px & 255); w.put(e & 0xFFFF, e >> 16); e = table(2, (px >> 16) & 255); w.put(e & 0xFFFF, e >> 16); }
+      if (ll_is_alpha(color)) { e = table(3, px >> 24); w.put(e & 0xFFFF, e >> 16); }
+    }
+    if (d >> 1) {
+      u32 sym, eb, ev; ll_run_symbol(d >> 1, sym, eb, ev);
+      const u32 e = table(1, sym);
+      w.put(e & 0xFFFF, e >> 16); w.put(ev, eb);
+    }
+  }
+  const size_t bytes = (size_t)((w.pos + 7) / 8);
+  memcpy(out, words.data(), bytes);
+  if (hist_out) memcpy(hist_out, hist.data(), 4 * 280 * 4);
+  if (codes_out) memcpy(codes_out, tab.data(), 4 * 280 * 4);
+  if (res_out) memcpy(res_out, res.data(), (size_t)npx * 4);
+  if (desc_out) memcpy(desc_out, desc.data(), (size_t)npx * 2);
+  return bytes;
+}
+int hc_ll_huffman(const u32* freq, u32 n, u32 limit, u8* lengths, u16* codes) {
+  static LlHuffScratch S;
+  return ll_build_huffman(freq, n, lengths, codes, limit, S) ? 1 : 0;
 }
 }

@@ -16,7 +16,7 @@ SO = os.path.join(ROOT, "tests", "hostcheck", "_build", "libzw_hostcheck.so")
 
 
 def _build():
-    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc", "zw_boolcoder.cuh", "zw_quad.cuh", "zw_types.cuh", "zw_dec.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "image_webp_b200", "csrc", f) for f in ("zw_prims.cuh", "zw_cost.cuh", "zw_tables.inc", "zw_boolcoder.cuh", "zw_quad.cuh", "zw_types.cuh", "zw_dec.cuh", "zw_lossless.cuh")]
     if (not os.path.exists(SO)) or any(os.path.getmtime(SO) < os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO])

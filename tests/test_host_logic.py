@@ -72,8 +72,24 @@ def test_encoder_params_mirror_reference_defaults():
     assert q.use_lossy and q.lossy_quality == 75 and q.method == 4
     assert Z.EncoderParams.lossy(10).with_method(6).method == 6
     assert Z.ColorType.Rgb8.bytes_per_pixel() == 3 and Z.ColorType.Rgba8.has_alpha() and not Z.ColorType.L8.has_alpha()
-    with pytest.raises(NotImplementedError):
-        Z.WebPEncoder(bytearray()).encode(b"", 1, 1, Z.ColorType.Rgb8)  # lossless default is out of scope
+
+
+def test_builder_api_mirrors_reference():
+    import image_webp_b200 as Z
+    c = Z.EncoderConfig.new()             # api.rs:501-513: lossy, quality 75, method 4
+    assert (c.get_quality(), c.get_preset(), c.is_lossless(), c.get_method()) == (75.0, Z.Preset.Default, False, 4)
+    assert Z.EncoderConfig.new_lossless().is_lossless()
+    assert c.quality(120).get_quality() == 100.0 and c.quality(-3).get_quality() == 0.0   # clamp, api.rs:548
+    assert c.method(9).get_method() == 6                                                   # min(6), api.rs:569
+    assert Z.EncoderConfig.with_preset(Z.Preset.Photo, 85).get_preset() == Z.Preset.Photo
+    for q, want in ((75.4, 75), (75.5, 76), (0.0, 0), (0.4, 0), (0.5, 1), (100.0, 100)):   # fast_math::roundf, fast_math.rs:129-137
+        p = Z.EncoderConfig().quality(q).to_params()
+        assert p.lossy_quality == want and p.use_lossy and p.use_predictor_transform
+    assert not Z.EncoderConfig().lossless(True).to_params().use_lossy
+    e = Z.Encoder.new_rgb(b"", 4, 4).quality(50).preset(Z.Preset.Text).near_lossless(200).alpha_quality(7).exact(True).target_size(9).sharp_yuv(True)
+    assert e._config._near_lossless == 100 and e._config._alpha_quality == 7 and e._config._target_size == 9
+    with pytest.raises(Z.InvalidBufferSize):   # validate_buffer_size runs before any device work (api.rs:871-876)
+        e.encode()
 
 
 def test_shard_ranges_cover_and_are_contiguous():
