@@ -263,6 +263,46 @@ def verify_leg(Z, ctx, workloads, params, check=4):
     return res
 
 
+def lossless_leg(Z, ctx, workloads, lib, cores, check=64):
+    """The lossless (VP8L) path of WebPEncoder::encode (SURVEY.md 8(f)4) on the same 1024-image workloads: device time of the
+    seven kernels, end to end through zw_encode_batch from pinned host memory (H2D + D2H inside), a sample of the files
+    checked byte for byte against the lossless oracle, and the oracle timed on all host cores."""
+    import numpy as np
+    import oracle_lib as O
+    res = {"api": "zw_encode_batch (EncoderParams::default(): lossless, predictor transform on), one blocking call per batch",
+           "pinned_by": "libwebp decodes the oracle's files to exactly the input pixels (the reference's own acceptance test, "
+                        "api.rs:1447-1511; tests/test_oracle_lossless.py); GPU == oracle byte for byte (tests/test_gpu_lossless.py)"}
+    p = Z.EncoderParams()
+    for name, imgs in workloads:
+        n = len(imgs)
+        px = sum(int(im.shape[0]) * int(im.shape[1]) for im in imgs)
+        best, best_wall = None, None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            outs, t = ctx.encode_batch(imgs, p, Z.ColorType.Rgb8)
+            wall = time.perf_counter() - t0
+            if best is None or t["device_total_ms"] < best["device_total_ms"]:
+                best = t
+            best_wall = wall if best_wall is None else min(best_wall, wall)
+        k = min(check, n)
+        sample = np.stack([np.asarray(im) for im in imgs[:k]])
+        ref, dt = O.webp_encode_batch_mt(sample, threads=cores, L=lib)
+        bad = [i for i in range(k) if outs[i] != ref[i]]
+        traffic = 3 + 4 + 4 + 2 + 6 + 6  # B/px: source read, residual written, read 3x, descriptors written, read 2x (+ the files)
+        out_bytes = sum(len(o) for o in outs)
+        res[name] = {"images": n, "kernel_only_mpix_s": px / best["device_total_ms"] / 1e3, "kernel_ms": best["device_total_ms"],
+                     "e2e_mpix_s": px / best_wall / 1e6, "e2e_ms": 1e3 * best_wall,
+                     "stage_ms": {"transforms": best["yuv_ms"], "tokens_hist": best["analysis_ms"], "huffman": best["stats_ms"],
+                                  "bit_counts": best["token_ms"], "pack": best["assemble_ms"], "h2d": best["h2d_ms"], "d2h": best["d2h_ms"]},
+                     "bytes_per_px": out_bytes / px, "h2d_bytes": best["h2d_bytes"], "d2h_bytes": best["d2h_bytes"],
+                     "hbm_gb_s": (px * traffic + 2 * out_bytes) / best["device_total_ms"] / 1e6,
+                     "parity": {"checked": k, "identical": k - len(bad), "against": "lossless oracle (oracle/zw_lossless_oracle.inc)"},
+                     "cpu_port": {"value": k * px / n / dt / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
+                                  "sample": "%d images, one image per thread on %d threads" % (k, cores)}}
+        assert not bad, "lossless %s: images %s differ from the oracle" % (name, bad[:8])
+    return res
+
+
 def other_configs(Z, torch, ctx, pipe, lib, cores, world):
     """BASELINE.json configs 1, 3, 4, 5 on one GPU (kernel-only + end to end + parity sample + CPU port)."""
     import numpy as np
@@ -542,6 +582,14 @@ def main():
                 raise
             except Exception as e:
                 line["verify"] = {"error": str(e)}
+        if not args.no_other and world == 1:
+            try:
+                wl = [("synthetic", imgs)] + ([("photo", pimgs)] if P else [])
+                line["lossless"] = lossless_leg(Z, ctx, wl, lib or native_oracle(), cores)
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["lossless"] = {"error": str(e)}
         if not args.no_other and world == 1:
             try:
                 line["other_configs"] = other_configs(Z, torch, ctx, pipe, lib or native_oracle(), cores, world)

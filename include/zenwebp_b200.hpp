@@ -1,7 +1,8 @@
-// zenwebp_b200.hpp -- C++ host-side mirror of the reference's encoder API for the lossy path,
-// header-only on top of the C ABI (zenwebp_b200.h).  Mirrors imazen/image-webp `zenwebp` 0.2.0:
+// zenwebp_b200.hpp -- C++ host-side mirror of the reference's encoder API (lossy VP8, lossless VP8L, every
+// container), header-only on top of the C ABI (zenwebp_b200.h).  Mirrors imazen/image-webp `zenwebp` 0.2.0:
 //   ColorType      src/encoder/api.rs:83-92      EncodingError  src/encoder/api.rs:35-48
 //   EncoderParams  src/encoder/api.rs:419-459    WebPEncoder    src/encoder/api.rs:1244-1398
+//   EncoderConfig  src/encoder/api.rs:488-672    Encoder        src/encoder/api.rs:703-914
 // plus the batch entry point.  The reference is Rust; with no Rust toolchain in the build image
 // this header (and the Python mirror) stand where the wrapper crate of rust/zenwebp-b200 would.
 #ifndef ZENWEBP_B200_HPP
@@ -50,16 +51,24 @@ class Context {
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   struct ImageRef { const uint8_t* data; size_t len; uint32_t width, height; ColorType color; };
-  // Batch entry: n images -> n .webp files (per-image errors throw for the first failing image).
-  std::vector<std::vector<uint8_t>> encode_batch(const std::vector<ImageRef>& imgs, const EncoderParams& p, zw_timing* t = nullptr) {
-    if (!p.use_lossy) throw std::logic_error("only the lossy VP8 path is implemented on the GPU");
+  struct Metadata { std::vector<uint8_t> icc_profile, exif, xmp; };
+  // Batch entry: n images -> n .webp files exactly as WebPEncoder::encode writes them (lossy or lossless frame, simple
+  // or extended container; `meta`: empty or one entry per image).  Per-image errors throw for the first failing image.
+  std::vector<std::vector<uint8_t>> encode_batch(const std::vector<ImageRef>& imgs, const EncoderParams& p, zw_timing* t = nullptr,
+                                                 const std::vector<Metadata>& meta = {}) {
+    if (!meta.empty() && meta.size() != imgs.size()) throw std::logic_error("one metadata entry per image");
     std::vector<zw_image> in(imgs.size());
     std::vector<zw_output> out(imgs.size());
+    std::vector<zw_metadata> md(meta.size());
     for (size_t i = 0; i < imgs.size(); i++) {
       in[i] = zw_image{imgs[i].data, imgs[i].len, imgs[i].width, imgs[i].height, (uint32_t)imgs[i].color, 0};
       out[i] = zw_output{nullptr, 0, 0, 0, 0};
     }
-    const int rc = zw_encode_webp_batch(h_, in.data(), in.size(), p.lossy_quality, p.method, out.data(), t);
+    for (size_t i = 0; i < meta.size(); i++)
+      md[i] = zw_metadata{meta[i].icc_profile.data(), meta[i].icc_profile.size(), meta[i].exif.data(), meta[i].exif.size(),
+                          meta[i].xmp.data(), meta[i].xmp.size()};
+    const zw_params zp{p.use_predictor_transform ? 1 : 0, p.use_lossy ? 1 : 0, p.lossy_quality, p.method};
+    const int rc = zw_encode_batch(h_, in.data(), in.size(), &zp, md.empty() ? nullptr : md.data(), out.data(), t);
     std::vector<std::vector<uint8_t>> res(imgs.size());
     int first_err = rc;
     for (size_t i = 0; i < imgs.size(); i++) {
@@ -188,20 +197,97 @@ class MultiContext {
   zw_multi* h_;
 };
 
-// WebPEncoder::new(&mut Vec<u8>) / set_params / encode: appends the .webp bytes to `writer`.
+// WebPEncoder::new(&mut Vec<u8>) / set_params / set_*_metadata / encode: appends the .webp bytes to `writer`.
 class WebPEncoder {
  public:
   explicit WebPEncoder(std::vector<uint8_t>& writer, Context& ctx) : w_(writer), ctx_(ctx) {}
   void set_params(const EncoderParams& p) { params_ = p; }
+  void set_icc_profile(std::vector<uint8_t> v) { meta_.icc_profile = std::move(v); }
+  void set_exif_metadata(std::vector<uint8_t> v) { meta_.exif = std::move(v); }
+  void set_xmp_metadata(std::vector<uint8_t> v) { meta_.xmp = std::move(v); }
   void encode(const uint8_t* data, size_t len, uint32_t width, uint32_t height, ColorType color) {
-    if (width > 65535 || height > 65535) throw InvalidDimensions();
-    auto out = ctx_.encode_batch({Context::ImageRef{data, len, width, height, color}}, params_);
+    const bool any = !meta_.icc_profile.empty() || !meta_.exif.empty() || !meta_.xmp.empty();
+    auto out = ctx_.encode_batch({Context::ImageRef{data, len, width, height, color}}, params_, nullptr,
+                                 any ? std::vector<Context::Metadata>{meta_} : std::vector<Context::Metadata>{});
     w_.insert(w_.end(), out[0].begin(), out[0].end());
   }
  private:
   std::vector<uint8_t>& w_;
   Context& ctx_;
   EncoderParams params_;
+  Context::Metadata meta_;
+};
+
+enum class Preset { Default, Picture, Photo, Drawing, Icon, Text };  // api.rs:54-76
+
+// EncoderConfig (api.rs:488-672): reusable builder.  Default: lossy, quality 75, method 4.  The knobs the reference
+// stores without reading (preset, near_lossless, alpha_quality, exact, target_size, sharp_yuv) are stored here too.
+class EncoderConfig {
+ public:
+  static EncoderConfig new_lossless() { EncoderConfig c; c.lossless_ = true; return c; }
+  static EncoderConfig with_preset(Preset p, float q) { EncoderConfig c; c.preset_ = p; c.quality_ = q; return c; }
+  EncoderConfig& quality(float q) { quality_ = q < 0.f ? 0.f : (q > 100.f ? 100.f : q); return *this; }
+  EncoderConfig& preset(Preset p) { preset_ = p; return *this; }
+  EncoderConfig& lossless(bool v) { lossless_ = v; return *this; }
+  EncoderConfig& method(uint8_t m) { method_ = m < 6 ? m : 6; return *this; }
+  EncoderConfig& near_lossless(uint8_t v) { near_lossless_ = v < 100 ? v : 100; return *this; }
+  EncoderConfig& alpha_quality(uint8_t v) { alpha_quality_ = v < 100 ? v : 100; return *this; }
+  EncoderConfig& exact(bool v) { exact_ = v; return *this; }
+  EncoderConfig& target_size(uint32_t v) { target_size_ = v; return *this; }
+  EncoderConfig& sharp_yuv(bool v) { sharp_yuv_ = v; return *this; }
+  float get_quality() const { return quality_; }
+  Preset get_preset() const { return preset_; }
+  bool is_lossless() const { return lossless_; }
+  uint8_t get_method() const { return method_; }
+  EncoderParams to_params() const {  // api.rs:633-640; fast_math::roundf = (x + 0.5) as i32
+    EncoderParams p;
+    p.use_predictor_transform = true; p.use_lossy = !lossless_; p.method = method_;
+    const int q = (int)(quality_ + 0.5f);
+    p.lossy_quality = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    return p;
+  }
+  std::vector<uint8_t> encode(Context& ctx, const uint8_t* data, size_t len, uint32_t w, uint32_t h, ColorType color,
+                              const Context::Metadata* meta = nullptr) const {
+    if ((uint64_t)len < (uint64_t)w * h * ((uint32_t)color + 1)) throw InvalidBufferSize();  // validate_buffer_size, api.rs:917
+    std::vector<uint8_t> out;
+    WebPEncoder enc(out, ctx);
+    enc.set_params(to_params());
+    if (meta) { enc.set_icc_profile(meta->icc_profile); enc.set_exif_metadata(meta->exif); enc.set_xmp_metadata(meta->xmp); }
+    enc.encode(data, len, w, h, color);
+    return out;
+  }
+  std::vector<uint8_t> encode_rgba(Context& ctx, const uint8_t* d, size_t n, uint32_t w, uint32_t h) const { return encode(ctx, d, n, w, h, ColorType::Rgba8); }
+  std::vector<uint8_t> encode_rgb(Context& ctx, const uint8_t* d, size_t n, uint32_t w, uint32_t h) const { return encode(ctx, d, n, w, h, ColorType::Rgb8); }
+ private:
+  float quality_ = 75.f;
+  Preset preset_ = Preset::Default;
+  bool lossless_ = false, exact_ = false, sharp_yuv_ = false;
+  uint8_t method_ = 4, near_lossless_ = 100, alpha_quality_ = 100;
+  uint32_t target_size_ = 0;
+};
+
+// Encoder (api.rs:703-914): Encoder::new_rgba(data, w, h).quality(85).encode(ctx).
+class Encoder {
+ public:
+  static Encoder new_rgba(const uint8_t* d, size_t n, uint32_t w, uint32_t h) { return Encoder(d, n, w, h, ColorType::Rgba8); }
+  static Encoder new_rgb(const uint8_t* d, size_t n, uint32_t w, uint32_t h) { return Encoder(d, n, w, h, ColorType::Rgb8); }
+  static Encoder new_l8(const uint8_t* d, size_t n, uint32_t w, uint32_t h) { return Encoder(d, n, w, h, ColorType::L8); }
+  static Encoder new_la8(const uint8_t* d, size_t n, uint32_t w, uint32_t h) { return Encoder(d, n, w, h, ColorType::La8); }
+  Encoder& quality(float q) { cfg_.quality(q); return *this; }
+  Encoder& preset(Preset p) { cfg_.preset(p); return *this; }
+  Encoder& lossless(bool v) { cfg_.lossless(v); return *this; }
+  Encoder& method(uint8_t m) { cfg_.method(m); return *this; }
+  Encoder& config(const EncoderConfig& c) { cfg_ = c; return *this; }
+  Encoder& icc_profile(std::vector<uint8_t> v) { meta_.icc_profile = std::move(v); return *this; }
+  Encoder& exif_metadata(std::vector<uint8_t> v) { meta_.exif = std::move(v); return *this; }
+  Encoder& xmp_metadata(std::vector<uint8_t> v) { meta_.xmp = std::move(v); return *this; }
+  std::vector<uint8_t> encode(Context& ctx) const { return cfg_.encode(ctx, d_, n_, w_, h_, color_, &meta_); }
+  void encode_into(Context& ctx, std::vector<uint8_t>& out) const { auto e = encode(ctx); out.insert(out.end(), e.begin(), e.end()); }
+ private:
+  Encoder(const uint8_t* d, size_t n, uint32_t w, uint32_t h, ColorType c) : d_(d), n_(n), w_(w), h_(h), color_(c) {}
+  const uint8_t* d_; size_t n_; uint32_t w_, h_; ColorType color_;
+  EncoderConfig cfg_;
+  Context::Metadata meta_;
 };
 
 }  // namespace zenwebp_b200

@@ -2855,6 +2855,35 @@ int zwo_build_huffman(const uint32_t* frequencies, size_t n, int length_limit, u
   return ll::build_huffman_tree(frequencies, n, lengths, codes, (u8)length_limit) ? 1 : 0;
 }
 
+// WebPEncoder::encode (lossy or lossless, no metadata) for n same-sized images on `threads` host threads; outputs as in
+// zwo_encode_batch_mt_out.  Used by bench.py's lossless CPU baseline and parity check.
+size_t zwo_webp_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32_t height, int color, int use_predictor,
+                                int use_lossy, int quality, int method, int threads, uint8_t* out, size_t out_stride,
+                                uint32_t* out_lens) {
+  std::atomic<size_t> next(0), total(0);
+  const size_t per = (size_t)width * height * (size_t)(color + 1);
+  auto work = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= n) break;
+      uint8_t* o = nullptr;
+      size_t len = 0;
+      const int rc = zwo_webp_encode(data + i * per, per, width, height, color, use_predictor, use_lossy, quality, method, nullptr, 0,
+                                     nullptr, 0, nullptr, 0, &o, &len);
+      if (rc != 0) { if (out_lens) out_lens[i] = 0; continue; }
+      if (out) memcpy(out + i * out_stride, o, len < out_stride ? len : out_stride);
+      if (out_lens) out_lens[i] = (uint32_t)len;
+      total.fetch_add(len);
+      free(o);
+    }
+  };
+  if (threads <= 1) { work(); return total.load(); }
+  std::vector<std::thread> ts;
+  for (int t = 0; t < threads; t++) ts.emplace_back(work);
+  for (auto& t : ts) t.join();
+  return total.load();
+}
+
 void zwo_free(void* p) { free(p); }
 // Counters of the calling thread: reset, then run zwo_encode_* on this thread, then read.
 void zwo_opcounts_reset(void) { memset(g_ops, 0, sizeof(g_ops)); }

@@ -134,6 +134,9 @@ int zwo_encode_alpha_lossless(const uint8_t* data, size_t data_len, uint32_t wid
 int zwo_webp_encode(const uint8_t* data, size_t data_len, uint32_t width, uint32_t height, int color, int use_predictor,
                     int use_lossy, int quality, int method, const uint8_t* icc, size_t icc_len, const uint8_t* exif,
                     size_t exif_len, const uint8_t* xmp, size_t xmp_len, uint8_t** out, size_t* out_len);
+size_t zwo_webp_encode_batch_mt(const uint8_t* data, size_t n, uint32_t width, uint32_t height, int color, int use_predictor,
+                                int use_lossy, int quality, int method, int threads, uint8_t* out, size_t out_stride,
+                                uint32_t* out_lens);
 /* build_huffman_tree (api.rs:163-287); returns 0 when at most one symbol is used. */
 int zwo_build_huffman(const uint32_t* frequencies, size_t n, int length_limit, uint8_t* lengths, uint16_t* codes);
 

@@ -75,5 +75,12 @@ extern "C" {
     pub fn zw_decode_batch(ctx: *mut zw_ctx, files: *const zw_blob, n: usize, upsampling: c_int, rgb_outs: *mut zw_output,
                            sources: *const zw_image, infos: *mut zw_decode_info, device_ms: *mut f32) -> c_int;
     pub fn zw_verify(ctx: *mut zw_ctx, ticket: c_int, upsampling: c_int, infos: *mut zw_decode_info, device_ms: *mut f32) -> c_int;
+    pub fn zw_encode_lossless_batch(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize, use_predictor_transform: c_int, container: c_int,
+                                    outs: *mut zw_output, timing: *mut zw_timing) -> c_int;
+    pub fn zw_encode_alpha_batch(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize, outs: *mut zw_output, timing: *mut zw_timing) -> c_int;
+    pub fn zw_params_default() -> zw_params;
+    pub fn zw_encode_batch(ctx: *mut zw_ctx, imgs: *const zw_image, n: usize, params: *const zw_params, meta: *const zw_metadata,
+                           outs: *mut zw_output, timing: *mut zw_timing) -> c_int;
+    pub fn zw_lossless_dump_stage(ctx: *mut zw_ctx, index: usize, stage: *const c_char, dst: *mut c_void, cap: usize, len: *mut usize) -> c_int;
     pub fn zw_decode_dump_stage(ctx: *mut zw_ctx, index: usize, stage: *const c_char, dst: *mut c_void, cap: usize, len: *mut usize) -> c_int;
 }

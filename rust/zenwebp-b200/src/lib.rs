@@ -36,6 +36,9 @@ impl EncoderParams {
     pub fn method(mut self, m: u8) -> Self { self.method = m; self }
 }
 
+#[derive(Default, Clone)]
+pub struct Metadata { pub icc_profile: Vec<u8>, pub exif: Vec<u8>, pub xmp: Vec<u8> }
+
 pub struct ImageRef<'a> { pub data: &'a [u8], pub width: u32, pub height: u32, pub color: ColorType }
 
 pub struct Context { h: *mut sys::zw_ctx }
@@ -46,22 +49,31 @@ impl Context {
     }
     /// Batch entry point: one `.webp` per image, byte-identical to `WebPEncoder::encode` of the reference.
     pub fn encode_batch(&mut self, imgs: &[ImageRef<'_>], p: &EncoderParams) -> Vec<Result<Vec<u8>, EncodingError>> {
-        if !p.use_lossy {  // the reference would emit VP8L here: never silently substitute a lossy file
-            return imgs.iter().map(|_| Err(EncodingError::Unsupported("lossless (VP8L) encoding"))).collect();
-        }
+        self.encode_batch_with_metadata(imgs, p, &[])
+    }
+    /// Same with ICC / EXIF / XMP per image (`meta`: empty, or one entry per image).  Lossy ("VP8 ") or lossless ("VP8L")
+    /// frame, simple or extended (VP8X + ICCP + ALPH + frame + EXIF + XMP) container -- everything `WebPEncoder::encode` writes.
+    pub fn encode_batch_with_metadata(&mut self, imgs: &[ImageRef<'_>], p: &EncoderParams, meta: &[Metadata]) -> Vec<Result<Vec<u8>, EncodingError>> {
+        assert!(meta.is_empty() || meta.len() == imgs.len());
+        let zp = sys::zw_params { use_predictor_transform: p.use_predictor_transform as i32, use_lossy: p.use_lossy as i32,
+                                  lossy_quality: p.lossy_quality as i32, method: p.method as i32 };
+        let cmeta: Vec<sys::zw_metadata> = meta.iter().map(|m| sys::zw_metadata {
+            icc_profile: m.icc_profile.as_ptr(), icc_len: m.icc_profile.len(), exif: m.exif.as_ptr(), exif_len: m.exif.len(),
+            xmp: m.xmp.as_ptr(), xmp_len: m.xmp.len() }).collect();
         let cimgs: Vec<sys::zw_image> = imgs.iter().map(|i| sys::zw_image {
             data: i.data.as_ptr(), len: i.data.len(), width: i.width, height: i.height,
             color: match i.color { ColorType::Rgb8 => sys::ZW_COLOR_RGB8, ColorType::Rgba8 => sys::ZW_COLOR_RGBA8, ColorType::L8 => 0, ColorType::La8 => 1 },
             reserved: 0 }).collect();
         let mut outs: Vec<sys::zw_output> = imgs.iter().map(|_| sys::zw_output { data: core::ptr::null_mut(), cap: 0, len: 0, status: 0, reserved: 0 }).collect();
-        let rc = unsafe { sys::zw_encode_webp_batch(self.h, cimgs.as_ptr(), cimgs.len(), p.lossy_quality as i32, p.method as i32, outs.as_mut_ptr(), core::ptr::null_mut()) };
+        let rc = unsafe { sys::zw_encode_batch(self.h, cimgs.as_ptr(), cimgs.len(), &zp, if cmeta.is_empty() { core::ptr::null() } else { cmeta.as_ptr() },
+                                               outs.as_mut_ptr(), core::ptr::null_mut()) };
         outs.iter().map(|o| {
             let st = if rc != 0 { rc } else { o.status };
             let r = match st {
                 0 => Ok(unsafe { core::slice::from_raw_parts(o.data, o.len) }.to_vec()),
                 1 => Err(EncodingError::InvalidDimensions),
                 2 => Err(EncodingError::InvalidBufferSize("width/height doesn't match data length".into())),
-                3 => Err(EncodingError::Unsupported("lossy + alpha needs the VP8X/ALPH container, or a bad parameter")),
+                3 => Err(EncodingError::Unsupported("bad parameter (quality > 100: the reference panics)")),
                 c => Err(EncodingError::Device(c)),
             };
             if !o.data.is_null() { unsafe { sys::zw_free(o.data as *mut _) }; }
@@ -78,16 +90,20 @@ thread_local! {
 }
 
 /// Same shape as the reference: `WebPEncoder::new(&mut out); set_params(..); encode(data, w, h, color)`.
-pub struct WebPEncoder<'a> { writer: &'a mut Vec<u8>, params: EncoderParams }
+pub struct WebPEncoder<'a> { writer: &'a mut Vec<u8>, params: EncoderParams, meta: Metadata }
 impl<'a> WebPEncoder<'a> {
-    pub fn new(w: &'a mut Vec<u8>) -> Self { Self { writer: w, params: EncoderParams::default() } }
+    pub fn new(w: &'a mut Vec<u8>) -> Self { Self { writer: w, params: EncoderParams::default(), meta: Metadata::default() } }
     pub fn set_params(&mut self, params: EncoderParams) { self.params = params; }
+    pub fn set_icc_profile(&mut self, v: Vec<u8>) { self.meta.icc_profile = v; }
+    pub fn set_exif_metadata(&mut self, v: Vec<u8>) { self.meta.exif = v; }
+    pub fn set_xmp_metadata(&mut self, v: Vec<u8>) { self.meta.xmp = v; }
     pub fn encode(self, data: &[u8], width: u32, height: u32, color: ColorType) -> Result<(), EncodingError> {
-        if width > 65535 || height > 65535 { return Err(EncodingError::InvalidDimensions); }
         let out = DEFAULT_CTX.with(|c| -> Result<Vec<u8>, EncodingError> {
             let mut c = c.borrow_mut();
             if c.is_none() { *c = Some(Context::new(0)?); }  // no CUDA device -> Device(code): there is no CPU fallback
-            c.as_mut().unwrap().encode_batch(&[ImageRef { data, width, height, color }], &self.params).pop().unwrap()
+            let any = !(self.meta.icc_profile.is_empty() && self.meta.exif.is_empty() && self.meta.xmp.is_empty());
+            let meta = if any { vec![self.meta.clone()] } else { Vec::new() };
+            c.as_mut().unwrap().encode_batch_with_metadata(&[ImageRef { data, width, height, color }], &self.params, &meta).pop().unwrap()
         })?;
         self.writer.extend_from_slice(&out);
         Ok(())

@@ -63,6 +63,13 @@ int main(int argc, char** argv) {
       write_file(prefix + ".decoded.rgb", dec[0].rgb);
       try { ctx.decode_batch({{file.data(), 5}}); return 8; } catch (const std::runtime_error&) {}
     }
+    {  // lossless + builder + metadata: <prefix>.lossless.webp (Encoder, default metadata-free), <prefix>.meta.webp (lossy + EXIF)
+      write_file(prefix + ".lossless.webp", Z::Encoder::new_rgb(rgb.data(), rgb.size(), w, h).lossless(true).encode(ctx));
+      write_file(prefix + ".meta.webp", Z::Encoder::new_rgb(rgb.data(), rgb.size(), w, h).quality(74.6f).method(9).exif_metadata({'E', 'X', 'I'}).encode(ctx));
+      Z::EncoderConfig cfg = Z::EncoderConfig::new_lossless();
+      if (!cfg.is_lossless() || cfg.to_params().use_lossy || Z::EncoderConfig().quality(75.5f).to_params().lossy_quality != 76) return 9;
+      try { Z::Encoder::new_rgb(rgb.data(), 5, w, h).encode(ctx); return 10; } catch (const Z::InvalidBufferSize&) {}
+    }
     printf("encode ok\n");
     return 0;
   }

@@ -244,3 +244,24 @@ def build_huffman(freqs, limit):
     L.zwo_build_huffman.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     ok = L.zwo_build_huffman(f.ctypes.data, len(f), int(limit), lengths.ctypes.data, codes.ctypes.data)
     return bool(ok), lengths, codes
+
+
+def webp_encode_batch_mt(imgs, color="Rgb8", use_predictor=True, use_lossy=False, quality=95, method=4, threads=None, L=None, keep=True):
+    """WebPEncoder::encode of n same-sized images ([n,h,w,c] uint8) on `threads` host threads -> (files or None, seconds)."""
+    import time
+    L = L or lib()
+    imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+    n, h, w = imgs.shape[0], imgs.shape[1], imgs.shape[2]
+    threads = threads or (os.cpu_count() or 1)
+    stride = 64 + 8 * w * h if keep else 0
+    arena = np.empty((n, stride), np.uint8) if keep else None
+    lens = np.zeros(n, np.uint32)
+    L.zwo_webp_encode_batch_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]
+    L.zwo_webp_encode_batch_mt.restype = C.c_size_t
+    t0 = time.perf_counter()
+    L.zwo_webp_encode_batch_mt(imgs.ctypes.data, n, w, h, COLOR[color], int(use_predictor), int(use_lossy), int(quality), int(method),
+                               int(threads), arena.ctypes.data if keep else None, stride, lens.ctypes.data)
+    dt = time.perf_counter() - t0
+    assert (lens > 0).all()
+    return ([arena[i, :lens[i]].tobytes() for i in range(n)] if keep else None), dt

@@ -41,5 +41,7 @@ def test_hpp_every_class_encodes_byte_identically(tmp_path):
     ref = O.encode(img, 75, 4)[1]
     for kind in ("batch", "encoder", "pipe", "multi"):
         assert (tmp_path / ("out.%s.webp" % kind)).read_bytes() == ref, kind
+    assert (tmp_path / "out.lossless.webp").read_bytes() == O.webp_encode(img, "Rgb8")[1]
+    assert (tmp_path / "out.meta.webp").read_bytes() == O.webp_encode(img, "Rgb8", use_lossy=True, quality=75, method=6, exif=b"EXI")[1]
     dec = np.frombuffer((tmp_path / "out.decoded.rgb").read_bytes(), np.uint8).reshape(112, 160, 3)
     assert np.array_equal(dec, O.decode(ref, True, ("rgb",))[1]["rgb"])
