@@ -505,7 +505,7 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     const int rows_per_cta = YUV_ROWPAIRS * YUV_STEPS * 2;
     dim3 grid((c->max_pw + YUV_TILE_W - 1) / YUV_TILE_W, (c->max_ph + rows_per_cta - 1) / rows_per_cta, ni);
     dim3 block(YUV_THREADS, YUV_ROWPAIRS);
-    const size_t sm = (size_t)YUV_ROWPAIRS * 2 * YUV_ROW_SLOTS * 16;
+    const size_t sm = (size_t)YUV_ROWPAIRS * 4 * YUV_ROW_SLOTS * 16;  // two buffers of two rows per warp
     k_yuv<<<grid, block, sm, s>>>(P);
     c->launches++;
   }

@@ -19,7 +19,7 @@ namespace zw {
 constexpr int YUV_TILE_W = 256;                 // luma pixels per CTA strip
 constexpr int YUV_THREADS = YUV_TILE_W / 8;     // 32 threads (one warp) per row pair, 8 px each
 constexpr int YUV_ROWPAIRS = 8;                 // row pairs per CTA step (blockDim.y)
-constexpr int YUV_STEPS = 2;                    // steps per CTA: 32 source rows x 256 px = 36 KB of RGB per CTA
+constexpr int YUV_STEPS = 4;                    // steps per CTA: 64 source rows x 256 px; step s+1 is in flight (cp.async) while step s is converted
 constexpr int YUV_ROW_SLOTS = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row (RGBA worst case + skew)
 
 __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P) {
@@ -38,29 +38,50 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
   u8* up = yp + (size_t)pw * ph;
   u8* vp = up + (size_t)(pw >> 1) * (ph >> 1);
   const int tx = x0 + threadIdx.x * 8;
-  // every warp (threadIdx.y) owns its two staged rows: no CTA-wide barrier, just __syncwarp
-  uint4* stage = smem4 + (threadIdx.y * 2) * YUV_ROW_SLOTS;
+  // every warp (threadIdx.y) owns its staged rows (two buffers of two rows): no CTA-wide barrier, just __syncwarp.
+  // The rows of step s+1 are fetched with 16-byte cp.async (LDGSTS: no registers held while the bytes are in flight)
+  // before step s is converted, so each warp keeps two steps' worth of loads outstanding.
+  uint4* stage0 = smem4 + (threadIdx.y * 4) * YUV_ROW_SLOTS;
+  auto rows_of = [&](int step, int& rp, int& rowA, int& rowB) {
+    rp = (blockIdx.y * YUV_STEPS + step) * YUV_ROWPAIRS + threadIdx.y;  // row pair in the padded plane
+    const int ccy = min(rp, chh - 1);
+    rowA = 2 * ccy; rowB = min(2 * ccy + 1, h - 1);
+  };
+  auto issue = [&](int step) {
+    int rp, rowA, rowB;
+    rows_of(step, rp, rowA, rowB);
+    if (step < YUV_STEPS && rp * 2 < ph) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
+        const size_t al = (d.rgb_off + byte0) & ~(size_t)15;  // arena is 16-byte aligned
+        const int nvec = ((int)((d.rgb_off + byte0) - al) + span_bytes + 15) >> 4;
+        const uint4* src = reinterpret_cast<const uint4*>(P.rgb + al);
+        const u32 dst = (u32)__cvta_generic_to_shared(stage0 + ((step & 1) * 2 + r) * YUV_ROW_SLOTS);
+        for (int i = threadIdx.x; i < nvec; i += YUV_THREADS)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (u32)i), "l"(src + i) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
 #pragma unroll 1
   for (int step = 0; step < YUV_STEPS; step++) {
-    const int rp = (blockIdx.y * YUV_STEPS + step) * YUV_ROWPAIRS + threadIdx.y;  // row pair in the padded plane
+    int rp, rowA, rowB;
+    rows_of(step, rp, rowA, rowB);
     if (rp * 2 >= ph) break;
-    const int ccy = min(rp, chh - 1);
-    const int rowA = 2 * ccy, rowB = min(2 * ccy + 1, h - 1);
+    issue(step + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     int skew[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
-      const size_t al = (d.rgb_off + byte0) & ~(size_t)15;  // arena is 16-byte aligned
-      skew[r] = (int)((d.rgb_off + byte0) - al);
-      const int nvec = (skew[r] + span_bytes + 15) >> 4;
-      const uint4* src = reinterpret_cast<const uint4*>(P.rgb + al);
-      uint4* dst = stage + r * YUV_ROW_SLOTS;
-      for (int i = threadIdx.x; i < nvec; i += YUV_THREADS) dst[i] = __ldg(src + i);
+      skew[r] = (int)((d.rgb_off + byte0) & (size_t)15);
     }
     __syncwarp();
     if (tx < pw) {
-      const u8* sA = sm + (size_t)(threadIdx.y * 2 + 0) * YUV_ROW_SLOTS * 16 + skew[0];
-      const u8* sB = sm + (size_t)(threadIdx.y * 2 + 1) * YUV_ROW_SLOTS * 16 + skew[1];
+      const u8* sA = sm + (size_t)(threadIdx.y * 4 + (step & 1) * 2 + 0) * YUV_ROW_SLOTS * 16 + skew[0];
+      const u8* sB = sm + (size_t)(threadIdx.y * 4 + (step & 1) * 2 + 1) * YUV_ROW_SLOTS * 16 + skew[1];
       // luma rows 2rp and 2rp+1: source rows min(2rp,h-1) and min(2rp+1,h-1)
       const bool lumaA_is_A = (rp <= chh - 1);  // else row h-1 == rowB
       u32 y0w[2] = {0, 0}, y1w[2] = {0, 0}, uw = 0, vw = 0;

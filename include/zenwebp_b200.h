@@ -1,4 +1,4 @@
-/* zenwebp_b200.h -- C ABI of the B200-native lossy WebP (VP8 key-frame) encoder core.
+/* zenwebp_b200.h -- C ABI of the B200-native WebP encoder core (lossy VP8 key frames; lossless VP8L; containers).
  *
  * This is the drop-in boundary for ONE path of imazen/image-webp (crate `zenwebp` 0.2.0):
  *     WebPEncoder::encode  ->  encode_frame_lossy(&mut Vec<u8>, &[u8], w, h, ColorType, quality, method)
@@ -113,11 +113,10 @@ int zw_encode_vp8_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality
                         zw_output* outs, zw_timing* timing);
 
 /* Same, wrapped in the simple RIFF container exactly as WebPEncoder::encode does for opaque
- * input without metadata (api.rs:1320-1329): these bytes ARE the .webp file.  For the alpha colour
- * types (ZW_COLOR_LA8 / ZW_COLOR_RGBA8) the reference writes a VP8X container with a lossless ALPH
- * chunk instead (api.rs:1330-1394), which this library does not build: images of those types get
- * outs[i].status = ZW_ERR_INVALID_PARAM here (zw_encode_vp8_batch accepts them: the VP8 payload ignores
- * alpha, vp8.rs:1296). */
+ * input without metadata (api.rs:1320-1329): these bytes ARE the .webp file.  This entry (like zw_submit /
+ * zw_wait and zw_multi_encode) writes the simple container only: for the alpha colour types (ZW_COLOR_LA8 /
+ * ZW_COLOR_RGBA8) the reference writes VP8X + a lossless ALPH chunk instead (api.rs:1330-1394), so images of those
+ * types get outs[i].status = ZW_ERR_INVALID_PARAM here -- zw_encode_batch below builds that file. */
 int zw_encode_webp_batch(zw_ctx* ctx, const zw_image* imgs, size_t n, int quality, int method,
                          zw_output* outs, zw_timing* timing);
 

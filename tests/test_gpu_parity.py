@@ -111,14 +111,17 @@ def test_grey_input_l8_la8(ctx, w, h, q, m):
     rc, ref2, _ = O.encode(la, q, m, color="La8", container=False)
     assert rc == 0 and outs[0] == ref2
     assert ref2 == ref[20:20 + len(ref2)]  # same VP8 payload as the L8 file: alpha is ignored by the VP8 path
-    # WebPEncoder drop-in: L8 accepted, alpha colours rejected (lossy+alpha needs VP8X/ALPH, not built)
+    # WebPEncoder drop-in: L8 in the simple container, La8 as VP8X + ALPH + "VP8 " (api.rs:1330-1394)
     out = bytearray()
     enc = Z.WebPEncoder(out)
     enc.set_params(_params(q, m))
     enc.encode(grey.tobytes(), w, h, Z.ColorType.L8)
     assert bytes(out) == ref
-    with pytest.raises(NotImplementedError):
-        Z.WebPEncoder(bytearray()).encode(la.tobytes(), w, h, Z.ColorType.La8)
+    out = bytearray()
+    enc = Z.WebPEncoder(out)
+    enc.set_params(_params(q, m))
+    enc.encode(la.tobytes(), w, h, Z.ColorType.La8)
+    assert bytes(out) == O.webp_encode(la, "La8", use_lossy=True, quality=q, method=m)[1]
 
 
 def test_decodes_with_libwebp_and_psnr(ctx):
