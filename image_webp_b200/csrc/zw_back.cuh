@@ -434,9 +434,24 @@ __device__ void frame_header_tokens(S& s, const ChunkParams& P, const ImageState
 
 // MODE 0: count tokens per macroblock.  MODE 1: emit them at the scanned offsets.
 // One warp per macroblock: lanes 0..24 = residual blocks; the macroblock header is shared by lanes 0..17.
+// MODE 0 also keeps the per-lane counts (block tokens | header-slot tokens << 16), so MODE 1 does not walk the levels a
+// second time just to find its offsets.  MODE 1 builds the macroblock's symbols in shared memory (the lanes write 2-byte
+// symbols at unrelated offsets) and the warp then copies them out with full 128-byte stores; a macroblock with more
+// symbols than the staging buffer holds (rare: > 6 symbols per pixel) is written in place.
 constexpr int TOK_WARPS = 8;
+constexpr u32 TOK_STAGE = 1536;  // symbols per warp (3 KB)
+__device__ __forceinline__ void tok_copy_out(const Token* sm, Token* dst, u32 n, int lane) {
+  if (n == 0) return;
+  const u32 head = (u32)((reinterpret_cast<size_t>(dst) >> 1) & 1u);  // one symbol up to 4-byte alignment
+  if (head && lane == 0) dst[0] = sm[0];
+  const u32 pairs = (n - (head ? 1u : 0u)) >> 1;
+  u32* d32 = reinterpret_cast<u32*>(dst + head);
+  for (u32 k = lane; k < pairs; k += 32) d32[k] = (u32)sm[head + 2 * k] | ((u32)sm[head + 2 * k + 1] << 16);
+  if (((n - head) & 1u) && lane == 31) dst[n - 1] = sm[n - 1];
+}
 template <int MODE>
 __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
+  __shared__ Token s_stage[MODE == 1 ? TOK_WARPS : 1][MODE == 1 ? TOK_STAGE : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.y;
   const ImageDesc d = P.img[img];
@@ -453,60 +468,51 @@ __global__ void __launch_bounds__(TOK_WARPS * 32) k_tokenize(ChunkParams P) {
   const u32 nzmask = __ballot_sync(FULL, nz);
   const BlockInfo I = block_info(r, lane, nzmask);
   const bool do_block = I.coded && !r.skip;
-  u32 cnt = 0;
+  const MbRecord* top = mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr;
+  const MbRecord* left = mbx > 0 ? &P.rec2[gmb - 1] : nullptr;
   if (MODE == 0) {
+    u32 cnt = 0;
     if (do_block) {
       CountSink s;
       block_tokens(s, r.levels[lane], I.type, I.first, I.ctx, probs);
       cnt = s.n;
     }
-    u32 tot = cnt;
+    CountSink hs;
+    if (lane < 18) mb_header_slot(hs, lane, IS, r, top, left);
+    P.mb_lane_cnt[(size_t)gmb * 32 + lane] = cnt | (hs.n << 16);
+    u32 tot = cnt, ht = hs.n;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-    if (lane == 0) P.mb_tok_cnt[gmb] = tot;
-    {
-      CountSink s;
-      if (lane < 18) mb_header_slot(s, lane, IS, r, mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr, mbx > 0 ? &P.rec2[gmb - 1] : nullptr);
-      u32 ht = s.n;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ht += __shfl_xor_sync(FULL, ht, o);
-      if (lane == 0) P.mb_hdr_cnt[gmb] = ht;
-    }
+    for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(FULL, tot, o); ht += __shfl_xor_sync(FULL, ht, o); }
+    if (lane == 0) { P.mb_tok_cnt[gmb] = tot; P.mb_hdr_cnt[gmb] = ht; }
   } else {
-    // recount to get the per-block offsets inside the macroblock (cheap; avoids a per-block array)
-    if (do_block) {
-      CountSink s;
-      block_tokens(s, r.levels[lane], I.type, I.first, I.ctx, probs);
-      cnt = s.n;
-    }
-    u32 incl = cnt;
+    const u32 packed = P.mb_lane_cnt[(size_t)gmb * 32 + lane];
+    const u32 cnt = packed & 0xFFFFu, hcnt = packed >> 16;
+    u32 incl = cnt, hincl = hcnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const u32 a = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += a;
+      const u32 a = __shfl_up_sync(FULL, incl, o), b = __shfl_up_sync(FULL, hincl, o);
+      if (lane >= o) { incl += a; hincl += b; }
     }
+    const u32 total = __shfl_sync(FULL, incl, 31), htotal = __shfl_sync(FULL, hincl, 31);
+    Token* dst = P.tok_tokens + P.lay[img].tok_off + P.mb_tok_cnt[gmb];
+    Token* hdst = P.hdr_tokens + P.lay[img].hdr_off + P.mb_hdr_cnt[gmb];  // frame-header length is folded into the scan
+    Token* stage = s_stage[warp];
+    const bool staged = total <= TOK_STAGE;
     if (do_block) {
       WriteSink s;
-      s.p = P.tok_tokens + P.lay[img].tok_off + P.mb_tok_cnt[gmb] + (incl - cnt);
+      s.p = (staged ? stage : dst) + (incl - cnt);
       block_tokens(s, r.levels[lane], I.type, I.first, I.ctx, probs);
     }
-    {
-      const MbRecord* top = mby > 0 ? &P.rec2[gmb - d.mbw] : nullptr;
-      const MbRecord* left = mbx > 0 ? &P.rec2[gmb - 1] : nullptr;
-      CountSink c;
-      if (lane < 18) mb_header_slot(c, lane, IS, r, top, left);
-      u32 hincl = c.n;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 a = __shfl_up_sync(FULL, hincl, o);
-        if (lane >= o) hincl += a;
-      }
-      if (lane < 18) {
-        WriteSink s;
-        s.p = P.hdr_tokens + P.lay[img].hdr_off + P.mb_hdr_cnt[gmb] + (hincl - c.n);  // frame-header length is folded into the scan
-        mb_header_slot(s, lane, IS, r, top, left);
-      }
+    __syncwarp();
+    if (staged) tok_copy_out(stage, dst, total, lane);
+    __syncwarp();
+    if (lane < 18) {  // the header: at most 122 symbols
+      WriteSink s;
+      s.p = stage + (hincl - hcnt);
+      mb_header_slot(s, lane, IS, r, top, left);
     }
+    __syncwarp();
+    tok_copy_out(stage, hdst, htotal, lane);
   }
 }
 

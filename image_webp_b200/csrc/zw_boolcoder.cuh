@@ -11,8 +11,14 @@
 namespace zw {
 
 // A symbol stream is cut into segments of BC_SEG symbols that are coded in parallel.
-constexpr u32 BC_SEG = 8192;   // symbols per segment (multiple of 8: segments start 16-byte aligned)
-constexpr u32 BC_WARM = 1024;  // symbols before a segment start over which the possible range states are narrowed down
+#ifndef ZW_BC_SEG
+#define ZW_BC_SEG 8192
+#endif
+#ifndef ZW_BC_WARM
+#define ZW_BC_WARM 1024
+#endif
+constexpr u32 BC_SEG = ZW_BC_SEG;    // symbols per segment (multiple of 8: segments start 16-byte aligned)
+constexpr u32 BC_WARM = ZW_BC_WARM;  // symbols before a segment start over which the possible range states are narrowed down
 ZW_HD u32 bc_segments(u32 n_symbols) { return n_symbols == 0 ? 1u : (n_symbols + BC_SEG - 1) / BC_SEG; }
 
 ZW_HD u32 bc_clz32(u32 v) {

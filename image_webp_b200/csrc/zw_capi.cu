@@ -162,7 +162,7 @@ struct PinBuf {
 // kernel waits for the previous lane's last one.
 enum { LANE_FREE = 0, LANE_STAGED = 1, LANE_IN_FLIGHT = 2, LANE_SIZED = 3, LANE_DONE = 4 };
 enum { EV_H2D0 = 0, EV_H2D1, EV_YUV0, EV_YUV1, EV_AN1, EV_P1, EV_C1, EV_ST0, EV_ST1, EV_C2, EV_P2, EV_TOK, EV_BC, EV_END, EV_START,
-       EV_D2H0, EV_D2H1, EV_SIZES, EV_COUNT };
+       EV_D2H0, EV_D2H1, EV_SIZES, EV_P1S, EV_COUNT };
 struct Lane {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -171,7 +171,7 @@ struct Lane {
   const SegParams* segtab = nullptr;  // shared constant tables (owned by the context)
   const u8* lut = nullptr;
   DevBuf d_img, d_lay, d_tot, d_st, d_rows, d_rgb, d_planes, d_alpha_hist, d_map256, d_alpha, d_segmap, d_rec1, d_rec2, d_bottom, d_nz,
-      d_derr1, d_derr2, d_c1, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_htok, d_ttok,
+      d_derr1, d_derr2, d_c1, d_uvflags, d_progress, d_ticket, d_rowstats, d_stats, d_probs, d_lcost, d_hcnt, d_tcnt, d_lcnt, d_htok, d_ttok,
       d_part, d_out, d_outoff, d_segoff, d_seg, d_segtrans;
   PinBuf h_st, h_outoff, h_tot, h_arena;  // pinned mirrors: ImageState[n], out offsets[n+1], ChunkTotals, the finished files
   std::vector<ImageDesc> img;
@@ -266,7 +266,7 @@ static void fill_params(Lane* c) {
   P.nz_after = c->d_nz.as<u16>(); P.derr1 = c->d_derr1.as<u32>(); P.derr2 = c->d_derr2.as<u32>(); P.c1info = c->d_c1.as<u32>(); P.uvflags = c->d_uvflags.as<u8>();
   P.progress = c->d_progress.as<int>(); P.ticket = c->d_ticket.as<u32>(); P.rowstats = c->d_rowstats.as<u32>();
   P.stats = c->d_stats.as<u32>(); P.probs = c->d_probs.as<u8>(); P.lcost = c->d_lcost.as<u16>();
-  P.mb_hdr_cnt = c->d_hcnt.as<u32>(); P.mb_tok_cnt = c->d_tcnt.as<u32>();
+  P.mb_hdr_cnt = c->d_hcnt.as<u32>(); P.mb_tok_cnt = c->d_tcnt.as<u32>(); P.mb_lane_cnt = c->d_lcnt.as<u32>();
   P.hdr_tokens = c->d_htok.as<Token>(); P.tok_tokens = c->d_ttok.as<Token>();
   P.part_bytes = c->d_part.as<u8>(); P.out = c->d_out.as<u8>();
   P.method = (u32)c->method; P.base_qidx = (u32)c->base_qidx; P.do_trellis = c->method >= 4;
@@ -293,7 +293,7 @@ static size_t image_footprint(u32 w, u32 h, u32 bpp) {
   const size_t mbw = (w + 15) / 16, mbh = (h + 15) / 16, nmb = mbw * mbh;
   size_t b = (size_t)w * h * bpp + 64;        // RGB
   b += nmb * 384;                              // planes
-  b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8 + 8);
+  b += nmb * (2 * sizeof(MbRecord) + sizeof(MbBottom) + 2 + 2 + 8 + 8 + 8 + 128);
   b += mbh * (2112 * 4 + 8 + 8);               // row statistics, progress, row table
   b += 1056 * 7 + 6528 * 2 + 2048 + 9700 * 2;  // per-image tables, frame-header symbols
   b += nmb * 256 * 10 + nmb * 256 * 5;         // token streams (estimate: 5 symbols/px) + partitions + files
@@ -304,7 +304,7 @@ static void lane_destroy(Lane* c) {
   if (!c) return;
   DevBuf* all[] = {&c->d_img, &c->d_lay, &c->d_tot, &c->d_st, &c->d_rows, &c->d_rgb, &c->d_planes, &c->d_alpha_hist, &c->d_map256, &c->d_alpha,
                    &c->d_segmap, &c->d_rec1, &c->d_rec2, &c->d_bottom, &c->d_nz, &c->d_derr1, &c->d_derr2, &c->d_c1, &c->d_uvflags, &c->d_progress,
-                   &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_htok,
+                   &c->d_ticket, &c->d_rowstats, &c->d_stats, &c->d_probs, &c->d_lcost, &c->d_hcnt, &c->d_tcnt, &c->d_lcnt, &c->d_htok,
                    &c->d_ttok, &c->d_part, &c->d_out, &c->d_outoff, &c->d_segoff, &c->d_seg, &c->d_segtrans};
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : all) b->release();
@@ -404,7 +404,7 @@ static int lane_stage(Lane* c, const zw_image* imgs, size_t n, Lane* copy_after 
   CK(c->d_derr1.reserve((size_t)n_mb * 4)); CK(c->d_derr2.reserve((size_t)n_mb * 4)); CK(c->d_c1.reserve((size_t)n_mb * 8)); CK(c->d_uvflags.reserve(n_mb));
   CK(c->d_progress.reserve((size_t)n_rows * 3 * sizeof(int))); CK(c->d_rowstats.reserve((size_t)n_rows * 2112 * 4));
   CK(c->d_stats.reserve((size_t)ni * 1056 * 4)); CK(c->d_probs.reserve((size_t)ni * 1056)); CK(c->d_lcost.reserve((size_t)ni * 6528 * 2));
-  CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4));
+  CK(c->d_hcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_tcnt.reserve(((size_t)n_mb + 1) * 4)); CK(c->d_lcnt.reserve((size_t)n_mb * 128));
   CK(c->d_outoff.reserve(((size_t)ni + 1) * 8));
   CK(c->h_st.reserve(ni * sizeof(ImageState))); CK(c->h_outoff.reserve(((size_t)ni + 1) * 8));
   // ticket order: macroblock row y of every image before row y+1 of any image ("many images
@@ -491,6 +491,10 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
   if (c->n_valid == 0) { c->state = LANE_IN_FLIGHT; return ZW_OK; }
   const u32 ni = c->n_valid;
   cudaStream_t s = c->stream;
+  // Kernels of different batches never overlap: a batch's first kernel waits for the last kernel of the batch before it.
+  // (Measured: letting the front end of batch N+1 -- colour conversion, analysis, segments, the pass-1 chroma chains --
+  // run under the tokeniser / boolean coder of batch N moves 11 ms of device time per batch but gains 0.5 ms per step:
+  // those kernels fill the machine, and the latency-bound chains starve under them as they do under the wavefront.)
   if (after && after != c && after->n_valid) CK(cudaStreamWaitEvent(s, after->ev[EV_END], 0));
   fill_params(c);
   ChunkParams& P = c->P;
@@ -522,9 +526,14 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     c->launches++;
   }
   CK(cudaEventRecord(c->ev[EV_AN1], s));
-  {  // (3) pass 1: luma wavefront, then the per-image chroma chains, then the bookkeeping.  (Running the
-     // chains on a side stream UNDER the wavefront was measured: they starve -- 43 ms instead of 8.8 ms,
-     // instruction-cache contention with the wavefront's code -- so the kernels stay back to back.)
+  {  // (3) pass 1: the per-image chroma chains (independent of luma: disjoint words of the records), then the luma
+     // wavefront, then the bookkeeping.  (Running the chains on a side stream UNDER the wavefront was measured: they
+     // starve -- 43 ms instead of 8.8 ms, instruction-cache contention with the wavefront's code -- so the kernels stay
+     // back to back.)
+    const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
+    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+    CK(cudaEventRecord(c->ev[EV_C1], s));
+    CK(cudaEventRecord(c->ev[EV_P1S], s));
     // Batches with an I4 search: four lanes per macroblock row (k_searchq), eight rows per warp -- the I4 candidates run
     // lane-private (measured on 1024 x 768x512: pass 1 20.7 -> 17.5 ms at method 4, 31.9 -> 24.1 ms at method 6).  One warp
     // per row (k_search) stays for: too few rows to fill the GPU with quads (single images); methods 0 / 1 (no I4: the
@@ -541,9 +550,6 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
       k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
     }
     CK(cudaEventRecord(c->ev[EV_P1], s));
-    const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    CK(cudaEventRecord(c->ev[EV_C1], s));
     k_finish1<<<ni, 256, 0, s>>>(P);
     c->launches += 3;
   }
@@ -599,8 +605,8 @@ static int lane_sync_sizes(Lane* c) {
   zw_timing Tm = zw_timing();  // per-call device times; keeps the staged chunk's H2D figures
   Tm.h2d_bytes = c->last.h2d_bytes; Tm.pixels = c->last.pixels;
   auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
-  Tm.yuv_ms = el(EV_YUV0, EV_YUV1); Tm.analysis_ms = el(EV_YUV1, EV_AN1); Tm.pass1_ms = el(EV_AN1, EV_P1);
-  Tm.chroma1_ms = el(EV_P1, EV_C1); Tm.stats_ms = el(EV_C1, EV_ST1);  // k_finish1 + statistics + probabilities
+  Tm.yuv_ms = el(EV_YUV0, EV_YUV1); Tm.analysis_ms = el(EV_YUV1, EV_AN1); Tm.chroma1_ms = el(EV_AN1, EV_C1);
+  Tm.pass1_ms = el(EV_P1S, EV_P1); Tm.stats_ms = el(EV_P1, EV_ST1);  // k_finish1 + statistics + probabilities
   Tm.chroma2_ms = el(EV_ST1, EV_C2); Tm.pass2_ms = el(EV_C2, EV_P2); Tm.token_ms = el(EV_P2, EV_TOK);
   Tm.boolcode_ms = el(EV_TOK, EV_BC); Tm.assemble_ms = el(EV_BC, EV_END); Tm.device_total_ms = el(EV_START, EV_END);
   Tm.h2d_ms = el(EV_H2D0, EV_H2D1);

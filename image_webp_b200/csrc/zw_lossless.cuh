@@ -390,15 +390,42 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_residual(LlParams P) {
   const u8* src = P.src + im.src_off;
   const u32 p0 = (tile - im.tile_off) * LL_TILE + threadIdx.x * LL_PPT;
   u32 r[LL_PPT];
-  u32 x = 0, y = 0;
-  if (p0 < im.npx) { y = p0 / im.width; x = p0 - y * im.width; }
+  const u32 row_bytes = im.width * im.bpp;
+  if (p0 + LL_PPT <= im.npx && p0 >= im.width && (row_bytes & 3u) == 0 && !(im.flags & LL_FLAG_ALPHA_PLANE) && (im.flags & LL_FLAG_PREDICTOR)) {
+    // interior fast path: the four pixels and the four pixels above them are two runs of 4 * bpp bytes, both 4-byte
+    // aligned (p0 is a multiple of 4, the source starts 16-byte aligned, row_bytes is a multiple of 4): word loads
+    u32 cw[4], aw[4];
+    const u32* cp = reinterpret_cast<const u32*>(src + (size_t)p0 * im.bpp);
+    const u32* ap = reinterpret_cast<const u32*>(src + (size_t)(p0 - im.width) * im.bpp);
 #pragma unroll
-  for (int j = 0; j < LL_PPT; j++) {
-    const u32 i = p0 + j;
-    r[j] = 0;
-    if (i < im.npx) {
-      r[j] = ll_residual(src, i, x, y, im.width, im.bpp, im.color, im.flags);
-      if (++x == im.width) { x = 0; y++; }
+    for (int k = 0; k < 4; k++) { cw[k] = k < (int)im.bpp ? __ldg(cp + k) : 0u; aw[k] = k < (int)im.bpp ? __ldg(ap + k) : 0u; }
+    auto byte_of = [](const u32* w, u32 b) { return (w[b >> 2] >> (8u * (b & 3u))) & 255u; };
+#pragma unroll
+    for (int j = 0; j < LL_PPT; j++) {
+      u32 px[2];
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const u32* w = t == 0 ? cw : aw;
+        u32 rr, g, b, a = 255;
+        if (im.bpp == 3) { rr = byte_of(w, 3 * j); g = byte_of(w, 3 * j + 1); b = byte_of(w, 3 * j + 2); }
+        else if (im.bpp == 4) { rr = w[j] & 255u; g = (w[j] >> 8) & 255u; b = (w[j] >> 16) & 255u; a = w[j] >> 24; }
+        else if (im.bpp == 1) { rr = g = b = byte_of(w, j); }
+        else { rr = g = b = byte_of(w, 2 * j); a = byte_of(w, 2 * j + 1); }
+        px[t] = ((rr - g) & 255u) | (g << 8) | (((b - g) & 255u) << 16) | (a << 24);
+      }
+      r[j] = ll_sub4(px[0], px[1]);
+    }
+  } else {
+    u32 x = 0, y = 0;
+    if (p0 < im.npx) { y = p0 / im.width; x = p0 - y * im.width; }
+#pragma unroll
+    for (int j = 0; j < LL_PPT; j++) {
+      const u32 i = p0 + j;
+      r[j] = 0;
+      if (i < im.npx) {
+        r[j] = ll_residual(src, i, x, y, im.width, im.bpp, im.color, im.flags);
+        if (++x == im.width) { x = 0; y++; }
+      }
     }
   }
   s_last[threadIdx.x + 1] = r[LL_PPT - 1];
@@ -459,8 +486,13 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_tokens(LlParams P) {
   const u32 p0 = (tile - im.tile_off) * LL_TILE + threadIdx.x * LL_PPT;
   const u32* res = P.res + im.px_off;
   u32 r[LL_PPT + 1];
+  if (p0 + LL_PPT < im.npx) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(res + p0));
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = res[p0 + LL_PPT];
+  } else {
 #pragma unroll
-  for (int j = 0; j <= LL_PPT; j++) r[j] = (p0 + j < im.npx) ? res[p0 + j] : 0;
+    for (int j = 0; j <= LL_PPT; j++) r[j] = (p0 + j < im.npx) ? res[p0 + j] : 0;
+  }
   const u32 prev = (p0 > 0 && p0 <= im.npx) ? res[p0 - 1] : 0;
   u32 last = 0;
   {
@@ -562,6 +594,23 @@ __global__ void __launch_bounds__(128) k_ll_huffman(LlParams P) {
   }
 }
 
+// The thread's four residuals and token descriptors: one 16-byte and one 8-byte load inside full, aligned groups.
+__device__ __forceinline__ void ll_load4(const LlParams& P, const LlImage& im, u32 p0, u32* px, u32* d) {
+  if (p0 + LL_PPT <= im.npx) {  // px_off and p0 are multiples of 4
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.res + im.px_off + p0));
+    const uint2 b = __ldg(reinterpret_cast<const uint2*>(P.desc + im.px_off + p0));
+    px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
+    d[0] = b.x & 0xFFFFu; d[1] = b.x >> 16; d[2] = b.y & 0xFFFFu; d[3] = b.y >> 16;
+  } else {
+#pragma unroll
+    for (int j = 0; j < LL_PPT; j++) {
+      const bool in = p0 + j < im.npx;
+      px[j] = in ? P.res[im.px_off + p0 + j] : 0u;
+      d[j] = in ? (u32)P.desc[im.px_off + p0 + j] : 0u;  // descriptor 0: the pixel emits nothing
+    }
+  }
+}
+
 // Bits of every tile.
 __global__ void __launch_bounds__(LL_THREADS) k_ll_bits(LlParams P) {
   __shared__ u32 s_tab[4 * 280];
@@ -573,11 +622,11 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_bits(LlParams P) {
   __syncthreads();
   const u32 p0 = (tile - im.tile_off) * LL_TILE + threadIdx.x * LL_PPT;
   u32 bits = 0;
-  for (int j = 0; j < LL_PPT; j++) {
-    const u32 i = p0 + j;
-    if (i < im.npx)
-      bits += ll_pixel_bits(P.res[im.px_off + i], P.desc[im.px_off + i], im.color, [&](u32 ch, u32 sym) { return s_tab[ch * 280 + sym]; });
-  }
+  u32 px[LL_PPT], d[LL_PPT];
+  ll_load4(P, im, p0, px, d);
+#pragma unroll
+  for (int j = 0; j < LL_PPT; j++)
+    if (d[j]) bits += ll_pixel_bits(px[j], d[j], im.color, [&](u32 ch, u32 sym) { return s_tab[ch * 280 + sym]; });
   u32 tot;
   ll_block_sum_excl(bits, s_red, tot);
   if (threadIdx.x == 0) P.tile_bits[tile] = tot;
@@ -626,15 +675,11 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_emit(LlParams P) {
   const u32 p0 = (tile - im.tile_off) * LL_TILE + threadIdx.x * LL_PPT;
   u32 px[LL_PPT], d[LL_PPT], nb[LL_PPT];
   u32 bits = 0;
+  ll_load4(P, im, p0, px, d);
 #pragma unroll
   for (int j = 0; j < LL_PPT; j++) {
-    const u32 i = p0 + j;
-    px[j] = 0; d[j] = 0; nb[j] = 0;
-    if (i < im.npx) {
-      px[j] = P.res[im.px_off + i]; d[j] = P.desc[im.px_off + i];
-      nb[j] = ll_pixel_bits(px[j], d[j], im.color, table);
-      bits += nb[j];
-    }
+    nb[j] = d[j] ? ll_pixel_bits(px[j], d[j], im.color, table) : 0u;
+    bits += nb[j];
   }
   u32 tot;
   const u64 tile_bit = P.tile_bitoff[tile];

@@ -186,6 +186,7 @@ struct ChunkParams {
   u16* lcost;        // [n_img][4*8*3*68]
   u32* mb_hdr_cnt;   // [n_mb+1] tokens per MB header (then exclusive scan)
   u32* mb_tok_cnt;   // [n_mb+1] tokens per MB residual
+  u32* mb_lane_cnt;  // [n_mb][32] k_tokenize<0>: residual tokens of the lane's block | header-slot tokens << 16
   Token* hdr_tokens; // first-partition streams
   Token* tok_tokens; // token-partition streams
   u8* part_bytes;    // scratch for coded partitions
