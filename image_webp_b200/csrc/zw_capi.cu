@@ -339,12 +339,12 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   ok &= cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2))) == cudaSuccess;
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2))) == cudaSuccess;
   int bq1 = 0, bq2 = 0;
-  ok &= cudaFuncSetAttribute(k_searchq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes()) == cudaSuccess;
-  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq1, k_searchq<1>, SQ_WARPS * 32, searchq_smem_bytes()) == cudaSuccess;
-  ok &= cudaFuncSetAttribute(k_searchq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes()) == cudaSuccess;
-  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq2, k_searchq<2>, SQ_WARPS * 32, searchq_smem_bytes()) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_searchq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes(1)) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq1, k_searchq<1>, sq_warps(1) * 32, searchq_smem_bytes(1)) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_searchq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes(2)) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq2, k_searchq<2>, sq_warps(2) * 32, searchq_smem_bytes(2)) == cudaSuccess;
   if (!ok) { lane_destroy(c); return nullptr; }
-  if (warps_hint > 0) { bq1 = std::min(bq1, std::max(1, warps_hint / SQ_WARPS)); bq2 = std::min(bq2, std::max(1, warps_hint / SQ_WARPS)); }
+  if (warps_hint > 0) { bq1 = std::min(bq1, std::max(1, warps_hint / sq_warps(1))); bq2 = std::min(bq2, std::max(1, warps_hint / sq_warps(2))); }
   c->quad_blocks1 = std::max(1, bq1) * ctx->sm_count;
   c->quad_blocks2 = std::max(1, bq2) * ctx->sm_count;
   if (const char* env = getenv("ZW_QUAD")) c->quad_mode = atoi(env);
@@ -539,11 +539,11 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     // per row (k_search) stays for: too few rows to fill the GPU with quads (single images); methods 0 / 1 (no I4: the
     // warp kernel's lane-private I16 layout is already dense, 7.2 vs 8.3 ms); pass 2 with trellis (a macroblock offers at
     // most two independent trellis blocks, so half a quad idles: 39 vs 54 ms).  ZW_QUAD=0 / 1 / 2 forces never / both / pass 1.
-    const bool quad_fill = c->n_rows >= (u32)(c->sm_count * SQ_QUADS * 2);
+    const bool quad_fill = c->n_rows >= (u32)(c->sm_count * sq_quads(1) * 2);
     use_quads = c->quad_mode < 0 ? (quad_fill && P.i4_modes > 0) : c->quad_mode != 0;
     if (use_quads) {
-      const int g1 = (int)std::min<u64>((u64)c->quad_blocks1, ((u64)c->n_rows + SQ_QUADS - 1) / SQ_QUADS);
-      k_searchq<1><<<g1, SQ_WARPS * 32, searchq_smem_bytes(), s>>>(P);
+      const int g1 = (int)std::min<u64>((u64)c->quad_blocks1, ((u64)c->n_rows + sq_quads(1) - 1) / sq_quads(1));
+      k_searchq<1><<<g1, sq_warps(1) * 32, searchq_smem_bytes(1), s>>>(P);
     } else {
       const int w1 = search_warps(1);
       const int g1 = (int)std::min<u64>((u64)c->search_blocks1, ((u64)c->n_rows + w1 - 1) / w1);
@@ -565,8 +565,8 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     k_chroma2<<<g4, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
     CK(cudaEventRecord(c->ev[EV_C2], s));
     if (c->quad_mode < 0 ? (use_quads && !P.do_trellis) : c->quad_mode == 1) {
-      const int g2 = (int)std::min<u64>((u64)c->quad_blocks2, ((u64)c->n_rows + SQ_QUADS - 1) / SQ_QUADS);
-      k_searchq<2><<<g2, SQ_WARPS * 32, searchq_smem_bytes(), s>>>(P);
+      const int g2 = (int)std::min<u64>((u64)c->quad_blocks2, ((u64)c->n_rows + sq_quads(2) - 1) / sq_quads(2));
+      k_searchq<2><<<g2, sq_warps(2) * 32, searchq_smem_bytes(2), s>>>(P);
     } else {
       const int w2 = search_warps(2);
       const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);

@@ -10,19 +10,25 @@
 
 namespace zw {
 
-#ifndef ZW_SQ_WARPS
-#define ZW_SQ_WARPS 8  // one CTA per SM: 8 warps = 64 macroblock rows in flight, ~150 KB of shared memory, up to 255 registers
+// One CTA per SM.  Pass 1 (all level costs zero, light on registers): 12 warps = 96 macroblock rows in flight, ~222 KB of
+// shared memory, 170 registers (measured 17.5 -> 16.6 ms against 8 warps).  Pass 2 (real cost tables; methods 2-3 only):
+// 8 warps = 64 rows, up to 255 registers -- 12 warps were measured slower there.
+#ifndef ZW_SQ_WARPS1
+#define ZW_SQ_WARPS1 12
+#endif
+#ifndef ZW_SQ_WARPS2
+#define ZW_SQ_WARPS2 8
 #endif
 #ifndef ZW_SQ_MIN_BLOCKS
 #define ZW_SQ_MIN_BLOCKS 1
 #endif
-constexpr int SQ_WARPS = ZW_SQ_WARPS;         // warps per CTA (8 quads each)
-constexpr int SQ_QUADS = SQ_WARPS * 8;
+__host__ __device__ constexpr int sq_warps(int pass) { return pass == 1 ? ZW_SQ_WARPS1 : ZW_SQ_WARPS2; }  // warps per CTA (8 quads each)
+__host__ __device__ constexpr int sq_quads(int pass) { return sq_warps(pass) * 8; }
 
 struct SearchQShared {
   u8 pred_idx[10][16];
   u16 dtaps[32];
-  QuadScratch q[SQ_QUADS];
+  QuadScratch q[1];  // sq_quads(pass) entries (dynamic shared memory)
 };
 
 struct QuadExecDev {
@@ -41,13 +47,13 @@ struct QuadExecDev {
 // of one phase fits.  A quad whose dependency is not ready (it never blocks inside a round) or that has no row left sits
 // the round out.
 template <int PASS>
-__global__ void __launch_bounds__(SQ_WARPS * 32, ZW_SQ_MIN_BLOCKS) k_searchq(ChunkParams P) {
+__global__ void __launch_bounds__(sq_warps(PASS) * 32, ZW_SQ_MIN_BLOCKS) k_searchq(ChunkParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchQShared& SH = *reinterpret_cast<SearchQShared*>(smem_raw);
   __shared__ int s_active;  // quads of this CTA that still have (or may get) a row
   for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
   if (threadIdx.x < 32) SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x];
-  if (threadIdx.x == 0) s_active = SQ_QUADS;
+  if (threadIdx.x == 0) s_active = sq_quads(PASS);
   __syncthreads();
   for (int i = threadIdx.x; i < 16; i += blockDim.x) SH.pred_idx[1][i] = (u8)(32 + i);  // TM pixels live in dtab[32 + n]
   __syncthreads();
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(SQ_WARPS * 32, ZW_SQ_MIN_BLOCKS) k_searchq(Chu
   }
 }
 
-__host__ __device__ constexpr size_t searchq_smem_bytes() { return sizeof(SearchQShared); }
+__host__ __device__ constexpr size_t searchq_smem_bytes(int pass) { return sizeof(SearchQShared) + (size_t)(sq_quads(pass) - 1) * sizeof(QuadScratch); }
 
 }  // namespace zw
 #endif
