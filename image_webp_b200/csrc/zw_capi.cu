@@ -217,21 +217,39 @@ struct DecCtx {
   }
 };
 
-// Buffers of the lossless (VP8L) entry points (zw_lossless_host.inc); allocated on first use.
-struct LlCtx {
+// Buffers of the lossless (VP8L) entry points (zw_lossless_host.inc); allocated on first use.  Two slots: two chunks of
+// a batch are in flight at a time.
+struct LlJob;
+struct LlSlot {
   DevBuf d_img, d_st, d_src, d_res, d_desc, d_tile_last, d_tile_carry, d_tile_bits, d_tile_bitoff, d_hist, d_codes, d_hdr, d_out, d_outoff;
   PinBuf h_st, h_arena, h_outoff;
+  cudaStream_t stream = nullptr;
   cudaEvent_t ev[9];
   bool ev_ok = false;
-  u32 last_n = 0;
+  std::vector<LlImage> img;
+  std::vector<size_t> slot;  // job index (inside the chunk) of image k
+  LlParams P;
+  const LlJob* jobs = nullptr;
+  zw_output* outs = nullptr;
+  int container = 0;
+  u32 ni = 0, n_tiles = 0;
+  u64 src_bytes = 0, total = 0;
   void release() {
     DevBuf* all[] = {&d_img, &d_st, &d_src, &d_res, &d_desc, &d_tile_last, &d_tile_carry, &d_tile_bits, &d_tile_bitoff, &d_hist, &d_codes, &d_hdr,
                      &d_out, &d_outoff};
+    if (stream) cudaStreamSynchronize(stream);
     for (DevBuf* b : all) b->release();
     h_st.release(); h_arena.release(); h_outoff.release();
     if (ev_ok) for (auto& e : ev) cudaEventDestroy(e);
     ev_ok = false;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
   }
+};
+struct LlCtx {
+  LlSlot slot[2];
+  int last = -1;  // slot of the last chunk (zw_lossless_dump_stage)
+  void release() { for (LlSlot& s : slot) s.release(); }
 };
 
 struct zw_ctx {

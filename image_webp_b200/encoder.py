@@ -109,13 +109,16 @@ class PendingBatch:
     """A batch in flight (zw_submit ticket).  `result()` blocks until it is finished and returns
     (list of .webp / VP8 bytes, timing dict); the pipeline slot is released then."""
 
-    def __init__(self, ctx, ticket, keep, container, raise_errors):
+    def __init__(self, ctx, ticket, keep, container, raise_errors, views=False):
+        self._views = views
         self._ctx, self._ticket, self._keep = ctx, ticket, keep
         self._n = len(keep[0])
         self._container, self._raise = container, raise_errors
         self._res = None
 
-    def result(self):
+    def result(self, views=None):
+        """views=True (or a batch submitted with views=True): the files come back as memoryviews into ONE copy of the slot's pinned arena (a single memcpy per
+        batch instead of one bytes object per image); they compare equal to bytes and go wherever a buffer is accepted."""
         if self._res is None:
             ctx = self._ctx
             view = _lib.ZwBatchView()
@@ -125,19 +128,43 @@ class PendingBatch:
                 ctx.lib.zw_release(ctx.h, self._ticket)
                 _raise_for(rc, ctx.lib)
             outs, first_bad = [], 0
-            for i in range(view.n):
-                st = view.status[i]
+            n = view.n
+            offs = np.ctypeslib.as_array(view.offsets, (n,)) if n else np.zeros(0, np.uint64)
+            lens = np.ctypeslib.as_array(view.lens, (n,)) if n else np.zeros(0, np.uint32)
+            stat = np.ctypeslib.as_array(view.status, (n,)) if n else np.zeros(0, np.int32)
+            blob, lo = None, 0
+            views = self._views if views is None else views
+            if views and n and (stat == 0).any():
+                ok = stat == 0
+                lo = int(offs[ok].min())
+                hi = int((offs[ok] + lens[ok]).max())
+                blob = memoryview(C.string_at(view.arena + lo, hi - lo))
+            for i in range(n):
+                st = int(stat[i])
                 if st != 0:
                     first_bad = first_bad or st
                     outs.append(None)
+                elif blob is not None:
+                    o = int(offs[i]) - lo
+                    outs.append(blob[o:o + int(lens[i])])
                 else:
-                    outs.append(C.string_at(view.arena + view.offsets[i], view.lens[i]))
+                    outs.append(C.string_at(view.arena + int(offs[i]), int(lens[i])))
             ctx.lib.zw_release(ctx.h, self._ticket)
             self._keep = None
             self._res = (outs, t.as_dict())
             if first_bad and self._raise:
                 _raise_for(first_bad, ctx.lib)
         return self._res
+
+
+class PreparedBatch:
+    """zw_image descriptors of a batch (Context.prepare)."""
+
+    def __init__(self, arr, keep, color):
+        self.arr, self.keep, self.color = arr, keep, color
+
+    def __len__(self):
+        return len(self.keep)
 
 
 class Context:
@@ -168,7 +195,17 @@ class Context:
 
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
+    def prepare(images, color=ColorType.Rgb8):
+        """Build the zw_image descriptors of a batch once; the result can be handed to encode_batch / submit any number
+        of times (the pixel buffers are referenced, not copied: keep them unchanged while a batch is in flight)."""
+        return PreparedBatch(*Context._as_images(images, color), color)
+
+    @staticmethod
     def _as_images(images, color):
+        if isinstance(images, PreparedBatch):
+            if images.color != color:
+                raise ValueError("batch was prepared for %s" % images.color)
+            return images.arr, images.keep
         arr = (_lib.ZwImage * len(images))()
         keep = []
         for i, im in enumerate(images):
@@ -269,7 +306,7 @@ class Context:
             _raise_for(rc, self.lib)
         return buf[:n.value].view(dtype)
 
-    def submit(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True):
+    def submit(self, images, params, color=ColorType.Rgb8, container=True, raise_errors=True, views=False):
         """Streaming entry (zw_submit): starts the batch and returns a PendingBatch at once, or None when every
         pipeline slot of the context is taken (take `.result()` of an earlier batch first).  The batch must fit
         the device budget in one chunk."""
@@ -281,7 +318,7 @@ class Context:
             return None
         if rc != 0:
             _raise_for(rc, self.lib)
-        return PendingBatch(self, ticket.value, (arr, keep), container, raise_errors)
+        return PendingBatch(self, ticket.value, (arr, keep), container, raise_errors, views)
 
     def stage(self, images, color=ColorType.Rgb8):
         arr, keep = self._as_images(images, color)
@@ -333,16 +370,17 @@ class BatchPipeline:
     .webp bytes, timing dict)); when every slot is taken it first completes the oldest batch.  Results are
     bit-identical to `Context.encode_batch`."""
 
-    def __init__(self, device=0, depth=3, **ctx_kwargs):
+    def __init__(self, device=0, depth=3, views=False, **ctx_kwargs):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.depth = depth
+        self.views = views  # hand the files back as memoryviews into one copy of the arena per batch
         self.ctx = Context(device, depth=depth, **ctx_kwargs)
         self._inflight = []
 
     def submit(self, images, params, color=ColorType.Rgb8, container=True):
         while True:
-            p = self.ctx.submit(images, params, color, container)
+            p = self.ctx.submit(images, params, color, container, views=self.views)
             if p is not None:
                 self._inflight.append(p)
                 return p
@@ -354,6 +392,12 @@ class BatchPipeline:
         """Encode an iterable of batches; returns the list of per-batch outputs, in order."""
         futs = [self.submit(b, params, color, container) for b in batches]
         return [f.result()[0] for f in futs]
+
+    def drain(self):
+        """Complete every batch in flight, oldest first; returns their (outputs, timing) pairs."""
+        res = [p.result() for p in self._inflight]
+        self._inflight = []
+        return res
 
     def close(self):
         for p in self._inflight:
