@@ -162,10 +162,11 @@ struct PinBuf {
 // kernel waits for the previous lane's last one.
 enum { LANE_FREE = 0, LANE_STAGED = 1, LANE_IN_FLIGHT = 2, LANE_SIZED = 3, LANE_DONE = 4 };
 enum { EV_H2D0 = 0, EV_H2D1, EV_YUV0, EV_YUV1, EV_AN1, EV_P1, EV_C1, EV_ST0, EV_ST1, EV_C2, EV_P2, EV_TOK, EV_BC, EV_END, EV_START,
-       EV_D2H0, EV_D2H1, EV_SIZES, EV_P1S, EV_COUNT };
+       EV_D2H0, EV_D2H1, EV_SIZES, EV_P1S, EV_F1S, EV_COUNT };
 struct Lane {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // small chunks: the pass-1 chroma chains run here, beside the luma wavefront
   cudaEvent_t ev[EV_COUNT];
   bool ev_ok = false;
   const SegParams* segtab = nullptr;  // shared constant tables (owned by the context)
@@ -328,6 +329,7 @@ static void lane_destroy(Lane* c) {
   for (DevBuf* b : all) b->release();
   c->h_st.release(); c->h_outoff.release(); c->h_tot.release(); c->h_arena.release();
   if (c->ev_ok) for (auto& ev : c->ev) cudaEventDestroy(ev);
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -338,6 +340,7 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   c->segtab = ctx->d_segtab.as<SegParams>();
   c->lut = ctx->d_lut.as<u8>();
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
   for (int i = 0; i < EV_COUNT; i++) {
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) {
       for (int k = 0; k < i; k++) cudaEventDestroy(c->ev[k]);
@@ -548,16 +551,25 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
      // wavefront, then the bookkeeping.  (Running the chains on a side stream UNDER the wavefront was measured: they
      // starve -- 43 ms instead of 8.8 ms, instruction-cache contention with the wavefront's code -- so the kernels stay
      // back to back.)
+    // Chunks too small to fill the GPU (single images): the chains run on a side stream BESIDE the luma wavefront, which
+    // then occupies a fraction of the SMs and starves nobody (4096 x 4096: 21 ms of luma under the 155 ms chain).
+    const bool quad_fill = c->n_rows >= (u32)(c->sm_count * 64 * 2);
+    const bool beside = c->n_rows < (u32)(c->sm_count * 8) && !getenv("ZW_NO_SIDE");
     const int g3 = (int)(((u64)ni + SEARCH_WARPS - 1) / SEARCH_WARPS);
-    k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
-    CK(cudaEventRecord(c->ev[EV_C1], s));
+    if (beside) {
+      CK(cudaStreamWaitEvent(c->side, c->ev[EV_AN1], 0));
+      k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), c->side>>>(P);
+      CK(cudaEventRecord(c->ev[EV_C1], c->side));
+    } else {
+      k_chroma1<<<g3, SEARCH_WARPS * 32, sizeof(SearchShared), s>>>(P);
+      CK(cudaEventRecord(c->ev[EV_C1], s));
+    }
     CK(cudaEventRecord(c->ev[EV_P1S], s));
     // Batches with an I4 search: four lanes per macroblock row (k_searchq), eight rows per warp -- the I4 candidates run
     // lane-private (measured on 1024 x 768x512: pass 1 20.7 -> 17.5 ms at method 4, 31.9 -> 24.1 ms at method 6).  One warp
     // per row (k_search) stays for: too few rows to fill the GPU with quads (single images); methods 0 / 1 (no I4: the
     // warp kernel's lane-private I16 layout is already dense, 7.2 vs 8.3 ms); pass 2 with trellis (a macroblock offers at
     // most two independent trellis blocks, so half a quad idles: 39 vs 54 ms).  ZW_QUAD=0 / 1 / 2 forces never / both / pass 1.
-    const bool quad_fill = c->n_rows >= (u32)(c->sm_count * sq_quads(1) * 2);
     use_quads = c->quad_mode < 0 ? (quad_fill && P.i4_modes > 0) : c->quad_mode != 0;
     if (use_quads) {
       const int g1 = (int)std::min<u64>((u64)c->quad_blocks1, ((u64)c->n_rows + sq_quads(1) - 1) / sq_quads(1));
@@ -568,6 +580,8 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
       k_search<1><<<g1, w1 * 32, search_smem_bytes(w1), s>>>(P);
     }
     CK(cudaEventRecord(c->ev[EV_P1], s));
+    if (beside) CK(cudaStreamWaitEvent(s, c->ev[EV_C1], 0));
+    CK(cudaEventRecord(c->ev[EV_F1S], s));
     k_finish1<<<ni, 256, 0, s>>>(P);
     c->launches += 3;
   }
@@ -624,7 +638,7 @@ static int lane_sync_sizes(Lane* c) {
   Tm.h2d_bytes = c->last.h2d_bytes; Tm.pixels = c->last.pixels;
   auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
   Tm.yuv_ms = el(EV_YUV0, EV_YUV1); Tm.analysis_ms = el(EV_YUV1, EV_AN1); Tm.chroma1_ms = el(EV_AN1, EV_C1);
-  Tm.pass1_ms = el(EV_P1S, EV_P1); Tm.stats_ms = el(EV_P1, EV_ST1);  // k_finish1 + statistics + probabilities
+  Tm.pass1_ms = el(EV_P1S, EV_P1); Tm.stats_ms = el(EV_F1S, EV_ST1);  // k_finish1 + statistics + probabilities
   Tm.chroma2_ms = el(EV_ST1, EV_C2); Tm.pass2_ms = el(EV_C2, EV_P2); Tm.token_ms = el(EV_P2, EV_TOK);
   Tm.boolcode_ms = el(EV_TOK, EV_BC); Tm.assemble_ms = el(EV_BC, EV_END); Tm.device_total_ms = el(EV_START, EV_END);
   Tm.h2d_ms = el(EV_H2D0, EV_H2D1);

@@ -30,7 +30,13 @@ for ln in open(disasm):
             # innermost, and the frame directly below the kernel body (second outermost)
             off2[int(m.group(1), 16)] = (frames[0], frames[-2] if len(frames) >= 2 else frames[-1])
 # --- ncu sass page
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".gz"):
+    import gzip
+    out = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 kern = None; hdr = None; base = None
 agg_out = collections.Counter(); agg_in = collections.Counter(); inst_out = collections.Counter(); inst_in = collections.Counter()
