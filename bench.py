@@ -430,6 +430,9 @@ def main():
         dist = dist_mod
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # the ranks that finish early wait for rank 0's extra legs on the CPU (gloo): an NCCL barrier would park a
+        # spinning kernel on their GPUs, which rank 0's one-process multi-GPU leg (config5_multi) is about to use
+        tail_group = dist.new_group(backend="gloo")
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
 
@@ -628,7 +631,8 @@ def main():
                 line["config5_multi"] = {"error": str(e)}
         print(json.dumps(line))
     if dist is not None:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=tail_group)
         dist.destroy_process_group()
     pipe.close()
     ctx.close()
