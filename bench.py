@@ -417,7 +417,7 @@ def config5_multi(Z, torch, n_dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU (default: the BASELINE config)")
