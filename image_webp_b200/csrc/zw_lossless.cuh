@@ -195,8 +195,21 @@ ZW_HD u32 ll_rev16(u32 v) {
   v = ((v >> 4) & 0x0F0Fu) | ((v & 0x0F0Fu) << 4);
   return ((v >> 8) & 0x00FFu) | ((v & 0x00FFu) << 8);
 }
+// Symbols in ascending frequency, equal frequencies by index (what the length-limiting branch of build_huffman_tree
+// walks, api.rs:248-260), as a rank sort shared by `nlanes` lanes: order[rank(i)] = i.  A photograph's residual
+// histogram regularly needs it (rare symbols sit deeper than 15), and a serial insertion sort of 256 entries costs
+// 2.4 M cycles on one lane -- more than the rest of the Huffman construction together.
+ZW_HD void ll_rank_order(const u32* freq, u32 n, u16* order, u32 lane, u32 nlanes) {
+  for (u32 i = lane; i < n; i += nlanes) {
+    const u32 fi = freq[i];
+    u32 r = 0;
+    for (u32 j = 0; j < n; j++) r += (freq[j] < fi || (freq[j] == fi && j < i)) ? 1u : 0u;
+    order[r] = (u16)i;
+  }
+}
 // build_huffman_tree (api.rs:163-287).  false (lengths and codes zeroed) when at most one symbol is used.
-ZW_HD bool ll_build_huffman(const u32* freq, u32 n, u8* lengths, u16* codes, u32 limit, LlHuffScratch& S) {
+// order_ready: S.order already holds ll_rank_order of `freq` (the kernel computes it with the whole warp).
+ZW_HD bool ll_build_huffman(const u32* freq, u32 n, u8* lengths, u16* codes, u32 limit, LlHuffScratch& S, bool order_ready = false) {
   u32 used = 0;
   for (u32 i = 0; i < n; i++) { lengths[i] = 0; codes[i] = 0; used += freq[i] > 0 ? 1 : 0; }
   if (used <= 1) return false;
@@ -237,11 +250,12 @@ ZW_HD bool ll_build_huffman(const u32* freq, u32 n, u8* lengths, u16* codes, u32
       counts[i] -= 1; counts[limit] -= 1; counts[i + 1] += 2;
       total -= 1;
     }
-    // ascending frequency, equal frequencies by index (insertion sort: stable)
-    for (u32 i = 0; i < n; i++) {
-      u32 j = i;
-      while (j > 0 && freq[S.order[j - 1]] > freq[i]) { S.order[j] = S.order[j - 1]; j--; }
-      S.order[j] = (u16)i;
+    if (!order_ready) {  // ascending frequency, equal frequencies by index (insertion sort: stable)
+      for (u32 i = 0; i < n; i++) {
+        u32 j = i;
+        while (j > 0 && freq[S.order[j - 1]] > freq[i]) { S.order[j] = S.order[j - 1]; j--; }
+        S.order[j] = (u16)i;
+      }
     }
     u32 len = limit;
     for (u32 k = 0; k < n; k++) {
@@ -274,8 +288,8 @@ ZW_HD void ll_write_single_entry_tree(LlBits& w, u32 symbol) {  // api.rs:152-16
   else { w.put(1, 1); w.put(symbol, 8); }
 }
 // write_huffman_tree (api.rs:289-354): builds the code of one channel and serialises it.
-ZW_HD void ll_write_huffman_tree(LlBits& w, const u32* freq, u32 n, u8* lengths, u16* codes, LlHuffScratch& S) {
-  if (!ll_build_huffman(freq, n, lengths, codes, 15, S)) {
+ZW_HD void ll_write_huffman_tree(LlBits& w, const u32* freq, u32 n, u8* lengths, u16* codes, LlHuffScratch& S, bool order_ready = false) {
+  if (!ll_build_huffman(freq, n, lengths, codes, 15, S, order_ready)) {
     u32 symbol = 0;
     for (u32 i = 0; i < n; i++) if (freq[i] > 0) { symbol = i; break; }
     ll_write_single_entry_tree(w, symbol & 255u);
@@ -567,10 +581,12 @@ __global__ void __launch_bounds__(128) k_ll_huffman(LlParams P) {
   }
   for (u32 k = lane; k < LL_TREE_WORDS; k += 32) S.tree[c][k] = 0;
   __syncwarp();
+  if (built) ll_rank_order(S.freq[c], n, S.scratch[c].order, lane, 32);
+  __syncwarp();
   if (lane == 0) {
     LlBits w;
     w.w = S.tree[c]; w.pos = 0;
-    if (built) ll_write_huffman_tree(w, S.freq[c], n, S.lengths[c], S.codes[c], S.scratch[c]);
+    if (built) ll_write_huffman_tree(w, S.freq[c], n, S.lengths[c], S.codes[c], S.scratch[c], true);
     else if (c == 3) ll_write_single_entry_tree(w, (im.flags & LL_FLAG_PREDICTOR) ? 0u : 255u);  // api.rs:1096-1100
     else ll_write_single_entry_tree(w, 0);
     S.tree_bits[c] = w.pos;

@@ -187,3 +187,23 @@ def test_builder_api_and_errors(ctx):
     assert Z.Encoder.new_l8(wide.tobytes(), 16384, 1).lossless(True).encode() == O.webp_encode(wide, "L8")[1]
     with pytest.raises(Z.InvalidDimensions):
         Z.Encoder.new_l8(wide.tobytes(), 16384, 1).encode()
+
+
+def test_length_limited_codes(ctx):
+    # Fibonacci histograms: the unconstrained Huffman depth exceeds 15 (api.rs:225-262) -- the device takes the symbol
+    # order of the limiting branch from a warp-wide rank sort; also the 7-bit limit of the code-length alphabet
+    import image_webp_b200 as Z
+    fib = [1, 1]
+    while len(fib) < 27:
+        fib.append(fib[-1] + fib[-2])
+    vals = np.repeat(np.arange(27, dtype=np.uint8), fib)
+    np.random.default_rng(5).shuffle(vals)
+    w = 701
+    h = len(vals) // w
+    grey = vals[: w * h].reshape(h, w)
+    rgb = np.dstack([grey, np.roll(grey, 3, axis=1), grey[::-1]])
+    for img, color in ((grey, "L8"), (rgb, "Rgb8")):
+        for pred in (False, True):
+            outs, _ = ctx.encode_batch([img], Z.EncoderParams(use_predictor_transform=pred), _ct(color))
+            assert outs[0] == O.webp_encode(img, color, use_predictor=pred)[1], (color, pred)
+            assert np.array_equal(_decode(outs[0], MODE[color]).reshape(img.shape), img)
