@@ -685,28 +685,20 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_emit(LlParams P) {
   const u32 ii = ll_find_image(P.img, P.n_img, tile);
   const LlImage im = P.img[ii];
   for (u32 k = threadIdx.x; k < 4 * 280; k += LL_THREADS) s_tab[k] = P.codes[(size_t)ii * 4 * 280 + k];
-  for (u32 k = threadIdx.x; k < LL_EMIT_WORDS; k += LL_THREADS) s_buf[k] = 0;
   __syncthreads();
   auto table = [&](u32 ch, u32 sym) { return s_tab[ch * 280 + sym]; };
   const u32 p0 = (tile - im.tile_off) * LL_TILE + threadIdx.x * LL_PPT;
-  u32 px[LL_PPT], d[LL_PPT], nb[LL_PPT];
-  u32 bits = 0;
-  ll_load4(P, im, p0, px, d);
-#pragma unroll
-  for (int j = 0; j < LL_PPT; j++) {
-    nb[j] = d[j] ? ll_pixel_bits(px[j], d[j], im.color, table) : 0u;
-    bits += nb[j];
-  }
-  u32 tot;
-  const u64 tile_bit = P.tile_bitoff[tile];
-  const u32 skew = (u32)(tile_bit & 31);
-  u32 pos = skew + ll_block_sum_excl(bits, s_red, tot);
   const bool color = ll_is_color(im.color), alpha = ll_is_alpha(im.color);
+  u32 px[LL_PPT], d[LL_PPT];
+  ll_load4(P, im, p0, px, d);
+  // every pixel's bit string once: literal (green, red, blue, alpha: api.rs:1115-1160) and run token
+  u64 lit[LL_PPT];
+  u32 lit_len[LL_PPT], run[LL_PPT], run_len[LL_PPT];
+  u32 bits = 0;
 #pragma unroll
   for (int j = 0; j < LL_PPT; j++) {
-    if (nb[j] == 0) continue;
-    u32 at = pos;
-    if (d[j] & 1u) {  // api.rs:1115-1160: green, red, blue, alpha
+    lit[j] = 0; lit_len[j] = 0; run[j] = 0; run_len[j] = 0;
+    if (d[j] & 1u) {
       u32 e = table(1, (px[j] >> 8) & 255u);
       u64 code = e & 0xFFFFu;
       u32 len = e >> 16;
@@ -715,21 +707,34 @@ __global__ void __launch_bounds__(LL_THREADS) k_ll_emit(LlParams P) {
         e = table(2, (px[j] >> 16) & 255u); code |= (u64)(e & 0xFFFFu) << len; len += e >> 16;
       }
       if (alpha) { e = table(3, px[j] >> 24); code |= (u64)(e & 0xFFFFu) << len; len += e >> 16; }
-      ll_smem_put(s_buf, at, code, len);
-      at += len;
+      lit[j] = code; lit_len[j] = len;
     }
     if (d[j] >> 1) {
       u32 sym, eb, ev;
       ll_run_symbol(d[j] >> 1, sym, eb, ev);
       const u32 e = table(1, sym);
-      ll_smem_put(s_buf, at, (u64)(e & 0xFFFFu) | ((u64)ev << (e >> 16)), (e >> 16) + eb);
+      run[j] = (e & 0xFFFFu) | (ev << (e >> 16));
+      run_len[j] = (e >> 16) + eb;
     }
-    pos += nb[j];
+    bits += lit_len[j] + run_len[j];
+  }
+  u32 tot;
+  const u64 tile_bit = P.tile_bitoff[tile];
+  const u32 skew = (u32)(tile_bit & 31);
+  u32 pos = skew + ll_block_sum_excl(bits, s_red, tot);
+  const u32 nw = (skew + tot + 31) >> 5;
+  for (u32 k = threadIdx.x; k < nw + 2 && k < (u32)LL_EMIT_WORDS; k += LL_THREADS) s_buf[k] = 0;  // only the words this tile fills
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < LL_PPT; j++) {
+    ll_smem_put(s_buf, pos, lit[j], lit_len[j]);
+    pos += lit_len[j];
+    ll_smem_put(s_buf, pos, (u64)run[j], run_len[j]);
+    pos += run_len[j];
   }
   __syncthreads();
   u32* out = reinterpret_cast<u32*>(P.out + P.out_off[ii]);
   const u64 w0 = tile_bit >> 5;
-  const u32 nw = (skew + tot + 31) >> 5;
   for (u32 k = threadIdx.x; k < nw; k += LL_THREADS) {
     const u32 v = s_buf[k];
     if (k == 0 || k == nw - 1) { if (v) atomicOr(&out[w0 + k], v); }
