@@ -230,8 +230,10 @@ int zw_decode_dump_stage(zw_ctx* ctx, size_t index, const char* stage, void* dst
  * Huffman code per channel, run-length back references), encode_alpha_lossless (:1175-1222) and the container logic of
  * WebPEncoder::encode (:1291-1394).  Bytes are identical to the CPU port (oracle/zw_lossless_oracle.inc), whose files
  * libwebp decodes back to exactly the input pixels (the reference's own acceptance test, api.rs:1447-1511).
- * Dimensions 1..16384 (api.rs:968); status codes as above.  These calls own the context while they run (batches in
- * flight from zw_submit are waited for).  zw_timing fields used: h2d_ms, yuv_ms (transforms + run heads), analysis_ms
+ * Dimensions 1..16384 (api.rs:968); status codes as above.  The lossless kernels have their own buffers and streams:
+ * batches in flight from zw_submit keep running and their tickets stay valid.  (zw_encode_batch with use_lossy goes
+ * through the blocking lossy batch call, which -- like zw_encode_vp8_batch / zw_encode_webp_batch -- takes every pipeline
+ * slot of the context: wait for and release outstanding tickets first, or they are dropped.)  zw_timing fields used: h2d_ms, yuv_ms (transforms + run heads), analysis_ms
  * (tokens + histograms), stats_ms (Huffman codes), token_ms (bit counts + scan), assemble_ms (bit packing), d2h_ms. */
 
 /* n raw VP8L streams (container == 0) or .webp files in the simple container (container != 0). */

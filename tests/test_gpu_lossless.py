@@ -207,3 +207,70 @@ def test_length_limited_codes(ctx):
             outs, _ = ctx.encode_batch([img], Z.EncoderParams(use_predictor_transform=pred), _ct(color))
             assert outs[0] == O.webp_encode(img, color, use_predictor=pred)[1], (color, pred)
             assert np.array_equal(_decode(outs[0], MODE[color]).reshape(img.shape), img)
+
+
+def test_raw_c_abi_mixed_colours_metadata_and_in_flight_batches(ctx):
+    """zw_encode_batch through ctypes: one batch mixing all four colour types, metadata on some images only, lossy and
+    lossless; called while a zw_submit batch of the same context is still in flight (the call waits for it; the ticket
+    stays valid)."""
+    import ctypes as C
+
+    import image_webp_b200 as Z
+    from image_webp_b200 import _lib
+    L = _lib.load()
+    rgba = _rgba(120, 161, 21, "photo")
+    items = [("Rgba8", rgba), ("Rgb8", _view(rgba, "Rgb8")), ("La8", _view(rgba, "La8")), ("L8", _view(rgba, "L8")),
+             ("Rgb8", _view(_rgba(33, 65, 3, "noise"), "Rgb8")), ("Rgba8", _rgba(1, 1, 4, "noise"))]
+    metas = [None, {"exif": b"E" * 5}, {"icc": b"I" * 3, "xmp": b"X"}, None, None, {"xmp": b"xx"}]
+    n = len(items)
+    arr = (_lib.ZwImage * n)()
+    keep = []
+    for i, (color, im) in enumerate(items):
+        buf = np.ascontiguousarray(im)
+        keep.append(buf)
+        arr[i] = _lib.ZwImage(buf.ctypes.data, buf.size, buf.shape[1], buf.shape[0], O.COLOR[color], 0)
+    marr = (_lib.ZwMetadata * n)()
+    for i, m in enumerate(metas):
+        m = m or {}
+        marr[i] = _lib.ZwMetadata(m.get("icc"), len(m.get("icc", b"")), m.get("exif"), len(m.get("exif", b"")), m.get("xmp"), len(m.get("xmp", b"")))
+    lossy_p = Z.EncoderParams.lossy(70)
+    pend = ctx.submit([_view(rgba, "Rgb8")] * 3, lossy_p)   # stays in flight across the lossless call below
+    for lossy in (False, True):
+        if lossy:  # the lossy batch call takes every pipeline slot: collect the ticket first
+            files, _ = pend.result()
+            assert files == [O.encode(_view(rgba, "Rgb8"), 70, 4)[1]] * 3
+        zp = _lib.ZwParams(1, 1 if lossy else 0, 70, 4)
+        outs = (_lib.ZwOutput * n)()
+        rc = L.zw_encode_batch(ctx.h, arr, n, C.byref(zp), marr, outs, None)
+        assert rc == 0
+        for i, (color, im) in enumerate(items):
+            m = metas[i] or {}
+            ref = O.webp_encode(im, color, use_lossy=lossy, quality=70, method=4, icc=m.get("icc", b""), exif=m.get("exif", b""), xmp=m.get("xmp", b""))[1]
+            assert outs[i].status == 0 and C.string_at(outs[i].data, outs[i].len) == ref, (lossy, i, color)
+            L.zw_free(outs[i].data)
+    # bad entries are reported per image, the rest of the batch is encoded
+    bad = (_lib.ZwImage * 3)()
+    bad[0] = arr[1]
+    bad[1] = _lib.ZwImage(keep[1].ctypes.data, keep[1].size - 1, 161, 120, 2, 0)
+    bad[2] = _lib.ZwImage(keep[3].ctypes.data, 0, 0, 0, 0, 0)
+    outs = (_lib.ZwOutput * 3)()
+    zp = L.zw_params_default()
+    assert L.zw_encode_batch(ctx.h, bad, 3, C.byref(zp), None, outs, None) == 0
+    assert [outs[i].status for i in range(3)] == [0, 2, 1]
+    assert C.string_at(outs[0].data, outs[0].len) == O.webp_encode(items[1][1], "Rgb8")[1]
+    L.zw_free(outs[0].data)
+
+
+def test_lossless_large_image_and_repeat(ctx):
+    # 16.8 Mpx in one image: 16384 tiles, carries / bit offsets across many warp-scan rounds; twice: same bytes
+    import hashlib
+
+    import image_webp_b200 as Z
+    img = synth.photo_like(4096, 4096, 3, freq_scale=4.0)
+    img[1000:1200] = img[1000, 0]       # 800 k identical pixels: run groups of 4097 across rows
+    a, _ = ctx.encode_batch([img], Z.EncoderParams(), Z.ColorType.Rgb8)
+    b, _ = ctx.encode_batch([img], Z.EncoderParams(), Z.ColorType.Rgb8)
+    assert a == b
+    ref = O.webp_encode(img, "Rgb8")[1]
+    assert hashlib.sha256(a[0]).hexdigest() == hashlib.sha256(ref).hexdigest()
+    assert np.array_equal(_decode(a[0], "RGB"), img)
