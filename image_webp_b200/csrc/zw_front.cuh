@@ -22,6 +22,12 @@ constexpr int YUV_ROWPAIRS = 8;                 // row pairs per CTA step (block
 constexpr int YUV_STEPS = 4;                    // steps per CTA: 64 source rows x 256 px; step s+1 is in flight (cp.async) while step s is converted
 constexpr int YUV_ROW_SLOTS = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row (RGBA worst case + skew)
 
+// dp2a: d = c + a.lo16 * b.byte(0|2) + a.hi16 * b.byte(1|3); unsigned or signed 16-bit coefficients x unsigned bytes
+__device__ __forceinline__ u32 dp2a_lo_uu(u32 a, u32 b, u32 c) { u32 d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ u32 dp2a_hi_uu(u32 a, u32 b, u32 c) { u32 d; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ i32 dp2a_lo_su(i32 a, u32 b, i32 c) { i32 d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ i32 dp2a_hi_su(i32 a, u32 b, i32 c) { i32 d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
 __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P) {
   const ImageDesc d = P.img[blockIdx.z];
   const int pw = d.mbw * 16, ph = d.mbh * 16;
@@ -101,23 +107,44 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P
 #pragma unroll
           for (int k = 0; k < 6; k++) a[r][k] = __funnelshift_r(wv[k], wv[k + 1], sh);
         }
-        auto byte_at = [&](int r, int j) -> int { return (int)((a[r][j >> 2] >> (8 * (j & 3))) & 255u); };
+        // Packed arithmetic: one PRMT gathers a pixel's [R, G, B, x] bytes, two dp2a (16-bit coefficients x bytes) give
+        // its luma; the result is below 2^24 with Y exactly in byte 2, so four pixels are packed with three more PRMTs.
+        // Chroma accumulates the same dp2a pair over the four pixels of a 2x2 block (the reference's sums are linear).
+        // The unpacked form of this path (byte extraction + IMAD) made the kernel issue-bound at 69 % of the HBM peak.
+        u32 pa[8], pb[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          const int ya = (16839 * byte_at(0, 3 * k) + 33059 * byte_at(0, 3 * k + 1) + 6420 * byte_at(0, 3 * k + 2) + 32768 + (16 << 16)) >> 16;
-          const int yb = (16839 * byte_at(1, 3 * k) + 33059 * byte_at(1, 3 * k + 1) + 6420 * byte_at(1, 3 * k + 2) + 32768 + (16 << 16)) >> 16;
-          y0w[k >> 2] |= (u32)ya << (8 * (k & 3));
-          y1w[k >> 2] |= (u32)yb << (8 * (k & 3));
+          const int w0 = (3 * k) >> 2, o = (3 * k) & 3, w1 = w0 + 1 < 6 ? w0 + 1 : w0;
+          const u32 sel = (u32)o | ((u32)(o + 1) << 4) | ((u32)(o + 2) << 8) | ((u32)(o + 2) << 12);  // byte 3: don't care
+          pa[k] = __byte_perm(a[0][w0], a[0][w1], sel);
+          pb[k] = __byte_perm(a[1][w0], a[1][w1], sel);
+        }
+        const u32 cyRG = 16839u | (33059u << 16), cyB = 6420u, cyK = 32768u + (16u << 16);
+        u32 ya[8], yb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          ya[k] = dp2a_hi_uu(cyB, pa[k], dp2a_lo_uu(cyRG, pa[k], cyK));
+          yb[k] = dp2a_hi_uu(cyB, pb[k], dp2a_lo_uu(cyRG, pb[k], cyK));
         }
 #pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          y0w[h2] = __byte_perm(__byte_perm(ya[4 * h2], ya[4 * h2 + 1], 0x0062), __byte_perm(ya[4 * h2 + 2], ya[4 * h2 + 3], 0x0062), 0x5410);
+          y1w[h2] = __byte_perm(__byte_perm(yb[4 * h2], yb[4 * h2 + 1], 0x0062), __byte_perm(yb[4 * h2 + 2], yb[4 * h2 + 3], 0x0062), 0x5410);
+        }
+        const i32 cuRG = (i32)((u32)(u16)(i16)-9719 | ((u32)(u16)(i16)-19081 << 16)), cuB = 28800;
+        const i32 cvRG = (i32)((u32)(u16)(i16)28800 | ((u32)(u16)(i16)-24116 << 16)), cvB = (i32)(u32)(u16)(i16)-4684;
+        const i32 cK = 4 * (128 << 16) + (32768 << 2);
+#pragma unroll
         for (int k = 0; k < 4; k++) {
-          const int r = byte_at(0, 6 * k) + byte_at(0, 6 * k + 3) + byte_at(1, 6 * k) + byte_at(1, 6 * k + 3);
-          const int g = byte_at(0, 6 * k + 1) + byte_at(0, 6 * k + 4) + byte_at(1, 6 * k + 1) + byte_at(1, 6 * k + 4);
-          const int b = byte_at(0, 6 * k + 2) + byte_at(0, 6 * k + 5) + byte_at(1, 6 * k + 2) + byte_at(1, 6 * k + 5);
-          const int u = (-9719 * r - 19081 * g + 28800 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
-          const int v = (28800 * r - 24116 * g - 4684 * b + 4 * (128 << 16) + (32768 << 2)) >> 18;
-          uw |= (u32)u << (8 * k);
-          vw |= (u32)v << (8 * k);
+          i32 u = cK, v = cK;
+          const u32 q[4] = {pa[2 * k], pa[2 * k + 1], pb[2 * k], pb[2 * k + 1]};
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            u = dp2a_hi_su(cuB, q[t], dp2a_lo_su(cuRG, q[t], u));
+            v = dp2a_hi_su(cvB, q[t], dp2a_lo_su(cvRG, q[t], v));
+          }
+          uw |= (u32)(u >> 18) << (8 * k);
+          vw |= (u32)(v >> 18) << (8 * k);
         }
       } else if (bpp <= 2) {
         // L8 / La8 (convert_image_y, src/decoder/yuv.rs:806-845): Y = the grey sample, U = V = 127
