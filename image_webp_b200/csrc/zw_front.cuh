@@ -19,7 +19,10 @@ namespace zw {
 constexpr int YUV_TILE_W = 256;                 // luma pixels per CTA strip
 constexpr int YUV_THREADS = YUV_TILE_W / 8;     // 32 threads (one warp) per row pair, 8 px each
 constexpr int YUV_ROWPAIRS = 8;                 // row pairs per CTA step (blockDim.y)
-constexpr int YUV_STEPS = 4;                    // steps per CTA: 64 source rows x 256 px; step s+1 is in flight (cp.async) while step s is converted
+#ifndef ZW_YUV_STEPS
+#define ZW_YUV_STEPS 8
+#endif
+constexpr int YUV_STEPS = ZW_YUV_STEPS;                    // steps per CTA: 128 source rows x 256 px; step s+1 is in flight (cp.async) while step s is converted
 constexpr int YUV_ROW_SLOTS = (YUV_TILE_W * 4 + 32) / 16;  // uint4 slots per staged row (RGBA worst case + skew)
 
 // dp2a: d = c + a.lo16 * b.byte(0|2) + a.hi16 * b.byte(1|3); unsigned or signed 16-bit coefficients x unsigned bytes
@@ -28,7 +31,10 @@ __device__ __forceinline__ u32 dp2a_hi_uu(u32 a, u32 b, u32 c) { u32 d; asm("dp2
 __device__ __forceinline__ i32 dp2a_lo_su(i32 a, u32 b, i32 c) { i32 d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ i32 dp2a_hi_su(i32 a, u32 b, i32 c) { i32 d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 
-__global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS) k_yuv(ChunkParams P) {
+#ifndef ZW_YUV_MIN_BLOCKS
+#define ZW_YUV_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS, ZW_YUV_MIN_BLOCKS) k_yuv(ChunkParams P) {
   const ImageDesc d = P.img[blockIdx.z];
   const int pw = d.mbw * 16, ph = d.mbh * 16;
   const int x0 = blockIdx.x * YUV_TILE_W;
