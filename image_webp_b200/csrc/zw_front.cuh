@@ -59,19 +59,23 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS, ZW_YUV_MIN_BLOCKS) 
     const int ccy = min(rp, chh - 1);
     rowA = 2 * ccy; rowB = min(2 * ccy + 1, h - 1);
   };
+  // 32-bit offsets inside the image (w * h * bpp < 2^32; every image starts 16-byte aligned in the arena)
+  const u8* img_rgb = P.rgb + d.rgb_off;
+  const u32 row_bytes = (u32)w * (u32)bpp, xs_bytes = (u32)xs * (u32)bpp;
+  const u32 stage_sm = (u32)__cvta_generic_to_shared(stage0);
   auto issue = [&](int step) {
     int rp, rowA, rowB;
     rows_of(step, rp, rowA, rowB);
     if (step < YUV_STEPS && rp * 2 < ph) {
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
-        const size_t al = (d.rgb_off + byte0) & ~(size_t)15;  // arena is 16-byte aligned
-        const int nvec = ((int)((d.rgb_off + byte0) - al) + span_bytes + 15) >> 4;
-        const uint4* src = reinterpret_cast<const uint4*>(P.rgb + al);
-        const u32 dst = (u32)__cvta_generic_to_shared(stage0 + ((step & 1) * 2 + r) * YUV_ROW_SLOTS);
+        const u32 byte0 = (u32)(r == 0 ? rowA : rowB) * row_bytes + xs_bytes;
+        const u32 al = byte0 & ~15u;
+        const int nvec = ((int)(byte0 - al) + span_bytes + 15) >> 4;
+        const u8* src = img_rgb + al;
+        const u32 dst = stage_sm + (u32)(((step & 1) * 2 + r) * YUV_ROW_SLOTS * 16);
         for (int i = threadIdx.x; i < nvec; i += YUV_THREADS)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (u32)i), "l"(src + i) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (u32)i), "l"(src + 16u * (u32)i) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -86,10 +90,7 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS, ZW_YUV_MIN_BLOCKS) 
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     int skew[2];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const size_t byte0 = ((size_t)(r == 0 ? rowA : rowB) * w + xs) * bpp;
-      skew[r] = (int)((d.rgb_off + byte0) & (size_t)15);
-    }
+    for (int r = 0; r < 2; r++) skew[r] = (int)(((u32)(r == 0 ? rowA : rowB) * row_bytes + xs_bytes) & 15u);
     __syncwarp();
     if (tx < pw) {
       const u8* sA = sm + (size_t)(threadIdx.y * 4 + (step & 1) * 2 + 0) * YUV_ROW_SLOTS * 16 + skew[0];
@@ -187,10 +188,11 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS, ZW_YUV_MIN_BLOCKS) 
         vw |= (u32)v << (8 * k);
       }
       }
-      *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp) * pw + tx) = make_uint2(y0w[0], y0w[1]);
-      *reinterpret_cast<uint2*>(yp + (size_t)(2 * rp + 1) * pw + tx) = make_uint2(y1w[0], y1w[1]);
-      *reinterpret_cast<u32*>(up + (size_t)rp * (pw >> 1) + (tx >> 1)) = uw;
-      *reinterpret_cast<u32*>(vp + (size_t)rp * (pw >> 1) + (tx >> 1)) = vw;
+      const u32 yo = (u32)(2 * rp) * (u32)pw + (u32)tx, co = (u32)rp * (u32)(pw >> 1) + (u32)(tx >> 1);
+      *reinterpret_cast<uint2*>(yp + yo) = make_uint2(y0w[0], y0w[1]);
+      *reinterpret_cast<uint2*>(yp + yo + (u32)pw) = make_uint2(y1w[0], y1w[1]);
+      *reinterpret_cast<u32*>(up + co) = uw;
+      *reinterpret_cast<u32*>(vp + co) = vw;
     }
     __syncwarp();
   }
