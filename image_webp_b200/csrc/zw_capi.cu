@@ -963,21 +963,33 @@ static int encode_batch(zw_ctx* c, const zw_image* imgs, size_t n, int quality, 
     l->state = LANE_FREE;
   }
   c->staged = false; c->encoded = false;
-  // Chunks: bounded by the device budget.  A large batch is cut into THREE chunks of growing size (1 : 3 : 9):
-  // only the first, small chunk's H2D copy is exposed, every later copy runs under the kernels of the chunk before
-  // it (the link moves pixels ~3.7x faster than the kernels consume them), and most images still go through the
-  // kernels in one large chunk (equal chunks cost ~10-20 % in wavefront ramps and tails, measured).
-  // ZW_SPLIT=n forces n equal chunks (1 = no split).
-  u64 total_px = 0;
-  for (size_t i = 0; i < n; i++) total_px += (u64)imgs[i].width * imgs[i].height;
+  // Chunks: bounded by the device budget.  A large batch is cut into up to THREE chunks of growing size (1 : 3 : 9):
+  // only the first, small chunk's H2D copy is exposed, every later copy runs under the kernels of the chunk before it
+  // (the link moves pixels ~3.7x faster than the kernels consume them), and most images still go through the kernels
+  // in one large chunk.  Every extra chunk pays the per-chunk latency floor once more -- above all the pass-1 chroma
+  // chains (one warp per image, ~2.4 us per macroblock: 3.7 ms for 768x512 images, 20 ms for 1920x1080) and about as
+  // much again in wavefront ramps and tails, which also grow with the image size -- so the number of chunks is the one
+  // with the smallest estimate of exposed copy + extra floors.  Measured, blocking call: 1024 x 768x512 m4 one chunk
+  // 101.9 ms, 1:3 98.9 ms, 1:3:9 ~118 ms; 256 x 1920x1080 m6 one chunk 200.7 ms, 1:3 222.5 ms, 1:3:9 270 ms;
+  // 8192 x 256x256 m0: 1:3:9 82.8 ms.  ZW_SPLIT=n forces n equal chunks (1 = no split).
+  u64 total_px = 0, total_bytes = 0, max_mb = 0;
+  for (size_t i = 0; i < n; i++) {
+    total_px += (u64)imgs[i].width * imgs[i].height;
+    total_bytes += imgs[i].len;
+    max_mb = std::max<u64>(max_mb, (u64)((imgs[i].width + 15) / 16) * ((imgs[i].height + 15) / 16));
+  }
   int split = 0;
   if (const char* env = getenv("ZW_SPLIT")) split = std::max(0, atoi(env));
   if (c->lanes.size() < 2) split = 1;
   std::vector<u64> px_targets;  // pixel budget of chunk 0, 1, ...; the last entry repeats
   if (split >= 1) px_targets.push_back((total_px + split - 1) / split);
-  else if (total_px >= (96ull << 20)) { px_targets = {total_px / 13, 3 * total_px / 13, total_px}; }
-  else if (total_px >= (24ull << 20)) { px_targets = {total_px / 4, total_px}; }
-  else px_targets.push_back(total_px + 1);
+  else {
+    const double h2d_ms = (double)total_bytes / 50e6, floor_ms = (double)max_mb * 4.8e-3 + 2.0;
+    const double est1 = h2d_ms, est2 = h2d_ms / 4 + floor_ms, est3 = h2d_ms / 13 + 2 * floor_ms;
+    if (total_px >= (96ull << 20) && est3 <= est2 && est3 < est1) px_targets = {total_px / 13, 3 * total_px / 13, total_px};
+    else if (total_px >= (24ull << 20) && est2 < est1) px_targets = {total_px / 4, total_px};
+    else px_targets.push_back(total_px + 1);
+  }
   struct Pending { int lane; size_t i0, i1; };
   std::vector<Pending> q;
   zw_timing acc = zw_timing();

@@ -284,6 +284,15 @@ class Context:
             _raise_for(rc, self.lib)
         return self._collect(outs, raise_errors), t.as_dict()
 
+    def encode_batch_raw(self, images, params, color=ColorType.Rgb8):
+        """zw_encode_webp_batch with library-allocated outputs left in place: returns (zw_output array, return code).  The
+        caller hands the array to `_collect` (copies the files out and frees them).  For timing the C call alone."""
+        self._check(params, color, True)
+        arr, keep = self._as_images(images, color)
+        outs = (_lib.ZwOutput * len(keep))()
+        rc = self.lib.zw_encode_webp_batch(self.h, arr, len(keep), int(params.lossy_quality), int(params.method), outs, None)
+        return outs, rc
+
     def encode_alpha_batch(self, images, color=ColorType.Rgba8, raise_errors=True):
         """ALPH chunk payloads (encode_alpha_lossless, api.rs:1175) of La8 / Rgba8 images."""
         arr, keep = self._as_images(images, color)
