@@ -357,8 +357,8 @@ static Lane* lane_create(zw_ctx* ctx, int warps_hint) {
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_chroma2, SEARCH_WARPS * 32, sizeof(SearchShared)) == cudaSuccess;
   ok &= cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(1))) == cudaSuccess;
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search<1>, search_warps(1) * 32, search_smem_bytes(search_warps(1))) == cudaSuccess;
-  ok &= cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(search_warps(2))) == cudaSuccess;
-  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_bytes(search_warps(2))) == cudaSuccess;
+  ok &= cudaFuncSetAttribute(k_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_total(2)) == cudaSuccess;
+  ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_search<2>, search_warps(2) * 32, search_smem_total(2)) == cudaSuccess;
   int bq1 = 0, bq2 = 0;
   ok &= cudaFuncSetAttribute(k_searchq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)searchq_smem_bytes(1)) == cudaSuccess;
   ok &= cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bq1, k_searchq<1>, sq_warps(1) * 32, searchq_smem_bytes(1)) == cudaSuccess;
@@ -602,7 +602,7 @@ static int lane_launch(Lane* c, int quality, int method, Lane* after) {
     } else {
       const int w2 = search_warps(2);
       const int g2 = (int)std::min<u64>((u64)c->search_blocks2, ((u64)c->n_rows + w2 - 1) / w2);
-      k_search<2><<<g2, w2 * 32, search_smem_bytes(w2), s>>>(P);
+      k_search<2><<<g2, w2 * 32, search_smem_total(2), s>>>(P);
     }
     c->launches += 2;
   }

@@ -39,6 +39,7 @@ ZW_HD u32 bit_cost(int bit, u32 prob) { return bit ? ZW_TAB(kEntropyCost)[255 - 
 struct CostCtx {
   const u8* probs;        // [4][8][3][11] token probabilities the estimates read (p0 terms)
   const u16* level_cost;  // [4][8][3][68] variable level costs; nullptr == the all-zero pass-1 tables (Q1)
+  const u16* lc3;         // k_search only: the I4 (type 3) part [8][3][68], in the warp's shared memory during pass 2
 };
 
 ZW_HD u32 level_cost_at(const CostCtx& cc, int ctype, int n, int ctx, int v) {

@@ -452,7 +452,7 @@ __device__ __forceinline__ u32 coop_cost_i4(i32 lv, int ctx0, const CostCtx& cc,
   const int pv = __shfl_up_sync(FULL, v, 1, 16);
   const int ctx = n == 0 ? ctx0 : imin(pv, 2);
   u32 c = ZW_TAB(kLevelFixedCosts)[imin(v, 2047)];
-  if (cc.level_cost) c += cc.level_cost[3 * 1632 + (band * 3 + ctx) * 68 + imin(v, 67)];
+  if (cc.level_cost) c += cc.lc3[(band * 3 + ctx) * 68 + imin(v, 67)];
   if (n == last) c += v == 1 ? (eob_pack & 0xffffu) : (eob_pack >> 16);  // eob_pack is 0 for n = 15
   if (n == 0) c += c1;
   if (n > last) c = 0;
@@ -515,7 +515,7 @@ __device__ __noinline__ bool trellis_half(bool active, i32 c, i32& dq, i16* zz_o
     dq = 0;
     return false;
   }
-  const u16* LC = cc.level_cost + ctype * (8 * 3 * 68);
+  const u16* LC = ctype == 3 ? cc.lc3 : cc.level_cost + ctype * (8 * 3 * 68);
   const int band = kb.x;
   i64 base[2];
   u32 fx[2];
@@ -884,8 +884,8 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           const bool nz = last >= 0;
           u32 t0 = ZW_TAB(kLevelFixedCosts)[imin(a0, 2047)], t1 = ZW_TAB(kLevelFixedCosts)[imin(a1, 2047)];
           if (cc.level_cost) {
-            t0 += cc.level_cost[3 * 1632 + (c8_band0 * 3 + ctxa) * 68 + imin(a0, 67)];
-            t1 += cc.level_cost[3 * 1632 + (c8_band1 * 3 + ctxb) * 68 + imin(a1, 67)];
+            t0 += cc.lc3[(c8_band0 * 3 + ctxa) * 68 + imin(a0, 67)];
+            t1 += cc.lc3[(c8_band1 * 3 + ctxb) * 68 + imin(a1, 67)];
           }
           if (c8_nc0 == last) t0 += a0 == 1 ? (c8_eob0 & 0xffffu) : (c8_eob0 >> 16);
           if (c8_nc1 == last) t1 += a1 == 1 ? (c8_eob1 & 0xffffu) : (c8_eob1 >> 16);
@@ -1435,6 +1435,12 @@ __host__ __device__ constexpr int search_min_blocks(int pass) {
 }
 // dynamic shared memory of a wavefront kernel launched with `nwarps` warps per CTA
 __host__ __device__ constexpr size_t search_smem_bytes(int nwarps) { return sizeof(SearchShared) + (size_t)(nwarps - SEARCH_WARPS) * sizeof(WarpScratch); }
+// k_search<2> keeps the I4 (type 3) level costs [8][3][68] of each warp's image behind the scratch: the most-read table of
+// the pass (measured: pass 2 39.0 -> 38.6 ms at method 4, 54.8 -> 52.5 ms at method 6; L1 alone thrashes with 20 images per SM)
+constexpr int LC3_ENTRIES = 8 * 3 * 68;
+__host__ __device__ constexpr size_t search_smem_total(int pass) {
+  return search_smem_bytes(search_warps(pass)) + (pass == 2 ? (size_t)search_warps(pass) * LC3_ENTRIES * sizeof(u16) : 0);
+}
 
 template <int PASS>
 __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PASS)) k_search(ChunkParams P) {
@@ -1487,6 +1493,13 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
         up_mb0 = row_mb0 - mbw;  // only dereferenced when mby > 0
         cc.probs = PASS == 1 ? ZW_TAB(kCoeffProbs) : P.probs + (size_t)img * 1056;
         cc.level_cost = PASS == 1 ? nullptr : P.lcost + (size_t)img * 6528;
+        cc.lc3 = nullptr;
+        if (PASS == 2) {  // the image's I4 level costs (3.2 KB): the most-read table of the pass, kept in shared memory per row
+          const u32* src3 = reinterpret_cast<const u32*>(cc.level_cost + 3 * 1632);
+          u16* lc3 = reinterpret_cast<u16*>(smem_raw + search_smem_bytes(search_warps(PASS))) + (threadIdx.x >> 5) * LC3_ENTRIES;
+          for (int k = lane; k < LC3_ENTRIES / 2; k += 32) reinterpret_cast<u32*>(lc3)[k] = __ldg(src3 + k);
+          cc.lc3 = lc3;
+        }
         seg_on = P.st[img].seg_enabled != 0;
         // row-start state (vp8.rs:1339-1344 / :1423-1429)
         left_nz = 0; mbx = 0; seen = 0;
