@@ -325,6 +325,7 @@ def lossless_leg(Z, ctx, workloads, lib, cores, check=64):
                                   "bit_counts": best["token_ms"], "pack": best["assemble_ms"], "h2d": best["h2d_ms"], "d2h": best["d2h_ms"]},
                      "bytes_per_px": out_bytes / px, "h2d_bytes": best["h2d_bytes"], "d2h_bytes": best["d2h_bytes"],
                      "hbm_gb_s": (px * traffic + 2 * out_bytes) / best["device_total_ms"] / 1e6,
+                     "hbm_frac_of_measured_peak": (px * traffic + 2 * out_bytes) / best["device_total_ms"] / 1e6 / measured_peaks()[0]["hbm_gbs"],
                      "parity": {"checked": k, "identical": k - len(bad), "against": "lossless oracle (oracle/zw_lossless_oracle.inc)"},
                      "cpu_port": {"value": k * px / n / dt / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
                                   "sample": "%d images, one image per thread on %d threads" % (k, cores)}}
