@@ -1281,12 +1281,15 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
     for (int k = 0; k < 8; k++) if (k == lane) c[0] = ndc[k];
     q[0] = quantize_coeff(c[0], SP.uv, 0);
     bool nz = false;
+    constexpr int ZZ[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};  // kZigzag: levels go to the record straight from registers
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       nz |= q[k] != 0;
-      W.nat[lane][k] = (i16)q[k];
       c[k] = dequantize(q[k], SP.uv, k);
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      reinterpret_cast<u32*>(W.rec.levels[17 + lane])[k] = (u32)(u16)(i16)q[ZZ[2 * k]] | ((u32)(u16)(i16)q[ZZ[2 * k + 1]] << 16);
     idct4x4(c);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -1296,10 +1299,6 @@ __device__ ChromaOut chroma_mb(WarpScratch& W, const SegParams& SP, const CostCt
     W.nzflag[lane] = nz;
   }
   __syncwarp();
-  if (lane < 8) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) W.rec.levels[17 + lane][k] = W.nat[lane][ZW_TAB(kZigzag)[k]];
-  }
   R.uvnz = __ballot_sync(FULL, lane < 8 && W.nzflag[lane] != 0) & 0xffu;
   R.uv_mode = uv_mode;
   __syncwarp();
@@ -1354,8 +1353,17 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
   const bool ahead = mbw > 1;
   uint2 n_src = make_uint2(0, 0);
   u32 n_top = 127, n_derr = 0, n_seg = 0;
-  auto fetch = [&](u32 i, uint2& o_src, u32& o_top, u32& o_derr, u32& o_seg) {
-    const int fy = (int)(i / (u32)mbw), fx = (int)(i % (u32)mbw);
+  // the (at most four) quantiser sets of the image, copied next to the scratch once: a macroblock's parameters are then a
+  // shared-memory read away instead of two dependent global loads at the head of every step of the chain
+  SegParams* seg4 = reinterpret_cast<SegParams*>(W.coef);  // pass-1 chroma never touches the luma trellis buffer
+  static_assert(4 * sizeof(SegParams) <= sizeof(W.coef), "segment parameters must fit the borrowed buffer");
+  for (int k = lane; k < (int)(4 * sizeof(SegParams) / 4); k += 32) {
+    const int sgm = k / (int)(sizeof(SegParams) / 4), wd = k % (int)(sizeof(SegParams) / 4);
+    const u32 qi = seg_on ? (u32)IS.seg_qidx[sgm] : P.base_qidx;
+    reinterpret_cast<u32*>(seg4)[k] = reinterpret_cast<const u32*>(&P.segtab[qi])[wd];
+  }
+  __syncwarp();
+  auto fetch = [&](u32 i, int fx, int fy, uint2& o_src, u32& o_top, u32& o_derr, u32& o_seg) {
     const u32 g = d.mb_off + i;
     if (lane < 16) {
       const u8* pl = lane < 8 ? up : vp;
@@ -1369,15 +1377,16 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
     }
     o_seg = seg_on ? (u32)P.segmap[g] : 0u;
   };
-  if (ahead) fetch(0, n_src, n_top, n_derr, n_seg);
+  if (ahead) fetch(0, 0, 0, n_src, n_top, n_derr, n_seg);
+  int mbx = 0, mby = 0;
   for (u32 i = 0; i < nmb; i++) {
-    const int mby = (int)(i / (u32)mbw), mbx = (int)(i % (u32)mbw);
     const u32 gmb = d.mb_off + i;
     uint2 c_src = n_src;
     u32 c_top = n_top, top_derr = n_derr, c_seg = n_seg;
-    if (!ahead) fetch(i, c_src, c_top, top_derr, c_seg);
-    else if (i + 1 < nmb) fetch(i + 1, n_src, n_top, n_derr, n_seg);
-    const SegParams& SP = P.segtab[seg_on ? IS.seg_qidx[c_seg] : P.base_qidx];
+    const int nx = mbx + 1 == mbw ? 0 : mbx + 1, ny = mbx + 1 == mbw ? mby + 1 : mby;  // the next macroblock in raster order
+    if (!ahead) fetch(i, mbx, mby, c_src, c_top, top_derr, c_seg);
+    else if (i + 1 < nmb) fetch(i + 1, nx, ny, n_src, n_top, n_derr, n_seg);
+    const SegParams& SP = seg4[seg_on ? c_seg : 0u];
     // stage the macroblock (load_chroma_mb with the prefetched values)
     if (lane < 8) *reinterpret_cast<uint2*>(&W.src_u[lane * 8]) = c_src;
     else if (lane < 16) *reinterpret_cast<uint2*>(&W.src_v[(lane - 8) * 8]) = c_src;
@@ -1415,6 +1424,7 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
     if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
     if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
     __syncwarp();
+    mbx = nx; mby = ny;
   }
 }
 
