@@ -1363,19 +1363,23 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
     reinterpret_cast<u32*>(seg4)[k] = reinterpret_cast<const u32*>(&P.segtab[qi])[wd];
   }
   __syncwarp();
+  // Every value is ONE load per lane whose result is not touched until the next step (addresses are selected, not values:
+  // a select or a conversion right after the load would make the warp wait for the L2 round trip it is meant to hide --
+  // measured: 600 cycles per macroblock).  Lanes 0..15: source row (8 bytes) and one pixel of the row above; every lane:
+  // the diffusion state of the macroblock above and the segment.
+  const u8* src_row = lane < 8 ? up + (size_t)(lane & 7) * cwid : vp + (size_t)(lane & 7) * cwid;
   auto fetch = [&](u32 i, int fx, int fy, uint2& o_src, u32& o_top, u32& o_derr, u32& o_seg) {
     const u32 g = d.mb_off + i;
-    if (lane < 16) {
-      const u8* pl = lane < 8 ? up : vp;
-      o_src = __ldg(reinterpret_cast<const uint2*>(pl + (size_t)(fy * 8 + (lane & 7)) * cwid + fx * 8));
-    }
-    o_top = 127; o_derr = 0;
+    if (lane < 16) o_src = __ldg(reinterpret_cast<const uint2*>(src_row + (size_t)(fy * 8) * cwid + fx * 8));
     if (fy > 0) {
       const MbBottom* bt = &P.bottom[g - mbw];
-      if (lane < 16) o_top = lane < 8 ? __ldcg(&bt->u[lane]) : __ldcg(&bt->v[lane - 8]);
+      const u8* tp = lane < 8 ? &bt->u[lane & 7] : &bt->v[lane & 7];
+      if (lane < 16) o_top = __ldcg(tp);
       o_derr = __ldcg(&P.derr1[g - mbw]);
+    } else {
+      o_top = 127; o_derr = 0;
     }
-    o_seg = seg_on ? (u32)P.segmap[g] : 0u;
+    if (seg_on) o_seg = (u32)P.segmap[g];
   };
   if (ahead) fetch(0, 0, 0, n_src, n_top, n_derr, n_seg);
   int mbx = 0, mby = 0;
@@ -1385,7 +1389,6 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
     u32 c_top = n_top, top_derr = n_derr, c_seg = n_seg;
     const int nx = mbx + 1 == mbw ? 0 : mbx + 1, ny = mbx + 1 == mbw ? mby + 1 : mby;  // the next macroblock in raster order
     if (!ahead) fetch(i, mbx, mby, c_src, c_top, top_derr, c_seg);
-    else if (i + 1 < nmb) fetch(i + 1, nx, ny, n_src, n_top, n_derr, n_seg);
     const SegParams& SP = seg4[seg_on ? c_seg : 0u];
     // stage the macroblock (load_chroma_mb with the prefetched values)
     if (lane < 8) *reinterpret_cast<uint2*>(&W.src_u[lane * 8]) = c_src;
@@ -1406,6 +1409,9 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
       W.uvws[16] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_v[0]);
     }
     __syncwarp();
+    // the next macroblock's loads are issued only now: a __syncwarp orders memory, i.e. waits for the loads in flight, and
+    // the next one is a whole mode search away (issued before the two above, the prefetch stalled the chain for an L2 round trip)
+    if (ahead && i + 1 < nmb) fetch(i + 1, nx, ny, n_src, n_top, n_derr, n_seg);
     const ChromaOut C = chroma_mb(W, SP, cc, mbx, mby, left_derr, top_derr, lane);
     MbRecord* r = &P.rec1[gmb];
     if (lane < 8) {

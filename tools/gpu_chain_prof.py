@@ -15,9 +15,10 @@ buf = (C.c_ulonglong * 16)()
 L.zw_debug_chain_prof(buf, 1)
 t = ctx.encode_resident(p)
 L.zw_debug_chain_prof(buf, 0)
-names = ["loop head+staging", "dc (2 reduces)", "pred+fdct+quant+cost", "dequant+idct+sse", "3 reduces+score+select", "transfer shuffles",
-         "dcbuf+diffusion", "final quant+idct+stores", "zigzag copy+ballot", "record/border stores"]
-tot = sum(buf[i] for i in range(10))
+names = ["fetch issue (after staging)", "dc (2 reduces)", "pred+fdct+quant+cost", "dequant+idct+sse", "3 reduces+score+select", "transfer shuffles",
+         "dcbuf+diffusion", "final quant+idct+stores", "ballot", "record/border stores", "loop top (copies, SP)", "staging stores + sync 1",
+         "left column + sync 2"]
+tot = sum(buf[i] for i in range(13))
 nmb = 48 * 32
 print("chroma1 %.3f ms; %d cycles per MB" % (t["chroma1_ms"], tot / nmb))
 for i, nm in enumerate(names):
