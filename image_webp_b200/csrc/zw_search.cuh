@@ -1383,6 +1383,7 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
   };
   if (ahead) fetch(0, 0, 0, n_src, n_top, n_derr, n_seg);
   int mbx = 0, mby = 0;
+  u32 lcap_u = 129, lcap_v = 129;
   for (u32 i = 0; i < nmb; i++) {
     const u32 gmb = d.mb_off + i;
     uint2 c_src = n_src;
@@ -1393,20 +1394,21 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
     // stage the macroblock (load_chroma_mb with the prefetched values)
     if (lane < 8) *reinterpret_cast<uint2*>(&W.src_u[lane * 8]) = c_src;
     else if (lane < 16) *reinterpret_cast<uint2*>(&W.src_v[(lane - 8) * 8]) = c_src;
+    // top row, left column and corner in ONE phase: the left column / corner were captured in registers from the previous
+    // macroblock's reconstruction (lane l < 8: row 1 + l, lane 8: the corner), so nothing is read here
     if (mby == 0) {
-      W.uvws[lane] = 127;
+      if (lane >= 1 && lane != 16) W.uvws[lane] = 127;  // [0] and [16] are the corners, written below
     } else {
       if (lane < 8) W.uvws[1 + lane] = (u8)c_top;
       else if (lane < 16) W.uvws[17 + (lane - 8)] = (u8)c_top;
     }
-    __syncwarp();
     if (lane < 8) {
-      W.uvws[(1 + lane) * 32] = (mbx == 0) ? 129 : W.left_u[1 + lane];
-      W.uvws[(1 + lane) * 32 + 16] = (mbx == 0) ? 129 : W.left_v[1 + lane];
+      W.uvws[(1 + lane) * 32] = (mbx == 0) ? 129 : (u8)lcap_u;
+      W.uvws[(1 + lane) * 32 + 16] = (mbx == 0) ? 129 : (u8)lcap_v;
     }
-    if (lane == 0) {
-      W.uvws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_u[0]);
-      W.uvws[16] = (mby == 0) ? 127 : (mbx == 0 ? 129 : W.left_v[0]);
+    if (lane == 8) {
+      W.uvws[0] = (mby == 0) ? 127 : (mbx == 0 ? 129 : (u8)lcap_u);
+      W.uvws[16] = (mby == 0) ? 127 : (mbx == 0 ? 129 : (u8)lcap_v);
     }
     __syncwarp();
     // the next macroblock's loads are issued only now: a __syncwarp orders memory, i.e. waits for the loads in flight, and
@@ -1425,7 +1427,8 @@ __device__ void chroma_chain1(WarpScratch& W, const ChunkParams& P, u32 img, int
       P.c1info[2 * gmb] = left_derr;
       P.c1info[2 * gmb + 1] = (u32)C.uv_mode | (C.uvnz << 8);
     }
-    if (lane < 9) { W.left_u[lane] = W.uvws[lane * 32 + 8]; W.left_v[lane] = W.uvws[lane * 32 + 24]; }
+    // left column (lanes 0..7: rows 1..8) and corner (lane 8: row 0 = the row above, untouched by the reconstruction) of the next macroblock
+    if (lane < 9) { const int rr = lane < 8 ? 1 + lane : 0; lcap_u = W.uvws[rr * 32 + 8]; lcap_v = W.uvws[rr * 32 + 24]; }
     MbBottom* bo = &P.bottom[gmb];
     if (lane >= 16 && lane < 24) bo->u[lane - 16] = W.uvws[8 * 32 + 1 + (lane - 16)];
     if (lane >= 24) bo->v[lane - 24] = W.uvws[8 * 32 + 17 + (lane - 24)];
