@@ -68,7 +68,6 @@ struct __align__(16) WarpScratch {
   i32 coef[16][16];  // natural-order DCT coefficients handed to / returned by the cooperative trellis
   u8 cand_px[10][16];   // I4 search: reconstructed pixels of each evaluated candidate (by rank)
   i16 cand_lv[10][16];  // I4 search: natural-order levels of each evaluated candidate (by rank)
-  u32 psse[10];         // I4 search: prediction SSE per mode
   u8 cand_mode[12];     // I4 search: mode with rank r
   u8 bmodes[16];
   u8 dtab[48];       // I4: the 23 distinct 3-tap edge filters of the current sub-block, its DC ([23]), its TM pixels ([32 + n])
@@ -795,7 +794,10 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
     const int n16 = lane & 15;
     const u32 taps = SH.dtaps[lane];
     // table indices of this lane's pixel for the modes 2r + hb of SSE steps r = 1..4, one per byte
-    const u32 pk = (u32)pidx[2 + hb][n16] | ((u32)pidx[4 + hb][n16] << 8) | ((u32)pidx[6 + hb][n16] << 16) | ((u32)pidx[8 + hb][n16] << 24);
+    // prediction-SSE ranking on packed bytes: this lane's (mode slot, pixel row) = (lane >> 2, lane & 3); the four table
+    // indices of that row of predicted pixels are one aligned word of pred_idx.  Step A: modes 0..7, step B: modes 8, 9.
+    const u32 pkA = *reinterpret_cast<const u32*>(&pidx[lane >> 2][(lane & 3) * 4]);
+    const u32 pkB = *reinterpret_cast<const u32*>(&pidx[8 + ((lane >> 2) & 1)][(lane & 3) * 4]);
     // this lane's quantiser entry, hoisted out of the sub-block loop (the compiler cannot: SP lives in global memory)
     const u32 lq_iq = SP.y1.iq[n16 > 0], lq_bias = SP.y1.bias[n16 > 0];
     const i32 lq_q = SP.y1.q[n16 > 0];
@@ -831,26 +833,26 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
       const int ctx0 = (sby == 0 ? 0 : (int)((tnz4 >> sbx) & 1)) + (sbx == 0 ? 0 : (int)((lnz4 >> sby) & 1));
       const i32 srcpx = W.src_y[(sby * 4 + (n16 >> 2)) * 16 + sbx * 4 + (n16 & 3)];
       const Pred4 P4 = pred4_prepare(W, x0, y0, taps, lane);
-      // prediction SSE of the ten modes, two modes per step; lane m < 10 ends up with the sort key
-      // (sse << 4 | m) of mode m: ascending key order == stable ascending SSE order
-      // (sort_unstable_by_key is an insertion sort at this length, Q11)
+      // prediction SSE of the ten modes; the sort key (sse << 4 | m) of mode m: ascending key order == stable
+      // ascending SSE order (sort_unstable_by_key is an insertion sort at this length, Q11)
+      // Four lanes per mode, one row of four pixels each: the predicted row is four dtab bytes packed into a word,
+      // |src - pred| per byte is one VABSDIFF4 and the row's sum of squares one DP4A; two xor-shuffles finish a mode.
+      u32 skey;
       {
-        const i32 d0 = srcpx - (hb ? P4.tm : P4.dc);
-        const int s0 = half_sum(d0 * d0);
-        if (n16 == 0) W.psse[hb] = (u32)s0;
-#pragma unroll
-        for (int r = 1; r < 5; r++) {
-          const i32 df = srcpx - (i32)W.dtab[(pk >> (8 * (r - 1))) & 255];
-          const int sse = half_sum(df * df);
-          if (n16 == 0) W.psse[2 * r + hb] = (u32)sse;
-        }
+        const u32 src4 = *reinterpret_cast<const u32*>(&W.src_y[(sby * 4 + (lane & 3)) * 16 + sbx * 4]);
+        const u32 pA = (u32)W.dtab[pkA & 255u] | ((u32)W.dtab[(pkA >> 8) & 255u] << 8) | ((u32)W.dtab[(pkA >> 16) & 255u] << 16) | ((u32)W.dtab[pkA >> 24] << 24);
+        const u32 pB = (u32)W.dtab[pkB & 255u] | ((u32)W.dtab[(pkB >> 8) & 255u] << 8) | ((u32)W.dtab[(pkB >> 16) & 255u] << 16) | ((u32)W.dtab[pkB >> 24] << 24);
+        const u32 dA = __vabsdiffu4(src4, pA), dB = __vabsdiffu4(src4, pB);
+        u32 sA = __dp4a(dA, dA, 0u), sB = __dp4a(dB, dB, 0u);
+        sA += __shfl_xor_sync(FULL, sA, 1); sB += __shfl_xor_sync(FULL, sB, 1);
+        sA += __shfl_xor_sync(FULL, sA, 2); sB += __shfl_xor_sync(FULL, sB, 2);
+        // key owners: lane 4m for mode m < 8; lanes 1 and 5 for modes 8 and 9 (every lane of a group holds the group's sum)
+        skey = (lane & 3) == 0 ? ((sA << 4) | (u32)(lane >> 2)) : ((lane == 1 || lane == 5) ? ((sB << 4) | (u32)(8 + (lane >> 2))) : 0xffffffffu);
       }
-      __syncwarp();
-      u32 skey = lane < 10 ? ((W.psse[lane] << 4) | (u32)lane) : 0xffffffffu;
 #pragma unroll 1
       for (int r = 0; r < max_modes; r++) {  // extract the `max_modes` smallest keys in order
         const u32 kmin = __reduce_min_sync(FULL, skey);
-        if (skey == kmin) { skey = 0xffffffffu; W.cand_mode[r] = (u8)lane; }
+        if (skey == kmin) { skey = 0xffffffffu; W.cand_mode[r] = (u8)(kmin & 15u); }
       }
       __syncwarp();
       u64 best_key = ~0ull;
