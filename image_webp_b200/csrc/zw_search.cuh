@@ -533,7 +533,8 @@ __device__ __noinline__ bool trellis_half(bool active, i32 c, i32& dq, i16* zz_o
     cx[d] = imin(level, 2);
   }
   // contexts of the previous position's two nodes (the initial context at `first`)
-  int pcx0 = __shfl_up_sync(FULL, cx[0], 1, 16), pcx1 = __shfl_up_sync(FULL, cx[1], 1, 16);
+  const int pcx = __shfl_up_sync(FULL, cx[0] | (cx[1] << 2), 1, 16);
+  int pcx0 = pcx & 3, pcx1 = pcx >> 2;
   if (n == first) { pcx0 = ctx0; pcx1 = ctx0; }
   if (n < first) { pcx0 = 0; pcx1 = 0; }
   i64 rate[2][2];  // [prev node][this node], already multiplied by lambda
@@ -572,10 +573,11 @@ __device__ __noinline__ bool trellis_half(bool active, i32 c, i32& dq, i16* zz_o
   s[0] = init + tmin(P00, P10);
   s[1] = init + tmin(P01, P11);
   // back pointers (ties keep predecessor 0, cost.rs:927)
-  i64 sp0 = shfl_up64_16(s[0], 1), sp1 = shfl_up64_16(s[1], 1);
-  if (n == first) { sp0 = init; sp1 = init; }
-  const bool bp0 = sp1 + rate[1][0] < sp0 + rate[0][0];
-  const bool bp1 = sp1 + rate[1][1] < sp0 + rate[0][1];
+  // sp1 + r1 < sp0 + r0  <=>  sp1 - sp0 < r0 - r1 (exact: every term is far inside i64): only the difference travels
+  i64 dsp = shfl_up64_16(s[1] - s[0], 1);
+  if (n == first) dsp = 0;
+  const bool bp0 = dsp < rate[0][0] - rate[1][0];
+  const bool bp1 = dsp < rate[0][1] - rate[1][1];
   u32 bpm0 = (__ballot_sync(FULL, inrange && bp0) >> (16 * h)) & 0xffffu;
   u32 bpm1 = (__ballot_sync(FULL, inrange && bp1) >> (16 * h)) & 0xffffu;
   // terminal candidates in (n, delta) order: key = score * 32 + (2n + delta) keeps that order on ties
@@ -588,8 +590,15 @@ __device__ __noinline__ bool trellis_half(bool active, i32 c, i32& dq, i16* zz_o
       best = tmin(best, key);
     }
   }
-#pragma unroll 1
-  for (int o = 8; o > 0; o >>= 1) best = tmin(best, shfl_xor64(best, o));
+  {  // minimum over the 16 lanes of each half-warp: per half, a warp-wide signed minimum of the high words (the other half
+     // masked out), then an unsigned minimum of the low words of the lanes that hold it -- four REDUX instead of eight shuffles
+    const i32 khi = (i32)(best >> 32);
+    const u32 klo = (u32)best;
+    const i32 mh0 = __reduce_min_sync(FULL, h == 0 ? khi : 0x7fffffff), mh1 = __reduce_min_sync(FULL, h == 1 ? khi : 0x7fffffff);
+    const u32 ml0 = __reduce_min_sync(FULL, (h == 0 && khi == mh0) ? klo : 0xffffffffu);
+    const u32 ml1 = __reduce_min_sync(FULL, (h == 1 && khi == mh1) ? klo : 0xffffffffu);
+    best = (i64)(((u64)(u32)(h ? mh1 : mh0) << 32) | (u64)(h ? ml1 : ml0));
+  }
   const int bidx = (int)(best & 31);
   const bool have = (best >> 5) < skip_score;  // arithmetic shift == floor division by 32
   const int best_n = have ? (bidx >> 1) : -1;
@@ -878,10 +887,12 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           const i32 a1 = quantdiv((u32)iabs(w1), c8_iq, c8_bias);
           const i32 q0 = w0 < 0 ? -a0 : a0, q1 = w1 < 0 ? -a1 : a1;
           // get_residual_cost in natural order: position n's context is min(|level[n - 1]|, 2)
-          const i32 e0 = __shfl_xor_sync(FULL, a0, 1), e1 = __shfl_xor_sync(FULL, a1, 1);
-          const i32 pl = __shfl_sync(FULL, a1, (lane & 24) | c8_psrc);  // last level of the previous coefficient row
-          const int ctxa = c8_t ? imin(e0, 2) : (c8_nc0 == 0 ? ctx0 : imin(pl, 2));
-          const int ctxb = c8_t ? imin(e1, 2) : imin(e0, 2);
+          // only min(|level|, 2) of the neighbouring positions is needed: both of a lane's values travel in one word
+          const u32 m2 = (u32)imin(a0, 2) | ((u32)imin(a1, 2) << 2);
+          const u32 em = __shfl_xor_sync(FULL, m2, 1);
+          const u32 pm = __shfl_sync(FULL, m2, (lane & 24) | c8_psrc);  // last level of the previous coefficient row
+          const int ctxa = c8_t ? (int)(em & 3u) : (c8_nc0 == 0 ? ctx0 : (int)(pm >> 2));
+          const int ctxb = c8_t ? (int)(em >> 2) : (int)(em & 3u);
           const int last = red8_max(a1 != 0 ? c8_nc1 : (a0 != 0 ? c8_nc0 : -1));
           const bool nz = last >= 0;
           u32 t0 = ZW_TAB(kLevelFixedCosts)[imin(a0, 2047)], t1 = ZW_TAB(kLevelFixedCosts)[imin(a1, 2047)];
@@ -909,12 +920,18 @@ __device__ LumaOut luma_mb(WarpScratch& W, const SearchShared& SH, const SegPara
           const u64 key = act ? ((score << 4) | (u64)rank) : ~0ull;
           if (key < best_key) { best_key = key; best_sse = sse; best_rate = rate; best_nz = (int)nz; }
         }
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {  // merge the four lane groups
-          const u64 k2 = (u64)shfl_xor64((i64)best_key, o);
-          const u32 s2 = __shfl_xor_sync(FULL, best_sse, o), r2 = __shfl_xor_sync(FULL, best_rate, o);
-          const int z2 = __shfl_xor_sync(FULL, best_nz, o);
-          if (k2 < best_key) { best_key = k2; best_sse = s2; best_rate = r2; best_nz = z2; }
+        {  // merge the four lane groups (every lane of a group holds its group's best): the 64-bit minimum is two warp-wide
+           // 32-bit minima (the high words, then the low words of the lanes holding the minimal high word); rank r was
+           // evaluated by lane group r & 3, whose first lane hands over the winner's sse / rate / non-zero flag
+          const u32 khi = (u32)(best_key >> 32), klo = (u32)best_key;
+          const u32 mhi = __reduce_min_sync(FULL, khi);
+          const u32 mlo = __reduce_min_sync(FULL, khi == mhi ? klo : 0xffffffffu);
+          best_key = ((u64)mhi << 32) | (u64)mlo;
+          const int wsrc = (int)(mlo & 3u) << 3;
+          const u32 pack = __shfl_sync(FULL, (best_rate & 0xffffu) | ((u32)best_nz << 16), wsrc);  // only 16 bits of the rate are used (Q8)
+          best_sse = __shfl_sync(FULL, best_sse, wsrc);
+          best_rate = pack & 0xffffu;
+          best_nz = (int)(pack >> 16);
         }
       }
       } else {

@@ -17,9 +17,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -f -o $O/prof
 echo "all rc=$?"
 ncu -i $O/prof_${TAG}_all.ncu-rep --page raw --csv > $O/prof_${TAG}_all_raw.csv 2>/dev/null
 ncu -i $O/prof_${TAG}_all.ncu-rep --page source --csv > $O/prof_${TAG}_all_source.csv 2>/dev/null
+if [ -z "$SKIP_LOSSLESS" ]; then  # SKIP_LOSSLESS=1: the lossless kernels did not change since the last capture
 timeout 600 ncu --set full --clock-control none -f -o $O/prof_${TAG}_lossless python tools/gpu_prof_lossless.py 1024 > $O/ncu_lossless.log 2>&1
 echo "lossless rc=$?"
 ncu -i $O/prof_${TAG}_lossless.ncu-rep --page raw --csv > $O/prof_${TAG}_lossless_raw.csv 2>/dev/null
+fi
 gzip -f $O/*_source.csv
 rm -f $O/*.ncu-rep
 du -sm $O
