@@ -63,7 +63,10 @@ __device__ __forceinline__ bool block_nonzero(const i16* zz) {
 //     in shared memory with atomics (order-free), then stores them per row.  The order-dependent
 //     halving (Q9) is reconstructed exactly in k_probs from these per-row counts.
 // ---------------------------------------------------------------------------------------------
-constexpr int STAT_WARPS = 4;
+#ifndef ZW_STAT_WARPS
+#define ZW_STAT_WARPS 2  // measured 4 -> 2 warps per CTA: 1.92 -> 1.85 ms
+#endif
+constexpr int STAT_WARPS = ZW_STAT_WARPS;
 
 __global__ void __launch_bounds__(STAT_WARPS * 32) k_rowstats(ChunkParams P) {
   __shared__ u32 s_cnt[STAT_WARPS][1056 * 2];
@@ -78,6 +81,10 @@ __global__ void __launch_bounds__(STAT_WARPS * 32) k_rowstats(ChunkParams P) {
     const MbRecord* recs = P.rec1 + d.mb_off + (size_t)rr.mby * d.mbw;
     for (u32 mbx = 0; mbx < d.mbw; mbx++) {
       const MbRecord& r = recs[mbx];
+      if (mbx + 1 < d.mbw) {  // the next record's header + this lane's levels on their way to L1 while this one is walked
+        const MbRecord& nx = recs[mbx + 1];
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(lane < 25 ? (const void*)nx.levels[lane] : (const void*)&nx));
+      }
       if (r.skip) continue;
       const bool nz = lane < 25 && block_nonzero(r.levels[lane < 25 ? lane : 0]);
       const u32 nzmask = __ballot_sync(FULL, nz);
@@ -438,7 +445,10 @@ __device__ void frame_header_tokens(S& s, const ChunkParams& P, const ImageState
 // second time just to find its offsets.  MODE 1 builds the macroblock's symbols in shared memory (the lanes write 2-byte
 // symbols at unrelated offsets) and the warp then copies them out with full 128-byte stores; a macroblock with more
 // symbols than the staging buffer holds (rare: > 6 symbols per pixel) is written in place.
-constexpr int TOK_WARPS = 8;
+#ifndef ZW_TOK_WARPS
+#define ZW_TOK_WARPS 2  // macroblocks finish at very different times: small CTAs free their slots early (measured 8 -> 4 -> 2 warps: 4.59 -> 4.28 -> 4.12 ms; 16: 5.56)
+#endif
+constexpr int TOK_WARPS = ZW_TOK_WARPS;
 constexpr u32 TOK_STAGE = 1536;  // symbols per warp (3 KB)
 __device__ __forceinline__ void tok_copy_out(const Token* sm, Token* dst, u32 n, int lane) {
   if (n == 0) return;
@@ -716,8 +726,10 @@ __global__ void __launch_bounds__(128) k_bc_cands(ChunkParams P) {
     const Token* tk = S.tk + (size_t)j * BC_SEG - BC_WARM;  // 16-byte aligned: stream starts and BC_SEG, BC_WARM are multiples of 8 tokens
     u32 st = 127u + (u32)tid, add, sh;
     auto run = [&](u32 from, u32 to) {
+      uint4 qn = __ldg(reinterpret_cast<const uint4*>(tk + from));  // the same address in every lane: one broadcast; one group ahead
       for (u32 i = from; i < to; i += 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));  // the same address in every lane: one broadcast
+        const uint4 q = qn;
+        if (i + 8 < to) qn = __ldg(reinterpret_cast<const uint4*>(tk + i + 8));
 #pragma unroll
         for (int e = 0; e < 8; e++) st = bc_step(st, bc_sym8(q.x, q.y, q.z, q.w, e), add, sh);
       }
@@ -766,8 +778,14 @@ __global__ void __launch_bounds__(128) k_bc_trans(ChunkParams P) {
     for (u32 c = gl; c < k; c += 4) {
       u32 st = 127u + bc_nth_bit(m0, m1, m2, m3, c), T = 0, add, sh;
       u32 i = 0;
+      // the symbols are requested two groups of eight ahead of the group being walked (a lane's chain otherwise pays one full
+      // memory latency per 16-byte load: the load sits behind the dependent steps of the previous group)
+      uint4 qn = n >= 8 ? __ldg(reinterpret_cast<const uint4*>(tk)) : make_uint4(0, 0, 0, 0);
+      uint4 qm = n >= 16 ? __ldg(reinterpret_cast<const uint4*>(tk + 8)) : make_uint4(0, 0, 0, 0);
       for (; i + 8 <= n; i += 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
+        const uint4 q = qn;
+        qn = qm;
+        if (i + 24 <= n) qm = __ldg(reinterpret_cast<const uint4*>(tk + i + 16));
 #pragma unroll
         for (int e = 0; e < 8; e++) { st = bc_step(st, bc_sym8(q.x, q.y, q.z, q.w, e), add, sh); T += sh; }
       }
@@ -813,8 +831,12 @@ __global__ void __launch_bounds__(128) k_bc_code(ChunkParams P) {
     BcCoder cd;
     cd.begin(sg.state, sg.start_bit, S.out, S.cap);
     u32 i = 0;
+    uint4 qn = n >= 8 ? __ldg(reinterpret_cast<const uint4*>(tk)) : make_uint4(0, 0, 0, 0);
+    uint4 qm = n >= 16 ? __ldg(reinterpret_cast<const uint4*>(tk + 8)) : make_uint4(0, 0, 0, 0);
     for (; i + 8 <= n; i += 8) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
+      const uint4 q = qn;
+      qn = qm;
+      if (i + 24 <= n) qm = __ldg(reinterpret_cast<const uint4*>(tk + i + 16));
 #pragma unroll
       for (int e = 0; e < 8; e++) cd.put(bc_sym8(q.x, q.y, q.z, q.w, e));
     }

@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(YUV_THREADS* YUV_ROWPAIRS, ZW_YUV_MIN_BLOCKS) 
 //     One warp per macroblock: lanes 0..23 own one 4x4 block each (16 Y, 4 U, 4 V) and transform
 //     it against both predictions; 32-bin histograms live in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int AN_WARPS = 8;
+#ifndef ZW_AN_WARPS
+#define ZW_AN_WARPS 2  // measured 8 -> 4 -> 2 warps per CTA: 2.43 -> 2.33 -> 2.31 ms (small CTAs free their slots early)
+#endif
+constexpr int AN_WARPS = ZW_AN_WARPS;
 
 __device__ __forceinline__ void an_fdct_hist(const i32* res, u32* hist) {
   i32 c[16];

@@ -26,8 +26,8 @@ def one():
     outs, _ = ctx.download()
     h = hashlib.sha256()
     for o in outs: h.update(bytes(o))
-    print("%-28s %s total %.2f  p1 %.2f c1 %.2f st %.2f c2 %.2f p2 %.2f tok %.2f bc %.2f  sha %s" % (
-        os.path.basename(os.environ.get("ZW_LIB_PATH", "default")), "photo" if photo else "synth", t["device_total_ms"], t["pass1_ms"], t["chroma1_ms"],
+    print("%-28s %s total %.2f  an %.2f p1 %.2f c1 %.2f st %.2f c2 %.2f p2 %.2f tok %.2f bc %.2f  sha %s" % (
+        os.path.basename(os.environ.get("ZW_LIB_PATH", "default")), "photo" if photo else "synth", t["device_total_ms"], t["analysis_ms"], t["pass1_ms"], t["chroma1_ms"],
         t["stats_ms"], t["chroma2_ms"], t["pass2_ms"], t["token_ms"], t["boolcode_ms"], h.hexdigest()[:12]), flush=True)
 
 if __name__ == "__main__":
