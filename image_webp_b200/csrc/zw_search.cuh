@@ -1486,9 +1486,10 @@ __global__ void __launch_bounds__(search_warps(PASS) * 32, search_min_blocks(PAS
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchShared& SH = *reinterpret_cast<SearchShared*>(smem_raw);
   __shared__ int s_active;  // LS: warps of this CTA that still have (or may get) a row
-  for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (&d_pred_idx[0][0])[i];
+  // (mode, pixel) -> dtab slot; the TM row (flat entries 16..31) points at dtab[32 + n], where the TM pixels live -- one
+  // writer per entry
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) (&SH.pred_idx[0][0])[i] = (i >= 16 && i < 32) ? (u8)(16 + i) : (&d_pred_idx[0][0])[i];
   if (threadIdx.x < 32) { SH.dtaps[threadIdx.x] = d_dtaps[threadIdx.x]; fill_lane_consts(SH.lk, threadIdx.x); fill_lane_consts8(SH.lk8, threadIdx.x); }
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) SH.pred_idx[1][i] = (u8)(32 + i);  // TM pixels live in dtab[32 + n]
   if (threadIdx.x == 0) s_active = (int)(blockDim.x >> 5);
   __syncthreads();
   const int lane = threadIdx.x & 31;
